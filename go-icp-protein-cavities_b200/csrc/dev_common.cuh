@@ -1,0 +1,103 @@
+// Device helpers shared by every kernel.  The whole library is compiled with -fmad=false: the reference is an
+// x86-64 build without FMA contraction, so every a*b+c below rounds twice, as there.
+#pragma once
+#include <cuda_runtime.h>
+#include "goicp_dev.h"
+
+#define GOICP_FULL 0xFFFFFFFFu
+
+// ROUND((v-min)*scale), jly_3ddt.cpp:30,1143-1145: double arithmetic, truncation toward zero.
+__device__ __forceinline__ int vox_round(float v, double mn, double scale) {
+    return (int)(((double)v - mn) * scale + 0.5);
+}
+__device__ __forceinline__ int vox_round_d(double v, double mn, double scale) {
+    return (int)((v - mn) * scale + 0.5);
+}
+
+// DT3D::Distance (jly_3ddt.cpp:1139-1191) for a position already rounded to float (every caller passes floats
+// widened to double: jly_goicp.cpp:123-135,368-369,601-604).
+__device__ __forceinline__ float dt_distance(const GridDev& g, const float* __restrict__ dist, float fx, float fy, float fz) {
+    const int S = g.S;
+    int x = vox_round(fx, g.xMin, g.scale), y = vox_round(fy, g.yMin, g.scale), z = vox_round(fz, g.zMin, g.scale);
+    if ((unsigned)x < (unsigned)S && (unsigned)y < (unsigned)S && (unsigned)z < (unsigned)S)
+        return __ldg(dist + ((z * S + y) * S + x));
+    float a = 0.f, b = 0.f, c = 0.f;
+    if (x < 0) { a = (float)x; x = 0; } else if (x >= S) { a = (float)(x - S + 1); x = S - 1; }
+    if (y < 0) { b = (float)y; y = 0; } else if (y >= S) { b = (float)(y - S + 1); y = S - 1; }
+    if (z < 0) { c = (float)z; z = 0; } else if (z >= S) { c = (float)(z - S + 1); z = S - 1; }
+    return (float)((double)sqrtf(a * a + b * b + c * c) / g.scale + (double)__ldg(dist + ((z * S + y) * S + x)));
+}
+__device__ __forceinline__ float dt_distance_d(const GridDev& g, double dx, double dy, double dz, int* ox, int* oy, int* oz) {
+    const int S = g.S;
+    int x = vox_round_d(dx, g.xMin, g.scale), y = vox_round_d(dy, g.yMin, g.scale), z = vox_round_d(dz, g.zMin, g.scale);
+    *ox = x; *oy = y; *oz = z;
+    if ((unsigned)x < (unsigned)S && (unsigned)y < (unsigned)S && (unsigned)z < (unsigned)S)
+        return g.dist[(z * S + y) * S + x];
+    float a = 0.f, b = 0.f, c = 0.f;
+    if (x < 0) { a = (float)x; x = 0; } else if (x >= S) { a = (float)(x - S + 1); x = S - 1; }
+    if (y < 0) { b = (float)y; y = 0; } else if (y >= S) { b = (float)(y - S + 1); y = S - 1; }
+    if (z < 0) { c = (float)z; z = 0; } else if (z >= S) { c = (float)(z - S + 1); z = S - 1; }
+    return (float)((double)sqrtf(a * a + b * b + c * c) / g.scale + (double)g.dist[(z * S + y) * S + x]);
+}
+
+// checkCompatibility's voxel (jly_goicp.cpp:976-984): same rounding, clamped INTO the grid; returns the compact id
+// of the closest occupied cell (emptyCells), ncells if that voxel is unresolved.
+__device__ __forceinline__ int clamp_cell(const GridDev& g, float fx, float fy, float fz) {
+    const int S = g.S;
+    int x = vox_round(fx, g.xMin, g.scale), y = vox_round(fy, g.yMin, g.scale), z = vox_round(fz, g.zMin, g.scale);
+    x = min(max(x, 0), S - 1); y = min(max(y, 0), S - 1); z = min(max(z, 0), S - 1);
+    return __ldg(g.vcell + ((z * S + y) * S + x));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = v + __shfl_xor_sync(GOICP_FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) { return __reduce_add_sync(GOICP_FULL, v); }
+
+// k-th smallest (1-based) of n non-negative floats v[0..n) by a warp: bitwise radix select on the float bit patterns
+// (replaces intro_select, jly_sorting.hpp:229-313).  Returns the bit pattern T of the k-th smallest and in *need_eq
+// how many elements equal to T belong to the k smallest (they are taken in index order).
+__device__ __forceinline__ unsigned warp_select_kth(const float* v, int n, int k, int lane, int* need_eq) {
+    unsigned prefix = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+        const unsigned hi = (bit == 31) ? 0u : (0xFFFFFFFFu << (bit + 1));
+        int c0 = 0;
+        for (int i = lane; i < n; i += 32) {
+            unsigned u = __float_as_uint(v[i]);
+            c0 += ((u & hi) == prefix && !((u >> bit) & 1u)) ? 1 : 0;
+        }
+        c0 = warp_sum_i(c0);
+        if (k > c0) { k -= c0; prefix |= (1u << bit); }
+    }
+    *need_eq = k;
+    return prefix;
+}
+
+// Sum over the k smallest of v[0..n) (set chosen by warp_select_kth) of f(v) for the two bound sums of
+// InnerBnB (jly_goicp.cpp:393-415).  Tree order: trimmed sums are compared at tolerance (the reference adds them in
+// intro_select's permutation order, which is not reproducible in closed form).
+__device__ __forceinline__ void warp_trimmed_sums(const float* v, int n, int k, int lane, int norm, float mtd, float* ub, float* lb) {
+    int need_eq;
+    const unsigned T = warp_select_kth(v, n, k, lane, &need_eq);
+    float su = 0.f, sl = 0.f;
+    int eq_seen = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        const float m = (i < n) ? v[i] : 0.f;
+        const unsigned u = __float_as_uint(m);
+        const bool valid = i < n;
+        const unsigned eqm = __ballot_sync(GOICP_FULL, valid && u == T);
+        const int rank = eq_seen + __popc(eqm & ((1u << lane) - 1u));
+        const bool inc = valid && (u < T || (u == T && rank < need_eq));
+        eq_seen += __popc(eqm);
+        if (inc) {
+            su += (norm == 2) ? m * m : m;
+            const float d = m - mtd;
+            if (d > 0.f) sl += (norm == 2) ? d * d : d;
+        }
+    }
+    *ub = warp_sum(su);
+    *lb = warp_sum(sl);
+}

@@ -1,0 +1,1109 @@
+// Host engine + C ABI of libgoicp_b200.so (include/goicp_b200.h).
+//
+// The rotation branch-and-bound of GoICP::OuterBnB (jly_goicp.cpp:582-876) stays on the host as a priority queue that
+// follows the reference's pop order exactly; what it needs from the device are InnerBnB results (one CTA per call,
+// k_bnb.cu), ICP refinements and pose scores (k_icp.cu).  To fill the GPU, every wave also evaluates SPECULATIVELY the
+// InnerBnB calls the reference would make next if the incumbent error does not change (the rest of the current
+// parent's children and the next `spec_width` queue nodes in pop order); a speculative result is consumed only when
+// the reference's own order reaches that call with the same entry error, so results, traces and node counters are
+// those of the sequential algorithm.  Pairs of a batch advance in lock-step waves that share each launch.
+//
+// There is no CPU fallback anywhere in this file: every numeric result comes from a kernel.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include "../../include/goicp_b200.h"
+#include "goicp_dev.h"
+#include "launch.h"
+
+namespace {
+
+using clk = std::chrono::steady_clock;
+static double secs_since(clk::time_point t0) { return std::chrono::duration<double>(clk::now() - t0).count(); }
+
+static std::string g_create_error;
+
+// colour codes of the `properties` enum (transformation.hpp:36) that are keys of the identity compatibility map
+// (jly_goicp.cpp:66-73); C = 1 is not a key.
+static const int KNOWN_PROPS[8] = {8204959, 30894, 15219528, 15231913, 4646984, 16741671, 7566712, 0};
+static bool known_prop(int p) { for (int k = 0; k < 8; k++) if (KNOWN_PROPS[k] == p) return true; return false; }
+
+#define ROUND_HOST(x) ((int)((x) + 0.5))   // jly_3ddt.cpp:30
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+struct PinBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes * 2 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+// ROTNODE (jly_goicp.h:59-73) + a unique id for the speculation cache
+struct RNode { float a, b, c, w, ub, lb; int l; int id; };
+static inline bool rnode_less(const RNode& n1, const RNode& n2) {   // operator< :64-71
+    if (n1.lb != n2.lb) return n1.lb > n2.lb;
+    return n1.w < n2.w;
+}
+// std::priority_queue<ROTNODE> as libstdc++ implements it; spelled out so that equal keys pop in the reference's order
+// independently of the standard library this file is compiled against.
+static void rheap_push(std::vector<RNode>& h, const RNode& val) {
+    h.push_back(val);
+    int hole = (int)h.size() - 1, parent = (hole - 1) / 2;
+    while (hole > 0 && rnode_less(h[parent], val)) { h[hole] = h[parent]; hole = parent; parent = (hole - 1) / 2; }
+    h[hole] = val;
+}
+static RNode rheap_pop(std::vector<RNode>& h) {
+    RNode top = h[0];
+    const int len = (int)h.size() - 1;
+    if (len > 0) {
+        RNode val = h[len];
+        int hole = 0, child = 0;
+        while (child < (len - 1) / 2) {
+            child = 2 * (child + 1);
+            if (rnode_less(h[child], h[child - 1])) child--;
+            h[hole] = h[child]; hole = child;
+        }
+        if ((len & 1) == 0 && child == (len - 2) / 2) { child = 2 * (child + 1); h[hole] = h[child - 1]; hole = child - 1; }
+        int parent = (hole - 1) / 2;
+        while (hole > 0 && rnode_less(h[parent], val)) { h[hole] = h[parent]; hole = parent; parent = (hole - 1) / 2; }
+        h[hole] = val;
+    }
+    h.pop_back();
+    return top;
+}
+
+struct CallRes { float entryOpt; float err; float tn[4]; int pops, subcubes; };
+
+enum Phase { PH_START, PH_WAIT_INIT, PH_POP, PH_CHILD_UB, PH_WAIT_ICP, PH_CHILD_LB, PH_DONE };
+
+struct Problem {
+    // ---- inputs (host copies) ----
+    int Nm = 0, NdAll = 0, Nd = 0;
+    std::vector<float> mxyz, dxyz;       // AoS as given
+    std::vector<int> mc, dc;
+    std::vector<float> mf, df;           // N x 41 or empty
+    // ---- grid (host-derived) ----
+    goicp_dt_info info{};
+    std::vector<int> cell_vox, cell_start, cell_pts, cell_colour;
+    std::vector<uint32_t> cmask;
+    std::vector<uint8_t> dprop, mprop, dknown;
+    bool prepared = false, dt_built = false, initialized = false;
+    // ---- device ----
+    PairDev dev{};
+    size_t inBytes = 0, workBytes = 0, inOff = 0, workOff = 0;
+    // ---- search state ----
+    Phase phase = PH_START;
+    std::vector<RNode> q;
+    float optError = 0; double optR[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, optT[3] = {0, 0, 0}; int optComp = 0;
+    long long cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    std::string trace;
+    RNode par{}, child{}; int j = 0; float R[9]; float ubChild = 0; float lastLb = 0;
+    std::unordered_map<unsigned long long, CallRes> cache;
+    int nextId = 1, quiet = 0;
+    int status = 0;
+    double t_dt = 0, t_reg = 0;
+    // ICP exchange
+    bool icpPending = false; int icpSlot[2] = {-1, -1};
+    float icpErr = 0; double icpR[9], icpT[3]; int icpIncomp = 0, compatPose = 0; float initErr = 0;
+};
+
+static void tracef(std::string& s, const char* fmt, ...) {
+    char buf[256]; va_list ap; va_start(ap, fmt); int n = vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (n > 0) s.append(buf, std::min(n, (int)sizeof buf - 1));
+}
+
+}  // namespace
+
+struct goicp_handle_s {
+    int device = 0; cudaStream_t stream = nullptr; bool ownStream = false; int numSM = 148;
+    goicp_params params; bool haveParams = false;
+    int exact_sums = 1, spec_width = 32, use_dt_replay = 1;
+    std::vector<Problem> probs;
+    DevBuf arenaIn, arenaWork, dPairs, dProbs, dOuts, dCounter, dHeaps, dBnbScratch, dIcp, dTmp, dTmp2, dTmp3, dSepBits, dSepNx, dSepNxy;
+    PinBuf hProbs, hOuts, hIcp, hStage;
+    std::string err, trace;
+    float ms[5] = {0, 0, 0, 0, 0}; long long launches[5] = {0, 0, 0, 0, 0};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int heapCap = 1 << 15;
+};
+
+namespace {
+
+typedef goicp_handle_s Eng;
+
+static goicp_status fail(Eng* h, goicp_status s, const char* fmt, ...) {
+    char buf[512]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return s;
+}
+#define CU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(h, GOICP_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); } while (0)
+
+static size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+struct EvTimer {   // CUDA-event time of a kernel group on the handle's stream
+    Eng* h; int slot;
+    EvTimer(Eng* h_, int slot_) : h(h_), slot(slot_) { cudaEventRecord(h->ev0, h->stream); }
+    void stop(int nlaunch) { cudaEventRecord(h->ev1, h->stream); cudaEventSynchronize(h->ev1); float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->ms[slot] += ms; h->launches[slot] += nlaunch; }
+};
+
+// ---- host preprocessing of one pair: bbox/scale (jly_3ddt.cpp:899-931), seeding (:976-995), cell lists and colour
+//      masks (assignCellColor jly_goicp.cpp:951-969, checkProperty :1068-1092) -----------------------------------------
+static goicp_status prepare_problem(Eng* h, Problem& P) {
+    const goicp_params& p = h->params;
+    const int S = p.distTransSize, num = P.Nm;
+    if (S < 2 || S > 1024) return fail(h, GOICP_ERR_UNSUPPORTED, "distTransSize %d outside [2,1024]", S);
+    if (num < 1 || P.NdAll < 1) return fail(h, GOICP_ERR_ARG, "empty cloud (Nm=%d Nd=%d)", num, P.NdAll);
+    const float* m = P.mxyz.data();
+    double xMin = m[0], xMax = m[0], yMin = m[1], yMax = m[1], zMin = m[2], zMax = m[2];
+    for (int i = 1; i < num; i++) {
+        double x = m[3 * i], y = m[3 * i + 1], z = m[3 * i + 2];
+        if (xMin > x) xMin = x; if (xMax < x) xMax = x;
+        if (yMin > y) yMin = y; if (yMax < y) yMax = y;
+        if (zMin > z) zMin = z; if (zMax < z) zMax = z;
+    }
+    const double ef = p.distTransExpandFactor;
+    const double xC = (xMin + xMax) / 2, yC = (yMin + yMax) / 2, zC = (zMin + zMax) / 2;
+    xMin = xC - ef * (xMax - xC); xMax = xC + ef * (xMax - xC);
+    yMin = yC - ef * (yMax - yC); yMax = yC + ef * (yMax - yC);
+    zMin = zC - ef * (zMax - zC); zMax = zC + ef * (zMax - zC);
+    double mx = xMax - xMin > yMax - yMin ? xMax - xMin : yMax - yMin;
+    mx = mx > zMax - zMin ? mx : zMax - zMin;
+    xMin = xC - mx / 2; xMax = xC + mx / 2; yMin = yC - mx / 2; yMax = yC + mx / 2; zMin = zC - mx / 2; zMax = zC + mx / 2;
+    P.info.xMin = xMin; P.info.xMax = xMax; P.info.yMin = yMin; P.info.yMax = yMax; P.info.zMin = zMin; P.info.zMax = zMax;
+    P.info.scale = S / mx; P.info.size = S;
+    const double scale = P.info.scale;
+    if (!(mx > 0)) return fail(h, GOICP_ERR_ARG, "degenerate model bounding box");
+
+    // colour dictionary (<= 32 distinct colours over both clouds)
+    std::map<int, int> dict;
+    for (int i = 0; i < num; i++) dict.emplace(P.mc.empty() ? 0 : P.mc[i], 0);
+    for (int i = 0; i < P.NdAll; i++) dict.emplace(P.dc.empty() ? 0 : P.dc[i], 0);
+    if (dict.size() > 32) return fail(h, GOICP_ERR_UNSUPPORTED, "more than 32 distinct colour codes in one pair (%zu)", dict.size());
+    { int k = 0; for (auto& kv : dict) kv.second = k++; }
+    P.mprop.resize(num); P.dprop.resize(P.NdAll); P.dknown.resize(P.NdAll);
+    for (int i = 0; i < num; i++) P.mprop[i] = (uint8_t)dict[P.mc.empty() ? 0 : P.mc[i]];
+    for (int i = 0; i < P.NdAll; i++) { int c = P.dc.empty() ? 0 : P.dc[i]; P.dprop[i] = (uint8_t)dict[c]; P.dknown[i] = known_prop(c) ? 1 : 0; }
+
+    // seeding: voxel of every model point, cells = occupied voxels in ascending voxel order, points in index order
+    std::vector<std::pair<int, int>> vp; vp.reserve(num);
+    for (int i = 0; i < num; i++) {
+        int x = ROUND_HOST(((double)m[3 * i] - xMin) * scale), y = ROUND_HOST(((double)m[3 * i + 1] - yMin) * scale), z = ROUND_HOST(((double)m[3 * i + 2] - zMin) * scale);
+        if (x < 0 || x >= S || y < 0 || y >= S || z < 0 || z >= S) continue;   // :989 (only reachable for expandFactor <= 1)
+        vp.emplace_back((z * S + y) * S + x, i);
+    }
+    std::sort(vp.begin(), vp.end());
+    P.cell_vox.clear(); P.cell_start.clear(); P.cell_pts.clear(); P.cell_colour.clear(); P.cmask.clear();
+    for (size_t k = 0; k < vp.size(); k++) {
+        if (k == 0 || vp[k].first != vp[k - 1].first) { P.cell_vox.push_back(vp[k].first); P.cell_start.push_back((int)k); }
+        P.cell_pts.push_back(vp[k].second);
+    }
+    P.cell_start.push_back((int)vp.size());
+    const int nc = (int)P.cell_vox.size();
+    P.info.ncells = nc;
+    P.cell_colour.resize(nc); P.cmask.assign(nc + 1, 0u);
+    for (int c = 0; c < nc; c++) {
+        const int b = P.cell_start[c], e = P.cell_start[c + 1];
+        auto col = [&](int k) { return P.mc.empty() ? 0 : P.mc[P.cell_pts[k]]; };
+        int prop = col(b); bool mixed = false; uint32_t orbits = 0;
+        for (int k = b; k < e; k++) { if (col(k) != prop) mixed = true; orbits |= 1u << dict[col(k)]; }
+        P.cell_colour[c] = mixed ? -1 : prop;
+        P.cmask[c] = mixed ? orbits : (known_prop(prop) ? (1u << dict[prop]) : 0u);   // checkProperty :1068-1092
+    }
+    P.prepared = true; P.dt_built = false; P.initialized = false;
+    return GOICP_OK;
+}
+
+static bool need_corner_terms(const goicp_params& p) { return p.regularization > 0 || (p.regularizationFPFH > 0 && p.cfpfh != 0); }
+
+// ---- device layout + upload of all problems ----------------------------------------------------------------------
+static goicp_status upload_problems(Eng* h) {
+    const goicp_params& p = h->params;
+    const int S = p.distTransSize; const size_t S3 = (size_t)S * S * S;
+    const bool useF = p.cfpfh != 0;
+    const bool wantVcell = true;
+    size_t inTot = 0, workTot = 0;
+    for (auto& P : h->probs) {
+        if (useF && (P.mf.empty() || P.df.empty())) return fail(h, GOICP_ERR_ARG, "cfpfh=%d needs c-FPFH descriptors for both clouds", p.cfpfh);
+        const int nc = P.info.ncells;
+        size_t in = 0;
+        in += 3 * al256(sizeof(float) * P.NdAll) + 3 * al256(sizeof(float) * P.Nm);
+        in += 2 * al256(P.NdAll) + al256(P.Nm);
+        if (useF) in += al256(sizeof(float) * 41 * (size_t)P.NdAll) + al256(sizeof(float) * 41 * (size_t)P.Nm);
+        in += al256(sizeof(int) * std::max(nc, 1)) + al256(sizeof(uint32_t) * (nc + 1)) + al256(sizeof(int) * (nc + 1)) + al256(sizeof(int) * P.Nm);
+        P.inBytes = in; P.inOff = inTot; inTot += in;
+        size_t w = 0;
+        w += al256(sizeof(float) * S3) + al256(sizeof(int) * S3) + (wantVcell ? al256(sizeof(int) * S3) : 0);
+        w += 2 * al256(sizeof(float) * P.NdAll) + al256(sizeof(float) * GOICP_MAXROTLEVEL * (size_t)P.NdAll);
+        if (useF && p.regularizationFPFH > 0) w += al256(sizeof(float) * (size_t)P.NdAll * (nc + 1));
+        w += al256(sizeof(unsigned long long) * P.NdAll) + al256(sizeof(int) * P.NdAll) + al256(sizeof(float) * 8 * (size_t)std::max(P.NdAll, 1));
+        P.workBytes = w; P.workOff = workTot; workTot += w;
+    }
+    CU(h->arenaIn.ensure(inTot));
+    CU(h->arenaWork.ensure(workTot));
+    CU(h->hStage.ensure(inTot));
+    char* stage = h->hStage.as<char>();
+    char* dIn = h->arenaIn.as<char>(); char* dWork = h->arenaWork.as<char>();
+    for (auto& P : h->probs) {
+        const int nc = P.info.ncells;
+        size_t o = P.inOff;
+        PairDev& D = P.dev;
+        memset(&D, 0, sizeof D);
+        auto putf = [&](float*& dptr, size_t count, auto fill) { dptr = reinterpret_cast<float*>(dIn + o); fill(reinterpret_cast<float*>(stage + o)); o += al256(sizeof(float) * count); };
+        putf(D.dx, P.NdAll, [&](float* s) { for (int i = 0; i < P.NdAll; i++) s[i] = P.dxyz[3 * i]; });
+        putf(D.dy, P.NdAll, [&](float* s) { for (int i = 0; i < P.NdAll; i++) s[i] = P.dxyz[3 * i + 1]; });
+        putf(D.dz, P.NdAll, [&](float* s) { for (int i = 0; i < P.NdAll; i++) s[i] = P.dxyz[3 * i + 2]; });
+        putf(D.mx, P.Nm, [&](float* s) { for (int i = 0; i < P.Nm; i++) s[i] = P.mxyz[3 * i]; });
+        putf(D.my, P.Nm, [&](float* s) { for (int i = 0; i < P.Nm; i++) s[i] = P.mxyz[3 * i + 1]; });
+        putf(D.mz, P.Nm, [&](float* s) { for (int i = 0; i < P.Nm; i++) s[i] = P.mxyz[3 * i + 2]; });
+        D.dprop = reinterpret_cast<uint8_t*>(dIn + o); memcpy(stage + o, P.dprop.data(), P.NdAll); o += al256(P.NdAll);
+        D.dknown = reinterpret_cast<uint8_t*>(dIn + o); memcpy(stage + o, P.dknown.data(), P.NdAll); o += al256(P.NdAll);
+        D.mprop = reinterpret_cast<uint8_t*>(dIn + o); memcpy(stage + o, P.mprop.data(), P.Nm); o += al256(P.Nm);
+        if (useF) {
+            D.dfpfh = reinterpret_cast<float*>(dIn + o); memcpy(stage + o, P.df.data(), sizeof(float) * 41 * (size_t)P.NdAll); o += al256(sizeof(float) * 41 * (size_t)P.NdAll);
+            D.mfpfh = reinterpret_cast<float*>(dIn + o); memcpy(stage + o, P.mf.data(), sizeof(float) * 41 * (size_t)P.Nm); o += al256(sizeof(float) * 41 * (size_t)P.Nm);
+        }
+        D.g.cell_vox = reinterpret_cast<int*>(dIn + o); memcpy(stage + o, P.cell_vox.data(), sizeof(int) * nc); o += al256(sizeof(int) * std::max(nc, 1));
+        D.g.cmask = reinterpret_cast<uint32_t*>(dIn + o); memcpy(stage + o, P.cmask.data(), sizeof(uint32_t) * (nc + 1)); o += al256(sizeof(uint32_t) * (nc + 1));
+        D.cell_start = reinterpret_cast<int*>(dIn + o); memcpy(stage + o, P.cell_start.data(), sizeof(int) * (nc + 1)); o += al256(sizeof(int) * (nc + 1));
+        D.cell_pts = reinterpret_cast<int*>(dIn + o); memcpy(stage + o, P.cell_pts.data(), sizeof(int) * P.cell_pts.size()); o += al256(sizeof(int) * P.Nm);
+        size_t w = P.workOff;
+        D.g.dist = reinterpret_cast<float*>(dWork + w); w += al256(sizeof(float) * S3);
+        D.g.vnear = reinterpret_cast<int*>(dWork + w); w += al256(sizeof(int) * S3);
+        if (wantVcell) { D.g.vcell = reinterpret_cast<int*>(dWork + w); w += al256(sizeof(int) * S3); }
+        D.normData = reinterpret_cast<float*>(dWork + w); w += al256(sizeof(float) * P.NdAll);
+        D.weights = reinterpret_cast<float*>(dWork + w); w += al256(sizeof(float) * P.NdAll);
+        D.maxRotDis = reinterpret_cast<float*>(dWork + w); w += al256(sizeof(float) * GOICP_MAXROTLEVEL * (size_t)P.NdAll);
+        if (useF && p.regularizationFPFH > 0) { D.fpfhD = reinterpret_cast<float*>(dWork + w); w += al256(sizeof(float) * (size_t)P.NdAll * (nc + 1)); }
+        D.nn = reinterpret_cast<unsigned long long*>(dWork + w); w += al256(sizeof(unsigned long long) * P.NdAll);
+        D.order = reinterpret_cast<int*>(dWork + w); w += al256(sizeof(int) * P.NdAll);
+        D.scratch = reinterpret_cast<float*>(dWork + w); w += al256(sizeof(float) * 8 * (size_t)std::max(P.NdAll, 1));
+        D.g.S = S; D.g.ncells = nc; D.g.xMin = P.info.xMin; D.g.yMin = P.info.yMin; D.g.zMin = P.info.zMin; D.g.scale = P.info.scale;
+        D.Nm = P.Nm; D.Nd = P.Nd;
+    }
+    CU(cudaMemcpyAsync(dIn, stage, inTot, cudaMemcpyHostToDevice, h->stream));
+    return GOICP_OK;
+}
+
+// fills the parameter-derived fields of every PairDev (GoICP::Initialize :180-267 scalars) and uploads the array
+static goicp_status upload_pairdevs(Eng* h) {
+    const goicp_params& p = h->params;
+    const bool doTrim = !(p.trimFraction < 0.001);   // GoICP() :54 sets true; readConfig clears it (jly_main.cpp:259)
+    for (auto& P : h->probs) {
+        PairDev& D = P.dev;
+        D.Nd = P.Nd;
+        D.doTrim = doTrim ? 1 : 0;
+        D.inlierNum = doTrim ? (int)(P.Nd * (1 - p.trimFraction)) : P.Nd;           // :244-252
+        D.norm = p.norm; D.cfpfh = p.cfpfh; D.ponderation = p.ponderation;
+        D.fpfh_b = 0; D.fpfh_e = 0;
+        if (p.cfpfh == 1) D.fpfh_e = 41; else if (p.cfpfh == 2) D.fpfh_e = 33; else if (p.cfpfh == 3) { D.fpfh_b = 33; D.fpfh_e = 41; }
+        D.use_reg = p.regularization > 0 ? 1 : 0;
+        D.use_fpfh = (p.regularizationFPFH > 0 && p.cfpfh != 0) ? 1 : 0;
+        D.reg = p.regularization; D.regF = p.regularizationFPFH;
+        D.MSEThresh = p.MSEThresh; D.trimFraction = p.trimFraction;
+        D.SSEThresh = p.MSEThresh * D.inlierNum;                                     // :266
+        D.tMinX = p.transMinX; D.tMinY = p.transMinY; D.tMinZ = p.transMinZ; D.tWidth = p.transWidth;
+        for (int l = 0; l < GOICP_MAXROTLEVEL; l++) {                                // :195-204, host libm as the reference
+            float sigma = (float)(p.rotWidth / pow(2.0, l) / 2.0);
+            float maxAngle = (float)(GOICP_SQRT3 * sigma);
+            if (maxAngle > GOICP_PI) maxAngle = (float)GOICP_PI;
+            D.s2[l] = 2 * sinf(maxAngle / 2);
+        }
+    }
+    const size_t n = h->probs.size();
+    CU(h->dPairs.ensure(sizeof(PairDev) * n));
+    CU(h->hProbs.ensure(sizeof(PairDev) * n));   // staging (re-used)
+    PairDev* st = h->hProbs.as<PairDev>();
+    for (size_t i = 0; i < n; i++) st[i] = h->probs[i].dev;
+    CU(cudaMemcpyAsync(h->dPairs.p, st, sizeof(PairDev) * n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return GOICP_OK;
+}
+
+static goicp_status build_dt_all(Eng* h, bool replay) {
+    const int S = h->params.distTransSize;
+    auto t0 = clk::now();
+    goicp_status s = upload_pairdevs(h);
+    if (s) return s;
+    EvTimer tm(h, 0);
+    int nl = 0;
+    if (replay) {
+        if (S > 32) return fail(h, GOICP_ERR_UNSUPPORTED, "the 8SED replay builder supports distTransSize <= 32 (got %d)", S);
+        CU(goicp_launch_dt_replay(h->dPairs.as<PairDev>(), 0, (int)h->probs.size(), S, h->stream)); nl = 1;
+    } else {
+        const int SW = (S + 31) / 32; const size_t S3 = (size_t)S * S * S;
+        CU(h->dSepBits.ensure((size_t)S * S * SW * sizeof(unsigned)));
+        CU(h->dSepNx.ensure(S3 * sizeof(unsigned short)));
+        CU(h->dSepNxy.ensure(S3 * sizeof(unsigned)));
+        for (auto& P : h->probs) { CU(goicp_launch_dt_separable(P.dev.g, h->dSepBits.as<unsigned>(), h->dSepNx.as<unsigned short>(), h->dSepNxy.as<unsigned>(), h->numSM, h->stream)); nl += 4; }
+    }
+    tm.stop(nl);
+    CU(cudaGetLastError());
+    const double dt = secs_since(t0) / std::max<size_t>(1, h->probs.size());
+    for (auto& P : h->probs) { P.dt_built = true; P.t_dt = dt; }
+    return GOICP_OK;
+}
+
+static goicp_status initialize_all(Eng* h) {
+    const goicp_params& p = h->params;
+    for (auto& P : h->probs) {
+        if (!P.dt_built) return fail(h, GOICP_ERR_ARG, "initialize before build_dt");
+        if (p.ponderation == 1 && P.Nd < 20) return fail(h, GOICP_ERR_UNSUPPORTED, "ponderation=1 needs Nd >= 20 (neighborsWeights never terminates below; Nd=%d)", P.Nd);
+        if (p.norm != 1 && p.norm != 2) return fail(h, GOICP_ERR_UNSUPPORTED, "norm must be 1 or 2");
+    }
+    goicp_status s = upload_pairdevs(h);
+    if (s) return s;
+    EvTimer tm(h, 1);
+    int nl = 1;
+    CU(goicp_launch_initialize(h->dPairs.as<PairDev>(), 0, (int)h->probs.size(), h->stream));
+    if (p.regularizationFPFH > 0 && p.cfpfh != 0) { CU(goicp_launch_fpfh_table(h->dPairs.as<PairDev>(), 0, (int)h->probs.size(), 32, h->stream)); nl++; }
+    tm.stop(nl);
+    CU(cudaGetLastError());
+    for (auto& P : h->probs) P.initialized = true;
+    return GOICP_OK;
+}
+
+// ---- one launch of InnerBnB calls (handles heap overflow by re-running the overflowed calls with larger heaps) -------
+static goicp_status run_inner(Eng* h, std::vector<InnerProb>& reqs, std::vector<InnerOut>& outs) {
+    const int n = (int)reqs.size();
+    outs.resize(n);
+    if (n == 0) return GOICP_OK;
+    int maxNd = 1; bool anyTrim = false, anyF = false;
+    for (auto& P : h->probs) { maxNd = std::max(maxNd, P.Nd); anyTrim |= P.dev.doTrim != 0; anyF |= P.dev.use_fpfh != 0; }
+    const int NdP = (maxNd + 31) & ~31, NdQ = NdP + 4;
+    const bool needMd = h->exact_sums || anyTrim, needFp = h->exact_sums && anyF;
+    const size_t smemFloats = goicp_bnb_smem_floats(NdP, NdQ, needMd, needFp);
+    const size_t smemBytes = smemFloats * sizeof(float);
+    const int useSmem = smemBytes <= 200 * 1024;
+    const int perSM = goicp_inner_bnb_occupancy(useSmem ? smemBytes : 0, h->exact_sums);
+    int maxCtas = h->numSM * perSM;
+    int heapCap = h->heapCap;
+    CU(h->dProbs.ensure(sizeof(InnerProb) * n));
+    CU(h->dOuts.ensure(sizeof(InnerOut) * n));
+    CU(h->dCounter.ensure(sizeof(int)));
+    CU(h->hProbs.ensure(std::max(sizeof(InnerProb) * (size_t)n, sizeof(PairDev) * h->probs.size())));
+    CU(h->hOuts.ensure(sizeof(InnerOut) * n));
+    std::vector<int> todo(n); for (int i = 0; i < n; i++) todo[i] = i;
+    for (int attempt = 0; attempt < 12 && !todo.empty(); attempt++) {
+        const int m = (int)todo.size();
+        InnerProb* hp = h->hProbs.as<InnerProb>();
+        for (int i = 0; i < m; i++) hp[i] = reqs[todo[i]];
+        const int ctas = std::min(m, maxCtas);
+        CU(h->dHeaps.ensure(sizeof(HeapEnt) * (size_t)ctas * heapCap));
+        if (!useSmem) CU(h->dBnbScratch.ensure(sizeof(float) * smemFloats * (size_t)ctas));
+        CU(cudaMemcpyAsync(h->dProbs.p, hp, sizeof(InnerProb) * m, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemsetAsync(h->dCounter.p, 0, sizeof(int), h->stream));
+        cudaEventRecord(h->ev0, h->stream);
+        int launched = 0;
+        CU(goicp_launch_inner_bnb(h->dPairs.as<PairDev>(), h->dProbs.as<InnerProb>(), h->dOuts.as<InnerOut>(), m, h->dCounter.as<int>(),
+                                  h->dHeaps.as<HeapEnt>(), heapCap, ctas, h->dBnbScratch.as<float>(), smemFloats, NdP, NdQ, smemFloats, useSmem,
+                                  h->exact_sums, h->stream, &launched));
+        cudaEventRecord(h->ev1, h->stream);
+        CU(cudaMemcpyAsync(h->hOuts.p, h->dOuts.p, sizeof(InnerOut) * m, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->ms[2] += ms; h->launches[2] += 1;
+        const InnerOut* ho = h->hOuts.as<InnerOut>();
+        std::vector<int> again;
+        for (int i = 0; i < m; i++) { if (ho[i].status == 4) again.push_back(todo[i]); else outs[todo[i]] = ho[i]; }
+        todo.swap(again);
+        if (!todo.empty()) { heapCap *= 4; const size_t fit = ((size_t)8 << 30) / sizeof(HeapEnt) / (size_t)heapCap; maxCtas = (int)std::max<size_t>(1, std::min<size_t>((size_t)maxCtas, fit)); }
+    }
+    if (!todo.empty()) return fail(h, GOICP_ERR_OVERFLOW, "translation queue exceeded %d entries", heapCap);
+    return GOICP_OK;
+}
+
+// ---- ICP / scoring pipeline for a set of states ----------------------------------------------------------------------
+static goicp_status run_icp(Eng* h, std::vector<IcpState>& states) {
+    const int n = (int)states.size();
+    if (n == 0) return GOICP_OK;
+    int maxNd = 1, maxNm = 1; bool anyIcp = false;
+    for (auto& s : states) { const Problem& P = h->probs[s.pair]; maxNd = std::max(maxNd, P.Nd); maxNm = std::max(maxNm, P.Nm); anyIcp |= s.mode == 0; }
+    CU(h->dIcp.ensure(sizeof(IcpState) * n));
+    CU(h->hIcp.ensure(sizeof(IcpState) * n));
+    IcpState* hs = h->hIcp.as<IcpState>();
+    for (int i = 0; i < n; i++) hs[i] = states[i];
+    EvTimer tm(h, 3);
+    int nl = 0;
+    CU(cudaMemcpyAsync(h->dIcp.p, hs, sizeof(IcpState) * n, cudaMemcpyHostToDevice, h->stream));
+    CU(goicp_launch_icp_begin(h->dPairs.as<PairDev>(), h->dIcp.as<IcpState>(), n, h->stream)); nl++;
+    if (anyIcp) {
+        int burst = 4;
+        for (int it = 0; it < 10000;) {
+            for (int b = 0; b < burst; b++) { CU(goicp_launch_icp_iter(h->dPairs.as<PairDev>(), h->dIcp.as<IcpState>(), n, maxNd, maxNm, h->numSM, h->stream)); nl += 2; }
+            it += burst;
+            CU(cudaMemcpyAsync(hs, h->dIcp.p, sizeof(IcpState) * n, cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+            bool all = true;
+            for (int i = 0; i < n; i++) if (hs[i].mode == 0 && !hs[i].done) all = false;
+            if (all) break;
+            if (burst < 16) burst *= 2;
+        }
+    }
+    CU(goicp_launch_icp_score(h->dPairs.as<PairDev>(), h->dIcp.as<IcpState>(), n, h->stream)); nl++;
+    CU(cudaMemcpyAsync(hs, h->dIcp.p, sizeof(IcpState) * n, cudaMemcpyDeviceToHost, h->stream));
+    tm.stop(nl);
+    CU(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < n; i++) states[i] = hs[i];
+    for (int i = 0; i < n; i++) if (states[i].status != 0) return fail(h, GOICP_ERR_UNSUPPORTED, "ICP with trimming supports Nd <= 2048");
+    return GOICP_OK;
+}
+
+static IcpState make_icp_state(int pair, int mode, const double* R, const double* t) {
+    IcpState s; memset(&s, 0, sizeof s);
+    s.pair = pair; s.mode = mode;
+    for (int k = 0; k < 9; k++) s.R[k] = R ? R[k] : (k % 4 == 0 ? 1.0 : 0.0);
+    for (int k = 0; k < 3; k++) s.t[k] = t ? t[k] : 0.0;
+    s.err = -1.f;
+    return s;
+}
+
+// ---- rotation of a child cube (jly_goicp.cpp:716-747): false if the cube lies outside the pi-ball --------------------
+static bool child_rotation(const RNode& nr, float* R) {
+    float v1 = nr.a + nr.w / 2, v2 = nr.b + nr.w / 2, v3 = nr.c + nr.w / 2;
+    if ((double)sqrtf(v1 * v1 + v2 * v2 + v3 * v3) - GOICP_SQRT3 * nr.w / 2 > GOICP_PI) return false;   // :723
+    float t = sqrtf(v1 * v1 + v2 * v2 + v3 * v3);                                                    // :729
+    if (t > 0) {
+        v1 /= t; v2 /= t; v3 /= t;
+        float ct = cosf(t), ct2 = 1 - ct, st = sinf(t);
+        float tmp121 = v1 * v2 * ct2, tmp122 = v3 * st, tmp131 = v1 * v3 * ct2, tmp132 = v2 * st, tmp231 = v2 * v3 * ct2, tmp232 = v1 * st;
+        R[0] = ct + v1 * v1 * ct2; R[1] = tmp121 - tmp122; R[2] = tmp131 + tmp132;
+        R[3] = tmp121 + tmp122; R[4] = ct + v2 * v2 * ct2; R[5] = tmp231 - tmp232;
+        R[6] = tmp131 - tmp132; R[7] = tmp231 + tmp232; R[8] = ct + v3 * v3 * ct2;
+    } else {
+        for (int k = 0; k < 9; k++) R[k] = (k % 4 == 0) ? 1.f : 0.f;   // :759-762 copies the cloud unrotated
+    }
+    return true;
+}
+static inline RNode child_of(const RNode& par, int j) {
+    RNode nr{}; nr.w = par.w / 2; nr.l = par.l + 1;
+    nr.a = par.a + (j & 1) * nr.w; nr.b = par.b + ((j >> 1) & 1) * nr.w; nr.c = par.c + ((j >> 2) & 1) * nr.w;   // :710-712
+    return nr;
+}
+static inline unsigned long long call_key(int nodeId, int j, int kind) { return ((unsigned long long)(unsigned)nodeId << 4) | (unsigned)(j << 1) | (unsigned)kind; }
+
+struct ReqTag { int prob; unsigned long long key; float entryOpt; };
+
+// Advance one problem's OuterBnB as far as cached results allow; on return P.phase tells what it waits for.
+static void advance(Eng* h, int pi) {
+    Problem& P = h->probs[pi];
+    const goicp_params& p = h->params;
+    const float SSE = P.dev.SSEThresh;
+    for (;;) {
+        switch (P.phase) {
+        case PH_START: case PH_WAIT_INIT: case PH_WAIT_ICP: case PH_DONE: return;
+        case PH_POP: {
+            if (P.q.empty()) { tracef(P.trace, "Rotation Queue Empty\nError*: %g, LB: %g\n", P.optError, P.lastLb); P.phase = PH_DONE; return; }   // :670-677
+            P.par = rheap_pop(P.q); P.cnt[3]++;
+            if ((P.optError - P.par.lb) <= SSE) {                                                      // :685
+                tracef(P.trace, "Threshold reached\nError*: %g, LB: %g, epsilon: %g\n", P.optError, P.par.lb, SSE);
+                P.phase = PH_DONE; return;
+            }
+            P.j = 0; P.phase = PH_CHILD_UB;
+            break;
+        }
+        case PH_CHILD_UB: {
+            if (P.j >= 8) { P.phase = PH_POP; break; }
+            P.child = child_of(P.par, P.j);
+            if (!child_rotation(P.child, P.R)) { P.j++; break; }
+            auto it = P.cache.find(call_key(P.par.id, P.j, 0));
+            if (it == P.cache.end() || it->second.entryOpt != P.optError) return;   // blocked
+            const CallRes r = it->second; P.cache.erase(it);
+            P.cnt[4]++; P.cnt[0]++; P.cnt[1] += r.pops; P.cnt[2] += r.subcubes;
+            P.ubChild = r.err;
+            if (r.err < P.optError) {   // :771-790
+                P.optError = r.err;
+                for (int k = 0; k < 9; k++) P.optR[k] = P.R[k];
+                P.optT[0] = r.tn[0] + r.tn[3] / 2; P.optT[1] = r.tn[1] + r.tn[3] / 2; P.optT[2] = r.tn[2] + r.tn[3] / 2;   // float expr -> double
+                P.cache.clear(); P.quiet = 0;
+                P.phase = PH_WAIT_ICP; P.icpPending = true;
+                return;
+            }
+            P.phase = PH_CHILD_LB;
+            break;
+        }
+        case PH_CHILD_LB: {
+            auto it = P.cache.find(call_key(P.par.id, P.j, 1));
+            if (it == P.cache.end() || it->second.entryOpt != P.optError) return;   // blocked
+            const CallRes r = it->second; P.cache.erase(it);
+            P.cnt[0]++; P.cnt[1] += r.pops; P.cnt[2] += r.subcubes;
+            P.lastLb = r.err;
+            if (!(r.err >= P.optError)) {   // :863-871
+                RNode nr = P.child; nr.ub = P.ubChild; nr.lb = r.err; nr.id = P.nextId++;
+                rheap_push(P.q, nr);
+            }
+            P.j++; P.phase = PH_CHILD_UB;
+            break;
+        }
+        }
+    }
+    (void)p;
+}
+
+// result of the post-improvement ICP (jly_goicp.cpp:791-854)
+static void finish_improvement(Eng* h, int pi) {
+    Problem& P = h->probs[pi];
+    P.optComp = P.compatPose;                                                                          // :791
+    tracef(P.trace, "Error*: %g (BNB)\n", P.optError);
+    P.cnt[5]++;
+    if (P.icpErr < P.optError) {                                                                       // :813-840
+        P.optError = P.icpErr;
+        memcpy(P.optR, P.icpR, sizeof P.optR); memcpy(P.optT, P.icpT, sizeof P.optT);
+        P.optComp = P.icpIncomp;
+        tracef(P.trace, "Error*: %g (ICP)\n", P.icpErr);
+    }
+    std::vector<RNode> qn;                                                                             // :843-853
+    while (!P.q.empty()) { RNode n = rheap_pop(P.q); if (n.lb < P.optError) rheap_push(qn, n); else break; }
+    P.q.swap(qn);
+    P.cache.clear();
+    P.phase = PH_CHILD_LB;
+}
+
+// Requests of one blocked problem: the blocking call first, then speculation in the reference's expected order.
+static void gather_requests(Eng* h, int pi, std::vector<InnerProb>& reqs, std::vector<ReqTag>& tags) {
+    Problem& P = h->probs[pi];
+    const float SSE = P.dev.SSEThresh;
+    std::unordered_set<unsigned long long> seen;
+    auto want = [&](const RNode& par, int j, int kind, const RNode& ch, const float* R) {
+        const unsigned long long key = call_key(par.id, j, kind);
+        auto it = P.cache.find(key);
+        if (it != P.cache.end() && it->second.entryOpt == P.optError) return;
+        if (!seen.insert(key).second) return;
+        // Q2: the reference indexes maxRotDis[level] without a bound check (undefined beyond level 19); we clamp.
+        InnerProb ip; ip.pair = pi; ip.level = kind ? std::min(ch.l, GOICP_MAXROTLEVEL - 1) : -1; ip.optError = P.optError;
+        memcpy(ip.R, R, sizeof ip.R);
+        reqs.push_back(ip); tags.push_back(ReqTag{pi, key, P.optError});
+    };
+    // current parent, from the blocking call on
+    for (int j = P.j; j < 8; j++) {
+        RNode ch = child_of(P.par, j); float R[9];
+        if (!child_rotation(ch, R)) continue;
+        if (!(j == P.j && P.phase == PH_CHILD_LB)) want(P.par, j, 0, ch, R);
+        want(P.par, j, 1, ch, R);
+    }
+    // the next queue nodes in pop order; width grows while the incumbent stays unchanged
+    int width = std::min(h->spec_width, P.quiet < 30 ? (1 << std::min(P.quiet, 20)) - 1 : h->spec_width);
+    if (width > 0 && !P.q.empty()) {
+        std::vector<RNode> top(P.q);
+        const int k = std::min<int>(width, (int)top.size());
+        std::partial_sort(top.begin(), top.begin() + k, top.end(), [](const RNode& a, const RNode& b) { return rnode_less(b, a); });
+        for (int i = 0; i < k; i++) {
+            if ((P.optError - top[i].lb) <= SSE) break;
+            for (int j = 0; j < 8; j++) {
+                RNode ch = child_of(top[i], j); float R[9];
+                if (!child_rotation(ch, R)) continue;
+                want(top[i], j, 0, ch, R); want(top[i], j, 1, ch, R);
+            }
+        }
+    }
+    P.quiet++;
+}
+
+// GoICP::Register (jly_goicp.cpp:878) for every problem of the handle, in lock-step waves.
+static goicp_status register_all(Eng* h) {
+    const goicp_params& p = h->params;
+    auto t0 = clk::now();
+    goicp_status s;
+    if ((s = initialize_all(h))) return s;
+    const int np = (int)h->probs.size();
+    for (int i = 0; i < np; i++) {
+        Problem& P = h->probs[i];
+        P.phase = PH_START; P.q.clear(); P.cache.clear(); P.trace.clear(); memset(P.cnt, 0, sizeof P.cnt);
+        P.nextId = 1; P.quiet = 0; P.optComp = 0; P.lastLb = 0; P.status = 0;
+        for (int k = 0; k < 9; k++) P.optR[k] = (k % 4 == 0); P.optT[0] = P.optT[1] = P.optT[2] = 0;   // :240-241
+    }
+    std::vector<InnerProb> reqs; std::vector<ReqTag> tags; std::vector<InnerOut> outs; std::vector<IcpState> icps; std::vector<int> icpOwner;
+    for (;;) {
+        reqs.clear(); tags.clear(); icps.clear(); icpOwner.clear();
+        bool active = false;
+        for (int i = 0; i < np; i++) {
+            Problem& P = h->probs[i];
+            if (P.phase == PH_START) {   // initial error (:601-627) and ICP from the identity (:634)
+                icps.push_back(make_icp_state(i, 1, nullptr, nullptr)); icpOwner.push_back(i);
+                icps.push_back(make_icp_state(i, 0, P.optR, P.optT)); icpOwner.push_back(i);
+                P.phase = PH_WAIT_INIT; active = true; continue;
+            }
+            advance(h, i);
+            if (P.phase == PH_DONE) continue;
+            active = true;
+            if (P.phase == PH_WAIT_ICP) {   // updateCompatibilities (:791) + ICP(R,t) (:810) at the new incumbent
+                icps.push_back(make_icp_state(i, 2, P.optR, P.optT)); icpOwner.push_back(i);
+                icps.push_back(make_icp_state(i, 0, P.optR, P.optT)); icpOwner.push_back(i);
+            } else gather_requests(h, i, reqs, tags);
+        }
+        if (!active) break;
+        if ((s = run_inner(h, reqs, outs))) return s;
+        if ((s = run_icp(h, icps))) return s;
+        for (size_t k = 0; k < tags.size(); k++) {
+            Problem& P = h->probs[tags[k].prob];
+            CallRes r; r.entryOpt = tags[k].entryOpt; r.err = outs[k].err; memcpy(r.tn, outs[k].node, sizeof r.tn); r.pops = outs[k].pops; r.subcubes = outs[k].subcubes;
+            P.cache[tags[k].key] = r;
+        }
+        for (size_t k = 0; k < icps.size(); k++) {
+            Problem& P = h->probs[icpOwner[k]];
+            const IcpState& st = icps[k];
+            if (st.mode == 1) P.initErr = st.error;
+            else if (st.mode == 2) P.compatPose = st.compat_pose;
+            else { P.icpErr = st.error; memcpy(P.icpR, st.R, sizeof P.icpR); memcpy(P.icpT, st.t, sizeof P.icpT); P.icpIncomp = st.incomp; }
+        }
+        for (int i = 0; i < np; i++) {
+            Problem& P = h->probs[i];
+            if (P.phase == PH_WAIT_INIT) {
+                float optError = P.initErr;
+                if (p.regularization > 0) optError += p.regularization * (P.Nd * P.Nd);                       // :623
+                if (p.regularizationFPFH > 0) optError += p.regularizationFPFH * (100 * 8 * 100 * 8);          // :624
+                if (p.regularizationNeighbors > 0) optError += p.regularizationNeighbors * (P.Nd * 6 * P.Nd * 6);
+                P.optError = optError;
+                tracef(P.trace, "Error*: %g (Init)\n", P.optError);
+                P.cnt[5]++;
+                if (P.icpErr < P.optError) {                                                                   // :636-661
+                    P.optError = P.icpErr; memcpy(P.optR, P.icpR, sizeof P.optR); memcpy(P.optT, P.icpT, sizeof P.optT);
+                    P.optComp = P.icpIncomp;
+                    tracef(P.trace, "Error*: %g (ICP)\n", P.icpErr);
+                }
+                RNode root{}; root.a = p.rotMinX; root.b = p.rotMinY; root.c = p.rotMinZ; root.w = p.rotWidth; root.l = 0; root.lb = 0; root.id = 0;
+                rheap_push(P.q, root);
+                P.phase = PH_POP;
+            } else if (P.phase == PH_WAIT_ICP && P.icpPending) {
+                P.icpPending = false;
+                finish_improvement(h, i);
+            }
+        }
+    }
+    const double dt = secs_since(t0) / std::max(1, np);
+    for (auto& P : h->probs) P.t_reg = dt;
+    return GOICP_OK;
+}
+
+static void fill_result(Eng* h, const Problem& P, goicp_result* out) {
+    memset(out, 0, sizeof *out);
+    memcpy(out->R, P.optR, sizeof out->R); memcpy(out->t, P.optT, sizeof out->t);
+    out->optError = P.optError; out->optComp = P.optComp;
+    for (int k = 0; k < 8; k++) out->counters[k] = P.cnt[k];
+    out->counters[6] = h->launches[0] + h->launches[1] + h->launches[2] + h->launches[3] + h->launches[4];
+    out->seconds_dt = P.t_dt; out->seconds_register = P.t_reg;
+    out->gpu_ms_dt = h->ms[0]; out->gpu_ms_bnb = h->ms[2]; out->gpu_ms_icp = h->ms[3];
+    out->status = P.status;
+}
+
+static goicp_status ensure_single(Eng* h) {
+    if (h->probs.size() != 1) return fail(h, GOICP_ERR_ARG, "no single registration problem set (call goicp_set_model/goicp_set_data)");
+    return GOICP_OK;
+}
+static goicp_status prepare_all(Eng* h) {
+    if (!h->haveParams) return fail(h, GOICP_ERR_ARG, "goicp_set_params not called");
+    goicp_status s;
+    for (auto& P : h->probs) if ((s = prepare_problem(h, P))) return s;
+    if ((s = upload_problems(h))) return s;
+    return GOICP_OK;
+}
+static void set_cloud(std::vector<float>& xyz, std::vector<int>& c, std::vector<float>& f, const float* pxyz, const int32_t* pc, const float* pf, int n) {
+    xyz.assign(pxyz, pxyz + 3 * (size_t)n);
+    if (pc) c.assign(pc, pc + n); else c.assign(n, 0);
+    if (pf) f.assign(pf, pf + 41 * (size_t)n); else f.clear();
+}
+
+}  // namespace
+
+// =====================================================================================================================
+extern "C" {
+
+const char* goicp_version(void) { return "goicp-b200 0.1 (sm_100a)"; }
+const char* goicp_last_error(goicp_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+void goicp_params_default(goicp_params* p) {   // shipped config.txt:4-53
+    p->MSEThresh = 0.01f;
+    p->rotMinX = p->rotMinY = p->rotMinZ = -3.1416f; p->rotWidth = 6.2832f;
+    p->transMinX = p->transMinY = p->transMinZ = -0.5f; p->transWidth = 1.0f;
+    p->trimFraction = 0.0f;
+    p->regularization = 0.0005f; p->regularizationNeighbors = 0.0f; p->regularizationFPFH = 0.0f;
+    p->cfpfh = 0; p->norm = 2; p->ponderation = 1;
+    p->distTransSize = 20; p->distTransExpandFactor = 2.0;
+}
+
+goicp_status goicp_create(goicp_handle* out, int device, void* stream_or_null) {
+    if (!out) return GOICP_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) return fail(nullptr, GOICP_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= ndev) return fail(nullptr, GOICP_ERR_ARG, "device %d out of range (0..%d)", device, ndev - 1);
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(nullptr, GOICP_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(nullptr, GOICP_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major < 10) return fail(nullptr, GOICP_ERR_CUDA, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
+    Eng* h = new Eng();
+    h->device = device; h->numSM = prop.multiProcessorCount;
+    if (stream_or_null) { h->stream = (cudaStream_t)stream_or_null; h->ownStream = false; }
+    else { if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete h; return fail(nullptr, GOICP_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); } h->ownStream = true; }
+    cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
+    goicp_params_default(&h->params); h->haveParams = true;
+    *out = h;
+    return GOICP_OK;
+}
+
+void goicp_destroy(goicp_handle h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    DevBuf* bufs[] = {&h->arenaIn, &h->arenaWork, &h->dPairs, &h->dProbs, &h->dOuts, &h->dCounter, &h->dHeaps, &h->dBnbScratch, &h->dIcp, &h->dTmp, &h->dTmp2, &h->dTmp3, &h->dSepBits, &h->dSepNx, &h->dSepNxy};
+    for (DevBuf* b : bufs) b->release();
+    PinBuf* pins[] = {&h->hProbs, &h->hOuts, &h->hIcp, &h->hStage};
+    for (PinBuf* b : pins) b->release();
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ownStream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+goicp_status goicp_set_model(goicp_handle h, const float* xyz, const int32_t* c, const float* fpfh41, int32_t Nm) {
+    if (!h || !xyz || Nm < 1) return h ? fail(h, GOICP_ERR_ARG, "set_model: bad arguments") : GOICP_ERR_ARG;
+    if (h->probs.size() != 1) { h->probs.clear(); h->probs.resize(1); }
+    Problem& P = h->probs[0];
+    set_cloud(P.mxyz, P.mc, P.mf, xyz, c, fpfh41, Nm); P.Nm = Nm;
+    P.prepared = P.dt_built = P.initialized = false;
+    return GOICP_OK;
+}
+goicp_status goicp_set_data(goicp_handle h, const float* xyz, const int32_t* c, const float* fpfh41, int32_t Nd) {
+    if (!h || !xyz || Nd < 1) return h ? fail(h, GOICP_ERR_ARG, "set_data: bad arguments") : GOICP_ERR_ARG;
+    if (h->probs.size() != 1) { h->probs.clear(); h->probs.resize(1); }
+    Problem& P = h->probs[0];
+    set_cloud(P.dxyz, P.dc, P.df, xyz, c, fpfh41, Nd); P.NdAll = Nd; P.Nd = Nd;
+    P.prepared = P.dt_built = P.initialized = false;
+    return GOICP_OK;
+}
+goicp_status goicp_set_params(goicp_handle h, const goicp_params* p) {
+    if (!h || !p) return GOICP_ERR_ARG;
+    const bool gridChanged = !h->haveParams || p->distTransSize != h->params.distTransSize || p->distTransExpandFactor != h->params.distTransExpandFactor ||
+                             p->cfpfh != h->params.cfpfh || p->regularizationFPFH != h->params.regularizationFPFH;
+    h->params = *p; h->haveParams = true;
+    for (auto& P : h->probs) { P.initialized = false; if (gridChanged) P.prepared = P.dt_built = false; }
+    return GOICP_OK;
+}
+goicp_status goicp_set_options(goicp_handle h, int32_t exact_sums, int32_t spec_width, int32_t use_dt_replay) {
+    if (!h) return GOICP_ERR_ARG;
+    if (exact_sums >= 0) h->exact_sums = exact_sums ? 1 : 0;
+    if (spec_width >= 0) h->spec_width = spec_width;
+    if (use_dt_replay >= 0) h->use_dt_replay = use_dt_replay ? 1 : 0;
+    return GOICP_OK;
+}
+
+static goicp_status build_dt_impl(goicp_handle h, goicp_dt_info* out, bool replay) {
+    goicp_status s;
+    if ((s = ensure_single(h))) return s;
+    Problem& P = h->probs[0];
+    if (P.Nm < 1 || P.NdAll < 1) return fail(h, GOICP_ERR_ARG, "build_dt: model and data clouds must be set first");
+    cudaSetDevice(h->device);
+    if ((s = prepare_all(h))) return s;
+    if ((s = build_dt_all(h, replay))) return s;
+    if (out) *out = P.info;
+    return GOICP_OK;
+}
+goicp_status goicp_build_dt(goicp_handle h, goicp_dt_info* out) {
+    if (!h) return GOICP_ERR_ARG;
+    return build_dt_impl(h, out, h->use_dt_replay && h->params.distTransSize <= 32);
+}
+goicp_status goicp_build_dt_replay(goicp_handle h, goicp_dt_info* out) { if (!h) return GOICP_ERR_ARG; return build_dt_impl(h, out, true); }
+
+goicp_status goicp_dt_upload(goicp_handle h, const float* dist, const int32_t* nearest_xyz) {
+    if (!h) return GOICP_ERR_ARG;
+    goicp_status s; if ((s = ensure_single(h))) return s;
+    Problem& P = h->probs[0];
+    if (!P.dt_built) return fail(h, GOICP_ERR_ARG, "dt_upload before build_dt");
+    cudaSetDevice(h->device);
+    const int S = P.info.size; const size_t S3 = (size_t)S * S * S;
+    if (dist) CU(cudaMemcpyAsync(P.dev.g.dist, dist, sizeof(float) * S3, cudaMemcpyHostToDevice, h->stream));
+    if (nearest_xyz) {
+        std::vector<int> vn(S3);
+        for (size_t i = 0; i < S3; i++) vn[i] = (nearest_xyz[3 * i + 2] * S + nearest_xyz[3 * i + 1]) * S + nearest_xyz[3 * i];
+        CU(cudaMemcpyAsync(P.dev.g.vnear, vn.data(), sizeof(int) * S3, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        CU(goicp_launch_dt_vcell(P.dev.g, h->numSM, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    P.initialized = false;
+    return GOICP_OK;
+}
+goicp_status goicp_dt_download(goicp_handle h, float* dist, int32_t* nearest, int32_t* cellc) {
+    if (!h) return GOICP_ERR_ARG;
+    goicp_status s; if ((s = ensure_single(h))) return s;
+    Problem& P = h->probs[0];
+    if (!P.dt_built) return fail(h, GOICP_ERR_ARG, "dt_download before build_dt");
+    cudaSetDevice(h->device);
+    const int S = P.info.size; const size_t S3 = (size_t)S * S * S;
+    if (dist) CU(cudaMemcpyAsync(dist, P.dev.g.dist, sizeof(float) * S3, cudaMemcpyDeviceToHost, h->stream));
+    std::vector<int> vn;
+    if (nearest) { vn.resize(S3); CU(cudaMemcpyAsync(vn.data(), P.dev.g.vnear, sizeof(int) * S3, cudaMemcpyDeviceToHost, h->stream)); }
+    CU(cudaStreamSynchronize(h->stream));
+    if (nearest) for (size_t i = 0; i < S3; i++) { int v = vn[i]; nearest[3 * i] = v % S; nearest[3 * i + 1] = (v / S) % S; nearest[3 * i + 2] = v / (S * S); }
+    if (cellc) {
+        for (size_t i = 0; i < S3; i++) cellc[i] = -2;
+        for (int c = 0; c < P.info.ncells; c++) cellc[P.cell_vox[c]] = P.cell_colour[c];
+    }
+    return GOICP_OK;
+}
+goicp_status goicp_dt_distance(goicp_handle h, const double* xyz, int32_t n, float* dist, int32_t* cell) {
+    if (!h || !xyz || !dist || n < 0) return GOICP_ERR_ARG;
+    goicp_status s; if ((s = ensure_single(h))) return s;
+    if (!h->probs[0].dt_built) return fail(h, GOICP_ERR_ARG, "dt_distance before build_dt");
+    if (n == 0) return GOICP_OK;
+    cudaSetDevice(h->device);
+    CU(h->dTmp.ensure(sizeof(double) * 3 * (size_t)n)); CU(h->dTmp2.ensure(sizeof(float) * (size_t)n)); CU(h->dTmp3.ensure(sizeof(int) * 3 * (size_t)n));
+    CU(cudaMemcpyAsync(h->dTmp.p, xyz, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    CU(goicp_launch_dt_distance(h->dPairs.as<PairDev>(), 0, h->dTmp.as<double>(), n, h->dTmp2.as<float>(), h->dTmp3.as<int>(), h->stream));
+    CU(cudaMemcpyAsync(dist, h->dTmp2.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    if (cell) CU(cudaMemcpyAsync(cell, h->dTmp3.p, sizeof(int) * 3 * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return GOICP_OK;
+}
+goicp_status goicp_set_nd(goicp_handle h, int32_t nd) {
+    if (!h) return GOICP_ERR_ARG;
+    goicp_status s; if ((s = ensure_single(h))) return s;
+    Problem& P = h->probs[0];
+    if (nd < 1 || nd > P.NdAll) return fail(h, GOICP_ERR_ARG, "set_nd: %d outside [1,%d]", nd, P.NdAll);
+    P.Nd = nd; P.initialized = false;
+    return GOICP_OK;
+}
+goicp_status goicp_initialize(goicp_handle h) {
+    if (!h) return GOICP_ERR_ARG;
+    goicp_status s; if ((s = ensure_single(h))) return s;
+    cudaSetDevice(h->device);
+    return initialize_all(h);
+}
+goicp_status goicp_get_weights(goicp_handle h, float* w) {
+    if (!h || !w) return GOICP_ERR_ARG;
+    goicp_status s; if ((s = ensure_single(h))) return s;
+    Problem& P = h->probs[0]; if (!P.initialized) return fail(h, GOICP_ERR_ARG, "not initialized");
+    CU(cudaMemcpyAsync(w, P.dev.weights, sizeof(float) * P.Nd, cudaMemcpyDeviceToHost, h->stream)); CU(cudaStreamSynchronize(h->stream));
+    return GOICP_OK;
+}
+goicp_status goicp_get_maxrotdis(goicp_handle h, float* out) {
+    if (!h || !out) return GOICP_ERR_ARG;
+    goicp_status s; if ((s = ensure_single(h))) return s;
+    Problem& P = h->probs[0]; if (!P.initialized) return fail(h, GOICP_ERR_ARG, "not initialized");
+    CU(cudaMemcpyAsync(out, P.dev.maxRotDis, sizeof(float) * GOICP_MAXROTLEVEL * P.Nd, cudaMemcpyDeviceToHost, h->stream)); CU(cudaStreamSynchronize(h->stream));
+    return GOICP_OK;
+}
+goicp_status goicp_get_thresholds(goicp_handle h, float* sse, int32_t* inlier) {
+    if (!h) return GOICP_ERR_ARG;
+    goicp_status s; if ((s = ensure_single(h))) return s;
+    Problem& P = h->probs[0]; if (!P.initialized) return fail(h, GOICP_ERR_ARG, "not initialized");
+    if (sse) *sse = P.dev.SSEThresh; if (inlier) *inlier = P.dev.inlierNum;
+    return GOICP_OK;
+}
+
+goicp_status goicp_eval_bounds(goicp_handle h, const float* R, const int32_t* level, int32_t nr, const float* tcube, const int32_t* rot_of,
+                               int32_t nt, float* ub, float* lb, int32_t* incomp_minmax, int32_t* fpfh_minmax) {
+    if (!h || !R || !level || !tcube || !ub || !lb || nr < 1 || nt < 0) return GOICP_ERR_ARG;
+    goicp_status s; if ((s = ensure_single(h))) return s;
+    Problem& P = h->probs[0]; if (!P.initialized) return fail(h, GOICP_ERR_ARG, "eval_bounds before initialize");
+    if (nt == 0) return GOICP_OK;
+    cudaSetDevice(h->device);
+    std::vector<WaveCube> cubes(nt);
+    for (int k = 0; k < nt; k++) { cubes[k].x = tcube[4 * k]; cubes[k].y = tcube[4 * k + 1]; cubes[k].z = tcube[4 * k + 2]; cubes[k].w = tcube[4 * k + 3]; cubes[k].rot = rot_of ? rot_of[k] : 0;
+        if (cubes[k].rot < 0 || cubes[k].rot >= nr) return fail(h, GOICP_ERR_ARG, "rot_of[%d]=%d out of range", k, cubes[k].rot); }
+    const int nwarps = std::min(nt, h->numSM * 8 * 8);
+    const size_t bR = al256(sizeof(float) * 9 * nr), bL = al256(sizeof(int) * nr), bC = al256(sizeof(WaveCube) * nt), bF = al256(sizeof(float) * nt), bI = al256(sizeof(int) * 2 * nt);
+    CU(h->dTmp.ensure(bR + bL + bC + 2 * bF + 2 * bI));
+    CU(h->dTmp2.ensure(sizeof(float) * (size_t)nwarps * P.Nd));
+    char* d = h->dTmp.as<char>();
+    float* dR = (float*)d; int* dL = (int*)(d + bR); WaveCube* dC = (WaveCube*)(d + bR + bL); float* dU = (float*)(d + bR + bL + bC); float* dLb = (float*)(d + bR + bL + bC + bF);
+    int* dI = (int*)(d + bR + bL + bC + 2 * bF); int* dFm = (int*)(d + bR + bL + bC + 2 * bF + bI);
+    CU(cudaMemcpyAsync(dR, R, sizeof(float) * 9 * nr, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(dL, level, sizeof(int) * nr, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(dC, cubes.data(), sizeof(WaveCube) * nt, cudaMemcpyHostToDevice, h->stream));
+    { EvTimer tm(h, 2);
+      CU(goicp_launch_eval_bounds(h->dPairs.as<PairDev>(), 0, dR, dL, dC, nt, dU, dLb, dI, dFm, h->dTmp2.as<float>(), nwarps, h->stream));
+      tm.stop(1); }
+    CU(cudaMemcpyAsync(ub, dU, sizeof(float) * nt, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(lb, dLb, sizeof(float) * nt, cudaMemcpyDeviceToHost, h->stream));
+    if (incomp_minmax) CU(cudaMemcpyAsync(incomp_minmax, dI, sizeof(int) * 2 * nt, cudaMemcpyDeviceToHost, h->stream));
+    if (fpfh_minmax) CU(cudaMemcpyAsync(fpfh_minmax, dFm, sizeof(int) * 2 * nt, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return GOICP_OK;
+}
+
+goicp_status goicp_inner_bnb(goicp_handle h, const float* R, const int32_t* level, const float* opt_error, int32_t n, float* err,
+                             float* tnode, int64_t* pops_subcubes) {
+    if (!h || !R || !level || !opt_error || !err || n < 0) return GOICP_ERR_ARG;
+    goicp_status s; if ((s = ensure_single(h))) return s;
+    Problem& P = h->probs[0]; if (!P.initialized) return fail(h, GOICP_ERR_ARG, "inner_bnb before initialize");
+    cudaSetDevice(h->device);
+    std::vector<InnerProb> reqs(n); std::vector<InnerOut> outs;
+    for (int k = 0; k < n; k++) {
+        if (level[k] >= GOICP_MAXROTLEVEL) return fail(h, GOICP_ERR_ARG, "level %d >= MAXROTLEVEL", level[k]);
+        reqs[k].pair = 0; reqs[k].level = level[k]; reqs[k].optError = opt_error[k]; memcpy(reqs[k].R, R + 9 * k, sizeof(float) * 9);
+    }
+    if ((s = run_inner(h, reqs, outs))) return s;
+    for (int k = 0; k < n; k++) {
+        err[k] = outs[k].err;
+        if (tnode) memcpy(tnode + 4 * k, outs[k].node, sizeof(float) * 4);
+        if (pops_subcubes) { pops_subcubes[2 * k] = outs[k].pops; pops_subcubes[2 * k + 1] = outs[k].subcubes; }
+    }
+    return GOICP_OK;
+}
+
+goicp_status goicp_icp(goicp_handle h, double* R, double* t, float* err, int32_t* corr) {
+    if (!h || !R || !t || !err) return GOICP_ERR_ARG;
+    goicp_status s; if ((s = ensure_single(h))) return s;
+    Problem& P = h->probs[0]; if (!P.initialized) return fail(h, GOICP_ERR_ARG, "icp before initialize");
+    cudaSetDevice(h->device);
+    std::vector<IcpState> st{make_icp_state(0, 0, R, t)};
+    if ((s = run_icp(h, st))) return s;
+    memcpy(R, st[0].R, sizeof(double) * 9); memcpy(t, st[0].t, sizeof(double) * 3); *err = st[0].error;
+    if (corr) {
+        std::vector<unsigned long long> nn(P.Nd);
+        CU(cudaMemcpyAsync(nn.data(), P.dev.nn, sizeof(unsigned long long) * P.Nd, cudaMemcpyDeviceToHost, h->stream)); CU(cudaStreamSynchronize(h->stream));
+        for (int i = 0; i < P.Nd; i++) corr[i] = (int)(nn[i] & 0xFFFFFFFFu);
+    }
+    return GOICP_OK;
+}
+
+goicp_status goicp_register(goicp_handle h, goicp_result* out) {
+    if (!h || !out) return GOICP_ERR_ARG;
+    goicp_status s; if ((s = ensure_single(h))) return s;
+    cudaSetDevice(h->device);
+    Problem& P = h->probs[0];
+    memset(h->ms, 0, sizeof h->ms); memset(h->launches, 0, sizeof h->launches);
+    if (!P.dt_built) { const int nd = P.Nd; if ((s = goicp_build_dt(h, nullptr))) return s; P.Nd = nd; }
+    if ((s = register_all(h))) return s;
+    h->trace = P.trace;
+    fill_result(h, P, out);
+    return GOICP_OK;
+}
+const char* goicp_last_trace(goicp_handle h) { return h ? h->trace.c_str() : ""; }
+
+// ---- batch -----------------------------------------------------------------------------------------------------------
+goicp_status goicp_batch_upload(goicp_handle h, const goicp_params* p, int32_t npairs, const goicp_pair_desc* pairs) {
+    if (!h || !p || npairs < 1 || !pairs) return GOICP_ERR_ARG;
+    cudaSetDevice(h->device);
+    h->params = *p; h->haveParams = true;
+    h->probs.clear(); h->probs.resize(npairs);
+    for (int i = 0; i < npairs; i++) {
+        const goicp_pair_desc& d = pairs[i]; Problem& P = h->probs[i];
+        if (!d.model_xyz || !d.data_xyz || d.Nm < 1 || d.NdAll < 1) return fail(h, GOICP_ERR_ARG, "pair %d: empty cloud", i);
+        set_cloud(P.mxyz, P.mc, P.mf, d.model_xyz, d.model_c, d.model_fpfh, d.Nm); P.Nm = d.Nm;
+        set_cloud(P.dxyz, P.dc, P.df, d.data_xyz, d.data_c, d.data_fpfh, d.NdAll); P.NdAll = d.NdAll;
+        P.Nd = (d.Nd > 0 && d.Nd <= d.NdAll) ? d.Nd : d.NdAll;
+    }
+    goicp_status s;
+    if ((s = prepare_all(h))) return s;
+    CU(cudaStreamSynchronize(h->stream));
+    return GOICP_OK;
+}
+goicp_status goicp_batch_run(goicp_handle h, goicp_result* results) {
+    if (!h || !results) return GOICP_ERR_ARG;
+    if (h->probs.empty()) return fail(h, GOICP_ERR_ARG, "batch_run before batch_upload");
+    cudaSetDevice(h->device);
+    memset(h->ms, 0, sizeof h->ms); memset(h->launches, 0, sizeof h->launches);
+    goicp_status s;
+    if ((s = build_dt_all(h, h->use_dt_replay && h->params.distTransSize <= 32))) return s;
+    if ((s = register_all(h))) return s;
+    for (size_t i = 0; i < h->probs.size(); i++) fill_result(h, h->probs[i], results + i);
+    h->trace = h->probs[0].trace;
+    return GOICP_OK;
+}
+goicp_status goicp_register_batch(goicp_handle h, const goicp_params* p, int32_t npairs, const goicp_pair_desc* pairs, goicp_result* results) {
+    goicp_status s;
+    if ((s = goicp_batch_upload(h, p, npairs, pairs))) return s;
+    return goicp_batch_run(h, results);
+}
+goicp_status goicp_get_timings(goicp_handle h, float* ms5, int64_t* launches5) {
+    if (!h) return GOICP_ERR_ARG;
+    for (int k = 0; k < 5; k++) { if (ms5) ms5[k] = h->ms[k]; if (launches5) launches5[k] = h->launches[k]; }
+    return GOICP_OK;
+}
+
+// ---- Transformation ----------------------------------------------------------------------------------------------------
+goicp_status goicp_normalize_cloud(goicp_handle h, double* xyz, int32_t n, double* mean3, double* max_norm) {
+    if (!h || !xyz || n < 1) return GOICP_ERR_ARG;
+    cudaSetDevice(h->device);
+    CU(h->dTmp.ensure(sizeof(double) * 3 * (size_t)n)); CU(h->dTmp2.ensure(sizeof(double) * 4));
+    CU(cudaMemcpyAsync(h->dTmp.p, xyz, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    CU(goicp_launch_normalize(h->dTmp.as<double>(), n, h->dTmp2.as<double>(), h->stream)); h->launches[4]++;
+    double out4[4];
+    CU(cudaMemcpyAsync(xyz, h->dTmp.p, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(out4, h->dTmp2.p, sizeof out4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (mean3) { mean3[0] = out4[0]; mean3[1] = out4[1]; mean3[2] = out4[2]; }
+    if (max_norm) *max_norm = out4[3];
+    return GOICP_OK;
+}
+goicp_status goicp_scale_cloud(goicp_handle h, double* xyz, int32_t n, double scale) {
+    if (!h || !xyz || n < 1) return GOICP_ERR_ARG;
+    cudaSetDevice(h->device);
+    CU(h->dTmp.ensure(sizeof(double) * 3 * (size_t)n));
+    CU(cudaMemcpyAsync(h->dTmp.p, xyz, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    CU(goicp_launch_scale(h->dTmp.as<double>(), n, scale, h->stream)); h->launches[4]++;
+    CU(cudaMemcpyAsync(xyz, h->dTmp.p, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return GOICP_OK;
+}
+goicp_status goicp_apply_rigid(goicp_handle h, const double* xyz, int32_t n, const double* R, const double* t, double* out) {
+    if (!h || !xyz || !R || !t || !out || n < 1) return GOICP_ERR_ARG;
+    cudaSetDevice(h->device);
+    CU(h->dTmp.ensure(sizeof(double) * 3 * (size_t)n)); CU(h->dTmp2.ensure(sizeof(double) * 3 * (size_t)n)); CU(h->dTmp3.ensure(sizeof(double) * 12));
+    double Rt[12]; memcpy(Rt, R, sizeof(double) * 9); memcpy(Rt + 9, t, sizeof(double) * 3);
+    CU(cudaMemcpyAsync(h->dTmp.p, xyz, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->dTmp3.p, Rt, sizeof Rt, cudaMemcpyHostToDevice, h->stream));
+    CU(goicp_launch_apply_rigid(h->dTmp.as<double>(), n, h->dTmp3.as<double>(), h->dTmp2.as<double>(), h->stream)); h->launches[4]++;
+    CU(cudaMemcpyAsync(out, h->dTmp2.p, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return GOICP_OK;
+}
+goicp_status goicp_rescale_translation(goicp_handle h, double scale, const double* meanT, const double* meanS, const double* R, const double* t, double* out3) {
+    if (!h || !meanT || !meanS || !R || !t || !out3) return GOICP_ERR_ARG;
+    cudaSetDevice(h->device);
+    double in[19]; in[0] = scale; memcpy(in + 1, meanT, 24); memcpy(in + 4, meanS, 24); memcpy(in + 7, R, 72); memcpy(in + 16, t, 24);
+    CU(h->dTmp.ensure(sizeof(double) * 24));
+    CU(cudaMemcpyAsync(h->dTmp.p, in, sizeof in, cudaMemcpyHostToDevice, h->stream));
+    CU(goicp_launch_rescale(h->dTmp.as<double>(), h->dTmp.as<double>() + 19, h->stream)); h->launches[4]++;
+    CU(cudaMemcpyAsync(out3, h->dTmp.as<double>() + 19, sizeof(double) * 3, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return GOICP_OK;
+}
+goicp_status goicp_rmsd(goicp_handle h, const double* a, const double* b, int32_t n, float* rmsd) {
+    if (!h || !a || !b || !rmsd || n < 1) return GOICP_ERR_ARG;
+    cudaSetDevice(h->device);
+    CU(h->dTmp.ensure(sizeof(double) * 3 * (size_t)n)); CU(h->dTmp2.ensure(sizeof(double) * 3 * (size_t)n)); CU(h->dTmp3.ensure(sizeof(double) * (size_t)n + 64));
+    CU(cudaMemcpyAsync(h->dTmp.p, a, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->dTmp2.p, b, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    float* dOut = reinterpret_cast<float*>(h->dTmp3.as<char>() + sizeof(double) * (size_t)n);
+    CU(goicp_launch_rmsd(h->dTmp.as<double>(), h->dTmp2.as<double>(), n, h->dTmp3.as<double>(), dOut, h->stream)); h->launches[4]++;
+    CU(cudaMemcpyAsync(rmsd, dOut, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return GOICP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,92 @@
+// Device-side data layout of one registration problem ("pair") resident in HBM, shared by all kernels.
+// Host code (engine.cu) fills these; kernels only read them (except the marked workspaces).
+// All file:line citations are relative to the reference checkout (guillaumebaldi/Go-ICP-protein-cavities).
+#pragma once
+#include <stdint.h>
+
+#define GOICP_MAXROTLEVEL 20               // jly_goicp.h:95
+#define GOICP_NBINS 41                     // c-FPFH descriptor length (jly_main.cpp:306)
+#define GOICP_FPFH_SENTINEL 1000000000.0f  // jly_goicp.cpp:1656
+#define GOICP_PI 3.1415926536              // jly_goicp.h:44
+#define GOICP_SQRT3 1.732050808            // jly_goicp.h:45
+#define GOICP_NN_EMPTY 0xFFFFFFFFFFFFFFFFull
+
+// DT3D (jly_3ddt.h:123-139) as laid out in HBM: structure-of-arrays, voxel index (z*S+y)*S+x.
+struct GridDev {
+    int S;
+    int ncells;              // occupied voxels ("cells", jly_3ddt.h:112); id ncells = the empty sentinel cell
+    double xMin, yMin, zMin, scale;
+    float* dist;             // S^3   DEucl3D.distance / scale   (the 4 B per cube.point bound eval)
+    int* vnear;              // S^3   linear voxel index of the nearest occupied voxel (EMPTYCELL); self if none
+    int* vcell;              // S^3   compact id of that cell (ncells if the voxel points at an empty cell)
+    int* cell_vox;           // ncells   voxel of each occupied cell, ascending
+    uint32_t* cmask;         // ncells+1   bit k set <=> a source point of colour index k is compatible (checkProperty)
+};
+
+// GoICP state after Initialize (jly_goicp.cpp:180-267) for one pair.
+struct PairDev {
+    GridDev g;
+    int Nd, Nm;
+    int inlierNum;
+    int norm;                // 1 or 2
+    int doTrim;
+    int cfpfh;               // config key; 0 = descriptors unused
+    int fpfh_b, fpfh_e;      // c-FPFH bin range selected by `cfpfh` (jly_goicp.cpp:1660-1674)
+    int use_reg, use_fpfh;   // regularization > 0 ; regularizationFPFH > 0 && cfpfh != 0 (corner terms, :436)
+    int ponderation;
+    float reg, regF;
+    float SSEThresh, MSEThresh, trimFraction;
+    float tMinX, tMinY, tMinZ, tWidth;   // initNodeTrans
+    float s2[GOICP_MAXROTLEVEL];         // 2*sinf(maxAngle/2) per rotation level, computed on the host (glibc sinf)
+    float *dx, *dy, *dz;                 // data (source) cloud, SoA
+    float *mx, *my, *mz;                 // model (target) cloud, SoA
+    float* normData;                     // Nd
+    float* weights;                      // Nd
+    float* maxRotDis;                    // [20][Nd]
+    uint8_t* dprop;                      // Nd colour index of each data point (0..31)
+    uint8_t* mprop;                      // Nm
+    uint8_t* dknown;                     // Nd: 1 if the colour is a key of the compatibility map (jly_goicp.cpp:66-73)
+    float* dfpfh;                        // Nd x 41
+    float* mfpfh;                        // Nm x 41
+    int* cell_start;                     // ncells+1 CSR of cellPoints[].points (insertion = index order)
+    int* cell_pts;                       // Nm
+    float* fpfhD;                        // Nd x (ncells+1): min over the cell's points of the L1 descriptor distance
+    // ICP workspace (written by the ICP kernels)
+    unsigned long long* nn;              // Nd packed (float bits of squared distance << 32 | model index)
+    int* order;                          // Nd: id_data of points[i] (identity unless trimmed, jly_icp3d.hpp:252)
+    float* scratch;                      // 2*max(Nd,Nm) floats
+};
+
+struct InnerProb {          // one GoICP::InnerBnB call (jly_goicp.cpp:286)
+    int pair;
+    int level;              // -1: upper bound (maxRotDisL == NULL)
+    float optError;
+    float R[9];
+};
+struct InnerOut {
+    float err;              // optErrorT
+    float node[4];          // best translation node x,y,z,w (valid if improved)
+    int improved;
+    int pops, subcubes;
+    int status;             // 0 ok, 4 heap overflow
+};
+
+struct alignas(16) HeapEnt { float lb, w, x, y, z, pad0, pad1, pad2; };   // TRANSNODE without ub (never read, jly_goicp.h:75-87)
+
+struct IcpState {           // one GoICP::ICP call (jly_goicp.cpp:102) in flight
+    int pair;
+    int mode;               // 0 ICP + re-score, 1 initial error at identity (:601-627), 2 updateCompatibilities (:933)
+    double R[9], t[3];
+    double mu_m[3], mu_d[3];  // never reset between iterations (jly_icp3d.hpp:221-222)
+    float err;              // previous err (-1 at start)
+    int iter;
+    int done;
+    int status;
+    // outputs of the final DT re-score (jly_goicp.cpp:117-175)
+    float error;
+    int incomp;             // countCompatibilities over the correspondences
+    float fpfh;
+    int compat_pose;        // checkCompatibility count at the pose (mode 2)
+};
+
+struct WaveCube { float x, y, z, w; int rot; };   // a child translation cube to evaluate under rotation `rot`

@@ -1,0 +1,382 @@
+// Branch-and-bound bound evaluation kernels (north_star (b)).
+//
+//  inner_bnb_kernel   one CTA runs one whole GoICP::InnerBnB call (jly_goicp.cpp:286-579): the rotated cloud, weights
+//                     and rotation-uncertainty radii are staged in shared memory once, then each pop of the
+//                     translation queue evaluates its 8 child cubes x Nd points (warp = child cube, lane = point:
+//                     translate, voxel index in FP64, DT gather, x weight, - radius, clamp) plus the 27 lattice corners
+//                     of the fork's incompatibility / c-FPFH terms.  Persistent CTAs pull calls from an atomic counter,
+//                     so one launch evaluates every (rotation cube, level) request of every pair of a wave.
+//                     EXACT=true reproduces the reference's sequential float sums bit for bit (16 independent
+//                     FADD chains on 16 lanes), EXACT=false uses warp-shuffle tree sums.
+//  eval_bounds_kernel flat wave: one warp per (rotation cube, translation sub-cube), leaf-level (ub, lb) only.
+//
+// The translation priority queue lives in global memory (one slab per CTA) and follows libstdc++'s
+// push_heap/pop_heap step for step so that ties between equal (lb, w) keys pop in the reference's order.
+#include "dev_common.cuh"
+#include "launch.h"
+
+namespace {
+
+constexpr int BNB_THREADS = 256;
+
+// TRANSNODE operator< (jly_goicp.h:79-86)
+__device__ __forceinline__ bool node_less(const HeapEnt& a, const HeapEnt& b) {
+    if (a.lb != b.lb) return a.lb > b.lb;
+    return a.w < b.w;
+}
+__device__ __forceinline__ void ent_store(HeapEnt* h, int i, const HeapEnt& e) {
+    float4* p = reinterpret_cast<float4*>(h + i);
+    p[0] = make_float4(e.lb, e.w, e.x, e.y);
+    p[1] = make_float4(e.z, 0.f, 0.f, 0.f);
+}
+__device__ __forceinline__ HeapEnt ent_load(const HeapEnt* h, int i) {
+    const float4* p = reinterpret_cast<const float4*>(h + i);
+    float4 a = p[0], b = p[1];
+    HeapEnt e; e.lb = a.x; e.w = a.y; e.x = a.z; e.y = a.w; e.z = b.x; e.pad0 = e.pad1 = e.pad2 = 0.f;
+    return e;
+}
+// std::push_heap (__push_heap) on h[0..n) + val
+__device__ void heap_push(HeapEnt* h, int& n, const HeapEnt& val) {
+    int hole = n++;
+    int parent = (hole - 1) / 2;
+    while (hole > 0) {
+        HeapEnt pe = ent_load(h, parent);
+        if (!node_less(pe, val)) break;
+        ent_store(h, hole, pe);
+        hole = parent; parent = (hole - 1) / 2;
+    }
+    ent_store(h, hole, val);
+}
+// std::pop_heap (__adjust_heap to the bottom, then __push_heap of the former last element)
+__device__ HeapEnt heap_pop(HeapEnt* h, int& n) {
+    HeapEnt top = ent_load(h, 0);
+    const int len = --n;
+    if (len > 0) {
+        HeapEnt val = ent_load(h, len);
+        int hole = 0, child = 0;
+        while (child < (len - 1) / 2) {
+            child = 2 * (child + 1);
+            HeapEnt c1 = ent_load(h, child), c0 = ent_load(h, child - 1);
+            if (node_less(c1, c0)) { child--; c1 = c0; }
+            ent_store(h, hole, c1); hole = child;
+        }
+        if ((len & 1) == 0 && child == (len - 2) / 2) {
+            child = 2 * (child + 1);
+            ent_store(h, hole, ent_load(h, child - 1)); hole = child - 1;
+        }
+        int parent = (hole - 1) / 2;
+        while (hole > 0) {
+            HeapEnt pe = ent_load(h, parent);
+            if (!node_less(pe, val)) break;
+            ent_store(h, hole, pe);
+            hole = parent; parent = (hole - 1) / 2;
+        }
+        ent_store(h, hole, val);
+    }
+    return top;
+}
+
+struct BnbShared {
+    float ub[8], lb[8];
+    int cnt[27];
+    float cf[27];
+    float X[3], Y[3], Z[3];
+    float wc, mtd;
+    float optErrorT;
+    int running, prob, heapN, status;
+    int pops, subcubes, improved;
+    float best[4];
+};
+
+template <bool EXACT>
+__global__ void __launch_bounds__(BNB_THREADS)
+inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* __restrict__ probs, InnerOut* __restrict__ outs,
+                 int nprob, int* __restrict__ counter, HeapEnt* __restrict__ heaps, int heapCap,
+                 float* __restrict__ gscratch, size_t gstride, int NdP, int NdQ, int useSmem) {
+    extern __shared__ float4 dyn_smem4[];
+    __shared__ BnbShared sh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* base = useSmem ? reinterpret_cast<float*>(dyn_smem4) : gscratch + (size_t)blockIdx.x * gstride;
+    float* tx = base; float* ty = tx + NdP; float* tz = ty + NdP; float* wgt = tz + NdP; float* mrd = wgt + NdP;
+    float* md = mrd + NdP;            // [8][NdQ]   (EXACT or trimmed)
+    float* fp = md + 8 * NdQ;         // [27][NdQ]  (EXACT with the c-FPFH term)
+    HeapEnt* heap = heaps + (size_t)blockIdx.x * heapCap;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) sh.prob = atomicAdd(counter, 1);
+        __syncthreads();
+        const int p = sh.prob;
+        if (p >= nprob) return;
+        const InnerProb pr = probs[p];
+        const PairDev& P = pairs[pr.pair];
+        const GridDev& g = P.g;
+        const int Nd = P.Nd;
+        const float* __restrict__ dist = g.dist;
+        const bool corners = P.use_reg || P.use_fpfh;
+        const bool useMd = EXACT || P.doTrim;
+        const int ncp1 = g.ncells + 1;
+
+        // ---- stage the rotated cloud (jly_goicp.cpp:750-756), weights and rotation radii ---------------------
+        for (int i = tid; i < Nd; i += BNB_THREADS) {
+            const float x = P.dx[i], y = P.dy[i], z = P.dz[i];
+            tx[i] = pr.R[0] * x + pr.R[1] * y + pr.R[2] * z;
+            ty[i] = pr.R[3] * x + pr.R[4] * y + pr.R[5] * z;
+            tz[i] = pr.R[6] * x + pr.R[7] * y + pr.R[8] * z;
+            wgt[i] = P.weights[i];
+            mrd[i] = pr.level >= 0 ? P.maxRotDis[(size_t)pr.level * Nd + i] : 0.f;   // d - 0 == d
+        }
+        if (tid == 0) {
+            sh.heapN = 0; sh.status = 0; sh.pops = 0; sh.subcubes = 0; sh.improved = 0;
+            sh.optErrorT = pr.optError;                                              // :297
+            sh.best[0] = sh.best[1] = sh.best[2] = sh.best[3] = 0.f;
+            HeapEnt init; init.lb = 0.f; init.w = P.tWidth; init.x = P.tMinX; init.y = P.tMinY; init.z = P.tMinZ;
+            init.pad0 = init.pad1 = init.pad2 = 0.f;
+            heap_push(heap, sh.heapN, init);                                         // :300
+        }
+
+        for (;;) {
+            // ---- pop (thread 0) -------------------------------------------------------------------------
+            if (tid == 0) {
+                if (sh.heapN == 0 || sh.status != 0) sh.running = 0;
+                else {
+                    HeapEnt par = heap_pop(heap, sh.heapN);
+                    sh.pops++;
+                    if (sh.optErrorT - par.lb < P.SSEThresh) sh.running = 0;         // :317
+                    else {
+                        sh.running = 1;
+                        const float wc = par.w / 2;                                  // :322
+                        sh.wc = wc;
+                        sh.mtd = (float)(GOICP_SQRT3 / 2.0 * wc);                    // :323
+                        sh.X[0] = par.x; sh.X[1] = par.x + wc; sh.X[2] = sh.X[1] + wc;   // child / corner lattice
+                        sh.Y[0] = par.y; sh.Y[1] = par.y + wc; sh.Y[2] = sh.Y[1] + wc;
+                        sh.Z[0] = par.z; sh.Z[1] = par.z + wc; sh.Z[2] = sh.Z[1] + wc;
+                    }
+                }
+            }
+            __syncthreads();
+            if (!sh.running) break;
+            const float wc = sh.wc, mtd = sh.mtd;
+
+            // ---- the cube.point bound evals: warp = child cube, lane = point (:343-382) -------------------
+            {
+                const int c = warp;
+                const float half = wc / 2;
+                const float transX = sh.X[c & 1] + half, transY = sh.Y[(c >> 1) & 1] + half, transZ = sh.Z[(c >> 2) & 1] + half;
+                float su = 0.f, sl = 0.f;
+                for (int i = lane; i < Nd; i += 32) {
+                    float d = wgt[i] * dt_distance(g, dist, tx[i] + transX, ty[i] + transY, tz[i] + transZ);
+                    d = d - mrd[i];
+                    if (d < 0.f) d = 0.f;
+                    if (useMd) md[c * NdQ + i] = d;
+                    else {
+                        su += (P.norm == 2) ? d * d : d;
+                        const float dis = d - mtd;
+                        if (dis > 0.f) sl += (P.norm == 2) ? dis * dis : dis;
+                    }
+                }
+                if (!useMd) {
+                    su = warp_sum(su); sl = warp_sum(sl);
+                    if (lane == 0) { sh.ub[c] = su; sh.lb[c] = sl; }
+                }
+            }
+            // ---- corner terms on the 3x3x3 lattice of child-cube corners (:431-550, checkCompatibilities :919,
+            //      sumFPFH :1689); pure functions of the corner, so the reference's memo is not needed ----------
+            if (corners) {
+                for (int c = warp; c < 27; c += 8) {
+                    const float cx = sh.X[c % 3], cy = sh.Y[(c / 3) % 3], cz = sh.Z[c / 9];
+                    int bad = 0; float fs = 0.f;
+                    for (int i = lane; i < Nd; i += 32) {
+                        const int cell = clamp_cell(g, tx[i] + cx, ty[i] + cy, tz[i] + cz);
+                        if (P.use_reg) bad += ((__ldg(g.cmask + cell) >> P.dprop[i]) & 1u) ? 0 : 1;
+                        if (P.use_fpfh) {
+                            const float v = __ldg(P.fpfhD + (size_t)i * ncp1 + cell);
+                            if (EXACT) fp[c * NdQ + i] = v; else fs += v;
+                        }
+                    }
+                    bad = warp_sum_i(bad);
+                    if (!EXACT) fs = warp_sum(fs);
+                    if (lane == 0) {
+                        sh.cnt[c] = bad;
+                        if (!EXACT) sh.cf[c] = (float)(int)(fs / (float)Nd);       // int truncation (H7)
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- sums ---------------------------------------------------------------------------------------
+            if (useMd) {
+                if (P.doTrim) {   // radix select replaces intro_select (:384-390); one warp per child
+                    float su, sl;
+                    warp_trimmed_sums(md + warp * NdQ, Nd, P.inlierNum, lane, P.norm, mtd, &su, &sl);
+                    if (lane == 0) { sh.ub[warp] = su; sh.lb[warp] = sl; }
+                } else if (warp == 0 && lane < 16) {
+                    // sequential float sums in index order (:393-415): lane = (child, ub|lb); 16 independent chains
+                    const int c = lane >> 1; const float off = (lane & 1) ? mtd : 0.f;
+                    const float* m = md + c * NdQ;
+                    float acc = 0.f;
+                    const int n = P.inlierNum;
+                    if (P.norm == 2) { for (int i = 0; i < n; ++i) { float v = fmaxf(m[i] - off, 0.f); acc = acc + v * v; } }
+                    else            { for (int i = 0; i < n; ++i) { float v = fmaxf(m[i] - off, 0.f); acc = acc + v; } }
+                    if (lane & 1) sh.lb[c] = acc; else sh.ub[c] = acc;
+                }
+            }
+            if (EXACT && corners && P.use_fpfh && warp == 1 && lane < 27) {
+                const float* f = fp + lane * NdQ;
+                float s = 0.f;
+                for (int i = 0; i < Nd; ++i) s = s + f[i];                        // sumFPFH :1692-1695
+                sh.cf[lane] = (float)(int)(s / (float)Nd);                         // :1696, int truncation :468,:495
+            }
+            __syncthreads();
+            // ---- decisions and pushes in child order (thread 0, :417-575) -----------------------------------
+            if (tid == 0) {
+                float optErrorT = sh.optErrorT;
+                for (int j = 0; j < 8; ++j) {
+                    float ub = sh.ub[j], lb = sh.lb[j];
+                    const int jx = j & 1, jy = (j >> 1) & 1, jz = (j >> 2) & 1;
+                    if (corners) {
+                        int minI = 0, maxI = 0; float minF = 0.f, maxF = 0.f;
+                        for (int k = 0; k < 8; ++k) {
+                            const int c = (jx + (k & 1)) + 3 * (jy + ((k >> 1) & 1)) + 9 * (jz + ((k >> 2) & 1));
+                            if (P.use_fpfh) { const float f = sh.cf[c]; if (k == 0) { minF = maxF = f; } else { if (f > maxF) maxF = f; if (f < minF) minF = f; } }
+                            if (P.use_reg) { const int n = sh.cnt[c]; if (k == 0) { minI = maxI = n; } else { if (n > maxI) maxI = n; if (n < minI) minI = n; } }
+                        }
+                        if (P.use_reg) { ub = ub + P.reg * (float)(maxI * maxI); lb = lb + P.reg * (float)(minI * minI); }      // :536-538
+                        if (P.use_fpfh) { ub = ub + P.regF * (maxF * maxF); lb = lb + P.regF * (minF * minF); }                  // :546-549
+                    }
+                    sh.subcubes++;
+                    const float nx = sh.X[jx], ny = sh.Y[jy], nz = sh.Z[jz];
+                    if (ub < optErrorT) {                                                                                         // :554-566
+                        optErrorT = ub; sh.improved = 1;
+                        sh.best[0] = nx; sh.best[1] = ny; sh.best[2] = nz; sh.best[3] = wc;
+                    }
+                    if (lb >= optErrorT) continue;                                                                                // :568-572
+                    if (sh.heapN >= heapCap) { sh.status = 4; break; }
+                    HeapEnt e; e.lb = lb; e.w = wc; e.x = nx; e.y = ny; e.z = nz; e.pad0 = e.pad1 = e.pad2 = 0.f;
+                    heap_push(heap, sh.heapN, e);
+                }
+                sh.optErrorT = optErrorT;
+            }
+            // thread 0 continues straight into the next pop; the barrier at the loop head orders it with the others
+        }
+        if (tid == 0) {
+            InnerOut o;
+            o.err = sh.optErrorT; o.node[0] = sh.best[0]; o.node[1] = sh.best[1]; o.node[2] = sh.best[2]; o.node[3] = sh.best[3];
+            o.improved = sh.improved; o.pops = sh.pops; o.subcubes = sh.subcubes; o.status = sh.status;
+            outs[p] = o;
+        }
+    }
+}
+
+// Flat wave: every (rotation cube, translation sub-cube) of a frontier in one launch, one warp per sub-cube.
+// Leaf-level bounds (pure functions) incl. the corner terms; tree sums.
+__global__ void __launch_bounds__(256)
+eval_bounds_kernel(const PairDev* __restrict__ pairs, int pair, const float* __restrict__ Rs, const int* __restrict__ levels,
+                   const WaveCube* __restrict__ cubes, int nt, float* __restrict__ ub_out, float* __restrict__ lb_out,
+                   int* __restrict__ incomp_mm, int* __restrict__ fpfh_mm, float* __restrict__ scratch) {
+    const int lane = threadIdx.x & 31;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    const PairDev& P = pairs[pair];
+    const GridDev& g = P.g;
+    const int Nd = P.Nd;
+    const int ncp1 = g.ncells + 1;
+    const float* __restrict__ dist = g.dist;
+    float* md = scratch + (size_t)wid * Nd;   // per-warp residual buffer (trimmed case only)
+    for (int k = wid; k < nt; k += nw) {
+        const WaveCube cb = cubes[k];
+        const float* R = Rs + 9 * cb.rot;
+        const int level = levels[cb.rot];
+        const float r0 = R[0], r1 = R[1], r2 = R[2], r3 = R[3], r4 = R[4], r5 = R[5], r6 = R[6], r7 = R[7], r8 = R[8];
+        const float half = cb.w / 2;
+        const float transX = cb.x + half, transY = cb.y + half, transZ = cb.z + half;
+        const float mtd = (float)(GOICP_SQRT3 / 2.0 * cb.w);
+        float su = 0.f, sl = 0.f;
+        int bad[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        float fs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int i = lane; i < Nd; i += 32) {
+            const float x = P.dx[i], y = P.dy[i], z = P.dz[i];
+            const float px = r0 * x + r1 * y + r2 * z, py = r3 * x + r4 * y + r5 * z, pz = r6 * x + r7 * y + r8 * z;
+            float d = P.weights[i] * dt_distance(g, dist, px + transX, py + transY, pz + transZ);
+            if (level >= 0) d = d - P.maxRotDis[(size_t)level * Nd + i];
+            if (d < 0.f) d = 0.f;
+            if (P.doTrim) md[i] = d;
+            else {
+                su += (P.norm == 2) ? d * d : d;
+                const float dis = d - mtd;
+                if (dis > 0.f) sl += (P.norm == 2) ? dis * dis : dis;
+            }
+            if (P.use_reg || P.use_fpfh) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float cx = cb.x + (float)(c & 1) * cb.w, cy = cb.y + (float)((c >> 1) & 1) * cb.w, cz = cb.z + (float)((c >> 2) & 1) * cb.w;
+                    const int cell = clamp_cell(g, px + cx, py + cy, pz + cz);
+                    if (P.use_reg) bad[c] += ((__ldg(g.cmask + cell) >> P.dprop[i]) & 1u) ? 0 : 1;
+                    if (P.use_fpfh) fs[c] += __ldg(P.fpfhD + (size_t)i * ncp1 + cell);
+                }
+            }
+        }
+        if (P.doTrim) { __syncwarp(); warp_trimmed_sums(md, Nd, P.inlierNum, lane, P.norm, mtd, &su, &sl); __syncwarp(); }
+        else { su = warp_sum(su); sl = warp_sum(sl); }
+        int minI = 0, maxI = 0; float minF = 0.f, maxF = 0.f;
+        if (P.use_reg || P.use_fpfh) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                if (P.use_fpfh) { const float f = (float)(int)(warp_sum(fs[c]) / (float)Nd); if (c == 0) { minF = maxF = f; } else { maxF = fmaxf(maxF, f); minF = fminf(minF, f); } }
+                if (P.use_reg) { const int n = warp_sum_i(bad[c]); if (c == 0) { minI = maxI = n; } else { maxI = max(maxI, n); minI = min(minI, n); } }
+            }
+            if (P.use_reg) { su = su + P.reg * (float)(maxI * maxI); sl = sl + P.reg * (float)(minI * minI); }
+            if (P.use_fpfh) { su = su + P.regF * (maxF * maxF); sl = sl + P.regF * (minF * minF); }
+        }
+        if (lane == 0) {
+            ub_out[k] = su; lb_out[k] = sl;
+            if (incomp_mm) { incomp_mm[2 * k] = minI; incomp_mm[2 * k + 1] = maxI; }
+            if (fpfh_mm) { fpfh_mm[2 * k] = (int)minF; fpfh_mm[2 * k + 1] = (int)maxF; }
+        }
+    }
+}
+
+}  // namespace
+
+// ---- launchers ---------------------------------------------------------------------------------------------
+size_t goicp_bnb_smem_floats(int NdP, int NdQ, bool needMd, bool needFp) {
+    return (size_t)5 * NdP + (needMd ? (size_t)8 * NdQ : 0) + (needFp ? (size_t)27 * NdQ : 0);
+}
+
+static int g_bnb_attr_set[2] = {0, 0};
+
+cudaError_t goicp_launch_inner_bnb(const PairDev* pairs, const InnerProb* probs, InnerOut* outs, int nprob, int* counter,
+                                   HeapEnt* heaps, int heapCap, int maxCtas, float* gscratch, size_t gstride,
+                                   int NdP, int NdQ, size_t smemFloats, int useSmem, int exact, cudaStream_t st, int* ctasLaunched) {
+    if (nprob <= 0) { if (ctasLaunched) *ctasLaunched = 0; return cudaSuccess; }
+    const size_t smem = useSmem ? smemFloats * sizeof(float) : 0;
+    auto kern = exact ? inner_bnb_kernel<true> : inner_bnb_kernel<false>;
+    if (!g_bnb_attr_set[exact ? 1 : 0]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        g_bnb_attr_set[exact ? 1 : 0] = 1;
+    }
+    int grid = nprob < maxCtas ? nprob : maxCtas;
+    if (ctasLaunched) *ctasLaunched = grid;
+    kern<<<grid, BNB_THREADS, smem, st>>>(pairs, probs, outs, nprob, counter, heaps, heapCap, gscratch, gstride, NdP, NdQ, useSmem);
+    return cudaGetLastError();
+}
+
+int goicp_inner_bnb_occupancy(size_t smemBytes, int exact) {
+    auto kern = exact ? inner_bnb_kernel<true> : inner_bnb_kernel<false>;
+    if (!g_bnb_attr_set[exact ? 1 : 0]) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return 1;
+        g_bnb_attr_set[exact ? 1 : 0] = 1;
+    }
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, BNB_THREADS, smemBytes) != cudaSuccess || n < 1) n = 1;
+    return n;
+}
+
+cudaError_t goicp_launch_eval_bounds(const PairDev* pairs, int pair, const float* Rs, const int* levels, const WaveCube* cubes,
+                                     int nt, float* ub, float* lb, int* incomp_mm, int* fpfh_mm, float* scratch, int nwarps,
+                                     cudaStream_t st) {
+    if (nt <= 0) return cudaSuccess;
+    const int blocks = (nwarps + 7) / 8;
+    eval_bounds_kernel<<<blocks, 256, 0, st>>>(pairs, pair, Rs, levels, cubes, nt, ub, lb, incomp_mm, fpfh_mm, scratch);
+    return cudaGetLastError();
+}

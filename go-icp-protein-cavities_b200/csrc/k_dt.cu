@@ -1,0 +1,304 @@
+// Distance-transform build kernels (north_star (a)); replaces DT3D::Build (jly_3ddt.cpp:897-1137).
+//
+// Two builders, both fed with the occupied-voxel list the host derives from the model cloud (seeding, :976-995):
+//
+//  dt_replay_kernel   S <= 32 (the cavity grids, distTransSize = 20): a bit-exact replay of the reference's sequential
+//                     8SED vector propagation (DEuclidean :716-750 and its six mask functions :57-712, including the two
+//                     copy-paste slips) and of the emptyCells sign-resolution order (:999-1136).  One warp per grid,
+//                     lane = z, the whole S^3 offset volume in shared memory ([x][y][z], conflict-free); the 13 mask
+//                     entries that read other columns are evaluated by all lanes at once, only the in-column z
+//                     dependency is walked sequentially with shuffles.  A batch of pairs runs one warp each.
+//  dt_sep_*           any S: an exact separable Euclidean DT (x, then y, then z pass; every pass one thread per voxel
+//                     searching outwards along its axis with early exit) that also emits the nearest occupied voxel.
+//                     Where 8SED is exact (it is not an exact EDT) values are identical; ties between equidistant
+//                     occupied voxels are resolved by the documented rule "smaller |offset| along the later axis
+//                     first, negative side before positive", which differs from 8SED's scan-order choice.
+//
+// Distances: an integer squared voxel offset q -> (float)((double)(float)sqrt(q) / scale), as :1004 computes it
+// (sqrt in double rounded to float equals the correctly rounded float sqrt for q < 2^24).
+#include "dev_common.cuh"
+#include "launch.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------------
+// mask tables (jly_3ddt.cpp:57-712), in the reference's evaluation order
+enum { ZM = 1, ZP = 2, YM = 4, YP = 8, XM = 16, XP = 32 };
+struct MaskE { int cond; int dz, dy, dx; unsigned inc; };   // inc = iv | ih<<8 | id<<16  (v = x-offset, h = y, d = z)
+#define INC(v, h, d) ((unsigned)(v) | ((unsigned)(h) << 8) | ((unsigned)(d) << 16))
+__constant__ MaskE M_FWD1[14] = {   // MINforwardDE1 :508-712
+    {ZM | YM | XM, -1, -1, -1, INC(1, 1, 1)}, {YM | XM, 0, -1, -1, INC(1, 1, 0)}, {ZP | YM | XM, 1, -1, -1, INC(1, 1, 1)},
+    {ZM | XM, -1, 0, -1, INC(1, 0, 1)},       {XM, 0, 0, -1, INC(1, 0, 0)},       {XM | ZP, 1, 0, -1, INC(1, 0, 1)},
+    {XM | ZM | YP, -1, 1, -1, INC(1, 1, 1)},  {XM | YP, 0, 1, -1, INC(1, 1, 0)},  {XM | YP | ZP, 1, 1, -1, INC(1, 1, 1)},
+    {ZM | YM, -1, -1, 0, INC(0, 1, 1)},       {YM, 0, -1, 0, INC(0, 1, 0)},       {ZP | YM, 1, -1, 0, INC(0, 1, 1)},
+    {0, 0, 0, 0, INC(0, 0, 0)},               {ZM, -1, 0, 0, INC(0, 0, 1)}};
+__constant__ MaskE M_BWD1[14] = {   // MINbackwardDE1 :301-506 (entry 10 reads [z+1][y][x], sic :459-464)
+    {ZM | YM | XP, -1, -1, 1, INC(1, 1, 1)},  {YM | XP, 0, -1, 1, INC(1, 1, 0)},  {ZP | YM | XP, 1, -1, 1, INC(1, 1, 1)},
+    {ZM | XP, -1, 0, 1, INC(1, 0, 1)},        {XP, 0, 0, 1, INC(1, 0, 0)},        {XP | ZP, 1, 0, 1, INC(1, 0, 1)},
+    {XP | ZM | YP, -1, 1, 1, INC(1, 1, 1)},   {XP | YP, 0, 1, 1, INC(1, 1, 0)},   {XP | YP | ZP, 1, 1, 1, INC(1, 1, 1)},
+    {ZP, 1, 0, 0, INC(0, 0, 1)},              {YP | ZP, 1, 0, 0, INC(0, 1, 1)},
+    {YP, 0, 1, 0, INC(0, 1, 0)},              {0, 0, 0, 0, INC(0, 0, 0)},         {ZM | YP, -1, 1, 0, INC(0, 1, 1)}};
+__constant__ MaskE M_FWD2[2] = {{ZP, 1, 0, 0, INC(0, 0, 1)}, {0, 0, 0, 0, INC(0, 0, 0)}};    // MINforwardDE2 :260-299
+__constant__ MaskE M_FWD4[2] = {{ZM, -1, 0, 0, INC(0, 0, 1)}, {0, 0, 0, 0, INC(0, 0, 0)}};   // MINforwardDE4 :139-175
+__constant__ MaskE M_FWD3[5] = {   // MINforwardDE3 :57-136 (entry 1 reads [z+1][y][x], sic :88-93)
+    {ZP, 1, 0, 0, INC(0, 0, 1)}, {YP | ZP, 1, 0, 0, INC(0, 1, 1)}, {YP, 0, 1, 0, INC(0, 1, 0)}, {0, 0, 0, 0, INC(0, 0, 0)}, {ZM | YP, -1, 1, 0, INC(0, 1, 1)}};
+__constant__ MaskE M_BWD3[5] = {   // MINbackwardDE3 :177-258
+    {ZM | YM, -1, -1, 0, INC(0, 1, 1)}, {YM, 0, -1, 0, INC(0, 1, 0)}, {ZP | YM, 1, -1, 0, INC(0, 1, 1)}, {0, 0, 0, 0, INC(0, 0, 0)}, {ZM, -1, 0, 0, INC(0, 0, 1)}};
+
+constexpr unsigned UNSET = 0xFFFFFFFFu;   // DEucl3D {infty,infty,infty,infty}
+__device__ __forceinline__ int qof(unsigned a) { int v = a & 255, h = (a >> 8) & 255, d = (a >> 16) & 255; return v * v + h * h + d * d; }
+// `if (mask[k].distance < min.distance) min = mask[k]` with NaN (unset source) never selected
+__device__ __forceinline__ void take_if_less(unsigned& best, unsigned cand) {
+    if (cand != UNSET && (best == UNSET || qof(cand) < qof(best))) best = cand;
+}
+
+// one z-sweep of column (y, x): table T[0..n), in-column entries [ic0, ic1), zdir = +1 ascending / -1 descending
+__device__ __forceinline__ void sweep_column(unsigned* A, int S, int x, int y, const MaskE* T, int n, int ic0, int ic1, int zdir, int lane) {
+    const int z = lane;
+    const bool act = z < S;
+    const int have = (z > 0 ? ZM : 0) | (z < S - 1 ? ZP : 0) | (y > 0 ? YM : 0) | (y < S - 1 ? YP : 0) | (x > 0 ? XM : 0) | (x < S - 1 ? XP : 0);
+    unsigned pre = UNSET, post = UNSET;
+    if (act) {
+        for (int k = 0; k < ic0; ++k) {
+            const MaskE m = T[k];
+            if ((m.cond & have) != m.cond) continue;
+            const unsigned s = A[((x + m.dx) * S + (y + m.dy)) * S + (z + m.dz)];
+            take_if_less(pre, s == UNSET ? UNSET : s + m.inc);
+        }
+        for (int k = ic1; k < n; ++k) {
+            const MaskE m = T[k];
+            if ((m.cond & have) != m.cond) continue;
+            const unsigned s = A[((x + m.dx) * S + (y + m.dy)) * S + (z + m.dz)];
+            take_if_less(post, s == UNSET ? UNSET : s + m.inc);
+        }
+    }
+    unsigned res = UNSET;
+    for (int step = 0; step < S; ++step) {
+        const int zc = zdir > 0 ? step : S - 1 - step;
+        const unsigned src = __shfl_sync(GOICP_FULL, res, (zc - zdir) & 31);   // new value of the in-column neighbour
+        if (lane == zc) {
+            unsigned best = pre;
+            for (int k = ic0; k < ic1; ++k) {
+                const MaskE m = T[k];
+                if ((m.cond & have) != m.cond) continue;
+                take_if_less(best, src == UNSET ? UNSET : src + m.inc);
+            }
+            take_if_less(best, post);
+            res = best;
+        }
+    }
+    __syncwarp();
+    if (act) A[(x * S + y) * S + z] = res;
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(32)
+dt_replay_kernel(PairDev* __restrict__ pairs, int first) {
+    extern __shared__ unsigned A[];   // [x][y][z]
+    const GridDev g = pairs[first + blockIdx.x].g;
+    const int S = g.S, lane = threadIdx.x;
+    const int S3 = S * S * S;
+    for (int i = lane; i < S3; i += 32) A[i] = UNSET;
+    __syncwarp();
+    for (int c = lane; c < g.ncells; c += 32) {   // seeds :991-994
+        const int v = g.cell_vox[c];
+        const int x = v % S, y = (v / S) % S, z = v / (S * S);
+        A[(x * S + y) * S + z] = 0u;
+    }
+    __syncwarp();
+    // DEuclidean :716-750
+    for (int x = 0; x < S; ++x) {
+        for (int y = 0; y < S; ++y) {
+            sweep_column(A, S, x, y, M_FWD1, 14, 13, 14, +1, lane);
+            sweep_column(A, S, x, y, M_FWD2, 2, 0, 1, -1, lane);
+        }
+        for (int y = S - 1; y > -1; --y) {
+            sweep_column(A, S, x, y, M_FWD3, 5, 0, 2, -1, lane);
+            sweep_column(A, S, x, y, M_FWD4, 2, 0, 1, +1, lane);
+        }
+    }
+    for (int x = S - 1; x > -1; --x) {
+        for (int y = S - 1; y > -1; --y) {
+            sweep_column(A, S, x, y, M_BWD1, 14, 9, 11, -1, lane);
+            sweep_column(A, S, x, y, M_FWD4, 2, 0, 1, +1, lane);
+        }
+        for (int y = 0; y < S; ++y) {
+            sweep_column(A, S, x, y, M_BWD3, 5, 4, 5, +1, lane);
+            sweep_column(A, S, x, y, M_FWD2, 2, 0, 1, -1, lane);
+        }
+    }
+    // distances and emptyCells :999-1136
+    for (int i = lane; i < S3; i += 32) {
+        const int x = i % S, y = (i / S) % S, z = i / (S * S);
+        const unsigned a = A[(x * S + y) * S + z];
+        float dist;
+        int cx = x, cy = y, cz = z;
+        if (a == UNSET) dist = (float)((double)32767.f / g.scale);
+        else {
+            const int xD = a & 255, yD = (a >> 8) & 255, zD = (a >> 16) & 255;
+            dist = (float)((double)sqrtf((float)(xD * xD + yD * yD + zD * zD)) / g.scale);
+            if (dist != 0.f) {
+                // sign combinations in the reference's order (+ before -); a zero offset collapses the list
+                // full order :1092-1131 on (x,y,z) signs: +++ -++ +-+ ++- --+ -+- +-- ---
+                const int sx[8] = {1, -1, 1, 1, -1, -1, 1, -1}, sy[8] = {1, 1, -1, 1, -1, 1, -1, -1}, sz[8] = {1, 1, 1, -1, 1, -1, -1, -1};
+                // xD==0 :1030-1047 -> (y,z): ++ +- -+ -- ; yD==0 :1055-1072 -> (x,z): ++ +- -+ -- ; zD==0 :1074-1091 -> (x,y): ++ -+ +- --
+                for (int k = 0; k < 8; ++k) {
+                    int ax, ay, az;
+                    if (xD != 0 && yD != 0 && zD != 0) { ax = sx[k]; ay = sy[k]; az = sz[k]; }
+                    else if (xD == 0 && yD != 0 && zD != 0) { if (k >= 4) break; ax = 0; ay = (k < 2) ? 1 : -1; az = (k & 1) ? -1 : 1; }
+                    else if (yD == 0 && xD != 0 && zD != 0) { if (k >= 4) break; ay = 0; ax = (k < 2) ? 1 : -1; az = (k & 1) ? -1 : 1; }
+                    else if (zD == 0 && xD != 0 && yD != 0) { if (k >= 4) break; az = 0; ax = (k & 1) ? -1 : 1; ay = (k < 2) ? 1 : -1; }
+                    else { if (k >= 2) break; const int s = k ? -1 : 1; ax = xD ? s : 0; ay = yD ? s : 0; az = zD ? s : 0; }
+                    const int nx = x + ax * xD, ny = y + ay * yD, nz = z + az * zD;
+                    if (nx < 0 || nx >= S || ny < 0 || ny >= S || nz < 0 || nz >= S) continue;
+                    if (A[(nx * S + ny) * S + nz] == 0u) { cx = nx; cy = ny; cz = nz; break; }
+                }
+            }
+        }
+        if (dist < 0.f) dist = 0.f;
+        g.dist[i] = dist;
+        const int vn = (cz * S + cy) * S + cx;
+        g.vnear[i] = vn;
+        if (g.vcell) {   // compact id of that cell: binary search in the ascending occupied-voxel list
+            int lo = 0, hi = g.ncells - 1, id = g.ncells;
+            while (lo <= hi) { const int mid = (lo + hi) >> 1; const int v = g.cell_vox[mid]; if (v == vn) { id = mid; break; } if (v < vn) lo = mid + 1; else hi = mid - 1; }
+            g.vcell[i] = id;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// separable exact EDT
+__global__ void dt_sep_seed_kernel(const int* __restrict__ cell_vox, int ncells, int S, int SW, unsigned* __restrict__ bits) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    const int v = cell_vox[c];
+    const int x = v % S, row = v / S;
+    atomicOr(bits + (size_t)row * SW + (x >> 5), 1u << (x & 31));
+}
+// pass X: nearest occupied x' in the row (ties: lower x first)
+__global__ void __launch_bounds__(256)
+dt_sep_x_kernel(const unsigned* __restrict__ bits, int S, int SW, unsigned short* __restrict__ nx) {
+    const size_t total = (size_t)S * S * S;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % S); const size_t row = i / S;
+        const unsigned* b = bits + row * SW;
+        int left = -1, right = -1;
+        {   // highest set bit <= x
+            int w = x >> 5; unsigned m = __ldg(b + w) & (0xFFFFFFFFu >> (31 - (x & 31)));
+            while (true) { if (m) { left = (w << 5) + 31 - __clz(m); break; } if (--w < 0) break; m = __ldg(b + w); }
+        }
+        {   // lowest set bit > x
+            int w = x >> 5; unsigned m = ((x & 31) == 31) ? 0u : (__ldg(b + w) & (0xFFFFFFFFu << ((x & 31) + 1)));
+            while (true) { if (m) { right = (w << 5) + __ffs(m) - 1; break; } if (++w >= SW) break; m = __ldg(b + w); }
+        }
+        int best = 0xFFFF;
+        if (left >= 0) best = left;
+        if (right >= 0 && (left < 0 || right - x < x - left)) best = right;
+        nx[i] = (unsigned short)best;
+    }
+}
+// pass Y: nearest (x', y') in the z-slice; outward search along y with early exit
+__global__ void __launch_bounds__(256)
+dt_sep_y_kernel(const unsigned short* __restrict__ nx, int S, unsigned* __restrict__ nxy) {
+    const size_t total = (size_t)S * S * S;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % S), y = (int)((i / S) % S);
+        const size_t zbase = (i / ((size_t)S * S)) * S * S;
+        int bestq = 0x7FFFFFFF; unsigned best = UNSET;
+        for (int r = 0; r < S; ++r) {
+            if (r * r >= bestq) break;
+            bool any = false;
+            const int y0 = y - r, y1 = y + r;
+            if (y0 >= 0) { any = true; const int c = __ldg(nx + zbase + (size_t)y0 * S + x); if (c != 0xFFFF) { const int q = r * r + (c - x) * (c - x); if (q < bestq) { bestq = q; best = (unsigned)c | ((unsigned)y0 << 16); } } }
+            if (r > 0 && y1 < S) { any = true; const int c = __ldg(nx + zbase + (size_t)y1 * S + x); if (c != 0xFFFF) { const int q = r * r + (c - x) * (c - x); if (q < bestq) { bestq = q; best = (unsigned)c | ((unsigned)y1 << 16); } } }
+            if (!any) break;
+        }
+        nxy[i] = best;
+    }
+}
+// pass Z: nearest occupied voxel; writes the distance and the index map
+__global__ void __launch_bounds__(256)
+dt_sep_z_kernel(const unsigned* __restrict__ nxy, GridDev g) {
+    const int S = g.S;
+    const size_t total = (size_t)S * S * S, plane = (size_t)S * S;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % S), y = (int)((i / S) % S), z = (int)(i / plane);
+        const size_t col = (size_t)y * S + x;
+        int bestq = 0x7FFFFFFF, bx = x, by = y, bz = z;
+        for (int r = 0; r < S; ++r) {
+            if (r * r >= bestq) break;
+            bool any = false;
+            const int z0 = z - r, z1 = z + r;
+            if (z0 >= 0) { any = true; const unsigned c = __ldg(nxy + (size_t)z0 * plane + col); if (c != UNSET) { const int cx = c & 0xFFFF, cy = c >> 16; const int q = r * r + (cx - x) * (cx - x) + (cy - y) * (cy - y); if (q < bestq) { bestq = q; bx = cx; by = cy; bz = z0; } } }
+            if (r > 0 && z1 < S) { any = true; const unsigned c = __ldg(nxy + (size_t)z1 * plane + col); if (c != UNSET) { const int cx = c & 0xFFFF, cy = c >> 16; const int q = r * r + (cx - x) * (cx - x) + (cy - y) * (cy - y); if (q < bestq) { bestq = q; bx = cx; by = cy; bz = z1; } } }
+            if (!any) break;
+        }
+        float dist = (bestq == 0x7FFFFFFF) ? (float)((double)32767.f / g.scale) : (float)((double)sqrtf((float)bestq) / g.scale);
+        g.dist[i] = dist;
+        const int vn = (bz * S + by) * S + bx;
+        g.vnear[i] = vn;
+        if (g.vcell) {
+            int lo = 0, hi = g.ncells - 1, id = g.ncells;
+            while (lo <= hi) { const int mid = (lo + hi) >> 1; const int v = __ldg(g.cell_vox + mid); if (v == vn) { id = mid; break; } if (v < vn) lo = mid + 1; else hi = mid - 1; }
+            g.vcell[i] = id;
+        }
+    }
+}
+
+// overwrite helper for the test hook goicp_dt_upload: vcell from vnear
+__global__ void dt_vcell_kernel(GridDev g) {
+    const size_t total = (size_t)g.S * g.S * g.S;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int vn = g.vnear[i];
+        int lo = 0, hi = g.ncells - 1, id = g.ncells;
+        while (lo <= hi) { const int mid = (lo + hi) >> 1; const int v = __ldg(g.cell_vox + mid); if (v == vn) { id = mid; break; } if (v < vn) lo = mid + 1; else hi = mid - 1; }
+        g.vcell[i] = id;
+    }
+}
+
+// DT3D::Distance (jly_3ddt.cpp:1139), batched
+__global__ void dt_distance_kernel(const PairDev* __restrict__ pairs, int pair, const double* __restrict__ xyz, int n, float* __restrict__ out, int* __restrict__ cell) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int x, y, z;
+    out[i] = dt_distance_d(pairs[pair].g, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], &x, &y, &z);
+    if (cell) { cell[3 * i] = x; cell[3 * i + 1] = y; cell[3 * i + 2] = z; }
+}
+
+}  // namespace
+
+cudaError_t goicp_launch_dt_replay(PairDev* pairs, int first, int count, int S, cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
+    const size_t smem = (size_t)S * S * S * sizeof(unsigned);
+    static bool attr = false;
+    if (!attr) { cudaError_t e = cudaFuncSetAttribute(dt_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 32 * 32 * 4); if (e != cudaSuccess) return e; attr = true; }
+    dt_replay_kernel<<<count, 32, smem, st>>>(pairs, first);
+    return cudaGetLastError();
+}
+
+cudaError_t goicp_launch_dt_separable(const GridDev& g, unsigned* bits, unsigned short* nx, unsigned* nxy, int numSM, cudaStream_t st) {
+    const int S = g.S, SW = (S + 31) / 32;
+    cudaError_t e = cudaMemsetAsync(bits, 0, (size_t)S * S * SW * sizeof(unsigned), st);
+    if (e != cudaSuccess) return e;
+    if (g.ncells > 0) dt_sep_seed_kernel<<<(g.ncells + 255) / 256, 256, 0, st>>>(g.cell_vox, g.ncells, S, SW, bits);
+    const size_t total = (size_t)S * S * S;
+    int blocks = (int)((total + 255) / 256);
+    const int cap = numSM * 8 * 16;
+    if (blocks > cap) blocks = cap;
+    dt_sep_x_kernel<<<blocks, 256, 0, st>>>(bits, S, SW, nx);
+    dt_sep_y_kernel<<<blocks, 256, 0, st>>>(nx, S, nxy);
+    dt_sep_z_kernel<<<blocks, 256, 0, st>>>(nxy, g);
+    return cudaGetLastError();
+}
+
+cudaError_t goicp_launch_dt_vcell(const GridDev& g, int numSM, cudaStream_t st) {
+    dt_vcell_kernel<<<numSM * 8, 256, 0, st>>>(g);
+    return cudaGetLastError();
+}
+
+cudaError_t goicp_launch_dt_distance(const PairDev* pairs, int pair, const double* xyz, int n, float* out, int* cell, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    dt_distance_kernel<<<(n + 255) / 256, 256, 0, st>>>(pairs, pair, xyz, n, out, cell);
+    return cudaGetLastError();
+}

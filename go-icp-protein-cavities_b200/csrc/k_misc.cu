@@ -1,0 +1,170 @@
+// GoICP::Initialize (jly_goicp.cpp:180-267), the c-FPFH cell table, and the Transformation kernels
+// (north_star (d): transformation.cpp normalise / scale / rigid transform / RMSD).
+#include "dev_common.cuh"
+#include "launch.h"
+
+namespace {
+
+// One CTA per pair: normData, maxRotDis[20][Nd], weights (neighborsWeights :1453-1498 when ponderation == 1).
+__global__ void __launch_bounds__(256)
+initialize_kernel(PairDev* __restrict__ pairs, int first) {
+    const PairDev& P = pairs[first + blockIdx.x];
+    const int Nd = P.Nd, tid = threadIdx.x;
+    __shared__ int s_max, s_min;
+    for (int i = tid; i < Nd; i += blockDim.x) {
+        const float x = P.dx[i], y = P.dy[i], z = P.dz[i];
+        const float nrm = sqrtf(x * x + y * y + z * z);                              // :191
+        P.normData[i] = nrm;
+        for (int l = 0; l < GOICP_MAXROTLEVEL; ++l) P.maxRotDis[(size_t)l * Nd + i] = P.s2[l] * nrm;   // :205
+        P.weights[i] = 1.f;
+    }
+    if (P.ponderation != 1) return;
+    if (tid == 0) { s_max = 0; s_min = 100; }
+    __syncthreads();
+    int* nb = reinterpret_cast<int*>(P.scratch);
+    float distance = 0.035f;
+    for (;;) {   // :1461-1480; maxN / minN run over every radius tried, nb[] keeps the last radius' counts
+        const double thr = (double)sqrtf(distance);
+        int lmax = 0, lmin = 0x7FFFFFFF;
+        for (int i = tid; i < Nd; i += blockDim.x) {
+            const float xi = P.dx[i], yi = P.dy[i], zi = P.dz[i];
+            int count = 0;
+            for (int j = 0; j < Nd; ++j) {
+                if (j == i) continue;
+                const double a = (double)(P.dx[j] - xi), b = (double)(P.dy[j] - yi), c = (double)(P.dz[j] - zi);   // isNeighbor :1097
+                const double d = sqrt(a * a + b * b + c * c);
+                if (d < thr) count++;
+            }
+            nb[i] = count;
+            lmax = max(lmax, count); lmin = min(lmin, count);
+        }
+        atomicMax(&s_max, lmax); atomicMin(&s_min, lmin);
+        __syncthreads();
+        const int maxN = s_max;
+        __syncthreads();
+        if (maxN >= 19) break;
+        distance = (float)((double)distance + 0.001);
+    }
+    int minN = s_min;
+    if (minN == 0) minN = 1;
+    for (int i = tid; i < Nd; i += blockDim.x) {
+        int c = nb[i]; if (c == 0) c = 1;
+        const float f = ((float)minN / (float)c) * 2;
+        P.weights[i] = 1.f + f;
+    }
+}
+
+// fpfhD[i][cell] = min over the cell's model points of the L1 c-FPFH distance (computeFPFHDifference(false) :1643-1681);
+// the empty sentinel cell keeps the 1e9 start value.
+__global__ void __launch_bounds__(256)
+fpfh_table_kernel(PairDev* __restrict__ pairs, int first) {
+    const PairDev& P = pairs[first + blockIdx.y];
+    const int ncp1 = P.g.ncells + 1;
+    const size_t total = (size_t)P.Nd * ncp1;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e / ncp1), cell = (int)(e % ncp1);
+        float minD = GOICP_FPFH_SENTINEL;
+        if (cell < P.g.ncells) {
+            for (int k = P.cell_start[cell]; k < P.cell_start[cell + 1]; ++k) {
+                const int p = P.cell_pts[k];
+                float diff = 0.f;
+                for (int b = P.fpfh_b; b < P.fpfh_e; ++b) diff = diff + fabsf(P.dfpfh[(size_t)i * GOICP_NBINS + b] - P.mfpfh[(size_t)p * GOICP_NBINS + b]);
+                if (diff < minD) minD = diff;
+            }
+        }
+        P.fpfhD[e] = minD;
+    }
+}
+
+// ---- Transformation -------------------------------------------------------------------------------------------------
+// normalizeMolCloud (transformation.cpp:311-335): sequential double centroid sums (3 chains), centre, max norm
+__global__ void __launch_bounds__(256)
+normalize_kernel(double* __restrict__ xyz, int n, double* __restrict__ out4) {
+    __shared__ double s_mean[3];
+    __shared__ unsigned long long s_max;
+    const int tid = threadIdx.x;
+    if (tid < 3) {
+        double s = 0;
+        for (int i = 0; i < n; ++i) s = s + xyz[3 * i + tid];
+        s_mean[tid] = s / (double)(unsigned long)n;
+    }
+    if (tid == 0) s_max = 0ull;
+    __syncthreads();
+    double lmax = 0;
+    for (int i = tid; i < n; i += blockDim.x) {
+        const double x = xyz[3 * i] - s_mean[0], y = xyz[3 * i + 1] - s_mean[1], z = xyz[3 * i + 2] - s_mean[2];
+        xyz[3 * i] = x; xyz[3 * i + 1] = y; xyz[3 * i + 2] = z;
+        const double nrm = sqrt(x * x + y * y + z * z);
+        if (nrm > lmax) lmax = nrm;
+    }
+    atomicMax(&s_max, (unsigned long long)__double_as_longlong(lmax));   // non-negative doubles order as integers
+    __syncthreads();
+    if (tid == 0) { out4[0] = s_mean[0]; out4[1] = s_mean[1]; out4[2] = s_mean[2]; out4[3] = __longlong_as_double((long long)s_max); }
+}
+__global__ void scale_kernel(double* __restrict__ xyz, int n3, double scale) {   // scaleCloud :355-361
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n3) xyz[i] = xyz[i] / scale;
+}
+__global__ void apply_rigid_kernel(const double* __restrict__ xyz, int n, const double* __restrict__ Rt, double* __restrict__ out) {   // :485-497
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { double v = Rt[3 * a] * x + Rt[3 * a + 1] * y + Rt[3 * a + 2] * z; v = v + Rt[9 + a]; out[3 * i + a] = v; }
+}
+// rescaleCloud :403-412: t' = -(R * mean_src) + scale * t + mean_tgt;  in = {scale, meanT[3], meanS[3], R[9], t[3]}
+__global__ void rescale_kernel(const double* __restrict__ in, double* __restrict__ out) {
+    const int a = threadIdx.x;
+    if (a >= 3) return;
+    const double scale = in[0]; const double* mT = in + 1; const double* mS = in + 4; const double* R = in + 7; const double* t = in + 16;
+    out[a] = -(R[3 * a] * mS[0] + R[3 * a + 1] * mS[1] + R[3 * a + 2] * mS[2]) + (scale * t[a]) + mT[a];
+}
+// computeRMSD :453-464: per-atom squared distances in parallel, then the float accumulator as one sequential chain
+__global__ void __launch_bounds__(256)
+rmsd_kernel(const double* __restrict__ a, const double* __restrict__ b, int n, double* __restrict__ terms, float* __restrict__ out) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double dx = a[3 * i] - b[3 * i], dy = a[3 * i + 1] - b[3 * i + 1], dz = a[3 * i + 2] - b[3 * i + 2];
+        terms[i] = dx * dx + dy * dy + dz * dz;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float r = 0.f;
+        for (int i = 0; i < n; ++i) r = (float)((double)r + terms[i]);
+        out[0] = sqrtf(r / (float)(unsigned long)n);
+    }
+}
+
+}  // namespace
+
+cudaError_t goicp_launch_initialize(PairDev* pairs, int first, int count, cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
+    initialize_kernel<<<count, 256, 0, st>>>(pairs, first);
+    return cudaGetLastError();
+}
+cudaError_t goicp_launch_fpfh_table(PairDev* pairs, int first, int count, int blocksPerPair, cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
+    fpfh_table_kernel<<<dim3(blocksPerPair, count), 256, 0, st>>>(pairs, first);
+    return cudaGetLastError();
+}
+cudaError_t goicp_launch_normalize(double* xyz, int n, double* out4, cudaStream_t st) {
+    normalize_kernel<<<1, 256, 0, st>>>(xyz, n, out4);
+    return cudaGetLastError();
+}
+cudaError_t goicp_launch_scale(double* xyz, int n, double scale, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    scale_kernel<<<(3 * n + 255) / 256, 256, 0, st>>>(xyz, 3 * n, scale);
+    return cudaGetLastError();
+}
+cudaError_t goicp_launch_apply_rigid(const double* xyz, int n, const double* Rt, double* out, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    apply_rigid_kernel<<<(n + 255) / 256, 256, 0, st>>>(xyz, n, Rt, out);
+    return cudaGetLastError();
+}
+cudaError_t goicp_launch_rescale(const double* in19, double* out3, cudaStream_t st) {
+    rescale_kernel<<<1, 32, 0, st>>>(in19, out3);
+    return cudaGetLastError();
+}
+cudaError_t goicp_launch_rmsd(const double* a, const double* b, int n, double* terms, float* out, cudaStream_t st) {
+    rmsd_kernel<<<1, 256, 0, st>>>(a, b, n, terms, out);
+    return cudaGetLastError();
+}
