@@ -1,0 +1,54 @@
+"""CPU: the C-ABI library loads and exports exactly the symbols include/goicp_b200.h declares; struct layouts match the
+oracle's; the product fails loudly without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "goicp_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(goicp_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_symbols_exported(g):
+    syms = _header_symbols()
+    assert sorted(g.ABI_SYMBOLS) == syms
+    L = g.lib()
+    for s in syms:
+        assert hasattr(L, s), s
+    out = subprocess.check_output(["nm", "-D", "--defined-only", g.LIB_PATH]).decode()
+    exported = set(re.findall(r" T (goicp_[a-z0-9_]+)", out))
+    assert exported == set(syms), exported ^ set(syms)
+
+
+def test_struct_layouts(g, po):
+    assert C.sizeof(g.Params) == C.sizeof(po.Params) == 80
+    assert [f[0] for f in g.Params._fields_] == [f[0] for f in po.Params._fields_]
+    assert C.sizeof(g.Result) == 9 * 8 + 3 * 8 + 4 + 4 + 8 * 8 + 16 + 12 + 4
+    p, q = g.shipped_config(), po.shipped_config()
+    assert bytes(p) == bytes(q)
+    assert bytes(g.upstream_config()) == bytes(po.upstream_config())
+
+
+def test_no_cpu_fallback(g):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(g.GoICPError) as e:
+        g.Engine()
+    assert e.value.status == 1 and "no CPU fallback" in str(e.value)
+
+
+def test_product_never_touches_oracle():
+    """the product path may not import, link, load or name anything under oracle/ (it is test infrastructure)"""
+    pkg = os.path.join(ROOT, "go-icp-protein-cavities_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")) or f == "Makefile":
+                assert "oracle" not in open(os.path.join(dp, f)).read().lower(), (dp, f)

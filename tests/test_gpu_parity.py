@@ -1,0 +1,237 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the same inputs and against the
+golden fixtures (the reference's own outputs).  Bars: bit-exact for DT values / index map / voxel indices / inclusion
+counts / node counters and for every float the exact-sum mode produces; 1e-5 relative for tree-sum bounds and trimmed
+sums; 1e-5 on R, t."""
+import numpy as np
+import pytest
+
+from conftest import BACKBONE, golden, pair_clouds, rand_rot
+
+pytestmark = pytest.mark.gpu
+REL = 1e-5   # north_star float tolerance
+
+
+def _pair(g, po, name, **kw):
+    z = golden(name)
+    reg = g.GoICP(z["model_xyz"], z["data_xyz"], g.shipped_config(**kw), **pair_clouds(z))
+    o = po.Oracle("port", z["model_xyz"], z["data_xyz"], po.shipped_config(**kw), **pair_clouds(z))
+    return z, reg, o
+
+
+@pytest.mark.parametrize("name", ["pair1", "pair2"])
+def test_dt_replay_bit_exact(g, po, name):
+    """S=20: distances, emptyCells index map and cell colours equal the reference's on every voxel (golden fixture)"""
+    z, reg, o = _pair(g, po, name)
+    info = reg.BuildDT()
+    assert [info.xMin, info.xMax, info.yMin, info.yMax, info.zMin, info.zMax, info.scale] == z["exp_dt_info"].tolist()
+    d, near, cc = reg.dt_download()
+    assert np.array_equal(d, z["exp_dt_dist"]) and np.array_equal(near, z["exp_dt_near"]) and np.array_equal(cc, z["exp_dt_cellc"])
+
+
+def test_dt_replay_ragged_sizes(g, po):
+    """replay builder at other grid sizes / tiny clouds (edge cases: single point, S=2, S=32)"""
+    rng = np.random.default_rng(5)
+    for S, nm in ((2, 1), (5, 3), (17, 40), (32, 300)):
+        m = rng.uniform(-1, 1, (nm, 3)).astype(np.float32)
+        if nm == 1:
+            m = np.concatenate([m, m + 0.25]).astype(np.float32)   # a degenerate box is rejected (scale = inf)
+        d = rng.uniform(-1, 1, (25, 3)).astype(np.float32)
+        reg = g.GoICP(m, d, g.shipped_config(distTransSize=S))
+        o = po.Oracle("port", m, d, po.shipped_config(distTransSize=S))
+        reg.BuildDT(); o.build_dt()
+        a, na, ca = reg.dt_download(); b, _, nb, cb = o.dt_download()
+        assert np.array_equal(a, b) and np.array_equal(na, nb) and np.array_equal(ca, cb), S
+
+
+def test_dt_separable_vs_8sed(g, po):
+    """exact separable EDT vs the reference's 8SED: identical wherever 8SED is exact; the index map is *a* nearest
+    occupied voxel everywhere (documented tie rule) -- checked as a property."""
+    z = golden("rand")
+    S = 64
+    reg = g.GoICP(z["model_xyz"], z["data_xyz"], g.upstream_config(distTransSize=S))
+    info = reg.BuildDT()
+    d, near, cc = reg.dt_download()
+    assert np.array_equal(d, z["exp64_dt_dist"])          # 8SED is exact on this cloud (SURVEY H1 probe)
+    zz, yy, xx = np.meshgrid(np.arange(S), np.arange(S), np.arange(S), indexing="ij")
+    q = (near[:, 0] - xx.ravel()) ** 2 + (near[:, 1] - yy.ravel()) ** 2 + (near[:, 2] - zz.ravel()) ** 2
+    assert np.array_equal((np.sqrt(q.astype(np.float32)).astype(np.float64) / info.scale).astype(np.float32), d)
+    assert (cc[(near[:, 2] * S + near[:, 1]) * S + near[:, 0]] != -2).all()   # every voxel points at an occupied one
+    eq = (near == z["exp64_dt_near"]).all(1).mean()
+    assert eq > 0.95   # ties (3 % of voxels here) may resolve differently from the scan-order dependent reference
+
+
+def test_distance_bit_exact(g, po):
+    z, reg, o = _pair(g, po, "pair1")
+    reg.BuildDT(); o.build_dt()
+    rng = np.random.default_rng(0)
+    q = np.concatenate([rng.uniform(-1.5, 1.5, (20000, 3)), rng.uniform(-40, 40, (2000, 3))])   # inside and far outside
+    a, ca = reg.Distance(q); b, cb = o.dt_distance(q)
+    assert np.array_equal(a, b) and np.array_equal(ca, cb)
+
+
+@pytest.mark.parametrize("name", ["pair1", "pair2"])
+def test_initialize_bit_exact(g, po, name):
+    z, reg, o = _pair(g, po, name)
+    reg.BuildDT(); o.build_dt()
+    reg.set_nd(int(z["nd"])); o.set_nd(int(z["nd"]))
+    reg.Initialize(); o.initialize()
+    assert np.array_equal(reg.weights(), o.weights()) and np.array_equal(reg.maxRotDis(), o.maxrotdis())
+    assert reg.thresholds() == (o.ssethresh(), o.inliernum())
+
+
+@pytest.mark.parametrize("fp", [False, True])
+def test_leaf_bounds(g, po, fp):
+    """every rotation cube x translation sub-cube x point bound in one launch: (ub, lb) within 1e-5, corner
+    incompatibility counts and truncated c-FPFH means (point-inclusion counts) bit-exact"""
+    kw = dict(cfpfh=1, regularizationFPFH=0.000005) if fp else {}
+    z, reg, o = _pair(g, po, "pair1", **kw)
+    reg.BuildDT(); o.build_dt(); reg.set_nd(int(z["nd"])); o.set_nd(int(z["nd"])); reg.Initialize(); o.initialize()
+    rng = np.random.default_rng(2)
+    for level in (-1, 0, 3, 7):
+        R = rand_rot(rng)
+        w = np.float32(2.0 ** -rng.integers(0, 6))
+        tc = np.concatenate([rng.uniform(-0.5, 0.5 - w, (500, 3)), np.full((500, 1), w)], 1).astype(np.float32)
+        ub, lb, inc, fpm = reg.eval_bounds(R, level, tc)
+        oub, olb, oinc, ofp = o.eval_leaf(R, level, tc)
+        assert np.abs(ub - oub).max() <= REL * oub.max() and np.abs(lb - olb).max() <= REL * max(olb.max(), 1e-6)
+        assert np.array_equal(inc, oinc) and np.array_equal(fpm, ofp)
+
+
+def test_leaf_bounds_multi_rotation_wave(g, po):
+    """one launch over several rotation cubes at different levels (the frontier-wave form of the API)"""
+    z, reg, o = _pair(g, po, "pair2")
+    reg.BuildDT(); o.build_dt(); reg.set_nd(int(z["nd"])); o.set_nd(int(z["nd"])); reg.Initialize(); o.initialize()
+    rng = np.random.default_rng(3)
+    Rs = np.stack([rand_rot(rng) for _ in range(5)]); lv = np.array([-1, 0, 1, 4, 9], np.int32)
+    tc = np.concatenate([rng.uniform(-0.5, 0.25, (300, 3)), np.full((300, 1), 0.25)], 1).astype(np.float32)
+    rot_of = rng.integers(0, 5, 300).astype(np.int32)
+    ub, lb, inc, _ = reg.eval_bounds(Rs, lv, tc, rot_of)
+    for r in range(5):
+        sel = rot_of == r
+        oub, olb, oinc, _ = o.eval_leaf(Rs[r], int(lv[r]), tc[sel])
+        assert np.abs(ub[sel] - oub).max() <= REL * oub.max() and np.abs(lb[sel] - olb).max() <= REL * max(olb.max(), 1e-6)
+        assert np.array_equal(inc[sel], oinc)
+
+
+@pytest.mark.parametrize("name,fp", [("pair1", False), ("pair1", True), ("pair2", False)])
+def test_inner_bnb(g, po, name, fp):
+    """GoICP::InnerBnB calls as OuterBnB makes them: exact-sum mode is bit-identical (value, best node, pop count);
+    tree-sum mode within 1e-5"""
+    kw = dict(cfpfh=1, regularizationFPFH=0.000005) if fp else {}
+    z, reg, o = _pair(g, po, name, **kw)
+    reg.BuildDT(); o.build_dt(); reg.set_nd(int(z["nd"])); o.set_nd(int(z["nd"])); reg.Initialize(); o.initialize()
+    rng = np.random.default_rng(4)
+    n = 16
+    Rs = np.stack([rand_rot(rng) for _ in range(n)]); lv = np.array([-1, 1, -1, 2] * 4, np.int32)
+    oe = np.full(n, 24.0, np.float32)
+    ref = [o.inner_bnb(Rs[k], int(lv[k]), 24.0) for k in range(n)]
+    reg.set_options(exact_sums=1)
+    err, tn, ps = reg.InnerBnB(Rs, lv, oe)
+    for k in range(n):
+        assert err[k] == np.float32(ref[k][0])
+        if lv[k] < 0 and err[k] < 24.0:
+            assert np.array_equal(tn[k], ref[k][1])
+    reg.set_options(exact_sums=0)
+    err2, _, _ = reg.InnerBnB(Rs, lv, oe)
+    assert np.abs(err2 - err).max() <= REL * 24.0
+
+
+def test_icp(g, po):
+    z, reg, o = _pair(g, po, "pair1")
+    reg.BuildDT(); o.build_dt(); reg.set_nd(int(z["nd"])); o.set_nd(int(z["nd"])); reg.Initialize(); o.initialize()
+    rng = np.random.default_rng(6)
+    for k in range(3):
+        R0 = np.eye(3) if k == 0 else rand_rot(rng).astype(np.float64)
+        t0 = np.zeros(3) if k == 0 else rng.uniform(-0.1, 0.1, 3)
+        e, R, t, corr = reg.ICP(R0, t0)
+        eo, Ro, to, co = o.icp(R0, t0)
+        assert e == eo and np.abs(R - Ro).max() < 1e-12 and np.abs(t - to).max() < 1e-12 and np.array_equal(corr, co)
+
+
+@pytest.mark.parametrize("name,fp,golden_err,compat", [("pair1", False, 8.45388, 133), ("pair1", True, 9.37283, 133), ("pair2", False, 16.1742, 118)])
+def test_register_cavity_golden(g, name, fp, golden_err, compat):
+    """full Register against the reference's shipped outputs: Error / Compatibilities / R / t (output/similar1.txt,
+    rot_2ktd_1) and, in exact-sum mode, the reference's node counters and improvement trace"""
+    z = golden(name)
+    kw = dict(cfpfh=1, regularizationFPFH=0.000005) if fp else {}
+    pre = "expf_" if fp else "exp_"
+    reg = g.GoICP(z["model_xyz"], z["data_xyz"], g.shipped_config(**kw), **pair_clouds(z))
+    reg.BuildDT(); reg.set_nd(int(z["nd"]))
+    r = reg.Register()
+    assert r["optError"] == float(z[pre + "optError"]) and abs(r["optError"] - golden_err) < 1e-4
+    assert int(z["nd"]) - r["optComp"] == compat
+    assert np.abs(r["R"] - z[pre + "R"]).max() < 1e-6 and np.abs(r["t"] - z[pre + "t"]).max() < 1e-6
+    assert r["counters"][:6] == z[pre + "counters"][:6].tolist()
+    assert g.error_trace(r["trace"]) == list(z[pre + "trace"])
+    reg.set_options(exact_sums=0)
+    r2 = reg.Register()
+    assert abs(r2["optError"] - r["optError"]) <= REL * r["optError"]
+    assert np.abs(r2["R"] - r["R"]).max() < 1e-5 and np.abs(r2["t"] - r["t"]).max() < 1e-5
+
+
+def test_register_rand_trim(g):
+    """trimFraction 0.1: the radix select replaces intro_select; same certified optimum (tolerance: sum order)"""
+    z = golden("rand")
+    reg = g.GoICP(z["model_xyz"], z["data_xyz"], g.upstream_config(trimFraction=0.1, distTransSize=64))
+    reg.BuildDT(); reg.set_nd(int(z["nd"]))
+    r = reg.Register()
+    assert abs(r["optError"] - float(z["exp64_optError"])) <= REL * float(z["exp64_optError"])
+    assert np.abs(r["R"] - z["exp64_R"]).max() < 1e-5 and np.abs(r["t"] - z["exp64_t"]).max() < 1e-5
+
+
+def test_register_bunny100(g, po):
+    """bunny, DT 100^3, with the GPU's own separable DT: same optimum, trace and node counters as the reference run"""
+    z = golden("bunny")
+    reg = g.GoICP(z["model_xyz"], z["data_xyz"], g.upstream_config(distTransSize=100))
+    reg.BuildDT(); reg.set_nd(int(z["nd"]))
+    r = reg.Register()
+    assert abs(r["optError"] - float(z["exp100_optError"])) <= REL * float(z["exp100_optError"])
+    assert np.abs(r["R"] - z["exp100_R"]).max() < 1e-5 and np.abs(r["t"] - z["exp100_t"]).max() < 1e-5
+    assert r["counters"][:6] == z["exp100_counters"][:6].tolist()
+
+
+def test_batch_equals_single(g):
+    """register_batch (lock-step waves over several pairs) returns per pair exactly what single registrations return"""
+    z1, z2 = golden("pair1"), golden("pair2")
+    pairs = []
+    for z in (z1, z2, z1):
+        p = dict(pair_clouds(z)); p.update(model_xyz=z["model_xyz"], data_xyz=z["data_xyz"], nd=int(z["nd"]))
+        pairs.append(p)
+    e = g.Engine()
+    res = e.register_batch(g.shipped_config(), pairs)
+    for r, z in zip(res, (z1, z2, z1)):
+        assert r["optError"] == float(z["exp_optError"]) and r["optComp"] == int(z["exp_optComp"])
+        assert r["counters"][:6] == z["exp_counters"][:6].tolist()
+        assert np.abs(r["R"] - z["exp_R"]).max() < 1e-6
+
+
+@pytest.mark.parametrize("name", ["pair1", "pair2"])
+def test_transformation(g, po, name):
+    z = golden(name)
+    e = g.Engine()
+    cen, mean, mx = e.normalizeMolCloud(z["src_raw"])
+    ocen, omean, omx = po.normalize("port", z["src_raw"])
+    assert np.array_equal(mean, omean) and abs(mx - omx) <= 1e-15 * omx and np.abs(cen - ocen).max() == 0
+    sc = e.scaleCloud(cen, float(z["scale"]))
+    assert np.array_equal(sc, po.scale("port", ocen, float(z["scale"])))
+    tt = e.rescaleCloud(float(z["scale"]), z["tgt_mean"], z["src_mean"], z["exp_R"], z["exp_t"])
+    assert np.abs(tt - z["exp_rescaled_t"]).max() < 5e-4
+    txt = str(z["rescaled_text"]).split("\n")
+    R = np.array([[float(v) for v in txt[i].split()] for i in (2, 3, 4)]); t = np.array([float(txt[i]) for i in (6, 7, 8)])
+    rot = e.applyTransformationProtein(z["protein_xyz"], R, t)
+    assert np.abs(rot[:-1] - z["rot_xyz"][:-1]).max() < 1e-6
+    sel = np.isin(z["aligned_c"], BACKBONE)
+    assert abs(e.computeRMSD(z["aligned_xyz"][sel], z["rot_xyz"][sel]) - float(z["rmsd"])) < 1e-6
+
+
+def test_argument_errors(g):
+    z = golden("pair1")
+    reg = g.GoICP(z["model_xyz"], z["data_xyz"], g.shipped_config(distTransSize=64), **pair_clouds(z))
+    with pytest.raises(g.GoICPError):
+        reg.BuildDT(replay=True)          # replay builder is S <= 32
+    with pytest.raises(g.GoICPError):
+        reg.Initialize()                  # before BuildDT
+    reg2 = g.GoICP(z["model_xyz"], z["data_xyz"][:10], g.shipped_config(), **{k: (v[:10] if k.startswith("data") else v) for k, v in pair_clouds(z).items()})
+    reg2.BuildDT()
+    with pytest.raises(g.GoICPError):
+        reg2.Initialize()                 # ponderation=1 with Nd < 20 never terminates in the reference
