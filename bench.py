@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs in the CPU-baseline sample (0: one per core, at least 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=4096)
+    ap.add_argument("--groups", type=int, default=-1, help="worker streams per GPU (-1: library default)")
+    ap.add_argument("--slots", type=int, default=-1, help="pairs advanced in lock-step per stream (-1: library default)")
+    ap.add_argument("--spec", type=int, default=-1, help="speculation width in rotation nodes (-1: library default)")
     return ap.parse_args()
 
 
@@ -152,7 +155,8 @@ def main():
     dev = torch.device("cuda", local)
     stream = torch.cuda.current_stream(dev)
     eng = g.Engine(local, stream.cuda_stream)          # kernels run on torch's current stream: torch events see them
-    eng.L.goicp_set_options(eng.h, args.exact, -1, -1)
+    eng.set_options(args.exact, args.spec, -1)
+    eng.set_batch_options(args.groups, args.slots)
     kw = dict(cfpfh=1, regularizationFPFH=0.000005) if args.fpfh else {}
     params = g.shipped_config(**kw)
     pairs = synth.bo1_pairs(args.pairs, seed=args.seed + 7919 * rank)
@@ -169,6 +173,7 @@ def main():
     # ---- resident leg: inputs uploaded before the timed region ----
     eng.batch_upload(params, pairs)
     for _ in range(args.warmup):
+        flush.zero_()
         res = eng.batch_run()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -184,6 +189,7 @@ def main():
         ev[k][1].record(stream)
         tm = eng.timings()
         kern_ms += tm["ms"][2]; launches += sum(tm["launches"]); total_evals += evals_of(res)
+        last_tm, last_stats = tm, eng.stats()
     barrier()
     wall = time.perf_counter() - t0
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
@@ -238,7 +244,9 @@ def main():
             "wall_ms_per_step": 1e3 * wall / args.steps,
             "e2e": {"value": e2e_evals / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "pairs_per_s": args.pairs * world * args.steps / (e2e_ms * 1e-3)},
-            "gpu_launches": int(launches), "roofline": roof, "clocks": sampler.summary()}
+            "gpu_launches": int(launches), "roofline": roof, "clocks": sampler.summary(),
+            "rank0_last_step": {"gpu_ms_sum_over_streams": {"dt": last_tm["ms"][0], "initialize": last_tm["ms"][1], "inner_bnb": last_tm["ms"][2], "icp": last_tm["ms"][3]},
+                                "launches": last_tm["launches"], **last_stats}}
     if not args.no_cpu_baseline and world == 1:
         n = args.cpu_pairs or max(8, cores)
         v, dt, kind, errs = cpu_arm(pairs[:n], args.fpfh, cores)

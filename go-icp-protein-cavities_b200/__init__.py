@@ -66,6 +66,7 @@ ABI_SYMBOLS = [
     "goicp_dt_download", "goicp_dt_distance", "goicp_set_nd", "goicp_initialize", "goicp_get_weights", "goicp_get_maxrotdis",
     "goicp_get_thresholds", "goicp_eval_bounds", "goicp_inner_bnb", "goicp_icp", "goicp_register", "goicp_last_trace",
     "goicp_set_options", "goicp_register_batch", "goicp_batch_upload", "goicp_batch_run", "goicp_get_timings",
+    "goicp_set_batch_options", "goicp_get_stats",
     "goicp_normalize_cloud", "goicp_scale_cloud", "goicp_rescale_translation", "goicp_apply_rigid", "goicp_rmsd",
 ]
 
@@ -112,6 +113,8 @@ def lib():
     L.goicp_batch_upload.argtypes = [vp, C.POINTER(Params), C.c_int32, C.POINTER(PairDesc)]
     L.goicp_batch_run.argtypes = [vp, C.POINTER(Result)]
     L.goicp_get_timings.argtypes = [vp, fp, C.POINTER(C.c_int64)]
+    L.goicp_set_batch_options.argtypes = [vp, C.c_int32, C.c_int32]
+    L.goicp_get_stats.argtypes = [vp, dp]
     L.goicp_normalize_cloud.argtypes = [vp, dp, C.c_int32, dp, dp]
     L.goicp_scale_cloud.argtypes = [vp, dp, C.c_int32, C.c_double]
     L.goicp_rescale_translation.argtypes = [vp, C.c_double, dp, dp, dp, dp, dp]
@@ -184,6 +187,17 @@ class Engine:
         ln = (C.c_int64 * 5)()
         self.check(self.L.goicp_get_timings(self.h, ms, ln))
         return dict(ms=list(ms), launches=list(ln))
+
+    def stats(self):
+        o = (C.c_double * 8)()
+        self.check(self.L.goicp_get_stats(self.h, o))
+        return dict(waves=int(o[0]), calls_launched=int(o[1]), calls_used=int(o[2]), streams=int(o[3]), host_seconds=o[4])
+
+    def set_options(self, exact_sums=-1, spec_width=-1, use_dt_replay=-1):
+        self.check(self.L.goicp_set_options(self.h, exact_sums, spec_width, use_dt_replay))
+
+    def set_batch_options(self, groups=-1, slots=-1):
+        self.check(self.L.goicp_set_batch_options(self.h, groups, slots))
 
     # ---- batch of pairs (bo1_GoICP.py:40-54) ----
     def _descs(self, pairs):

@@ -16,7 +16,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <memory>
+#include <mutex>
+#include <thread>
 #include <map>
 #include <string>
 #include <unordered_map>
@@ -147,17 +151,51 @@ static void tracef(std::string& s, const char* fmt, ...) {
 
 }  // namespace
 
+// Everything one stream of waves needs: a worker thread of a batch owns one, the handle's own stream has `main`.
+struct WaveCtx {
+    cudaStream_t stream = nullptr; bool ownStream = false;
+    DevBuf dProbs, dOuts, dCounter, dHeaps, dBnbScratch, dIcp;
+    PinBuf hProbs, hOuts, hIcp;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evDone = nullptr;
+    float ms[5] = {0, 0, 0, 0, 0}; long long launches[5] = {0, 0, 0, 0, 0};
+    long long waves = 0, callsLaunched = 0, callsUsed = 0;
+    int heapCap = 1 << 14;
+    int ctaCap = 0;   // 0: numSM x occupancy
+    goicp_status init(bool own, cudaStream_t st) {
+        ownStream = own; stream = st;
+        if (own && cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) return GOICP_ERR_CUDA;
+        if (cudaEventCreate(&ev0) != cudaSuccess || cudaEventCreate(&ev1) != cudaSuccess ||
+            cudaEventCreateWithFlags(&evDone, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess) return GOICP_ERR_CUDA;
+        return GOICP_OK;
+    }
+    // waits without spinning a host core (worker threads outnumber cores)
+    cudaError_t sync() { cudaError_t e = cudaEventRecord(evDone, stream); if (e != cudaSuccess) return e; return cudaEventSynchronize(evDone); }
+    void release() {
+        DevBuf* bufs[] = {&dProbs, &dOuts, &dCounter, &dHeaps, &dBnbScratch, &dIcp};
+        for (DevBuf* b : bufs) b->release();
+        PinBuf* pins[] = {&hProbs, &hOuts, &hIcp};
+        for (PinBuf* b : pins) b->release();
+        if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1); if (evDone) cudaEventDestroy(evDone);
+        ev0 = ev1 = evDone = nullptr;
+        if (ownStream && stream) cudaStreamDestroy(stream);
+        stream = nullptr;
+    }
+};
+
 struct goicp_handle_s {
     int device = 0; cudaStream_t stream = nullptr; bool ownStream = false; int numSM = 148;
     goicp_params params; bool haveParams = false;
     int exact_sums = 1, spec_width = 32, use_dt_replay = 1;
+    int groups = 0, slots = 4;   // batch: worker streams (0 = auto) and pairs advanced in lock-step per stream
     std::vector<Problem> probs;
-    DevBuf arenaIn, arenaWork, dPairs, dProbs, dOuts, dCounter, dHeaps, dBnbScratch, dIcp, dTmp, dTmp2, dTmp3, dSepBits, dSepNx, dSepNxy;
-    PinBuf hProbs, hOuts, hIcp, hStage;
+    DevBuf arenaIn, arenaWork, dPairs, dTmp, dTmp2, dTmp3, dSepBits, dSepNx, dSepNxy;
+    PinBuf hStage, hPairs;
+    WaveCtx main;
+    std::vector<std::unique_ptr<WaveCtx>> workers;
+    std::mutex errMutex;
     std::string err, trace;
     float ms[5] = {0, 0, 0, 0, 0}; long long launches[5] = {0, 0, 0, 0, 0};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    int heapCap = 1 << 15;
+    double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // waves, calls launched, calls consumed, worker streams, host seconds
 };
 
 namespace {
@@ -166,17 +204,17 @@ typedef goicp_handle_s Eng;
 
 static goicp_status fail(Eng* h, goicp_status s, const char* fmt, ...) {
     char buf[512]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
-    if (h) h->err = buf; else g_create_error = buf;
+    if (h) { std::lock_guard<std::mutex> lk(h->errMutex); h->err = buf; } else g_create_error = buf;
     return s;
 }
 #define CU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(h, GOICP_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); } while (0)
 
 static size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
 
-struct EvTimer {   // CUDA-event time of a kernel group on the handle's stream
-    Eng* h; int slot;
-    EvTimer(Eng* h_, int slot_) : h(h_), slot(slot_) { cudaEventRecord(h->ev0, h->stream); }
-    void stop(int nlaunch) { cudaEventRecord(h->ev1, h->stream); cudaEventSynchronize(h->ev1); float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->ms[slot] += ms; h->launches[slot] += nlaunch; }
+struct EvTimer {   // CUDA-event time of a kernel group on a wave context's stream
+    WaveCtx& c; int slot;
+    EvTimer(WaveCtx& c_, int slot_) : c(c_), slot(slot_) { cudaEventRecord(c.ev0, c.stream); }
+    void stop(int nlaunch) { cudaEventRecord(c.ev1, c.stream); cudaEventSynchronize(c.ev1); float ms = 0; cudaEventElapsedTime(&ms, c.ev0, c.ev1); c.ms[slot] += ms; c.launches[slot] += nlaunch; }
 };
 
 // ---- host preprocessing of one pair: bbox/scale (jly_3ddt.cpp:899-931), seeding (:976-995), cell lists and colour
@@ -344,8 +382,8 @@ static goicp_status upload_pairdevs(Eng* h) {
     }
     const size_t n = h->probs.size();
     CU(h->dPairs.ensure(sizeof(PairDev) * n));
-    CU(h->hProbs.ensure(sizeof(PairDev) * n));   // staging (re-used)
-    PairDev* st = h->hProbs.as<PairDev>();
+    CU(h->hPairs.ensure(sizeof(PairDev) * n));
+    PairDev* st = h->hPairs.as<PairDev>();
     for (size_t i = 0; i < n; i++) st[i] = h->probs[i].dev;
     CU(cudaMemcpyAsync(h->dPairs.p, st, sizeof(PairDev) * n, cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -357,7 +395,7 @@ static goicp_status build_dt_all(Eng* h, bool replay) {
     auto t0 = clk::now();
     goicp_status s = upload_pairdevs(h);
     if (s) return s;
-    EvTimer tm(h, 0);
+    EvTimer tm(h->main, 0);
     int nl = 0;
     if (replay) {
         if (S > 32) return fail(h, GOICP_ERR_UNSUPPORTED, "the 8SED replay builder supports distTransSize <= 32 (got %d)", S);
@@ -385,7 +423,7 @@ static goicp_status initialize_all(Eng* h) {
     }
     goicp_status s = upload_pairdevs(h);
     if (s) return s;
-    EvTimer tm(h, 1);
+    EvTimer tm(h->main, 1);
     int nl = 1;
     CU(goicp_launch_initialize(h->dPairs.as<PairDev>(), 0, (int)h->probs.size(), h->stream));
     if (p.regularizationFPFH > 0 && p.cfpfh != 0) { CU(goicp_launch_fpfh_table(h->dPairs.as<PairDev>(), 0, (int)h->probs.size(), 32, h->stream)); nl++; }
@@ -396,85 +434,100 @@ static goicp_status initialize_all(Eng* h) {
 }
 
 // ---- one launch of InnerBnB calls (handles heap overflow by re-running the overflowed calls with larger heaps) -------
-static goicp_status run_inner(Eng* h, std::vector<InnerProb>& reqs, std::vector<InnerOut>& outs) {
+struct BnbCfg { int NdP, NdQ; size_t smemFloats; int useSmem, perSM; };
+static BnbCfg bnb_config(Eng* h) {
+    int maxNd = 1; bool anyTrim = false, anyF = false;
+    for (auto& P : h->probs) { maxNd = std::max(maxNd, P.Nd); anyTrim |= P.dev.doTrim != 0; anyF |= P.dev.use_fpfh != 0; }
+    BnbCfg c;
+    c.NdP = (maxNd + 31) & ~31; c.NdQ = c.NdP + 4;
+    const bool needMd = h->exact_sums || anyTrim, needFp = h->exact_sums && anyF;
+    c.smemFloats = goicp_bnb_smem_floats(c.NdP, c.NdQ, needMd, needFp);
+    const size_t smemBytes = c.smemFloats * sizeof(float);
+    c.useSmem = smemBytes <= 200 * 1024;
+    c.perSM = goicp_inner_bnb_occupancy(c.useSmem ? smemBytes : 0, h->exact_sums);
+    return c;
+}
+static goicp_status run_inner(Eng* h, WaveCtx& c, const BnbCfg& cfg, std::vector<InnerProb>& reqs, std::vector<InnerOut>& outs) {
     const int n = (int)reqs.size();
     outs.resize(n);
     if (n == 0) return GOICP_OK;
-    int maxNd = 1; bool anyTrim = false, anyF = false;
-    for (auto& P : h->probs) { maxNd = std::max(maxNd, P.Nd); anyTrim |= P.dev.doTrim != 0; anyF |= P.dev.use_fpfh != 0; }
-    const int NdP = (maxNd + 31) & ~31, NdQ = NdP + 4;
-    const bool needMd = h->exact_sums || anyTrim, needFp = h->exact_sums && anyF;
-    const size_t smemFloats = goicp_bnb_smem_floats(NdP, NdQ, needMd, needFp);
-    const size_t smemBytes = smemFloats * sizeof(float);
-    const int useSmem = smemBytes <= 200 * 1024;
-    const int perSM = goicp_inner_bnb_occupancy(useSmem ? smemBytes : 0, h->exact_sums);
-    int maxCtas = h->numSM * perSM;
-    int heapCap = h->heapCap;
-    CU(h->dProbs.ensure(sizeof(InnerProb) * n));
-    CU(h->dOuts.ensure(sizeof(InnerOut) * n));
-    CU(h->dCounter.ensure(sizeof(int)));
-    CU(h->hProbs.ensure(std::max(sizeof(InnerProb) * (size_t)n, sizeof(PairDev) * h->probs.size())));
-    CU(h->hOuts.ensure(sizeof(InnerOut) * n));
+    int maxCtas = h->numSM * cfg.perSM;
+    if (c.ctaCap > 0) maxCtas = std::min(maxCtas, c.ctaCap);
+    int heapCap = c.heapCap;
+    CU(c.dProbs.ensure(sizeof(InnerProb) * n));
+    CU(c.dOuts.ensure(sizeof(InnerOut) * n));
+    CU(c.dCounter.ensure(sizeof(int)));
+    CU(c.hProbs.ensure(sizeof(InnerProb) * (size_t)n));
+    CU(c.hOuts.ensure(sizeof(InnerOut) * n));
     std::vector<int> todo(n); for (int i = 0; i < n; i++) todo[i] = i;
     for (int attempt = 0; attempt < 12 && !todo.empty(); attempt++) {
         const int m = (int)todo.size();
-        InnerProb* hp = h->hProbs.as<InnerProb>();
+        InnerProb* hp = c.hProbs.as<InnerProb>();
         for (int i = 0; i < m; i++) hp[i] = reqs[todo[i]];
         const int ctas = std::min(m, maxCtas);
-        CU(h->dHeaps.ensure(sizeof(HeapEnt) * (size_t)ctas * heapCap));
-        if (!useSmem) CU(h->dBnbScratch.ensure(sizeof(float) * smemFloats * (size_t)ctas));
-        CU(cudaMemcpyAsync(h->dProbs.p, hp, sizeof(InnerProb) * m, cudaMemcpyHostToDevice, h->stream));
-        CU(cudaMemsetAsync(h->dCounter.p, 0, sizeof(int), h->stream));
-        cudaEventRecord(h->ev0, h->stream);
+        CU(c.dHeaps.ensure(sizeof(HeapEnt) * (size_t)ctas * heapCap));
+        if (!cfg.useSmem) CU(c.dBnbScratch.ensure(sizeof(float) * cfg.smemFloats * (size_t)ctas));
+        CU(cudaMemcpyAsync(c.dProbs.p, hp, sizeof(InnerProb) * m, cudaMemcpyHostToDevice, c.stream));
+        CU(cudaMemsetAsync(c.dCounter.p, 0, sizeof(int), c.stream));
+        cudaEventRecord(c.ev0, c.stream);
         int launched = 0;
-        CU(goicp_launch_inner_bnb(h->dPairs.as<PairDev>(), h->dProbs.as<InnerProb>(), h->dOuts.as<InnerOut>(), m, h->dCounter.as<int>(),
-                                  h->dHeaps.as<HeapEnt>(), heapCap, ctas, h->dBnbScratch.as<float>(), smemFloats, NdP, NdQ, smemFloats, useSmem,
-                                  h->exact_sums, h->stream, &launched));
-        cudaEventRecord(h->ev1, h->stream);
-        CU(cudaMemcpyAsync(h->hOuts.p, h->dOuts.p, sizeof(InnerOut) * m, cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-        float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->ms[2] += ms; h->launches[2] += 1;
-        const InnerOut* ho = h->hOuts.as<InnerOut>();
+        CU(goicp_launch_inner_bnb(h->dPairs.as<PairDev>(), c.dProbs.as<InnerProb>(), c.dOuts.as<InnerOut>(), m, c.dCounter.as<int>(),
+                                  c.dHeaps.as<HeapEnt>(), heapCap, ctas, c.dBnbScratch.as<float>(), cfg.smemFloats, cfg.NdP, cfg.NdQ, cfg.smemFloats, cfg.useSmem,
+                                  h->exact_sums, c.stream, &launched));
+        cudaEventRecord(c.ev1, c.stream);
+        CU(cudaMemcpyAsync(c.hOuts.p, c.dOuts.p, sizeof(InnerOut) * m, cudaMemcpyDeviceToHost, c.stream));
+        CU(c.sync());
+        float ms = 0; cudaEventElapsedTime(&ms, c.ev0, c.ev1); c.ms[2] += ms; c.launches[2] += 1;
+        const InnerOut* ho = c.hOuts.as<InnerOut>();
         std::vector<int> again;
         for (int i = 0; i < m; i++) { if (ho[i].status == 4) again.push_back(todo[i]); else outs[todo[i]] = ho[i]; }
         todo.swap(again);
-        if (!todo.empty()) { heapCap *= 4; const size_t fit = ((size_t)8 << 30) / sizeof(HeapEnt) / (size_t)heapCap; maxCtas = (int)std::max<size_t>(1, std::min<size_t>((size_t)maxCtas, fit)); }
+        if (!todo.empty()) { heapCap *= 4; const size_t fit = ((size_t)4 << 30) / sizeof(HeapEnt) / (size_t)heapCap; maxCtas = (int)std::max<size_t>(1, std::min<size_t>((size_t)maxCtas, fit)); }
     }
     if (!todo.empty()) return fail(h, GOICP_ERR_OVERFLOW, "translation queue exceeded %d entries", heapCap);
+    c.callsLaunched += n;
     return GOICP_OK;
 }
 
 // ---- ICP / scoring pipeline for a set of states ----------------------------------------------------------------------
-static goicp_status run_icp(Eng* h, std::vector<IcpState>& states) {
+static goicp_status run_icp(Eng* h, WaveCtx& c, std::vector<IcpState>& states) {
     const int n = (int)states.size();
     if (n == 0) return GOICP_OK;
-    int maxNd = 1, maxNm = 1; bool anyIcp = false;
-    for (auto& s : states) { const Problem& P = h->probs[s.pair]; maxNd = std::max(maxNd, P.Nd); maxNm = std::max(maxNm, P.Nm); anyIcp |= s.mode == 0; }
-    CU(h->dIcp.ensure(sizeof(IcpState) * n));
-    CU(h->hIcp.ensure(sizeof(IcpState) * n));
-    IcpState* hs = h->hIcp.as<IcpState>();
-    for (int i = 0; i < n; i++) hs[i] = states[i];
-    EvTimer tm(h, 3);
-    int nl = 0;
-    CU(cudaMemcpyAsync(h->dIcp.p, hs, sizeof(IcpState) * n, cudaMemcpyHostToDevice, h->stream));
-    CU(goicp_launch_icp_begin(h->dPairs.as<PairDev>(), h->dIcp.as<IcpState>(), n, h->stream)); nl++;
-    if (anyIcp) {
-        int burst = 4;
-        for (int it = 0; it < 10000;) {
-            for (int b = 0; b < burst; b++) { CU(goicp_launch_icp_iter(h->dPairs.as<PairDev>(), h->dIcp.as<IcpState>(), n, maxNd, maxNm, h->numSM, h->stream)); nl += 2; }
-            it += burst;
-            CU(cudaMemcpyAsync(hs, h->dIcp.p, sizeof(IcpState) * n, cudaMemcpyDeviceToHost, h->stream));
-            CU(cudaStreamSynchronize(h->stream));
-            bool all = true;
-            for (int i = 0; i < n; i++) if (hs[i].mode == 0 && !hs[i].done) all = false;
-            if (all) break;
-            if (burst < 16) burst *= 2;
-        }
+    int maxNd = 1, maxNm = 1; bool anyIcp = false; bool small = true;
+    for (auto& s : states) {
+        const Problem& P = h->probs[s.pair]; maxNd = std::max(maxNd, P.Nd); maxNm = std::max(maxNm, P.Nm); anyIcp |= s.mode == 0;
+        if ((size_t)P.Nd * P.Nm > ((size_t)1 << 21) || (P.dev.doTrim && P.Nd > 2048)) small = false;
     }
-    CU(goicp_launch_icp_score(h->dPairs.as<PairDev>(), h->dIcp.as<IcpState>(), n, h->stream)); nl++;
-    CU(cudaMemcpyAsync(hs, h->dIcp.p, sizeof(IcpState) * n, cudaMemcpyDeviceToHost, h->stream));
-    tm.stop(nl);
-    CU(cudaStreamSynchronize(h->stream));
+    CU(c.dIcp.ensure(sizeof(IcpState) * n));
+    CU(c.hIcp.ensure(sizeof(IcpState) * n));
+    IcpState* hs = c.hIcp.as<IcpState>();
+    for (int i = 0; i < n; i++) hs[i] = states[i];
+    cudaEventRecord(c.ev0, c.stream);
+    int nl = 0;
+    CU(cudaMemcpyAsync(c.dIcp.p, hs, sizeof(IcpState) * n, cudaMemcpyHostToDevice, c.stream));
+    if (small) {   // whole ICP (begin, every iteration, re-score) in one launch, one CTA per request
+        CU(goicp_launch_icp_fused(h->dPairs.as<PairDev>(), c.dIcp.as<IcpState>(), n, c.stream)); nl++;
+    } else {
+        CU(goicp_launch_icp_begin(h->dPairs.as<PairDev>(), c.dIcp.as<IcpState>(), n, c.stream)); nl++;
+        if (anyIcp) {
+            int burst = 4;
+            for (int it = 0; it < 10000;) {
+                for (int b = 0; b < burst; b++) { CU(goicp_launch_icp_iter(h->dPairs.as<PairDev>(), c.dIcp.as<IcpState>(), n, maxNd, maxNm, h->numSM, c.stream)); nl += 2; }
+                it += burst;
+                CU(cudaMemcpyAsync(hs, c.dIcp.p, sizeof(IcpState) * n, cudaMemcpyDeviceToHost, c.stream));
+                CU(c.sync());
+                bool all = true;
+                for (int i = 0; i < n; i++) if (hs[i].mode == 0 && !hs[i].done) all = false;
+                if (all) break;
+                if (burst < 16) burst *= 2;
+            }
+        }
+        CU(goicp_launch_icp_score(h->dPairs.as<PairDev>(), c.dIcp.as<IcpState>(), n, c.stream)); nl++;
+    }
+    cudaEventRecord(c.ev1, c.stream);
+    CU(cudaMemcpyAsync(hs, c.dIcp.p, sizeof(IcpState) * n, cudaMemcpyDeviceToHost, c.stream));
+    CU(c.sync());
+    float ms = 0; cudaEventElapsedTime(&ms, c.ev0, c.ev1); c.ms[3] += ms; c.launches[3] += nl;
     for (int i = 0; i < n; i++) states[i] = hs[i];
     for (int i = 0; i < n; i++) if (states[i].status != 0) return fail(h, GOICP_ERR_UNSUPPORTED, "ICP with trimming supports Nd <= 2048");
     return GOICP_OK;
@@ -630,41 +683,45 @@ static void gather_requests(Eng* h, int pi, std::vector<InnerProb>& reqs, std::v
     P.quiet++;
 }
 
-// GoICP::Register (jly_goicp.cpp:878) for every problem of the handle, in lock-step waves.
-static goicp_status register_all(Eng* h) {
+// Start-of-search state of one problem (GoICP::Initialize :240-241 resets optR/optT)
+static void reset_search(Problem& P) {
+    P.phase = PH_START; P.q.clear(); P.cache.clear(); P.trace.clear(); memset(P.cnt, 0, sizeof P.cnt);
+    P.nextId = 1; P.quiet = 0; P.optComp = 0; P.lastLb = 0; P.status = 0; P.icpPending = false;
+    for (int k = 0; k < 9; k++) P.optR[k] = (k % 4 == 0);
+    P.optT[0] = P.optT[1] = P.optT[2] = 0;
+}
+
+// One stream of lock-step waves over up to `slots` problems at a time; finished problems are replaced from the shared
+// counter `next` (so a deep pair never stalls more than its own stream).  GoICP::OuterBnB (jly_goicp.cpp:582) per problem.
+static goicp_status register_group(Eng* h, WaveCtx& c, const BnbCfg& cfg, std::atomic<int>& next, int slots) {
     const goicp_params& p = h->params;
-    auto t0 = clk::now();
-    goicp_status s;
-    if ((s = initialize_all(h))) return s;
     const int np = (int)h->probs.size();
-    for (int i = 0; i < np; i++) {
-        Problem& P = h->probs[i];
-        P.phase = PH_START; P.q.clear(); P.cache.clear(); P.trace.clear(); memset(P.cnt, 0, sizeof P.cnt);
-        P.nextId = 1; P.quiet = 0; P.optComp = 0; P.lastLb = 0; P.status = 0;
-        for (int k = 0; k < 9; k++) P.optR[k] = (k % 4 == 0); P.optT[0] = P.optT[1] = P.optT[2] = 0;   // :240-241
-    }
+    std::vector<int> active;
     std::vector<InnerProb> reqs; std::vector<ReqTag> tags; std::vector<InnerOut> outs; std::vector<IcpState> icps; std::vector<int> icpOwner;
+    goicp_status s;
     for (;;) {
+        while ((int)active.size() < slots) { const int i = next.fetch_add(1); if (i >= np) break; reset_search(h->probs[i]); active.push_back(i); }
+        if (active.empty()) break;
         reqs.clear(); tags.clear(); icps.clear(); icpOwner.clear();
-        bool active = false;
-        for (int i = 0; i < np; i++) {
+        for (int i : active) {
             Problem& P = h->probs[i];
             if (P.phase == PH_START) {   // initial error (:601-627) and ICP from the identity (:634)
                 icps.push_back(make_icp_state(i, 1, nullptr, nullptr)); icpOwner.push_back(i);
                 icps.push_back(make_icp_state(i, 0, P.optR, P.optT)); icpOwner.push_back(i);
-                P.phase = PH_WAIT_INIT; active = true; continue;
+                P.phase = PH_WAIT_INIT; continue;
             }
             advance(h, i);
             if (P.phase == PH_DONE) continue;
-            active = true;
             if (P.phase == PH_WAIT_ICP) {   // updateCompatibilities (:791) + ICP(R,t) (:810) at the new incumbent
                 icps.push_back(make_icp_state(i, 2, P.optR, P.optT)); icpOwner.push_back(i);
                 icps.push_back(make_icp_state(i, 0, P.optR, P.optT)); icpOwner.push_back(i);
             } else gather_requests(h, i, reqs, tags);
         }
-        if (!active) break;
-        if ((s = run_inner(h, reqs, outs))) return s;
-        if ((s = run_icp(h, icps))) return s;
+        active.erase(std::remove_if(active.begin(), active.end(), [&](int i) { return h->probs[i].phase == PH_DONE; }), active.end());
+        if (reqs.empty() && icps.empty()) continue;
+        c.waves++;
+        if ((s = run_inner(h, c, cfg, reqs, outs))) return s;
+        if ((s = run_icp(h, c, icps))) return s;
         for (size_t k = 0; k < tags.size(); k++) {
             Problem& P = h->probs[tags[k].prob];
             CallRes r; r.entryOpt = tags[k].entryOpt; r.err = outs[k].err; memcpy(r.tn, outs[k].node, sizeof r.tn); r.pops = outs[k].pops; r.subcubes = outs[k].subcubes;
@@ -677,7 +734,7 @@ static goicp_status register_all(Eng* h) {
             else if (st.mode == 2) P.compatPose = st.compat_pose;
             else { P.icpErr = st.error; memcpy(P.icpR, st.R, sizeof P.icpR); memcpy(P.icpT, st.t, sizeof P.icpT); P.icpIncomp = st.incomp; }
         }
-        for (int i = 0; i < np; i++) {
+        for (int i : active) {
             Problem& P = h->probs[i];
             if (P.phase == PH_WAIT_INIT) {
                 float optError = P.initErr;
@@ -701,8 +758,53 @@ static goicp_status register_all(Eng* h) {
             }
         }
     }
-    const double dt = secs_since(t0) / std::max(1, np);
-    for (auto& P : h->probs) P.t_reg = dt;
+    return GOICP_OK;
+}
+
+// GoICP::Register (jly_goicp.cpp:878) for every problem of the handle.  One problem: waves on the handle's stream.
+// A batch: `groups` worker threads, each with its own stream, pull pairs from a shared counter.
+static goicp_status register_all(Eng* h) {
+    auto t0 = clk::now();
+    goicp_status s;
+    if ((s = initialize_all(h))) return s;
+    const int np = (int)h->probs.size();
+    const BnbCfg cfg = bnb_config(h);
+    std::atomic<int> next(0);
+    int groups = 1;
+    if (np > 1) {
+        groups = h->groups > 0 ? h->groups : (int)std::min<unsigned>(32u, std::max(4u, 2 * std::thread::hardware_concurrency()));
+        groups = std::min(groups, (np + h->slots - 1) / h->slots);
+    }
+    if (groups <= 1) {
+        h->main.ctaCap = 0;
+        if ((s = register_group(h, h->main, cfg, next, std::max(1, np == 1 ? 1 : h->slots)))) return s;
+    } else {
+        while ((int)h->workers.size() < groups) {
+            std::unique_ptr<WaveCtx> w(new WaveCtx());
+            if (w->init(true, nullptr) != GOICP_OK) return fail(h, GOICP_ERR_CUDA, "worker stream creation failed");
+            h->workers.push_back(std::move(w));
+        }
+        CU(cudaStreamSynchronize(h->stream));   // inputs / DT / Initialize were enqueued on the handle's stream
+        std::vector<goicp_status> st(groups, GOICP_OK);
+        std::vector<std::thread> th;
+        for (int g = 0; g < groups; g++) {
+            WaveCtx* w = h->workers[g].get();
+            w->ctaCap = std::max(64, 2 * h->numSM * cfg.perSM / groups);
+            memset(w->ms, 0, sizeof w->ms); memset(w->launches, 0, sizeof w->launches); w->waves = w->callsLaunched = 0;
+            th.emplace_back([h, w, &cfg, &next, &st, g]() { cudaSetDevice(h->device); st[g] = register_group(h, *w, cfg, next, h->slots); });
+        }
+        for (auto& t : th) t.join();
+        for (int g = 0; g < groups; g++) if (st[g]) return st[g];
+        for (int g = 0; g < groups; g++) {
+            WaveCtx* w = h->workers[g].get();
+            for (int k = 0; k < 5; k++) { h->main.ms[k] += w->ms[k]; h->main.launches[k] += w->launches[k]; }
+            h->main.waves += w->waves; h->main.callsLaunched += w->callsLaunched;
+        }
+    }
+    const double dt = secs_since(t0);
+    for (auto& P : h->probs) P.t_reg = dt / std::max(1, np);
+    long long used = 0; for (auto& P : h->probs) used += P.cnt[0];
+    h->stats[0] = (double)h->main.waves; h->stats[1] = (double)h->main.callsLaunched; h->stats[2] = (double)used; h->stats[3] = groups; h->stats[4] = dt;
     return GOICP_OK;
 }
 
@@ -711,9 +813,10 @@ static void fill_result(Eng* h, const Problem& P, goicp_result* out) {
     memcpy(out->R, P.optR, sizeof out->R); memcpy(out->t, P.optT, sizeof out->t);
     out->optError = P.optError; out->optComp = P.optComp;
     for (int k = 0; k < 8; k++) out->counters[k] = P.cnt[k];
-    out->counters[6] = h->launches[0] + h->launches[1] + h->launches[2] + h->launches[3] + h->launches[4];
+    out->counters[6] = h->main.launches[0] + h->main.launches[1] + h->main.launches[2] + h->main.launches[3] + h->main.launches[4];
+    out->counters[7] = (long long)h->stats[1] - (long long)h->stats[2];
     out->seconds_dt = P.t_dt; out->seconds_register = P.t_reg;
-    out->gpu_ms_dt = h->ms[0]; out->gpu_ms_bnb = h->ms[2]; out->gpu_ms_icp = h->ms[3];
+    out->gpu_ms_dt = h->main.ms[0]; out->gpu_ms_bnb = h->main.ms[2]; out->gpu_ms_icp = h->main.ms[3];
     out->status = P.status;
 }
 
@@ -767,7 +870,7 @@ goicp_status goicp_create(goicp_handle* out, int device, void* stream_or_null) {
     h->device = device; h->numSM = prop.multiProcessorCount;
     if (stream_or_null) { h->stream = (cudaStream_t)stream_or_null; h->ownStream = false; }
     else { if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete h; return fail(nullptr, GOICP_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); } h->ownStream = true; }
-    cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
+    if (h->main.init(false, h->stream) != GOICP_OK) { delete h; return fail(nullptr, GOICP_ERR_CUDA, "event creation failed"); }
     goicp_params_default(&h->params); h->haveParams = true;
     *out = h;
     return GOICP_OK;
@@ -777,12 +880,11 @@ void goicp_destroy(goicp_handle h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf* bufs[] = {&h->arenaIn, &h->arenaWork, &h->dPairs, &h->dProbs, &h->dOuts, &h->dCounter, &h->dHeaps, &h->dBnbScratch, &h->dIcp, &h->dTmp, &h->dTmp2, &h->dTmp3, &h->dSepBits, &h->dSepNx, &h->dSepNxy};
+    DevBuf* bufs[] = {&h->arenaIn, &h->arenaWork, &h->dPairs, &h->dTmp, &h->dTmp2, &h->dTmp3, &h->dSepBits, &h->dSepNx, &h->dSepNxy};
     for (DevBuf* b : bufs) b->release();
-    PinBuf* pins[] = {&h->hProbs, &h->hOuts, &h->hIcp, &h->hStage};
-    for (PinBuf* b : pins) b->release();
-    if (h->ev0) cudaEventDestroy(h->ev0);
-    if (h->ev1) cudaEventDestroy(h->ev1);
+    h->hStage.release(); h->hPairs.release();
+    h->main.release();
+    for (auto& w : h->workers) w->release();
     if (h->ownStream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -943,7 +1045,7 @@ goicp_status goicp_eval_bounds(goicp_handle h, const float* R, const int32_t* le
     CU(cudaMemcpyAsync(dR, R, sizeof(float) * 9 * nr, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(dL, level, sizeof(int) * nr, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(dC, cubes.data(), sizeof(WaveCube) * nt, cudaMemcpyHostToDevice, h->stream));
-    { EvTimer tm(h, 2);
+    { EvTimer tm(h->main, 2);
       CU(goicp_launch_eval_bounds(h->dPairs.as<PairDev>(), 0, dR, dL, dC, nt, dU, dLb, dI, dFm, h->dTmp2.as<float>(), nwarps, h->stream));
       tm.stop(1); }
     CU(cudaMemcpyAsync(ub, dU, sizeof(float) * nt, cudaMemcpyDeviceToHost, h->stream));
@@ -965,7 +1067,9 @@ goicp_status goicp_inner_bnb(goicp_handle h, const float* R, const int32_t* leve
         if (level[k] >= GOICP_MAXROTLEVEL) return fail(h, GOICP_ERR_ARG, "level %d >= MAXROTLEVEL", level[k]);
         reqs[k].pair = 0; reqs[k].level = level[k]; reqs[k].optError = opt_error[k]; memcpy(reqs[k].R, R + 9 * k, sizeof(float) * 9);
     }
-    if ((s = run_inner(h, reqs, outs))) return s;
+    const BnbCfg cfg = bnb_config(h);
+    h->main.ctaCap = 0;
+    if ((s = run_inner(h, h->main, cfg, reqs, outs))) return s;
     for (int k = 0; k < n; k++) {
         err[k] = outs[k].err;
         if (tnode) memcpy(tnode + 4 * k, outs[k].node, sizeof(float) * 4);
@@ -980,7 +1084,7 @@ goicp_status goicp_icp(goicp_handle h, double* R, double* t, float* err, int32_t
     Problem& P = h->probs[0]; if (!P.initialized) return fail(h, GOICP_ERR_ARG, "icp before initialize");
     cudaSetDevice(h->device);
     std::vector<IcpState> st{make_icp_state(0, 0, R, t)};
-    if ((s = run_icp(h, st))) return s;
+    if ((s = run_icp(h, h->main, st))) return s;
     memcpy(R, st[0].R, sizeof(double) * 9); memcpy(t, st[0].t, sizeof(double) * 3); *err = st[0].error;
     if (corr) {
         std::vector<unsigned long long> nn(P.Nd);
@@ -995,7 +1099,7 @@ goicp_status goicp_register(goicp_handle h, goicp_result* out) {
     goicp_status s; if ((s = ensure_single(h))) return s;
     cudaSetDevice(h->device);
     Problem& P = h->probs[0];
-    memset(h->ms, 0, sizeof h->ms); memset(h->launches, 0, sizeof h->launches);
+    memset(h->main.ms, 0, sizeof h->main.ms); memset(h->main.launches, 0, sizeof h->main.launches); h->main.waves = h->main.callsLaunched = 0;
     if (!P.dt_built) { const int nd = P.Nd; if ((s = goicp_build_dt(h, nullptr))) return s; P.Nd = nd; }
     if ((s = register_all(h))) return s;
     h->trace = P.trace;
@@ -1026,7 +1130,7 @@ goicp_status goicp_batch_run(goicp_handle h, goicp_result* results) {
     if (!h || !results) return GOICP_ERR_ARG;
     if (h->probs.empty()) return fail(h, GOICP_ERR_ARG, "batch_run before batch_upload");
     cudaSetDevice(h->device);
-    memset(h->ms, 0, sizeof h->ms); memset(h->launches, 0, sizeof h->launches);
+    memset(h->main.ms, 0, sizeof h->main.ms); memset(h->main.launches, 0, sizeof h->main.launches); h->main.waves = h->main.callsLaunched = 0;
     goicp_status s;
     if ((s = build_dt_all(h, h->use_dt_replay && h->params.distTransSize <= 32))) return s;
     if ((s = register_all(h))) return s;
@@ -1039,9 +1143,20 @@ goicp_status goicp_register_batch(goicp_handle h, const goicp_params* p, int32_t
     if ((s = goicp_batch_upload(h, p, npairs, pairs))) return s;
     return goicp_batch_run(h, results);
 }
+goicp_status goicp_set_batch_options(goicp_handle h, int32_t groups, int32_t slots) {
+    if (!h) return GOICP_ERR_ARG;
+    if (groups >= 0) h->groups = groups;
+    if (slots >= 1) h->slots = slots;
+    return GOICP_OK;
+}
+goicp_status goicp_get_stats(goicp_handle h, double* out8) {
+    if (!h || !out8) return GOICP_ERR_ARG;
+    for (int k = 0; k < 8; k++) out8[k] = h->stats[k];
+    return GOICP_OK;
+}
 goicp_status goicp_get_timings(goicp_handle h, float* ms5, int64_t* launches5) {
     if (!h) return GOICP_ERR_ARG;
-    for (int k = 0; k < 5; k++) { if (ms5) ms5[k] = h->ms[k]; if (launches5) launches5[k] = h->launches[k]; }
+    for (int k = 0; k < 5; k++) { if (ms5) ms5[k] = h->main.ms[k]; if (launches5) launches5[k] = h->main.launches[k]; }
     return GOICP_OK;
 }
 
@@ -1051,7 +1166,7 @@ goicp_status goicp_normalize_cloud(goicp_handle h, double* xyz, int32_t n, doubl
     cudaSetDevice(h->device);
     CU(h->dTmp.ensure(sizeof(double) * 3 * (size_t)n)); CU(h->dTmp2.ensure(sizeof(double) * 4));
     CU(cudaMemcpyAsync(h->dTmp.p, xyz, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
-    CU(goicp_launch_normalize(h->dTmp.as<double>(), n, h->dTmp2.as<double>(), h->stream)); h->launches[4]++;
+    CU(goicp_launch_normalize(h->dTmp.as<double>(), n, h->dTmp2.as<double>(), h->stream)); h->main.launches[4]++;
     double out4[4];
     CU(cudaMemcpyAsync(xyz, h->dTmp.p, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(out4, h->dTmp2.p, sizeof out4, cudaMemcpyDeviceToHost, h->stream));
@@ -1065,7 +1180,7 @@ goicp_status goicp_scale_cloud(goicp_handle h, double* xyz, int32_t n, double sc
     cudaSetDevice(h->device);
     CU(h->dTmp.ensure(sizeof(double) * 3 * (size_t)n));
     CU(cudaMemcpyAsync(h->dTmp.p, xyz, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
-    CU(goicp_launch_scale(h->dTmp.as<double>(), n, scale, h->stream)); h->launches[4]++;
+    CU(goicp_launch_scale(h->dTmp.as<double>(), n, scale, h->stream)); h->main.launches[4]++;
     CU(cudaMemcpyAsync(xyz, h->dTmp.p, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return GOICP_OK;
@@ -1077,7 +1192,7 @@ goicp_status goicp_apply_rigid(goicp_handle h, const double* xyz, int32_t n, con
     double Rt[12]; memcpy(Rt, R, sizeof(double) * 9); memcpy(Rt + 9, t, sizeof(double) * 3);
     CU(cudaMemcpyAsync(h->dTmp.p, xyz, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->dTmp3.p, Rt, sizeof Rt, cudaMemcpyHostToDevice, h->stream));
-    CU(goicp_launch_apply_rigid(h->dTmp.as<double>(), n, h->dTmp3.as<double>(), h->dTmp2.as<double>(), h->stream)); h->launches[4]++;
+    CU(goicp_launch_apply_rigid(h->dTmp.as<double>(), n, h->dTmp3.as<double>(), h->dTmp2.as<double>(), h->stream)); h->main.launches[4]++;
     CU(cudaMemcpyAsync(out, h->dTmp2.p, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return GOICP_OK;
@@ -1088,7 +1203,7 @@ goicp_status goicp_rescale_translation(goicp_handle h, double scale, const doubl
     double in[19]; in[0] = scale; memcpy(in + 1, meanT, 24); memcpy(in + 4, meanS, 24); memcpy(in + 7, R, 72); memcpy(in + 16, t, 24);
     CU(h->dTmp.ensure(sizeof(double) * 24));
     CU(cudaMemcpyAsync(h->dTmp.p, in, sizeof in, cudaMemcpyHostToDevice, h->stream));
-    CU(goicp_launch_rescale(h->dTmp.as<double>(), h->dTmp.as<double>() + 19, h->stream)); h->launches[4]++;
+    CU(goicp_launch_rescale(h->dTmp.as<double>(), h->dTmp.as<double>() + 19, h->stream)); h->main.launches[4]++;
     CU(cudaMemcpyAsync(out3, h->dTmp.as<double>() + 19, sizeof(double) * 3, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return GOICP_OK;
@@ -1100,7 +1215,7 @@ goicp_status goicp_rmsd(goicp_handle h, const double* a, const double* b, int32_
     CU(cudaMemcpyAsync(h->dTmp.p, a, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->dTmp2.p, b, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
     float* dOut = reinterpret_cast<float*>(h->dTmp3.as<char>() + sizeof(double) * (size_t)n);
-    CU(goicp_launch_rmsd(h->dTmp.as<double>(), h->dTmp2.as<double>(), n, h->dTmp3.as<double>(), dOut, h->stream)); h->launches[4]++;
+    CU(goicp_launch_rmsd(h->dTmp.as<double>(), h->dTmp2.as<double>(), n, h->dTmp3.as<double>(), dOut, h->stream)); h->main.launches[4]++;
     CU(cudaMemcpyAsync(rmsd, dOut, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return GOICP_OK;

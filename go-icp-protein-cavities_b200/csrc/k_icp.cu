@@ -14,18 +14,14 @@ constexpr int NN_THREADS = 128;
 constexpr int NN_TILE = 512;
 
 // ---- begin: reset workspaces, optional updateCompatibilities at the entry pose (jly_goicp.cpp:933-946) ------------
-__global__ void __launch_bounds__(256)
-icp_begin_kernel(const PairDev* __restrict__ pairs, IcpState* __restrict__ states) {
-    IcpState& st = states[blockIdx.x];
-    const PairDev& P = pairs[st.pair];
+__device__ __forceinline__ void icp_begin_part(const PairDev& P, IcpState& st) {
     const int Nd = P.Nd;
     __shared__ int s_cnt;
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
     int bad = 0;
     for (int i = threadIdx.x; i < Nd; i += blockDim.x) {
-        P.nn[i] = GOICP_NN_EMPTY;
-        P.order[i] = i;
+        if (st.mode == 0) { P.nn[i] = GOICP_NN_EMPTY; P.order[i] = i; }   // modes 1/2 may share a launch with a mode-0 state of the same pair
         if (st.mode == 2) {
             const double x0 = P.dx[i], y0 = P.dy[i], z0 = P.dz[i];
             const float x = (float)(st.R[0] * x0 + st.R[1] * y0 + st.R[2] * z0 + st.t[0]);
@@ -41,6 +37,11 @@ icp_begin_kernel(const PairDev* __restrict__ pairs, IcpState* __restrict__ state
         __syncthreads();
         if (threadIdx.x == 0) { st.compat_pose = s_cnt; st.done = 1; }
     }
+}
+__global__ void __launch_bounds__(256)
+icp_begin_kernel(const PairDev* __restrict__ pairs, IcpState* __restrict__ states) {
+    IcpState& st = states[blockIdx.x];
+    icp_begin_part(pairs[st.pair], st);
 }
 
 // ---- exact nearest neighbours (replaces nanoflann knnSearch, jly_icp3d.hpp:234-250) --------------------------------
@@ -121,11 +122,8 @@ __device__ void svd3(const double H[9], double U[9], double W[3], double V[9]) {
 
 // ---- per-iteration update: [trim sort], centroids, err, H, SVD, compose (jly_icp3d.hpp:252-308) ---------------------
 constexpr int SORT_CAP = 2048;
-__global__ void __launch_bounds__(256)
-icp_update_kernel(const PairDev* __restrict__ pairs, IcpState* __restrict__ states) {
-    IcpState& st = states[blockIdx.x];
-    if (st.done || st.mode != 0) return;
-    const PairDev& P = pairs[st.pair];
+// returns true (uniformly) when the call has finished (converged / maxIter / error)
+__device__ __forceinline__ bool icp_update_part(const PairDev& P, IcpState& st) {
     const int n = P.Nd, num = P.inlierNum, tid = threadIdx.x;
     const int iter0 = st.iter;   // st.iter is only written by thread 0 after the last barrier below
     __shared__ unsigned long long keys[SORT_CAP];
@@ -136,7 +134,7 @@ icp_update_kernel(const PairDev* __restrict__ pairs, IcpState* __restrict__ stat
     float* T = P.scratch;   // [7][n]: p_m xyz, p_d xyz, dis  (positions follow `order`)
 
     if (P.doTrim) {   // qsort of POINTREF by dis (:252-255); ties keep index order
-        if (n > SORT_CAP) { if (tid == 0) { st.status = 3; st.done = 1; } return; }
+        if (n > SORT_CAP) { if (tid == 0) { st.status = 3; st.done = 1; } return true; }
         for (int i = tid; i < SORT_CAP; i += blockDim.x)
             keys[i] = (i < n) ? (((P.nn[i] >> 32) << 32) | (unsigned)i) : GOICP_NN_EMPTY;
         __syncthreads();
@@ -197,7 +195,7 @@ icp_update_kernel(const PairDev* __restrict__ pairs, IcpState* __restrict__ stat
         if (done) st.done = 1;
     }
     __syncthreads();
-    if (s_done) return;
+    if (s_done) return true;
     if (tid < 9) {   // H = ~q_t * q_m (:284), Matrix operator* accumulates over k in order
         const int a = tid / 3, b = tid % 3;
         const float* pd = T + (size_t)(3 + a) * n; const float* pm = T + (size_t)b * n;
@@ -228,16 +226,19 @@ icp_update_kernel(const PairDev* __restrict__ pairs, IcpState* __restrict__ stat
     }
     if (iter0 + 1 < 10000)   // reset for the next nearest-neighbour pass (kept after the last iteration: `points`)
         for (int i = tid; i < n; i += blockDim.x) P.nn[i] = GOICP_NN_EMPTY;
+    return iter0 + 1 >= 10000;
+}
+__global__ void __launch_bounds__(256)
+icp_update_kernel(const PairDev* __restrict__ pairs, IcpState* __restrict__ states) {
+    IcpState& st = states[blockIdx.x];
+    if (st.done || st.mode != 0) return;
+    icp_update_part(pairs[st.pair], st);
 }
 
 // ---- scoring: initial error at identity (jly_goicp.cpp:601-627) or the DT re-score of GoICP::ICP (:117-175) ---------
-__global__ void __launch_bounds__(256)
-icp_score_kernel(const PairDev* __restrict__ pairs, IcpState* __restrict__ states) {
-    IcpState& st = states[blockIdx.x];
-    if (st.mode == 2 || (st.mode == 0 && (!st.done || st.status != 0))) return;
-    const PairDev& P = pairs[st.pair];
+__device__ __forceinline__ void icp_score_part(const PairDev& P, IcpState& st) {
     const int Nd = P.Nd, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float* val = P.scratch + (st.mode == 1 ? 2 * Nd : 0);   // Nd: per data index (mode 1 may share a launch with mode 0)
+    float* val = P.scratch + (st.mode == 1 ? 7 * Nd : 0);   // Nd: per data index; mode 1 may run beside a mode-0 state whose update uses [0, 7 Nd)
     float* fd = P.scratch + Nd;        // Nd: per position of `order`
     __shared__ int s_bad;
     __shared__ float s_geom, s_fpfh, s_trim;
@@ -297,6 +298,62 @@ icp_score_kernel(const PairDev* __restrict__ pairs, IcpState* __restrict__ state
         st.done = 1;
     }
 }
+__global__ void __launch_bounds__(256)
+icp_score_kernel(const PairDev* __restrict__ pairs, IcpState* __restrict__ states) {
+    IcpState& st = states[blockIdx.x];
+    if (st.mode == 2 || (st.mode == 0 && (!st.done || st.status != 0))) return;
+    icp_score_part(pairs[st.pair], st);
+}
+
+// ---- small problems: the whole GoICP::ICP call (begin, every ICP3D::Run iteration, DT re-score) in ONE launch, one CTA per
+//      request; the model cloud is tiled through shared memory for the exact nearest-neighbour pass ---------------------
+__global__ void __launch_bounds__(256)
+icp_fused_kernel(const PairDev* __restrict__ pairs, IcpState* __restrict__ states) {
+    IcpState& st = states[blockIdx.x];
+    const PairDev& P = pairs[st.pair];
+    const int Nd = P.Nd, Nm = P.Nm, tid = threadIdx.x;
+    __shared__ float sx[NN_TILE], sy[NN_TILE], sz[NN_TILE];
+    icp_begin_part(P, st);
+    __syncthreads();
+    if (st.mode == 2) return;
+    if (st.mode == 0) {
+        for (;;) {
+            const float r00 = (float)st.R[0], r01 = (float)st.R[1], r02 = (float)st.R[2], r10 = (float)st.R[3], r11 = (float)st.R[4],
+                        r12 = (float)st.R[5], r20 = (float)st.R[6], r21 = (float)st.R[7], r22 = (float)st.R[8];
+            const float t0 = (float)st.t[0], t1 = (float)st.t[1], t2 = (float)st.t[2];
+            for (int i0 = 0; i0 < Nd; i0 += 256) {   // uniform trip count: every thread takes part in the tile loads
+                const int i = i0 + tid;
+                float q0 = 0.f, q1 = 0.f, q2 = 0.f;
+                if (i < Nd) {
+                    const float x = P.dx[i], y = P.dy[i], z = P.dz[i];
+                    q0 = r00 * x + r01 * y + r02 * z + t0;
+                    q1 = r10 * x + r11 * y + r12 * z + t1;
+                    q2 = r20 * x + r21 * y + r22 * z + t2;
+                }
+                float best = __int_as_float(0x7f800000); int bi = 0;
+                for (int base = 0; base < Nm; base += NN_TILE) {
+                    const int cnt = min(NN_TILE, Nm - base);
+                    __syncthreads();
+                    for (int k = tid; k < cnt; k += 256) { sx[k] = P.mx[base + k]; sy[k] = P.my[base + k]; sz[k] = P.mz[base + k]; }
+                    __syncthreads();
+#pragma unroll 4
+                    for (int k = 0; k < cnt; ++k) {
+                        const float d0 = q0 - sx[k], d1 = q1 - sy[k], d2 = q2 - sz[k];
+                        float d = d0 * d0; d = d + d1 * d1; d = d + d2 * d2;
+                        if (d < best) { best = d; bi = base + k; }
+                    }
+                }
+                if (i < Nd) P.nn[i] = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned)bi;
+            }
+            __syncthreads();
+            const bool done = icp_update_part(P, st);
+            __syncthreads();
+            if (done) break;
+        }
+        if (st.status != 0) return;
+    }
+    icp_score_part(P, st);
+}
 
 }  // namespace
 
@@ -315,6 +372,11 @@ cudaError_t goicp_launch_icp_iter(const PairDev* pairs, IcpState* states, int n,
     if (gy > 65535) gy = 65535;
     icp_nn_kernel<<<dim3(gx, gy, n), NN_THREADS, 0, st>>>(pairs, states, gy);
     icp_update_kernel<<<n, 256, 0, st>>>(pairs, states);
+    return cudaGetLastError();
+}
+cudaError_t goicp_launch_icp_fused(const PairDev* pairs, IcpState* states, int n, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    icp_fused_kernel<<<n, 256, 0, st>>>(pairs, states);
     return cudaGetLastError();
 }
 cudaError_t goicp_launch_icp_score(const PairDev* pairs, IcpState* states, int n, cudaStream_t st) {

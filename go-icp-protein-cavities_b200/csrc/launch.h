@@ -21,6 +21,7 @@ cudaError_t goicp_launch_dt_distance(const PairDev* pairs, int pair, const doubl
 // k_icp.cu
 cudaError_t goicp_launch_icp_begin(const PairDev* pairs, IcpState* states, int n, cudaStream_t st);
 cudaError_t goicp_launch_icp_iter(const PairDev* pairs, IcpState* states, int n, int maxNd, int maxNm, int numSM, cudaStream_t st);
+cudaError_t goicp_launch_icp_fused(const PairDev* pairs, IcpState* states, int n, cudaStream_t st);
 cudaError_t goicp_launch_icp_score(const PairDev* pairs, IcpState* states, int n, cudaStream_t st);
 // k_misc.cu
 cudaError_t goicp_launch_initialize(PairDev* pairs, int first, int count, cudaStream_t st);
