@@ -26,6 +26,7 @@ import time
 
 import numpy as np
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # one hardware queue per worker stream (default 8 aliases them)
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 METRIC, UNIT = "cube_point_bound_evals_per_sec", "evals/s"

@@ -191,7 +191,8 @@ class Engine:
     def stats(self):
         o = (C.c_double * 8)()
         self.check(self.L.goicp_get_stats(self.h, o))
-        return dict(waves=int(o[0]), calls_launched=int(o[1]), calls_used=int(o[2]), streams=int(o[3]), host_seconds=o[4])
+        return dict(waves=int(o[0]), calls_launched=int(o[1]), calls_used=int(o[2]), streams=int(o[3]), host_seconds=o[4],
+                    stream_seconds=dict(inner_enqueue=o[5], inner_wait=o[6], icp=o[7]))
 
     def set_options(self, exact_sums=-1, spec_width=-1, use_dt_replay=-1):
         self.check(self.L.goicp_set_options(self.h, exact_sums, spec_width, use_dt_replay))

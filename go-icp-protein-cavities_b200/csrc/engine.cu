@@ -13,6 +13,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -76,6 +77,24 @@ struct PinBuf {
 };
 
 // ROTNODE (jly_goicp.h:59-73) + a unique id for the speculation cache
+// pinned host memory mapped into the device address space: kernels read requests / write results directly over the bus,
+// so a wave is one launch + one wait (no copies, no memset)
+struct MapBuf {
+    void* h = nullptr; void* d = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (h) cudaFreeHost(h);
+        h = d = nullptr; cap = 0;
+        size_t want = bytes * 2 + 4096;
+        cudaError_t e = cudaHostAlloc(&h, want, cudaHostAllocMapped | cudaHostAllocPortable);
+        if (e != cudaSuccess) return e;
+        if ((e = cudaHostGetDevicePointer(&d, h, 0)) != cudaSuccess) return e;
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() { if (h) cudaFreeHost(h); h = d = nullptr; cap = 0; }
+};
+
 struct RNode { float a, b, c, w, ub, lb; int l; int id; };
 static inline bool rnode_less(const RNode& n1, const RNode& n2) {   // operator< :64-71
     if (n1.lb != n2.lb) return n1.lb > n2.lb;
@@ -154,11 +173,14 @@ static void tracef(std::string& s, const char* fmt, ...) {
 // Everything one stream of waves needs: a worker thread of a batch owns one, the handle's own stream has `main`.
 struct WaveCtx {
     cudaStream_t stream = nullptr; bool ownStream = false;
-    DevBuf dProbs, dOuts, dCounter, dHeaps, dBnbScratch, dIcp;
-    PinBuf hProbs, hOuts, hIcp;
+    DevBuf dCounter, dHeaps, dBnbScratch, dIcp;
+    PinBuf hIcp;
+    MapBuf mProbs, mOuts, mIcp;
+    bool counterReady = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evDone = nullptr;
     float ms[5] = {0, 0, 0, 0, 0}; long long launches[5] = {0, 0, 0, 0, 0};
     long long waves = 0, callsLaunched = 0, callsUsed = 0;
+    double tLogic = 0, tInnerEnq = 0, tInnerWait = 0, tIcp = 0;   // host seconds
     int heapCap = 1 << 14;
     int ctaCap = 0;   // 0: numSM x occupancy
     goicp_status init(bool own, cudaStream_t st) {
@@ -169,12 +191,17 @@ struct WaveCtx {
         return GOICP_OK;
     }
     // waits without spinning a host core (worker threads outnumber cores)
-    cudaError_t sync() { cudaError_t e = cudaEventRecord(evDone, stream); if (e != cudaSuccess) return e; return cudaEventSynchronize(evDone); }
+    cudaError_t sync() {
+        static const int mode = [] { const char* e = getenv("GOICP_SYNC"); return e ? atoi(e) : 0; }();   // 0 blocking event, 1 stream sync (spin), 2 query + yield
+        if (mode == 1) return cudaStreamSynchronize(stream);
+        cudaError_t e = cudaEventRecord(evDone, stream); if (e != cudaSuccess) return e;
+        if (mode == 2) { while ((e = cudaEventQuery(evDone)) == cudaErrorNotReady) std::this_thread::yield(); return e; }
+        return cudaEventSynchronize(evDone);
+    }
     void release() {
-        DevBuf* bufs[] = {&dProbs, &dOuts, &dCounter, &dHeaps, &dBnbScratch, &dIcp};
+        DevBuf* bufs[] = {&dCounter, &dHeaps, &dBnbScratch, &dIcp};
         for (DevBuf* b : bufs) b->release();
-        PinBuf* pins[] = {&hProbs, &hOuts, &hIcp};
-        for (PinBuf* b : pins) b->release();
+        hIcp.release(); mProbs.release(); mOuts.release(); mIcp.release();
         if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1); if (evDone) cudaEventDestroy(evDone);
         ev0 = ev1 = evDone = nullptr;
         if (ownStream && stream) cudaStreamDestroy(stream);
@@ -454,31 +481,29 @@ static goicp_status run_inner(Eng* h, WaveCtx& c, const BnbCfg& cfg, std::vector
     int maxCtas = h->numSM * cfg.perSM;
     if (c.ctaCap > 0) maxCtas = std::min(maxCtas, c.ctaCap);
     int heapCap = c.heapCap;
-    CU(c.dProbs.ensure(sizeof(InnerProb) * n));
-    CU(c.dOuts.ensure(sizeof(InnerOut) * n));
-    CU(c.dCounter.ensure(sizeof(int)));
-    CU(c.hProbs.ensure(sizeof(InnerProb) * (size_t)n));
-    CU(c.hOuts.ensure(sizeof(InnerOut) * n));
+    CU(c.mProbs.ensure(sizeof(InnerProb) * (size_t)n));
+    CU(c.mOuts.ensure(sizeof(InnerOut) * (size_t)n));
+    if (!c.counterReady) { CU(c.dCounter.ensure(2 * sizeof(int))); CU(cudaMemsetAsync(c.dCounter.p, 0, 2 * sizeof(int), c.stream)); c.counterReady = true; }
     std::vector<int> todo(n); for (int i = 0; i < n; i++) todo[i] = i;
     for (int attempt = 0; attempt < 12 && !todo.empty(); attempt++) {
         const int m = (int)todo.size();
-        InnerProb* hp = c.hProbs.as<InnerProb>();
+        InnerProb* hp = reinterpret_cast<InnerProb*>(c.mProbs.h);
         for (int i = 0; i < m; i++) hp[i] = reqs[todo[i]];
         const int ctas = std::min(m, maxCtas);
         CU(c.dHeaps.ensure(sizeof(HeapEnt) * (size_t)ctas * heapCap));
         if (!cfg.useSmem) CU(c.dBnbScratch.ensure(sizeof(float) * cfg.smemFloats * (size_t)ctas));
-        CU(cudaMemcpyAsync(c.dProbs.p, hp, sizeof(InnerProb) * m, cudaMemcpyHostToDevice, c.stream));
-        CU(cudaMemsetAsync(c.dCounter.p, 0, sizeof(int), c.stream));
+        auto tq = clk::now();
         cudaEventRecord(c.ev0, c.stream);
         int launched = 0;
-        CU(goicp_launch_inner_bnb(h->dPairs.as<PairDev>(), c.dProbs.as<InnerProb>(), c.dOuts.as<InnerOut>(), m, c.dCounter.as<int>(),
+        CU(goicp_launch_inner_bnb(h->dPairs.as<PairDev>(), reinterpret_cast<const InnerProb*>(c.mProbs.d), reinterpret_cast<InnerOut*>(c.mOuts.d), m, c.dCounter.as<int>(),
                                   c.dHeaps.as<HeapEnt>(), heapCap, ctas, c.dBnbScratch.as<float>(), cfg.smemFloats, cfg.NdP, cfg.NdQ, cfg.smemFloats, cfg.useSmem,
                                   h->exact_sums, c.stream, &launched));
         cudaEventRecord(c.ev1, c.stream);
-        CU(cudaMemcpyAsync(c.hOuts.p, c.dOuts.p, sizeof(InnerOut) * m, cudaMemcpyDeviceToHost, c.stream));
+        c.tInnerEnq += secs_since(tq); tq = clk::now();
         CU(c.sync());
+        c.tInnerWait += secs_since(tq);
         float ms = 0; cudaEventElapsedTime(&ms, c.ev0, c.ev1); c.ms[2] += ms; c.launches[2] += 1;
-        const InnerOut* ho = c.hOuts.as<InnerOut>();
+        const InnerOut* ho = reinterpret_cast<const InnerOut*>(c.mOuts.h);
         std::vector<int> again;
         for (int i = 0; i < m; i++) { if (ho[i].status == 4) again.push_back(todo[i]); else outs[todo[i]] = ho[i]; }
         todo.swap(again);
@@ -498,6 +523,20 @@ static goicp_status run_icp(Eng* h, WaveCtx& c, std::vector<IcpState>& states) {
         const Problem& P = h->probs[s.pair]; maxNd = std::max(maxNd, P.Nd); maxNm = std::max(maxNm, P.Nm); anyIcp |= s.mode == 0;
         if ((size_t)P.Nd * P.Nm > ((size_t)1 << 21) || (P.dev.doTrim && P.Nd > 2048)) small = false;
     }
+    { static const char* env = getenv("GOICP_ICP_FUSED"); if (env && env[0] == '0') small = false; }   // debugging aid
+    if (small) {   // whole ICP (begin, every iteration, re-score) in one launch, one CTA per request; states in mapped host memory
+        CU(c.mIcp.ensure(sizeof(IcpState) * n));
+        IcpState* ms_ = reinterpret_cast<IcpState*>(c.mIcp.h);
+        for (int i = 0; i < n; i++) ms_[i] = states[i];
+        cudaEventRecord(c.ev0, c.stream);
+        CU(goicp_launch_icp_fused(h->dPairs.as<PairDev>(), reinterpret_cast<IcpState*>(c.mIcp.d), n, c.stream));
+        cudaEventRecord(c.ev1, c.stream);
+        CU(c.sync());
+        float ms = 0; cudaEventElapsedTime(&ms, c.ev0, c.ev1); c.ms[3] += ms; c.launches[3] += 1;
+        for (int i = 0; i < n; i++) states[i] = ms_[i];
+        for (int i = 0; i < n; i++) if (states[i].status != 0) return fail(h, GOICP_ERR_UNSUPPORTED, "ICP with trimming supports Nd <= 2048");
+        return GOICP_OK;
+    }
     CU(c.dIcp.ensure(sizeof(IcpState) * n));
     CU(c.hIcp.ensure(sizeof(IcpState) * n));
     IcpState* hs = c.hIcp.as<IcpState>();
@@ -505,9 +544,7 @@ static goicp_status run_icp(Eng* h, WaveCtx& c, std::vector<IcpState>& states) {
     cudaEventRecord(c.ev0, c.stream);
     int nl = 0;
     CU(cudaMemcpyAsync(c.dIcp.p, hs, sizeof(IcpState) * n, cudaMemcpyHostToDevice, c.stream));
-    if (small) {   // whole ICP (begin, every iteration, re-score) in one launch, one CTA per request
-        CU(goicp_launch_icp_fused(h->dPairs.as<PairDev>(), c.dIcp.as<IcpState>(), n, c.stream)); nl++;
-    } else {
+    {
         CU(goicp_launch_icp_begin(h->dPairs.as<PairDev>(), c.dIcp.as<IcpState>(), n, c.stream)); nl++;
         if (anyIcp) {
             int burst = 4;
@@ -699,6 +736,7 @@ static goicp_status register_group(Eng* h, WaveCtx& c, const BnbCfg& cfg, std::a
     std::vector<int> active;
     std::vector<InnerProb> reqs; std::vector<ReqTag> tags; std::vector<InnerOut> outs; std::vector<IcpState> icps; std::vector<int> icpOwner;
     goicp_status s;
+    auto tl = clk::now();
     for (;;) {
         while ((int)active.size() < slots) { const int i = next.fetch_add(1); if (i >= np) break; reset_search(h->probs[i]); active.push_back(i); }
         if (active.empty()) break;
@@ -720,8 +758,10 @@ static goicp_status register_group(Eng* h, WaveCtx& c, const BnbCfg& cfg, std::a
         active.erase(std::remove_if(active.begin(), active.end(), [&](int i) { return h->probs[i].phase == PH_DONE; }), active.end());
         if (reqs.empty() && icps.empty()) continue;
         c.waves++;
+        c.tLogic += secs_since(tl);
         if ((s = run_inner(h, c, cfg, reqs, outs))) return s;
-        if ((s = run_icp(h, c, icps))) return s;
+        { auto ti = clk::now(); if ((s = run_icp(h, c, icps))) return s; c.tIcp += secs_since(ti); }
+        tl = clk::now();
         for (size_t k = 0; k < tags.size(); k++) {
             Problem& P = h->probs[tags[k].prob];
             CallRes r; r.entryOpt = tags[k].entryOpt; r.err = outs[k].err; memcpy(r.tn, outs[k].node, sizeof r.tn); r.pops = outs[k].pops; r.subcubes = outs[k].subcubes;
@@ -791,6 +831,7 @@ static goicp_status register_all(Eng* h) {
             WaveCtx* w = h->workers[g].get();
             w->ctaCap = std::max(64, 2 * h->numSM * cfg.perSM / groups);
             memset(w->ms, 0, sizeof w->ms); memset(w->launches, 0, sizeof w->launches); w->waves = w->callsLaunched = 0;
+            w->tLogic = w->tInnerEnq = w->tInnerWait = w->tIcp = 0;
             th.emplace_back([h, w, &cfg, &next, &st, g]() { cudaSetDevice(h->device); st[g] = register_group(h, *w, cfg, next, h->slots); });
         }
         for (auto& t : th) t.join();
@@ -799,12 +840,14 @@ static goicp_status register_all(Eng* h) {
             WaveCtx* w = h->workers[g].get();
             for (int k = 0; k < 5; k++) { h->main.ms[k] += w->ms[k]; h->main.launches[k] += w->launches[k]; }
             h->main.waves += w->waves; h->main.callsLaunched += w->callsLaunched;
+            h->main.tLogic += w->tLogic; h->main.tInnerEnq += w->tInnerEnq; h->main.tInnerWait += w->tInnerWait; h->main.tIcp += w->tIcp;
         }
     }
     const double dt = secs_since(t0);
     for (auto& P : h->probs) P.t_reg = dt / std::max(1, np);
     long long used = 0; for (auto& P : h->probs) used += P.cnt[0];
     h->stats[0] = (double)h->main.waves; h->stats[1] = (double)h->main.callsLaunched; h->stats[2] = (double)used; h->stats[3] = groups; h->stats[4] = dt;
+    h->stats[5] = h->main.tInnerEnq; h->stats[6] = h->main.tInnerWait; h->stats[7] = h->main.tIcp;
     return GOICP_OK;
 }
 
@@ -1099,7 +1142,7 @@ goicp_status goicp_register(goicp_handle h, goicp_result* out) {
     goicp_status s; if ((s = ensure_single(h))) return s;
     cudaSetDevice(h->device);
     Problem& P = h->probs[0];
-    memset(h->main.ms, 0, sizeof h->main.ms); memset(h->main.launches, 0, sizeof h->main.launches); h->main.waves = h->main.callsLaunched = 0;
+    memset(h->main.ms, 0, sizeof h->main.ms); memset(h->main.launches, 0, sizeof h->main.launches); h->main.waves = h->main.callsLaunched = 0; h->main.tLogic = h->main.tInnerEnq = h->main.tInnerWait = h->main.tIcp = 0;
     if (!P.dt_built) { const int nd = P.Nd; if ((s = goicp_build_dt(h, nullptr))) return s; P.Nd = nd; }
     if ((s = register_all(h))) return s;
     h->trace = P.trace;
@@ -1130,7 +1173,7 @@ goicp_status goicp_batch_run(goicp_handle h, goicp_result* results) {
     if (!h || !results) return GOICP_ERR_ARG;
     if (h->probs.empty()) return fail(h, GOICP_ERR_ARG, "batch_run before batch_upload");
     cudaSetDevice(h->device);
-    memset(h->main.ms, 0, sizeof h->main.ms); memset(h->main.launches, 0, sizeof h->main.launches); h->main.waves = h->main.callsLaunched = 0;
+    memset(h->main.ms, 0, sizeof h->main.ms); memset(h->main.launches, 0, sizeof h->main.launches); h->main.waves = h->main.callsLaunched = 0; h->main.tLogic = h->main.tInnerEnq = h->main.tInnerWait = h->main.tIcp = 0;
     goicp_status s;
     if ((s = build_dt_all(h, h->use_dt_replay && h->params.distTransSize <= 32))) return s;
     if ((s = register_all(h))) return s;

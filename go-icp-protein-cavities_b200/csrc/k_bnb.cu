@@ -92,7 +92,7 @@ template <bool EXACT>
 __global__ void __launch_bounds__(BNB_THREADS)
 inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* __restrict__ probs, InnerOut* __restrict__ outs,
                  int nprob, int* __restrict__ counter, HeapEnt* __restrict__ heaps, int heapCap,
-                 float* __restrict__ gscratch, size_t gstride, int NdP, int NdQ, int useSmem) {
+                 float* gscratch, size_t gstride, int NdP, int NdQ, int useSmem) {   // gscratch is exchanged between threads: no __restrict__
     extern __shared__ float4 dyn_smem4[];
     __shared__ BnbShared sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -107,7 +107,10 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* __restrict_
         if (tid == 0) sh.prob = atomicAdd(counter, 1);
         __syncthreads();
         const int p = sh.prob;
-        if (p >= nprob) return;
+        if (p >= nprob) {   // the last CTA to leave re-arms the counters, so the host never has to memset them
+            if (tid == 0) { __threadfence(); if (atomicAdd(counter + 1, 1) == (int)gridDim.x - 1) { counter[0] = 0; counter[1] = 0; } }
+            return;
+        }
         const InnerProb pr = probs[p];
         const PairDev& P = pairs[pr.pair];
         const GridDev& g = P.g;

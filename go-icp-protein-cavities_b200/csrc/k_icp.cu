@@ -308,14 +308,18 @@ icp_score_kernel(const PairDev* __restrict__ pairs, IcpState* __restrict__ state
 // ---- small problems: the whole GoICP::ICP call (begin, every ICP3D::Run iteration, DT re-score) in ONE launch, one CTA per
 //      request; the model cloud is tiled through shared memory for the exact nearest-neighbour pass ---------------------
 __global__ void __launch_bounds__(256)
-icp_fused_kernel(const PairDev* __restrict__ pairs, IcpState* __restrict__ states) {
-    IcpState& st = states[blockIdx.x];
+icp_fused_kernel(const PairDev* __restrict__ pairs, IcpState* states) {
+    // `states` may live in mapped host memory: the request is staged in shared memory and written back once at the end
+    __shared__ IcpState st;
+    const int tid = threadIdx.x;
+    if (tid == 0) st = states[blockIdx.x];
+    __syncthreads();
     const PairDev& P = pairs[st.pair];
-    const int Nd = P.Nd, Nm = P.Nm, tid = threadIdx.x;
+    const int Nd = P.Nd, Nm = P.Nm;
     __shared__ float sx[NN_TILE], sy[NN_TILE], sz[NN_TILE];
     icp_begin_part(P, st);
     __syncthreads();
-    if (st.mode == 2) return;
+    if (st.mode == 2) { if (tid == 0) states[blockIdx.x] = st; return; }
     if (st.mode == 0) {
         for (;;) {
             const float r00 = (float)st.R[0], r01 = (float)st.R[1], r02 = (float)st.R[2], r10 = (float)st.R[3], r11 = (float)st.R[4],
@@ -350,9 +354,11 @@ icp_fused_kernel(const PairDev* __restrict__ pairs, IcpState* __restrict__ state
             __syncthreads();
             if (done) break;
         }
-        if (st.status != 0) return;
+        if (st.status != 0) { if (tid == 0) states[blockIdx.x] = st; return; }
     }
     icp_score_part(P, st);
+    __syncthreads();
+    if (tid == 0) states[blockIdx.x] = st;
 }
 
 }  // namespace

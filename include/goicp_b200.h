@@ -152,7 +152,8 @@ goicp_status goicp_get_timings(goicp_handle h, float* ms5, int64_t* launches5);
  * lock-step waves and pulling the next pair from a shared counter when one finishes (bo1_GoICP.py:40-54 is serial). */
 goicp_status goicp_set_batch_options(goicp_handle h, int32_t groups, int32_t slots);
 /* search statistics of the last register / batch_run: out[0] waves, [1] InnerBnB calls launched (incl. speculative),
- * [2] InnerBnB calls the reference order consumed, [3] worker streams, [4] host seconds of the search, [5..7] reserved */
+ * [2] InnerBnB calls the reference order consumed, [3] worker streams, [4] host seconds of the search,
+ * [5..7] host seconds summed over worker streams: InnerBnB enqueue, InnerBnB wait, ICP launches */
 goicp_status goicp_get_stats(goicp_handle h, double* out8);
 
 /* ---- Transformation (transformation.cpp), per-pair pre/post-processing -------------------------------- */
