@@ -213,7 +213,8 @@ struct goicp_handle_s {
     int device = 0; cudaStream_t stream = nullptr; bool ownStream = false; int numSM = 148;
     goicp_params params; bool haveParams = false;
     int exact_sums = 1, spec_width = 32, use_dt_replay = 1;
-    int groups = 0, slots = 4;   // batch: worker streams (0 = auto) and pairs advanced in lock-step per stream
+    int groups = 0, slots = 32;
+    int bnb_threads = 512;   // threads per InnerBnB CTA (256..1024): more threads = shorter pops, fewer resident calls   // batch: worker streams (0 = auto) and pairs advanced in lock-step per stream
     std::vector<Problem> probs;
     DevBuf arenaIn, arenaWork, dPairs, dTmp, dTmp2, dTmp3, dSepBits, dSepNx, dSepNxy;
     PinBuf hStage, hPairs;
@@ -461,7 +462,7 @@ static goicp_status initialize_all(Eng* h) {
 }
 
 // ---- one launch of InnerBnB calls (handles heap overflow by re-running the overflowed calls with larger heaps) -------
-struct BnbCfg { int NdP, NdQ; size_t smemFloats; int useSmem, perSM; };
+struct BnbCfg { int NdP, NdQ; size_t smemFloats; int useSmem, perSM, threads; };
 static BnbCfg bnb_config(Eng* h) {
     int maxNd = 1; bool anyTrim = false, anyF = false;
     for (auto& P : h->probs) { maxNd = std::max(maxNd, P.Nd); anyTrim |= P.dev.doTrim != 0; anyF |= P.dev.use_fpfh != 0; }
@@ -471,7 +472,8 @@ static BnbCfg bnb_config(Eng* h) {
     c.smemFloats = goicp_bnb_smem_floats(c.NdP, c.NdQ, needMd, needFp);
     const size_t smemBytes = c.smemFloats * sizeof(float);
     c.useSmem = smemBytes <= 200 * 1024;
-    c.perSM = goicp_inner_bnb_occupancy(c.useSmem ? smemBytes : 0, h->exact_sums);
+    c.threads = h->bnb_threads;
+    c.perSM = goicp_inner_bnb_occupancy(c.useSmem ? smemBytes : 0, h->exact_sums, c.threads);
     return c;
 }
 static goicp_status run_inner(Eng* h, WaveCtx& c, const BnbCfg& cfg, std::vector<InnerProb>& reqs, std::vector<InnerOut>& outs) {
@@ -497,7 +499,7 @@ static goicp_status run_inner(Eng* h, WaveCtx& c, const BnbCfg& cfg, std::vector
         int launched = 0;
         CU(goicp_launch_inner_bnb(h->dPairs.as<PairDev>(), reinterpret_cast<const InnerProb*>(c.mProbs.d), reinterpret_cast<InnerOut*>(c.mOuts.d), m, c.dCounter.as<int>(),
                                   c.dHeaps.as<HeapEnt>(), heapCap, ctas, c.dBnbScratch.as<float>(), cfg.smemFloats, cfg.NdP, cfg.NdQ, cfg.smemFloats, cfg.useSmem,
-                                  h->exact_sums, c.stream, &launched));
+                                  h->exact_sums, cfg.threads, c.stream, &launched));
         cudaEventRecord(c.ev1, c.stream);
         c.tInnerEnq += secs_since(tq); tq = clk::now();
         CU(c.sync());
@@ -1190,6 +1192,7 @@ goicp_status goicp_set_batch_options(goicp_handle h, int32_t groups, int32_t slo
     if (!h) return GOICP_ERR_ARG;
     if (groups >= 0) h->groups = groups;
     if (slots >= 1) h->slots = slots;
+    { const char* e = getenv("GOICP_BNB_THREADS"); if (e) { int t = atoi(e); if (t >= 256 && t <= 1024 && t % 32 == 0) h->bnb_threads = t; } }
     return GOICP_OK;
 }
 goicp_status goicp_get_stats(goicp_handle h, double* out8) {

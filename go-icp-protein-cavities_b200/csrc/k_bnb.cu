@@ -17,61 +17,68 @@
 
 namespace {
 
-constexpr int BNB_THREADS = 256;
+constexpr int BNB_MAX_THREADS = 1024;
 
 // TRANSNODE operator< (jly_goicp.h:79-86)
 __device__ __forceinline__ bool node_less(const HeapEnt& a, const HeapEnt& b) {
     if (a.lb != b.lb) return a.lb > b.lb;
     return a.w < b.w;
 }
-__device__ __forceinline__ void ent_store(HeapEnt* h, int i, const HeapEnt& e) {
-    float4* p = reinterpret_cast<float4*>(h + i);
-    p[0] = make_float4(e.lb, e.w, e.x, e.y);
-    p[1] = make_float4(e.z, 0.f, 0.f, 0.f);
-}
-__device__ __forceinline__ HeapEnt ent_load(const HeapEnt* h, int i) {
-    const float4* p = reinterpret_cast<const float4*>(h + i);
-    float4 a = p[0], b = p[1];
-    HeapEnt e; e.lb = a.x; e.w = a.y; e.x = a.z; e.y = a.w; e.z = b.x; e.pad0 = e.pad1 = e.pad2 = 0.f;
-    return e;
-}
+// The translation queue: entries [0, HEAP_SMEM) live in shared memory (the levels every pop walks), the rest in the
+// CTA's global slab.  Only thread 0 touches it.
+constexpr int HEAP_SMEM = 256;
+struct Heap {
+    float4* s;       // shared: 2 x float4 per entry
+    HeapEnt* g;      // global slab
+    __device__ __forceinline__ void store(int i, const HeapEnt& e) const {
+        float4* p = (i < HEAP_SMEM) ? s + 2 * i : reinterpret_cast<float4*>(g + i);
+        p[0] = make_float4(e.lb, e.w, e.x, e.y);
+        p[1] = make_float4(e.z, 0.f, 0.f, 0.f);
+    }
+    __device__ __forceinline__ HeapEnt load(int i) const {
+        const float4* p = (i < HEAP_SMEM) ? s + 2 * i : reinterpret_cast<const float4*>(g + i);
+        const float4 a = p[0], b = p[1];
+        HeapEnt e; e.lb = a.x; e.w = a.y; e.x = a.z; e.y = a.w; e.z = b.x; e.pad0 = e.pad1 = e.pad2 = 0.f;
+        return e;
+    }
+};
 // std::push_heap (__push_heap) on h[0..n) + val
-__device__ void heap_push(HeapEnt* h, int& n, const HeapEnt& val) {
+__device__ __forceinline__ void heap_push(const Heap& h, int& n, const HeapEnt& val) {
     int hole = n++;
     int parent = (hole - 1) / 2;
     while (hole > 0) {
-        HeapEnt pe = ent_load(h, parent);
+        const HeapEnt pe = h.load(parent);
         if (!node_less(pe, val)) break;
-        ent_store(h, hole, pe);
+        h.store(hole, pe);
         hole = parent; parent = (hole - 1) / 2;
     }
-    ent_store(h, hole, val);
+    h.store(hole, val);
 }
 // std::pop_heap (__adjust_heap to the bottom, then __push_heap of the former last element)
-__device__ HeapEnt heap_pop(HeapEnt* h, int& n) {
-    HeapEnt top = ent_load(h, 0);
+__device__ __forceinline__ HeapEnt heap_pop(const Heap& h, int& n) {
+    const HeapEnt top = h.load(0);
     const int len = --n;
     if (len > 0) {
-        HeapEnt val = ent_load(h, len);
+        const HeapEnt val = h.load(len);
         int hole = 0, child = 0;
         while (child < (len - 1) / 2) {
             child = 2 * (child + 1);
-            HeapEnt c1 = ent_load(h, child), c0 = ent_load(h, child - 1);
+            HeapEnt c1 = h.load(child); const HeapEnt c0 = h.load(child - 1);
             if (node_less(c1, c0)) { child--; c1 = c0; }
-            ent_store(h, hole, c1); hole = child;
+            h.store(hole, c1); hole = child;
         }
         if ((len & 1) == 0 && child == (len - 2) / 2) {
             child = 2 * (child + 1);
-            ent_store(h, hole, ent_load(h, child - 1)); hole = child - 1;
+            h.store(hole, h.load(child - 1)); hole = child - 1;
         }
         int parent = (hole - 1) / 2;
         while (hole > 0) {
-            HeapEnt pe = ent_load(h, parent);
+            const HeapEnt pe = h.load(parent);
             if (!node_less(pe, val)) break;
-            ent_store(h, hole, pe);
+            h.store(hole, pe);
             hole = parent; parent = (hole - 1) / 2;
         }
-        ent_store(h, hole, val);
+        h.store(hole, val);
     }
     return top;
 }
@@ -88,19 +95,26 @@ struct BnbShared {
     float best[4];
 };
 
+// Per pop of the translation queue:
+//   phase A (all warps)  flat list of (child cube | lattice corner) x 32-point chunks, dealt round-robin to the warps;
+//   phase B (warp 0)     the 16 sequential (ub, lb) sums [EXACT] or the fixed-order combine of per-chunk partial sums;
+//                        warp 1 does the 27 c-FPFH corner sums meanwhile; trimmed sums use warps 0..7;
+//   phase C (warp 0)     per-child corner min/max on 8 lanes, then lane 0: decisions, pushes and the next pop.
 template <bool EXACT>
-__global__ void __launch_bounds__(BNB_THREADS)
+__global__ void __launch_bounds__(BNB_MAX_THREADS)
 inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* __restrict__ probs, InnerOut* __restrict__ outs,
                  int nprob, int* __restrict__ counter, HeapEnt* __restrict__ heaps, int heapCap,
                  float* gscratch, size_t gstride, int NdP, int NdQ, int useSmem) {   // gscratch is exchanged between threads: no __restrict__
     extern __shared__ float4 dyn_smem4[];
     __shared__ BnbShared sh;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ float4 sheap[2 * HEAP_SMEM];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = blockDim.x >> 5;
     float* base = useSmem ? reinterpret_cast<float*>(dyn_smem4) : gscratch + (size_t)blockIdx.x * gstride;
     float* tx = base; float* ty = tx + NdP; float* tz = ty + NdP; float* wgt = tz + NdP; float* mrd = wgt + NdP;
-    float* md = mrd + NdP;            // [8][NdQ]   (EXACT or trimmed)
+    float* part = mrd + NdP;          // [8][nchunks][2] + [27][nchunks] per-chunk partial sums (tree-sum mode)
+    float* md = part + 43 * (NdP >> 5);   // [8][NdQ]   (EXACT or trimmed)
     float* fp = md + 8 * NdQ;         // [27][NdQ]  (EXACT with the c-FPFH term)
-    HeapEnt* heap = heaps + (size_t)blockIdx.x * heapCap;
+    Heap heap; heap.s = sheap; heap.g = heaps + (size_t)blockIdx.x * heapCap;
 
     for (;;) {
         __syncthreads();
@@ -115,13 +129,16 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* __restrict_
         const PairDev& P = pairs[pr.pair];
         const GridDev& g = P.g;
         const int Nd = P.Nd;
+        const int nchunks = (Nd + 31) >> 5;
         const float* __restrict__ dist = g.dist;
         const bool corners = P.use_reg || P.use_fpfh;
         const bool useMd = EXACT || P.doTrim;
         const int ncp1 = g.ncells + 1;
+        const int norm = P.norm;
+        const int evalItems = 8 * nchunks, allItems = evalItems + (corners ? 27 * nchunks : 0);
 
         // ---- stage the rotated cloud (jly_goicp.cpp:750-756), weights and rotation radii ---------------------
-        for (int i = tid; i < Nd; i += BNB_THREADS) {
+        for (int i = tid; i < Nd; i += nthreads) {
             const float x = P.dx[i], y = P.dy[i], z = P.dz[i];
             tx[i] = pr.R[0] * x + pr.R[1] * y + pr.R[2] * z;
             ty[i] = pr.R[3] * x + pr.R[4] * y + pr.R[5] * z;
@@ -129,137 +146,160 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* __restrict_
             wgt[i] = P.weights[i];
             mrd[i] = pr.level >= 0 ? P.maxRotDis[(size_t)pr.level * Nd + i] : 0.f;   // d - 0 == d
         }
+        if (tid < 27) sh.cnt[tid] = 0;
         if (tid == 0) {
-            sh.heapN = 0; sh.status = 0; sh.pops = 0; sh.subcubes = 0; sh.improved = 0;
+            sh.heapN = 0; sh.status = 0; sh.pops = 1; sh.subcubes = 0; sh.improved = 0;
             sh.optErrorT = pr.optError;                                              // :297
             sh.best[0] = sh.best[1] = sh.best[2] = sh.best[3] = 0.f;
-            HeapEnt init; init.lb = 0.f; init.w = P.tWidth; init.x = P.tMinX; init.y = P.tMinY; init.z = P.tMinZ;
-            init.pad0 = init.pad1 = init.pad2 = 0.f;
-            heap_push(heap, sh.heapN, init);                                         // :300
+            // the first pop is always the initial node (:300,:314) with lb = 0
+            if (pr.optError - 0.f < P.SSEThresh) sh.running = 0;                     // :317
+            else {
+                sh.running = 1;
+                const float wc = P.tWidth / 2;
+                sh.wc = wc; sh.mtd = (float)(GOICP_SQRT3 / 2.0 * wc);
+                sh.X[0] = P.tMinX; sh.X[1] = P.tMinX + wc; sh.X[2] = sh.X[1] + wc;
+                sh.Y[0] = P.tMinY; sh.Y[1] = P.tMinY + wc; sh.Y[2] = sh.Y[1] + wc;
+                sh.Z[0] = P.tMinZ; sh.Z[1] = P.tMinZ + wc; sh.Z[2] = sh.Z[1] + wc;
+            }
         }
 
         for (;;) {
-            // ---- pop (thread 0) -------------------------------------------------------------------------
-            if (tid == 0) {
-                if (sh.heapN == 0 || sh.status != 0) sh.running = 0;
-                else {
-                    HeapEnt par = heap_pop(heap, sh.heapN);
-                    sh.pops++;
-                    if (sh.optErrorT - par.lb < P.SSEThresh) sh.running = 0;         // :317
-                    else {
-                        sh.running = 1;
-                        const float wc = par.w / 2;                                  // :322
-                        sh.wc = wc;
-                        sh.mtd = (float)(GOICP_SQRT3 / 2.0 * wc);                    // :323
-                        sh.X[0] = par.x; sh.X[1] = par.x + wc; sh.X[2] = sh.X[1] + wc;   // child / corner lattice
-                        sh.Y[0] = par.y; sh.Y[1] = par.y + wc; sh.Y[2] = sh.Y[1] + wc;
-                        sh.Z[0] = par.z; sh.Z[1] = par.z + wc; sh.Z[2] = sh.Z[1] + wc;
-                    }
-                }
-            }
-            __syncthreads();
+            __syncthreads();                                                         // (1) the popped node is visible
             if (!sh.running) break;
             const float wc = sh.wc, mtd = sh.mtd;
+            const float half = wc / 2;
 
-            // ---- the cube.point bound evals: warp = child cube, lane = point (:343-382) -------------------
-            {
-                const int c = warp;
-                const float half = wc / 2;
-                const float transX = sh.X[c & 1] + half, transY = sh.Y[(c >> 1) & 1] + half, transZ = sh.Z[(c >> 2) & 1] + half;
-                float su = 0.f, sl = 0.f;
-                for (int i = lane; i < Nd; i += 32) {
-                    float d = wgt[i] * dt_distance(g, dist, tx[i] + transX, ty[i] + transY, tz[i] + transZ);
-                    d = d - mrd[i];
-                    if (d < 0.f) d = 0.f;
-                    if (useMd) md[c * NdQ + i] = d;
-                    else {
-                        su += (P.norm == 2) ? d * d : d;
-                        const float dis = d - mtd;
-                        if (dis > 0.f) sl += (P.norm == 2) ? dis * dis : dis;
+            // ---- phase A ---------------------------------------------------------------------------------------
+            for (int it = warp; it < allItems; it += nwarps) {
+                if (it < evalItems) {   // the cube.point bound evals (:343-382)
+                    const int c = it / nchunks, ch = it - c * nchunks, i = (ch << 5) + lane;
+                    const float transX = sh.X[c & 1] + half, transY = sh.Y[(c >> 1) & 1] + half, transZ = sh.Z[(c >> 2) & 1] + half;   // :331-333
+                    float su = 0.f, sl = 0.f;
+                    if (i < Nd) {
+                        float d = wgt[i] * dt_distance(g, dist, tx[i] + transX, ty[i] + transY, tz[i] + transZ);
+                        d = d - mrd[i];
+                        if (d < 0.f) d = 0.f;
+                        if (useMd) md[c * NdQ + i] = d;
+                        else {
+                            su = (norm == 2) ? d * d : d;
+                            const float dis = d - mtd;
+                            if (dis > 0.f) sl = (norm == 2) ? dis * dis : dis;
+                        }
                     }
-                }
-                if (!useMd) {
-                    su = warp_sum(su); sl = warp_sum(sl);
-                    if (lane == 0) { sh.ub[c] = su; sh.lb[c] = sl; }
-                }
-            }
-            // ---- corner terms on the 3x3x3 lattice of child-cube corners (:431-550, checkCompatibilities :919,
-            //      sumFPFH :1689); pure functions of the corner, so the reference's memo is not needed ----------
-            if (corners) {
-                for (int c = warp; c < 27; c += 8) {
+                    if (!useMd) {
+                        su = warp_sum(su); sl = warp_sum(sl);
+                        if (lane == 0) { part[2 * it] = su; part[2 * it + 1] = sl; }
+                    }
+                } else {   // corner terms on the 3x3x3 lattice of child-cube corners (:431-550, checkCompatibilities :919,
+                           // sumFPFH :1689); pure functions of the corner, so the reference's memo is not needed
+                    const int k = it - evalItems;
+                    const int c = k / nchunks, ch = k - c * nchunks, i = (ch << 5) + lane;
                     const float cx = sh.X[c % 3], cy = sh.Y[(c / 3) % 3], cz = sh.Z[c / 9];
-                    int bad = 0; float fs = 0.f;
-                    for (int i = lane; i < Nd; i += 32) {
+                    int bad = 0; float fv = 0.f;
+                    if (i < Nd) {
                         const int cell = clamp_cell(g, tx[i] + cx, ty[i] + cy, tz[i] + cz);
-                        if (P.use_reg) bad += ((__ldg(g.cmask + cell) >> P.dprop[i]) & 1u) ? 0 : 1;
+                        if (P.use_reg) bad = ((__ldg(g.cmask + cell) >> P.dprop[i]) & 1u) ? 0 : 1;
                         if (P.use_fpfh) {
-                            const float v = __ldg(P.fpfhD + (size_t)i * ncp1 + cell);
-                            if (EXACT) fp[c * NdQ + i] = v; else fs += v;
+                            fv = __ldg(P.fpfhD + (size_t)i * ncp1 + cell);
+                            if (EXACT) fp[c * NdQ + i] = fv;
                         }
                     }
-                    bad = warp_sum_i(bad);
-                    if (!EXACT) fs = warp_sum(fs);
-                    if (lane == 0) {
-                        sh.cnt[c] = bad;
-                        if (!EXACT) sh.cf[c] = (float)(int)(fs / (float)Nd);       // int truncation (H7)
-                    }
+                    if (P.use_reg) { bad = warp_sum_i(bad); if (lane == 0 && bad) atomicAdd(&sh.cnt[c], bad); }
+                    if (!EXACT && P.use_fpfh) { fv = warp_sum(fv); if (lane == 0) part[16 * nchunks + k] = fv; }
                 }
             }
-            __syncthreads();
-            // ---- sums ---------------------------------------------------------------------------------------
-            if (useMd) {
-                if (P.doTrim) {   // radix select replaces intro_select (:384-390); one warp per child
+            __syncthreads();                                                         // (2)
+            // ---- phase B ---------------------------------------------------------------------------------------
+            if (P.doTrim) {   // radix select replaces intro_select (:384-390); one warp per child
+                if (warp < 8) {
                     float su, sl;
-                    warp_trimmed_sums(md + warp * NdQ, Nd, P.inlierNum, lane, P.norm, mtd, &su, &sl);
+                    warp_trimmed_sums(md + warp * NdQ, Nd, P.inlierNum, lane, norm, mtd, &su, &sl);
                     if (lane == 0) { sh.ub[warp] = su; sh.lb[warp] = sl; }
-                } else if (warp == 0 && lane < 16) {
-                    // sequential float sums in index order (:393-415): lane = (child, ub|lb); 16 independent chains
-                    const int c = lane >> 1; const float off = (lane & 1) ? mtd : 0.f;
-                    const float* m = md + c * NdQ;
-                    float acc = 0.f;
-                    const int n = P.inlierNum;
-                    if (P.norm == 2) { for (int i = 0; i < n; ++i) { float v = fmaxf(m[i] - off, 0.f); acc = acc + v * v; } }
-                    else            { for (int i = 0; i < n; ++i) { float v = fmaxf(m[i] - off, 0.f); acc = acc + v; } }
-                    if (lane & 1) sh.lb[c] = acc; else sh.ub[c] = acc;
                 }
+                __syncthreads();
             }
-            if (EXACT && corners && P.use_fpfh && warp == 1 && lane < 27) {
-                const float* f = fp + lane * NdQ;
-                float s = 0.f;
-                for (int i = 0; i < Nd; ++i) s = s + f[i];                        // sumFPFH :1692-1695
-                sh.cf[lane] = (float)(int)(s / (float)Nd);                         // :1696, int truncation :468,:495
+            if (warp == 1 && P.use_fpfh) {
+                if (lane < 27) {
+                    float s_ = 0.f;
+                    if (EXACT) { const float* f = fp + lane * NdQ; for (int i = 0; i < Nd; ++i) s_ = s_ + f[i]; }   // sumFPFH :1692-1695
+                    else { const float* f = part + 16 * nchunks + lane * nchunks; for (int k = 0; k < nchunks; ++k) s_ = s_ + f[k]; }
+                    sh.cf[lane] = (float)(int)(s_ / (float)Nd);                       // :1696, int truncation :468,:495 (H7)
+                }
+                __syncwarp();
+                asm volatile("bar.sync 1, 64;" ::: "memory");
             }
-            __syncthreads();
-            // ---- decisions and pushes in child order (thread 0, :417-575) -----------------------------------
-            if (tid == 0) {
-                float optErrorT = sh.optErrorT;
-                for (int j = 0; j < 8; ++j) {
-                    float ub = sh.ub[j], lb = sh.lb[j];
-                    const int jx = j & 1, jy = (j >> 1) & 1, jz = (j >> 2) & 1;
-                    if (corners) {
-                        int minI = 0, maxI = 0; float minF = 0.f, maxF = 0.f;
-                        for (int k = 0; k < 8; ++k) {
-                            const int c = (jx + (k & 1)) + 3 * (jy + ((k >> 1) & 1)) + 9 * (jz + ((k >> 2) & 1));
-                            if (P.use_fpfh) { const float f = sh.cf[c]; if (k == 0) { minF = maxF = f; } else { if (f > maxF) maxF = f; if (f < minF) minF = f; } }
-                            if (P.use_reg) { const int n = sh.cnt[c]; if (k == 0) { minI = maxI = n; } else { if (n > maxI) maxI = n; if (n < minI) minI = n; } }
-                        }
-                        if (P.use_reg) { ub = ub + P.reg * (float)(maxI * maxI); lb = lb + P.reg * (float)(minI * minI); }      // :536-538
-                        if (P.use_fpfh) { ub = ub + P.regF * (maxF * maxF); lb = lb + P.regF * (minF * minF); }                  // :546-549
+            if (warp != 0) continue;
+            if (!P.doTrim && lane < 16) {
+                const int c = lane >> 1;
+                float acc = 0.f;
+                if (EXACT) {   // sequential float sums in index order (:393-415): lane = (child, ub|lb); 16 independent chains
+                    const float off = (lane & 1) ? mtd : 0.f;
+                    const float* m = md + c * NdQ;
+                    const int n = P.inlierNum;
+                    if (norm == 2) {
+#pragma unroll 4
+                        for (int i = 0; i < n; ++i) { const float v = fmaxf(m[i] - off, 0.f); acc = acc + v * v; }
+                    } else {
+#pragma unroll 4
+                        for (int i = 0; i < n; ++i) { const float v = fmaxf(m[i] - off, 0.f); acc = acc + v; }
                     }
-                    sh.subcubes++;
-                    const float nx = sh.X[jx], ny = sh.Y[jy], nz = sh.Z[jz];
+                } else {
+                    const float* q = part + 2 * c * nchunks + (lane & 1);
+                    for (int k = 0; k < nchunks; ++k) acc = acc + q[2 * k];
+                }
+                if (lane & 1) sh.lb[c] = acc; else sh.ub[c] = acc;
+            }
+            __syncwarp();
+            if (P.use_fpfh) asm volatile("bar.sync 1, 64;" ::: "memory");
+            // ---- phase C: corner min/max per child on 8 lanes (:431-550), then lane 0 alone -------------------------
+            if (corners && lane < 8) {
+                const int j = lane, jx = j & 1, jy = (j >> 1) & 1, jz = (j >> 2) & 1;
+                float ub = sh.ub[j], lb = sh.lb[j];
+                int minI = 0, maxI = 0; float minF = 0.f, maxF = 0.f;
+                for (int k = 0; k < 8; ++k) {
+                    const int c = (jx + (k & 1)) + 3 * (jy + ((k >> 1) & 1)) + 9 * (jz + ((k >> 2) & 1));
+                    if (P.use_fpfh) { const float f = sh.cf[c]; if (k == 0) { minF = maxF = f; } else { if (f > maxF) maxF = f; if (f < minF) minF = f; } }
+                    if (P.use_reg) { const int n = sh.cnt[c]; if (k == 0) { minI = maxI = n; } else { if (n > maxI) maxI = n; if (n < minI) minI = n; } }
+                }
+                if (P.use_reg) { ub = ub + P.reg * (float)(maxI * maxI); lb = lb + P.reg * (float)(minI * minI); }      // :536-538
+                if (P.use_fpfh) { ub = ub + P.regF * (maxF * maxF); lb = lb + P.regF * (minF * minF); }                  // :546-549
+                sh.ub[j] = ub; sh.lb[j] = lb;
+            }
+            __syncwarp();
+            if (lane < 27) sh.cnt[lane] = 0;                                         // re-armed for the next pop's atomics
+            if (lane == 0) {   // decisions and pushes in child order (:417-575), then the next pop (:314-320)
+                float optErrorT = sh.optErrorT;
+                int heapN = sh.heapN;
+                for (int j = 0; j < 8; ++j) {
+                    const float ub = sh.ub[j], lb = sh.lb[j];
+                    const float nx = sh.X[j & 1], ny = sh.Y[(j >> 1) & 1], nz = sh.Z[(j >> 2) & 1];
                     if (ub < optErrorT) {                                                                                         // :554-566
                         optErrorT = ub; sh.improved = 1;
                         sh.best[0] = nx; sh.best[1] = ny; sh.best[2] = nz; sh.best[3] = wc;
                     }
                     if (lb >= optErrorT) continue;                                                                                // :568-572
-                    if (sh.heapN >= heapCap) { sh.status = 4; break; }
+                    if (heapN >= heapCap) { sh.status = 4; break; }
                     HeapEnt e; e.lb = lb; e.w = wc; e.x = nx; e.y = ny; e.z = nz; e.pad0 = e.pad1 = e.pad2 = 0.f;
-                    heap_push(heap, sh.heapN, e);
+                    heap_push(heap, heapN, e);
                 }
+                sh.subcubes += 8;
                 sh.optErrorT = optErrorT;
+                if (heapN == 0 || sh.status != 0) sh.running = 0;
+                else {
+                    const HeapEnt par = heap_pop(heap, heapN);
+                    sh.pops++;
+                    if (optErrorT - par.lb < P.SSEThresh) sh.running = 0;            // :317
+                    else {
+                        const float w2 = par.w / 2;                                  // :322
+                        sh.wc = w2;
+                        sh.mtd = (float)(GOICP_SQRT3 / 2.0 * w2);                    // :323
+                        sh.X[0] = par.x; sh.X[1] = par.x + w2; sh.X[2] = sh.X[1] + w2;   // child / corner lattice
+                        sh.Y[0] = par.y; sh.Y[1] = par.y + w2; sh.Y[2] = sh.Y[1] + w2;
+                        sh.Z[0] = par.z; sh.Z[1] = par.z + w2; sh.Z[2] = sh.Z[1] + w2;
+                    }
+                }
+                sh.heapN = heapN;
             }
-            // thread 0 continues straight into the next pop; the barrier at the loop head orders it with the others
         }
         if (tid == 0) {
             InnerOut o;
@@ -342,14 +382,14 @@ eval_bounds_kernel(const PairDev* __restrict__ pairs, int pair, const float* __r
 
 // ---- launchers ---------------------------------------------------------------------------------------------
 size_t goicp_bnb_smem_floats(int NdP, int NdQ, bool needMd, bool needFp) {
-    return (size_t)5 * NdP + (needMd ? (size_t)8 * NdQ : 0) + (needFp ? (size_t)27 * NdQ : 0);
+    return (size_t)5 * NdP + (size_t)43 * (NdP >> 5) + (needMd ? (size_t)8 * NdQ : 0) + (needFp ? (size_t)27 * NdQ : 0);
 }
 
 static int g_bnb_attr_set[2] = {0, 0};
 
 cudaError_t goicp_launch_inner_bnb(const PairDev* pairs, const InnerProb* probs, InnerOut* outs, int nprob, int* counter,
                                    HeapEnt* heaps, int heapCap, int maxCtas, float* gscratch, size_t gstride,
-                                   int NdP, int NdQ, size_t smemFloats, int useSmem, int exact, cudaStream_t st, int* ctasLaunched) {
+                                   int NdP, int NdQ, size_t smemFloats, int useSmem, int exact, int threads, cudaStream_t st, int* ctasLaunched) {
     if (nprob <= 0) { if (ctasLaunched) *ctasLaunched = 0; return cudaSuccess; }
     const size_t smem = useSmem ? smemFloats * sizeof(float) : 0;
     auto kern = exact ? inner_bnb_kernel<true> : inner_bnb_kernel<false>;
@@ -360,18 +400,18 @@ cudaError_t goicp_launch_inner_bnb(const PairDev* pairs, const InnerProb* probs,
     }
     int grid = nprob < maxCtas ? nprob : maxCtas;
     if (ctasLaunched) *ctasLaunched = grid;
-    kern<<<grid, BNB_THREADS, smem, st>>>(pairs, probs, outs, nprob, counter, heaps, heapCap, gscratch, gstride, NdP, NdQ, useSmem);
+    kern<<<grid, threads, smem, st>>>(pairs, probs, outs, nprob, counter, heaps, heapCap, gscratch, gstride, NdP, NdQ, useSmem);
     return cudaGetLastError();
 }
 
-int goicp_inner_bnb_occupancy(size_t smemBytes, int exact) {
+int goicp_inner_bnb_occupancy(size_t smemBytes, int exact, int threads) {
     auto kern = exact ? inner_bnb_kernel<true> : inner_bnb_kernel<false>;
     if (!g_bnb_attr_set[exact ? 1 : 0]) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return 1;
         g_bnb_attr_set[exact ? 1 : 0] = 1;
     }
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, BNB_THREADS, smemBytes) != cudaSuccess || n < 1) n = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, smemBytes) != cudaSuccess || n < 1) n = 1;
     return n;
 }
 

@@ -6,10 +6,10 @@
 
 // k_bnb.cu
 size_t goicp_bnb_smem_floats(int NdP, int NdQ, bool needMd, bool needFp);
-int goicp_inner_bnb_occupancy(size_t smemBytes, int exact);
+int goicp_inner_bnb_occupancy(size_t smemBytes, int exact, int threads);
 cudaError_t goicp_launch_inner_bnb(const PairDev* pairs, const InnerProb* probs, InnerOut* outs, int nprob, int* counter,
                                    HeapEnt* heaps, int heapCap, int maxCtas, float* gscratch, size_t gstride,
-                                   int NdP, int NdQ, size_t smemFloats, int useSmem, int exact, cudaStream_t st, int* ctasLaunched);
+                                   int NdP, int NdQ, size_t smemFloats, int useSmem, int exact, int threads, cudaStream_t st, int* ctasLaunched);
 cudaError_t goicp_launch_eval_bounds(const PairDev* pairs, int pair, const float* Rs, const int* levels, const WaveCube* cubes,
                                      int nt, float* ub, float* lb, int* incomp_mm, int* fpfh_mm, float* scratch, int nwarps,
                                      cudaStream_t st);
