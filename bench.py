@@ -37,11 +37,11 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--pairs", type=int, default=256, help="cavity pairs per GPU per step")
+    ap.add_argument("--pairs", type=int, default=1024, help="cavity pairs per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--exact", type=int, default=1, help="1: reference-identical sequential float sums; 0: warp-tree sums")
     ap.add_argument("--fpfh", type=int, default=0, help="1: add the c-FPFH term (cfpfh=1, regularizationFPFH=5e-6)")
-    ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs in the CPU-baseline sample (0: one per core, at least 8)")
+    ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs in the CPU-baseline sample (0: two per core, at least 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=4096)
     ap.add_argument("--groups", type=int, default=-1, help="worker streams per GPU (-1: library default)")
@@ -129,7 +129,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        n = args.cpu_pairs or max(8, cores)
+        n = args.cpu_pairs or max(8, 2 * cores)
         pairs = synth.bo1_pairs(n, seed=args.seed)
         vals = []
         for _ in range(args.warmup):
@@ -249,7 +249,7 @@ def main():
             "rank0_last_step": {"gpu_ms_sum_over_streams": {"dt": last_tm["ms"][0], "initialize": last_tm["ms"][1], "inner_bnb": last_tm["ms"][2], "icp": last_tm["ms"][3]},
                                 "launches": last_tm["launches"], **last_stats}}
     if not args.no_cpu_baseline and world == 1:
-        n = args.cpu_pairs or max(8, cores)
+        n = args.cpu_pairs or max(8, 2 * cores)
         v, dt, kind, errs = cpu_arm(pairs[:n], args.fpfh, cores)
         same = all(np.float32(e) == np.float32(r["optError"]) for e, r in zip(errs, res[:n]))
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "seconds": dt,

@@ -40,6 +40,23 @@ __device__ __forceinline__ float dt_distance_d(const GridDev& g, double dx, doub
     return (float)((double)sqrtf(a * a + b * b + c * c) / g.scale + (double)g.dist[(z * S + y) * S + x]);
 }
 
+// register-argument forms of the two lookups for the hot loop (grid constants hoisted out of the PairDev)
+__device__ __forceinline__ float dt_distance_v(int S, double x0, double y0, double z0, double scale, const float* __restrict__ dist, float fx, float fy, float fz) {
+    int x = vox_round(fx, x0, scale), y = vox_round(fy, y0, scale), z = vox_round(fz, z0, scale);
+    if ((unsigned)x < (unsigned)S && (unsigned)y < (unsigned)S && (unsigned)z < (unsigned)S)
+        return __ldg(dist + ((z * S + y) * S + x));
+    float a = 0.f, b = 0.f, c = 0.f;
+    if (x < 0) { a = (float)x; x = 0; } else if (x >= S) { a = (float)(x - S + 1); x = S - 1; }
+    if (y < 0) { b = (float)y; y = 0; } else if (y >= S) { b = (float)(y - S + 1); y = S - 1; }
+    if (z < 0) { c = (float)z; z = 0; } else if (z >= S) { c = (float)(z - S + 1); z = S - 1; }
+    return (float)((double)sqrtf(a * a + b * b + c * c) / scale + (double)__ldg(dist + ((z * S + y) * S + x)));
+}
+__device__ __forceinline__ int clamp_cell_v(int S, double x0, double y0, double z0, double scale, const int* __restrict__ vcell, float fx, float fy, float fz) {
+    int x = vox_round(fx, x0, scale), y = vox_round(fy, y0, scale), z = vox_round(fz, z0, scale);
+    x = min(max(x, 0), S - 1); y = min(max(y, 0), S - 1); z = min(max(z, 0), S - 1);
+    return __ldg(vcell + ((z * S + y) * S + x));
+}
+
 // checkCompatibility's voxel (jly_goicp.cpp:976-984): same rounding, clamped INTO the grid; returns the compact id
 // of the closest occupied cell (emptyCells), ncells if that voxel is unresolved.
 __device__ __forceinline__ int clamp_cell(const GridDev& g, float fx, float fy, float fz) {

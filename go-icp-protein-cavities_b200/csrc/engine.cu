@@ -213,8 +213,9 @@ struct goicp_handle_s {
     int device = 0; cudaStream_t stream = nullptr; bool ownStream = false; int numSM = 148;
     goicp_params params; bool haveParams = false;
     int exact_sums = 1, spec_width = 32, use_dt_replay = 1;
-    int groups = 0, slots = 32;
-    int bnb_threads = 512;   // threads per InnerBnB CTA (256..1024): more threads = shorter pops, fewer resident calls   // batch: worker streams (0 = auto) and pairs advanced in lock-step per stream
+    int groups = 0, slots = 0;   // 0 = auto
+    int batch_spec_width = 4;    // speculation width inside a batch (pairs already fill the GPU)
+    int bnb_threads = 256;   // threads per InnerBnB CTA (64..512): more threads = shorter pops, fewer resident calls   // batch: worker streams (0 = auto) and pairs advanced in lock-step per stream
     std::vector<Problem> probs;
     DevBuf arenaIn, arenaWork, dPairs, dTmp, dTmp2, dTmp3, dSepBits, dSepNx, dSepNxy;
     PinBuf hStage, hPairs;
@@ -705,7 +706,8 @@ static void gather_requests(Eng* h, int pi, std::vector<InnerProb>& reqs, std::v
         want(P.par, j, 1, ch, R);
     }
     // the next queue nodes in pop order; width grows while the incumbent stays unchanged
-    int width = std::min(h->spec_width, P.quiet < 30 ? (1 << std::min(P.quiet, 20)) - 1 : h->spec_width);
+    const int specw = h->probs.size() > 1 ? std::min(h->spec_width, h->batch_spec_width) : h->spec_width;
+    int width = std::min(specw, P.quiet < 30 ? (1 << std::min(P.quiet, 20)) - 1 : specw);
     if (width > 0 && !P.q.empty()) {
         std::vector<RNode> top(P.q);
         const int k = std::min<int>(width, (int)top.size());
@@ -812,14 +814,15 @@ static goicp_status register_all(Eng* h) {
     const int np = (int)h->probs.size();
     const BnbCfg cfg = bnb_config(h);
     std::atomic<int> next(0);
-    int groups = 1;
+    int groups = 1, slots = 1;
     if (np > 1) {
-        groups = h->groups > 0 ? h->groups : (int)std::min<unsigned>(32u, std::max(4u, 2 * std::thread::hardware_concurrency()));
-        groups = std::min(groups, (np + h->slots - 1) / h->slots);
+        groups = h->groups > 0 ? h->groups : (int)std::min<unsigned>(32u, std::max(4u, std::thread::hardware_concurrency()));
+        slots = h->slots > 0 ? h->slots : std::min(128, std::max(8, (np + groups - 1) / groups));
+        groups = std::min(groups, (np + slots - 1) / slots);
     }
     if (groups <= 1) {
         h->main.ctaCap = 0;
-        if ((s = register_group(h, h->main, cfg, next, std::max(1, np == 1 ? 1 : h->slots)))) return s;
+        if ((s = register_group(h, h->main, cfg, next, slots))) return s;
     } else {
         while ((int)h->workers.size() < groups) {
             std::unique_ptr<WaveCtx> w(new WaveCtx());
@@ -834,7 +837,7 @@ static goicp_status register_all(Eng* h) {
             w->ctaCap = std::max(64, 2 * h->numSM * cfg.perSM / groups);
             memset(w->ms, 0, sizeof w->ms); memset(w->launches, 0, sizeof w->launches); w->waves = w->callsLaunched = 0;
             w->tLogic = w->tInnerEnq = w->tInnerWait = w->tIcp = 0;
-            th.emplace_back([h, w, &cfg, &next, &st, g]() { cudaSetDevice(h->device); st[g] = register_group(h, *w, cfg, next, h->slots); });
+            th.emplace_back([h, w, &cfg, &next, &st, g, slots]() { cudaSetDevice(h->device); st[g] = register_group(h, *w, cfg, next, slots); });
         }
         for (auto& t : th) t.join();
         for (int g = 0; g < groups; g++) if (st[g]) return st[g];
@@ -1191,8 +1194,8 @@ goicp_status goicp_register_batch(goicp_handle h, const goicp_params* p, int32_t
 goicp_status goicp_set_batch_options(goicp_handle h, int32_t groups, int32_t slots) {
     if (!h) return GOICP_ERR_ARG;
     if (groups >= 0) h->groups = groups;
-    if (slots >= 1) h->slots = slots;
-    { const char* e = getenv("GOICP_BNB_THREADS"); if (e) { int t = atoi(e); if (t >= 256 && t <= 1024 && t % 32 == 0) h->bnb_threads = t; } }
+    if (slots >= 0) h->slots = slots;
+    { const char* e = getenv("GOICP_BNB_THREADS"); if (e) { int t = atoi(e); if (t >= 64 && t <= 512 && t % 32 == 0) h->bnb_threads = t; } }
     return GOICP_OK;
 }
 goicp_status goicp_get_stats(goicp_handle h, double* out8) {

@@ -17,7 +17,7 @@
 
 namespace {
 
-constexpr int BNB_MAX_THREADS = 1024;
+constexpr int BNB_MAX_THREADS = 512;
 
 // TRANSNODE operator< (jly_goicp.h:79-86)
 __device__ __forceinline__ bool node_less(const HeapEnt& a, const HeapEnt& b) {
@@ -101,7 +101,7 @@ struct BnbShared {
 //                        warp 1 does the 27 c-FPFH corner sums meanwhile; trimmed sums use warps 0..7;
 //   phase C (warp 0)     per-child corner min/max on 8 lanes, then lane 0: decisions, pushes and the next pop.
 template <bool EXACT>
-__global__ void __launch_bounds__(BNB_MAX_THREADS)
+__global__ void __launch_bounds__(BNB_MAX_THREADS, 2)
 inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* __restrict__ probs, InnerOut* __restrict__ outs,
                  int nprob, int* __restrict__ counter, HeapEnt* __restrict__ heaps, int heapCap,
                  float* gscratch, size_t gstride, int NdP, int NdQ, int useSmem) {   // gscratch is exchanged between threads: no __restrict__
@@ -111,7 +111,8 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* __restrict_
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = blockDim.x >> 5;
     float* base = useSmem ? reinterpret_cast<float*>(dyn_smem4) : gscratch + (size_t)blockIdx.x * gstride;
     float* tx = base; float* ty = tx + NdP; float* tz = ty + NdP; float* wgt = tz + NdP; float* mrd = wgt + NdP;
-    float* part = mrd + NdP;          // [8][nchunks][2] + [27][nchunks] per-chunk partial sums (tree-sum mode)
+    uint8_t* dprop_s = reinterpret_cast<uint8_t*>(mrd + NdP);   // [NdP] colour index of each data point
+    float* part = mrd + NdP + (NdP >> 2);   // [8][nchunks][2] + [27][nchunks] per-chunk partial sums (tree-sum mode)
     float* md = part + 43 * (NdP >> 5);   // [8][NdQ]   (EXACT or trimmed)
     float* fp = md + 8 * NdQ;         // [27][NdQ]  (EXACT with the c-FPFH term)
     Heap heap; heap.s = sheap; heap.g = heaps + (size_t)blockIdx.x * heapCap;
@@ -136,6 +137,13 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* __restrict_
         const int ncp1 = g.ncells + 1;
         const int norm = P.norm;
         const int evalItems = 8 * nchunks, allItems = evalItems + (corners ? 27 * nchunks : 0);
+        // per-problem constants in registers (the PairDev lives in global memory)
+        const int S = g.S;
+        const double gx0 = g.xMin, gy0 = g.yMin, gz0 = g.zMin, gscale = g.scale;
+        const int* __restrict__ vcell = g.vcell;
+        const uint32_t* __restrict__ cmask = g.cmask;
+        const float* __restrict__ fpfhD = P.fpfhD;
+        const bool use_reg = P.use_reg != 0, use_fpfh = P.use_fpfh != 0;
 
         // ---- stage the rotated cloud (jly_goicp.cpp:750-756), weights and rotation radii ---------------------
         for (int i = tid; i < Nd; i += nthreads) {
@@ -145,6 +153,7 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* __restrict_
             tz[i] = pr.R[6] * x + pr.R[7] * y + pr.R[8] * z;
             wgt[i] = P.weights[i];
             mrd[i] = pr.level >= 0 ? P.maxRotDis[(size_t)pr.level * Nd + i] : 0.f;   // d - 0 == d
+            dprop_s[i] = P.dprop[i];
         }
         if (tid < 27) sh.cnt[tid] = 0;
         if (tid == 0) {
@@ -170,51 +179,60 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* __restrict_
             const float half = wc / 2;
 
             // ---- phase A ---------------------------------------------------------------------------------------
-            for (int it = warp; it < allItems; it += nwarps) {
-                if (it < evalItems) {   // the cube.point bound evals (:343-382)
-                    const int c = it / nchunks, ch = it - c * nchunks, i = (ch << 5) + lane;
-                    const float transX = sh.X[c & 1] + half, transY = sh.Y[(c >> 1) & 1] + half, transZ = sh.Z[(c >> 2) & 1] + half;   // :331-333
-                    float su = 0.f, sl = 0.f;
-                    if (i < Nd) {
-                        float d = wgt[i] * dt_distance(g, dist, tx[i] + transX, ty[i] + transY, tz[i] + transZ);
-                        d = d - mrd[i];
-                        if (d < 0.f) d = 0.f;
-                        if (useMd) md[c * NdQ + i] = d;
-                        else {
-                            su = (norm == 2) ? d * d : d;
-                            const float dis = d - mtd;
-                            if (dis > 0.f) sl = (norm == 2) ? dis * dis : dis;
+            // item `it` = (row, chunk): rows 0..7 are the child cubes, rows 8..34 the lattice corners; (row, chunk) advance
+            // incrementally (no integer division in the loop)
+            {
+                int row = 0, ch = warp;
+                while (ch >= nchunks) { ch -= nchunks; ++row; }
+                for (int it = warp; it < allItems; it += nwarps) {
+                    const int i = (ch << 5) + lane;
+                    if (row < 8) {   // the cube.point bound evals (:343-382)
+                        const int c = row;
+                        const float transX = sh.X[c & 1] + half, transY = sh.Y[(c >> 1) & 1] + half, transZ = sh.Z[(c >> 2) & 1] + half;   // :331-333
+                        float su = 0.f, sl = 0.f;
+                        if (i < Nd) {
+                            float d = wgt[i] * dt_distance_v(S, gx0, gy0, gz0, gscale, dist, tx[i] + transX, ty[i] + transY, tz[i] + transZ);
+                            d = d - mrd[i];
+                            if (d < 0.f) d = 0.f;
+                            if (useMd) md[c * NdQ + i] = d;
+                            else {
+                                su = (norm == 2) ? d * d : d;
+                                const float dis = d - mtd;
+                                if (dis > 0.f) sl = (norm == 2) ? dis * dis : dis;
+                            }
                         }
-                    }
-                    if (!useMd) {
-                        su = warp_sum(su); sl = warp_sum(sl);
-                        if (lane == 0) { part[2 * it] = su; part[2 * it + 1] = sl; }
-                    }
-                } else {   // corner terms on the 3x3x3 lattice of child-cube corners (:431-550, checkCompatibilities :919,
-                           // sumFPFH :1689); pure functions of the corner, so the reference's memo is not needed
-                    const int k = it - evalItems;
-                    const int c = k / nchunks, ch = k - c * nchunks, i = (ch << 5) + lane;
-                    const float cx = sh.X[c % 3], cy = sh.Y[(c / 3) % 3], cz = sh.Z[c / 9];
-                    int bad = 0; float fv = 0.f;
-                    if (i < Nd) {
-                        const int cell = clamp_cell(g, tx[i] + cx, ty[i] + cy, tz[i] + cz);
-                        if (P.use_reg) bad = ((__ldg(g.cmask + cell) >> P.dprop[i]) & 1u) ? 0 : 1;
-                        if (P.use_fpfh) {
-                            fv = __ldg(P.fpfhD + (size_t)i * ncp1 + cell);
-                            if (EXACT) fp[c * NdQ + i] = fv;
+                        if (!useMd) {
+                            su = warp_sum(su); sl = warp_sum(sl);
+                            if (lane == 0) { part[2 * it] = su; part[2 * it + 1] = sl; }
                         }
+                    } else {   // corner terms on the 3x3x3 lattice of child-cube corners (:431-550, checkCompatibilities :919,
+                               // sumFPFH :1689); pure functions of the corner, so the reference's memo is not needed
+                        const int c = row - 8;
+                        const int cz_ = c / 9, cy_ = (c - 9 * cz_) / 3, cx_ = c - 9 * cz_ - 3 * cy_;
+                        const float cx = sh.X[cx_], cy = sh.Y[cy_], cz = sh.Z[cz_];
+                        int bad = 0; float fv = 0.f;
+                        if (i < Nd) {
+                            const int cell = clamp_cell_v(S, gx0, gy0, gz0, gscale, vcell, tx[i] + cx, ty[i] + cy, tz[i] + cz);
+                            if (use_reg) bad = ((__ldg(cmask + cell) >> dprop_s[i]) & 1u) ? 0 : 1;
+                            if (use_fpfh) {
+                                fv = __ldg(fpfhD + (size_t)i * ncp1 + cell);
+                                if (EXACT) fp[c * NdQ + i] = fv;
+                            }
+                        }
+                        if (use_reg) { bad = warp_sum_i(bad); if (lane == 0 && bad) atomicAdd(&sh.cnt[c], bad); }
+                        if (!EXACT && use_fpfh) { fv = warp_sum(fv); if (lane == 0) part[16 * nchunks + (it - evalItems)] = fv; }
                     }
-                    if (P.use_reg) { bad = warp_sum_i(bad); if (lane == 0 && bad) atomicAdd(&sh.cnt[c], bad); }
-                    if (!EXACT && P.use_fpfh) { fv = warp_sum(fv); if (lane == 0) part[16 * nchunks + k] = fv; }
+                    ch += nwarps;
+                    while (ch >= nchunks) { ch -= nchunks; ++row; }
                 }
             }
             __syncthreads();                                                         // (2)
             // ---- phase B ---------------------------------------------------------------------------------------
             if (P.doTrim) {   // radix select replaces intro_select (:384-390); one warp per child
-                if (warp < 8) {
+                for (int c = warp; c < 8; c += nwarps) {
                     float su, sl;
-                    warp_trimmed_sums(md + warp * NdQ, Nd, P.inlierNum, lane, norm, mtd, &su, &sl);
-                    if (lane == 0) { sh.ub[warp] = su; sh.lb[warp] = sl; }
+                    warp_trimmed_sums(md + c * NdQ, Nd, P.inlierNum, lane, norm, mtd, &su, &sl);
+                    if (lane == 0) { sh.ub[c] = su; sh.lb[c] = sl; }
                 }
                 __syncthreads();
             }
@@ -382,7 +400,7 @@ eval_bounds_kernel(const PairDev* __restrict__ pairs, int pair, const float* __r
 
 // ---- launchers ---------------------------------------------------------------------------------------------
 size_t goicp_bnb_smem_floats(int NdP, int NdQ, bool needMd, bool needFp) {
-    return (size_t)5 * NdP + (size_t)43 * (NdP >> 5) + (needMd ? (size_t)8 * NdQ : 0) + (needFp ? (size_t)27 * NdQ : 0);
+    return (size_t)5 * NdP + (size_t)(NdP >> 2) + (size_t)43 * (NdP >> 5) + (needMd ? (size_t)8 * NdQ : 0) + (needFp ? (size_t)27 * NdQ : 0);
 }
 
 static int g_bnb_attr_set[2] = {0, 0};

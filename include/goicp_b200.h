@@ -148,8 +148,8 @@ goicp_status goicp_batch_run(goicp_handle h, goicp_result* results);
 /* device-event timings (ms) and launch counts of the last batch_run / register:
  * out[0] dt build, [1] initialize, [2] inner-BnB kernels, [3] ICP kernels, [4] other; launches[0..4] likewise */
 goicp_status goicp_get_timings(goicp_handle h, float* ms5, int64_t* launches5);
-/* batch scheduling: `groups` worker streams (0 = auto: 2 x host cores, at most 32), each advancing `slots` pairs in
- * lock-step waves and pulling the next pair from a shared counter when one finishes (bo1_GoICP.py:40-54 is serial). */
+/* batch scheduling: `groups` worker streams (0 = auto: one per host core, 4..32), each advancing `slots` pairs
+ * (0 = auto: npairs / groups, 8..128) in lock-step waves and pulling the next pair from a shared counter when one finishes (bo1_GoICP.py:40-54 is serial). */
 goicp_status goicp_set_batch_options(goicp_handle h, int32_t groups, int32_t slots);
 /* search statistics of the last register / batch_run: out[0] waves, [1] InnerBnB calls launched (incl. speculative),
  * [2] InnerBnB calls the reference order consumed, [3] worker streams, [4] host seconds of the search,
