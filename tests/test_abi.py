@@ -52,3 +52,9 @@ def test_product_never_touches_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")) or f == "Makefile":
                 assert "oracle" not in open(os.path.join(dp, f)).read().lower(), (dp, f)
+
+
+def test_cpp_dropin_builds(g):
+    """the header-only C++ mirror of the reference classes compiles and links against the C-ABI library"""
+    subprocess.check_call(["make", "-s", "-B", "-C", os.path.join(ROOT, "examples")])
+    assert os.path.exists(os.path.join(ROOT, "examples", "goicp_demo"))

@@ -235,3 +235,32 @@ def test_argument_errors(g):
     reg2.BuildDT()
     with pytest.raises(g.GoICPError):
         reg2.Initialize()                 # ponderation=1 with Nd < 20 never terminates in the reference
+
+
+def test_cpp_dropin_demo(g, tmp_path):
+    """the C++ caller built on include/goicp_dropin.hpp (reference class surface: GoICP, POINT3D, config.txt keys)
+    registers the rand demo clouds (trimFraction 0.1) and prints the reference's optimum"""
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "examples", "goicp_demo")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "examples")])
+    z = golden("rand")
+
+    def dump(path, a):
+        with open(path, "w") as f:
+            f.write("%d\n" % len(a))
+            for p in a:
+                f.write("%.9g %.9g %.9g\n" % (p[0], p[1], p[2]))
+    dump(tmp_path / "model.txt", z["model_xyz"]); dump(tmp_path / "data.txt", z["data_xyz"])
+    (tmp_path / "config.txt").write_text("MSEThresh=0.001\nrotMinX=-3.1416\nrotMinY=-3.1416\nrotMinZ=-3.1416\nrotWidth=6.2832\n"
+                                         "transMinX=-0.5\ntransMinY=-0.5\ntransMinZ=-0.5\ntransWidth=1.0\ntrimFraction=0.1\n"
+                                         "distTransSize=64\ndistTransExpandFactor=2.0\n# no fork terms\nnorm=2\n")
+    out = subprocess.run([exe, str(tmp_path / "model.txt"), str(tmp_path / "data.txt"), "100", str(tmp_path / "config.txt"), str(tmp_path / "out.txt")],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    rows = open(tmp_path / "out.txt").read().split("\n")
+    R = np.array([[float(v) for v in rows[i].split()] for i in (1, 2, 3)])
+    t = np.array([float(rows[i]) for i in (4, 5, 6)])
+    assert np.abs(R - z["exp64_R"]).max() < 1e-5 and np.abs(t - z["exp64_t"]).max() < 1e-5
