@@ -230,9 +230,12 @@ def main():
         pass
     kern_evals_per_gpu = total_evals / world
     achieved = kern_evals_per_gpu * 4 / (kern_ms * 1e-3) / 1e9
+    agg = total_evals / world * 4 / (dev_ms * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": "inner_bnb_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-            "traffic": None, "peak_source": peak_src,
-            "note": "4 algorithmic bytes per eval; S=20 grids are L1/L2-resident, so the binding limit is SM issue (FP64 voxel index math), see DESIGN.md"}
+            "traffic": None, "peak_source": peak_src, "achieved_aggregate": agg, "frac_aggregate": agg / peaks["hbm_gbs"],
+            "note": "4 algorithmic bytes per eval. `achieved` is the per-launch rate (evals x 4 B / summed CUDA-event time of the inner_bnb launches; the worker "
+                    "streams' launches overlap), `achieved_aggregate` = evals x 4 B / step time per GPU. S=20 grids are L1-resident (99 % L1 hit, <1 MB DRAM per "
+                    "launch): the binding limit is SM issue, not HBM -- see DESIGN.md section 4"}
     prof = os.path.join(ROOT, "profiles", "r01_inner_bnb_traffic.json")
     if os.path.exists(prof):
         try:

@@ -133,3 +133,29 @@ if "demo" in which:
     section("bunny S=100 fast", lambda: t_demo("bunny", 100, exact=0))
 if "xform" in which:
     section("transformation", t_xform)
+
+def t_bunny300():
+    z = G("bunny"); nd = int(z["nd"])
+    reg = g.GoICP(z["model_xyz"], z["data_xyz"], g.upstream_config(distTransSize=300))
+    for exact in (1, 0):
+        reg.set_options(exact_sums=exact)
+        t = time.time(); reg.BuildDT(); tdt = time.time() - t; reg.set_nd(nd)
+        t = time.time(); r = reg.Register(); dt = time.time() - t
+        print(f"  bunny S=300 exact={exact}: DT {tdt:.3f}s register {dt:.3f}s optError {r['optError']:.9g} (ref {float(z['exp300_optError']):.9g}) counters {r['counters']} ref {z['exp300_counters'][:6].tolist()} {reg.eng.timings()} {reg.eng.stats()}")
+        print("   trace", g.error_trace(r["trace"]), list(z["exp300_trace"]))
+        print("   dR", np.abs(r["R"] - z["exp300_R"]).max(), "dt", np.abs(r["t"] - z["exp300_t"]).max())
+
+def t_deep():
+    import importlib
+    synth = importlib.import_module("goicp_b200.synth")
+    p = synth.deep_pair()
+    reg = g.GoICP(p["model_xyz"], p["data_xyz"], g.upstream_config(distTransSize=512, MSEThresh=1e-4))
+    reg.set_options(exact_sums=int(os.environ.get("DEEP_EXACT", "0")))
+    t = time.time(); reg.BuildDT(); tdt = time.time() - t
+    t = time.time(); r = reg.Register(); dt = time.time() - t
+    Rt, tt = p["R_true"], p["t_true"]
+    print(f"  deep: DT 512^3 {tdt:.3f}s register {dt:.3f}s optError {r['optError']:.6g} counters {r['counters']} {reg.eng.timings()} {reg.eng.stats()}")
+    print("   |R - R_true|", np.abs(r["R"] - Rt).max(), "|t - t_true|", np.abs(r["t"] - tt).max(), g.error_trace(r["trace"]))
+
+if "bunny300" in which: section("bunny S=300", t_bunny300)
+if "deep" in which: section("deep config #4", t_deep)
