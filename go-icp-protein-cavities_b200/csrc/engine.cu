@@ -15,6 +15,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <atomic>
@@ -46,10 +47,12 @@ static bool known_prop(int p) { for (int k = 0; k < 8; k++) if (KNOWN_PROPS[k] =
 
 #define ROUND_HOST(x) ((int)((x) + 0.5))   // jly_3ddt.cpp:30
 
+static std::atomic<bool> g_no_device_alloc(false);   // set while a persistent kernel is resident: cudaMalloc/cudaFree would dead-lock on it
 struct DevBuf {
     void* p = nullptr; size_t cap = 0;
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
+        if (g_no_device_alloc.load()) return cudaErrorMemoryAllocation;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
         size_t want = bytes + bytes / 4 + 256;
@@ -65,6 +68,7 @@ struct PinBuf {
     void* p = nullptr; size_t cap = 0;
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
+        if (g_no_device_alloc.load()) return cudaErrorMemoryAllocation;
         if (p) cudaFreeHost(p);
         p = nullptr; cap = 0;
         size_t want = bytes * 2 + 256;
@@ -83,6 +87,7 @@ struct MapBuf {
     void* h = nullptr; void* d = nullptr; size_t cap = 0;
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
+        if (g_no_device_alloc.load()) return cudaErrorMemoryAllocation;
         if (h) cudaFreeHost(h);
         h = d = nullptr; cap = 0;
         size_t want = bytes * 2 + 4096;
@@ -158,6 +163,11 @@ struct Problem {
     int nextId = 1, quiet = 0;
     int status = 0;
     double t_dt = 0, t_reg = 0;
+    // persistent-queue mode: requests in flight
+    struct PendReq { int slot; unsigned long long key; float entryOpt; };
+    std::vector<PendReq> pend;
+    std::unordered_set<unsigned long long> inflight;
+    bool icpQueued = false;
     // ICP exchange
     bool icpPending = false; int icpSlot[2] = {-1, -1};
     float icpErr = 0; double icpR[9], icpT[3]; int icpIncomp = 0, compatPose = 0; float initErr = 0;
@@ -220,6 +230,8 @@ struct goicp_handle_s {
     DevBuf arenaIn, arenaWork, dPairs, dTmp, dTmp2, dTmp3, dSepBits, dSepNx, dSepNxy;
     PinBuf hStage, hPairs;
     WaveCtx main;
+    MapBuf qProbs, qOuts, qOrder; DevBuf qClaim, qHeaps, qScratch;   // persistent-queue mode (batches)
+    int persistent = 1;          // batches: 1 = resident kernel + request ring, 0 = one launch per wave
     std::vector<std::unique_ptr<WaveCtx>> workers;
     std::mutex errMutex;
     std::string err, trace;
@@ -639,7 +651,7 @@ static void advance(Eng* h, int pi) {
                 P.optError = r.err;
                 for (int k = 0; k < 9; k++) P.optR[k] = P.R[k];
                 P.optT[0] = r.tn[0] + r.tn[3] / 2; P.optT[1] = r.tn[1] + r.tn[3] / 2; P.optT[2] = r.tn[2] + r.tn[3] / 2;   // float expr -> double
-                P.cache.clear(); P.quiet = 0;
+                P.cache.clear(); P.inflight.clear(); P.quiet = 0;
                 P.phase = PH_WAIT_ICP; P.icpPending = true;
                 return;
             }
@@ -679,7 +691,7 @@ static void finish_improvement(Eng* h, int pi) {
     std::vector<RNode> qn;                                                                             // :843-853
     while (!P.q.empty()) { RNode n = rheap_pop(P.q); if (n.lb < P.optError) rheap_push(qn, n); else break; }
     P.q.swap(qn);
-    P.cache.clear();
+    P.cache.clear(); P.inflight.clear();
     P.phase = PH_CHILD_LB;
 }
 
@@ -692,6 +704,7 @@ static void gather_requests(Eng* h, int pi, std::vector<InnerProb>& reqs, std::v
         const unsigned long long key = call_key(par.id, j, kind);
         auto it = P.cache.find(key);
         if (it != P.cache.end() && it->second.entryOpt == P.optError) return;
+        if (P.inflight.count(key)) return;
         if (!seen.insert(key).second) return;
         // Q2: the reference indexes maxRotDis[level] without a bound check (undefined beyond level 19); we clamp.
         InnerProb ip; ip.pair = pi; ip.level = kind ? std::min(ch.l, GOICP_MAXROTLEVEL - 1) : -1; ip.optError = P.optError;
@@ -724,10 +737,43 @@ static void gather_requests(Eng* h, int pi, std::vector<InnerProb>& reqs, std::v
     P.quiet++;
 }
 
+// results of an ICP / scoring request -> the problem's exchange fields
+static void absorb_icp(Problem& P, const IcpState& st) {
+    if (st.mode == 1) P.initErr = st.error;
+    else if (st.mode == 2) P.compatPose = st.compat_pose;
+    else { P.icpErr = st.error; memcpy(P.icpR, st.R, sizeof P.icpR); memcpy(P.icpT, st.t, sizeof P.icpT); P.icpIncomp = st.incomp; }
+}
+// continue a problem whose ICP results have arrived: start of OuterBnB (:601-664) or post-improvement (:791-854)
+static void after_icp(Eng* h, int i) {
+    const goicp_params& p = h->params;
+    Problem& P = h->probs[i];
+    if (P.phase == PH_WAIT_INIT) {
+        float optError = P.initErr;
+        if (p.regularization > 0) optError += p.regularization * (P.Nd * P.Nd);                       // :623
+        if (p.regularizationFPFH > 0) optError += p.regularizationFPFH * (100 * 8 * 100 * 8);          // :624
+        if (p.regularizationNeighbors > 0) optError += p.regularizationNeighbors * (P.Nd * 6 * P.Nd * 6);
+        P.optError = optError;
+        tracef(P.trace, "Error*: %g (Init)\n", P.optError);
+        P.cnt[5]++;
+        if (P.icpErr < P.optError) {                                                                   // :636-661
+            P.optError = P.icpErr; memcpy(P.optR, P.icpR, sizeof P.optR); memcpy(P.optT, P.icpT, sizeof P.optT);
+            P.optComp = P.icpIncomp;
+            tracef(P.trace, "Error*: %g (ICP)\n", P.icpErr);
+        }
+        RNode root{}; root.a = p.rotMinX; root.b = p.rotMinY; root.c = p.rotMinZ; root.w = p.rotWidth; root.l = 0; root.lb = 0; root.id = 0;
+        rheap_push(P.q, root);
+        P.phase = PH_POP;
+    } else if (P.phase == PH_WAIT_ICP && P.icpPending) {
+        P.icpPending = false;
+        finish_improvement(h, i);
+    }
+}
+
 // Start-of-search state of one problem (GoICP::Initialize :240-241 resets optR/optT)
 static void reset_search(Problem& P) {
     P.phase = PH_START; P.q.clear(); P.cache.clear(); P.trace.clear(); memset(P.cnt, 0, sizeof P.cnt);
-    P.nextId = 1; P.quiet = 0; P.optComp = 0; P.lastLb = 0; P.status = 0; P.icpPending = false;
+    P.nextId = 1; P.quiet = 0; P.optComp = 0; P.lastLb = 0; P.status = 0; P.icpPending = false; P.icpQueued = false;
+    P.pend.clear(); P.inflight.clear();
     for (int k = 0; k < 9; k++) P.optR[k] = (k % 4 == 0);
     P.optT[0] = P.optT[1] = P.optT[2] = 0;
 }
@@ -771,36 +817,196 @@ static goicp_status register_group(Eng* h, WaveCtx& c, const BnbCfg& cfg, std::a
             CallRes r; r.entryOpt = tags[k].entryOpt; r.err = outs[k].err; memcpy(r.tn, outs[k].node, sizeof r.tn); r.pops = outs[k].pops; r.subcubes = outs[k].subcubes;
             P.cache[tags[k].key] = r;
         }
-        for (size_t k = 0; k < icps.size(); k++) {
-            Problem& P = h->probs[icpOwner[k]];
-            const IcpState& st = icps[k];
-            if (st.mode == 1) P.initErr = st.error;
-            else if (st.mode == 2) P.compatPose = st.compat_pose;
-            else { P.icpErr = st.error; memcpy(P.icpR, st.R, sizeof P.icpR); memcpy(P.icpT, st.t, sizeof P.icpT); P.icpIncomp = st.incomp; }
+        for (size_t k = 0; k < icps.size(); k++) absorb_icp(h->probs[icpOwner[k]], icps[k]);
+        for (int i : active) after_icp(h, i);
+    }
+    return GOICP_OK;
+}
+
+
+// ---- persistent-queue scheduler (batches) -----------------------------------------------------------------------------
+// One resident inner_bnb_kernel<.., PERSIST> serves a request ring in mapped host memory for the whole batch; host worker
+// threads advance their pairs INDEPENDENTLY (no lock-step): a pair publishes the InnerBnB calls it needs (+ speculation),
+// keeps going as soon as the call its OuterBnB order waits for has completed, and sends ICP requests through its thread's
+// side stream.  A deep pair therefore delays nobody else, and the GPU always holds a mix of calls of hundreds of pairs.
+struct PQ {
+    InnerProb* probs; InnerOut* outs; volatile unsigned* order; unsigned orderMask;
+    std::atomic<unsigned> reserve{0};
+    void publish(unsigned value) {   // value = slot + 1, or the shut-down marker
+        const unsigned idx = reserve.fetch_add(1);
+        volatile unsigned* cell = order + (idx & orderMask);
+        while (*cell != 0u) std::this_thread::yield();   // ring full: the GPU has not consumed the previous lap yet
+        std::atomic_thread_fence(std::memory_order_release);
+        *cell = value;
+    }
+};
+
+static goicp_status persistent_worker(Eng* h, WaveCtx& c, PQ& pq, std::atomic<int>& next, int slots, int slotLo, int slotHi, const BnbCfg& cfg) {
+    const int np = (int)h->probs.size();
+    std::vector<int> freeSlots; freeSlots.reserve(slotHi - slotLo);
+    for (int sidx = slotHi - 1; sidx >= slotLo; --sidx) freeSlots.push_back(sidx);
+    std::vector<int> active, icpWait, icpOwner;
+    std::vector<Problem::PendReq> zombies;
+    std::vector<InnerProb> reqs; std::vector<ReqTag> tags; std::vector<IcpState> icps;
+    bool icpInFlight = false; int icpN = 0;
+    goicp_status s;
+    Problem dummy;
+    auto lastProgress = clk::now();
+    auto harvest = [&](Problem& P, std::vector<Problem::PendReq>& pend, bool live) {
+        bool any = false;
+        for (size_t k = 0; k < pend.size();) {
+            const InnerOut& o = pq.outs[pend[k].slot];
+            if (*reinterpret_cast<const volatile int*>(&o.done) == 0) { ++k; continue; }
+            std::atomic_thread_fence(std::memory_order_acquire);
+            if (o.status == 4) { P.status = GOICP_ERR_OVERFLOW; }
+            if (live && pend[k].entryOpt == P.optError) {
+                CallRes r; r.entryOpt = pend[k].entryOpt; r.err = o.err; memcpy(r.tn, (const void*)o.node, sizeof r.tn); r.pops = o.pops; r.subcubes = o.subcubes;
+                P.cache[pend[k].key] = r;
+                P.inflight.erase(pend[k].key);
+            }
+            freeSlots.push_back(pend[k].slot);
+            pend[k] = pend.back(); pend.pop_back();
+            any = true;
         }
+        return any;
+    };
+    for (;;) {
+        while ((int)active.size() < slots) { const int i = next.fetch_add(1); if (i >= np) break; reset_search(h->probs[i]); active.push_back(i); }
+        if (active.empty() && zombies.empty() && !icpInFlight) break;
+        bool progressed = false;
+        // ---- ICP batch of this thread finished? ----
+        if (icpInFlight && cudaEventQuery(c.evDone) == cudaSuccess) {
+            float ms = 0; cudaEventElapsedTime(&ms, c.ev0, c.ev1); c.ms[3] += ms; c.launches[3] += 1;
+            const IcpState* ms_ = reinterpret_cast<const IcpState*>(c.mIcp.h);
+            for (int k = 0; k < icpN; k++) { if (ms_[k].status != 0) return fail(h, GOICP_ERR_UNSUPPORTED, "ICP with trimming supports Nd <= 2048"); absorb_icp(h->probs[icpOwner[k]], ms_[k]); }
+            for (int k = 0; k < icpN; k += 2) { h->probs[icpOwner[k]].icpQueued = false; after_icp(h, icpOwner[k]); }
+            icpInFlight = false; progressed = true;
+        }
+        // ---- every active pair: harvest finished calls, advance, publish what it needs next ----
         for (int i : active) {
             Problem& P = h->probs[i];
-            if (P.phase == PH_WAIT_INIT) {
-                float optError = P.initErr;
-                if (p.regularization > 0) optError += p.regularization * (P.Nd * P.Nd);                       // :623
-                if (p.regularizationFPFH > 0) optError += p.regularizationFPFH * (100 * 8 * 100 * 8);          // :624
-                if (p.regularizationNeighbors > 0) optError += p.regularizationNeighbors * (P.Nd * 6 * P.Nd * 6);
-                P.optError = optError;
-                tracef(P.trace, "Error*: %g (Init)\n", P.optError);
-                P.cnt[5]++;
-                if (P.icpErr < P.optError) {                                                                   // :636-661
-                    P.optError = P.icpErr; memcpy(P.optR, P.icpR, sizeof P.optR); memcpy(P.optT, P.icpT, sizeof P.optT);
-                    P.optComp = P.icpIncomp;
-                    tracef(P.trace, "Error*: %g (ICP)\n", P.icpErr);
-                }
-                RNode root{}; root.a = p.rotMinX; root.b = p.rotMinY; root.c = p.rotMinZ; root.w = p.rotWidth; root.l = 0; root.lb = 0; root.id = 0;
-                rheap_push(P.q, root);
-                P.phase = PH_POP;
-            } else if (P.phase == PH_WAIT_ICP && P.icpPending) {
-                P.icpPending = false;
-                finish_improvement(h, i);
+            if (harvest(P, P.pend, true)) progressed = true;
+            if (P.status) return fail(h, GOICP_ERR_OVERFLOW, "translation queue of a call exceeded the resident kernel's heap slab");
+            if (P.phase == PH_START) { P.phase = PH_WAIT_INIT; P.icpQueued = true; icpWait.push_back(i); progressed = true; continue; }
+            if (P.phase == PH_WAIT_INIT || P.phase == PH_WAIT_ICP) { if (!P.icpQueued) { P.icpQueued = true; icpWait.push_back(i); } continue; }
+            const Phase before = P.phase; const int jb = P.j; const int idb = P.par.id;
+            advance(h, i);
+            if (P.phase != before || P.j != jb || P.par.id != idb) progressed = true;
+            if (P.phase == PH_DONE) { for (auto& r : P.pend) zombies.push_back(r); P.pend.clear(); P.inflight.clear(); continue; }
+            if (P.phase == PH_WAIT_ICP) { if (!P.icpQueued) { P.icpQueued = true; icpWait.push_back(i); } continue; }
+            // blocked on an InnerBnB result: is it already on its way?
+            const unsigned long long need = call_key(P.par.id, P.j, P.phase == PH_CHILD_LB ? 1 : 0);
+            if (P.inflight.count(need)) continue;
+            reqs.clear(); tags.clear();
+            gather_requests(h, i, reqs, tags);
+            for (size_t k = 0; k < reqs.size(); k++) {
+                if (freeSlots.empty()) break;   // out of slots: the rest is regathered later
+                const int slot = freeSlots.back(); freeSlots.pop_back();
+                pq.probs[slot] = reqs[k];
+                *reinterpret_cast<volatile int*>(&pq.outs[slot].done) = 0;
+                P.pend.push_back(Problem::PendReq{slot, tags[k].key, tags[k].entryOpt});
+                P.inflight.insert(tags[k].key);
+                pq.publish((unsigned)slot + 1u);
+                c.callsLaunched++;
             }
+            if (!reqs.empty()) { progressed = true; c.waves++; }
         }
+        active.erase(std::remove_if(active.begin(), active.end(), [&](int i) { return h->probs[i].phase == PH_DONE; }), active.end());
+        // ---- results of calls whose pair has already finished (speculation): just recycle the slots ----
+        if (!zombies.empty()) { if (harvest(dummy, zombies, false)) progressed = true; }
+        // ---- start the next ICP batch of this thread ----
+        if (!icpInFlight && !icpWait.empty()) {
+            icps.clear(); icpOwner.clear();
+            bool small = true;
+            for (int i : icpWait) {
+                Problem& P = h->probs[i];
+                icps.push_back(make_icp_state(i, P.phase == PH_WAIT_INIT ? 1 : 2, P.phase == PH_WAIT_INIT ? nullptr : P.optR, P.phase == PH_WAIT_INIT ? nullptr : P.optT)); icpOwner.push_back(i);
+                icps.push_back(make_icp_state(i, 0, P.optR, P.optT)); icpOwner.push_back(i);
+                if ((size_t)P.Nd * P.Nm > ((size_t)1 << 21) || (P.dev.doTrim && P.Nd > 2048)) small = false;
+            }
+            icpWait.clear();
+            icpN = (int)icps.size();
+            if (small) {
+                CU(c.mIcp.ensure(sizeof(IcpState) * icpN));
+                IcpState* ms_ = reinterpret_cast<IcpState*>(c.mIcp.h);
+                for (int k = 0; k < icpN; k++) ms_[k] = icps[k];
+                cudaEventRecord(c.ev0, c.stream);
+                CU(goicp_launch_icp_fused(h->dPairs.as<PairDev>(), reinterpret_cast<IcpState*>(c.mIcp.d), icpN, c.stream));
+                cudaEventRecord(c.ev1, c.stream);
+                CU(cudaEventRecord(c.evDone, c.stream));
+                icpInFlight = true;
+            } else {   // large clouds: the multi-kernel ICP path (blocks this thread only)
+                if ((s = run_icp(h, c, icps))) return s;
+                for (int k = 0; k < icpN; k++) absorb_icp(h->probs[icpOwner[k]], icps[k]);
+                for (int k = 0; k < icpN; k += 2) { h->probs[icpOwner[k]].icpQueued = false; after_icp(h, icpOwner[k]); }
+            }
+            progressed = true;
+        }
+        if (progressed) lastProgress = clk::now();
+        else {
+            if (secs_since(lastProgress) > 45.0) return fail(h, GOICP_ERR_CUDA, "persistent scheduler: no progress for 45 s (device stalled?)");
+            struct timespec ts = {0, 20000}; nanosleep(&ts, nullptr);
+        }
+    }
+    return GOICP_OK;
+}
+
+static goicp_status register_persistent(Eng* h, const BnbCfg& cfg, int groups, int slots) {
+    const int NSLOT = 1 << 17, ORDER = 1 << 18;
+    const int np = (int)h->probs.size();
+    // everything is allocated BEFORE the resident kernel starts (cudaMalloc / cudaFree would wait for it forever)
+    CU(h->qProbs.ensure(sizeof(InnerProb) * (size_t)NSLOT));
+    CU(h->qOuts.ensure(sizeof(InnerOut) * (size_t)NSLOT));
+    CU(h->qOrder.ensure(sizeof(unsigned) * (size_t)ORDER));
+    CU(h->qClaim.ensure(sizeof(unsigned)));
+    const int perSM = std::max(1, std::min(cfg.perSM, 4) - 1);   // leave room on every SM for the ICP kernels of the side streams
+    const int ctas = h->numSM * perSM;
+    const int heapCap = 1 << 15;
+    CU(h->qHeaps.ensure(sizeof(HeapEnt) * (size_t)ctas * heapCap));
+    if (!cfg.useSmem) CU(h->qScratch.ensure(sizeof(float) * cfg.smemFloats * (size_t)ctas));
+    while ((int)h->workers.size() < groups) {
+        std::unique_ptr<WaveCtx> w(new WaveCtx());
+        if (w->init(true, nullptr) != GOICP_OK) return fail(h, GOICP_ERR_CUDA, "worker stream creation failed");
+        h->workers.push_back(std::move(w));
+    }
+    int maxStates = 2 * std::min(np, slots) + 2;
+    for (int g = 0; g < groups; g++) {
+        WaveCtx* w = h->workers[g].get();
+        CU(w->mIcp.ensure(sizeof(IcpState) * (size_t)maxStates));
+        CU(w->dIcp.ensure(sizeof(IcpState) * (size_t)maxStates)); CU(w->hIcp.ensure(sizeof(IcpState) * (size_t)maxStates));
+        memset(w->ms, 0, sizeof w->ms); memset(w->launches, 0, sizeof w->launches); w->waves = w->callsLaunched = 0;
+        w->tLogic = w->tInnerEnq = w->tInnerWait = w->tIcp = 0;
+    }
+    memset(h->qOrder.h, 0, sizeof(unsigned) * (size_t)ORDER);
+    CU(cudaMemsetAsync(h->qClaim.p, 0, sizeof(unsigned), h->stream));
+    PQ pq; pq.probs = reinterpret_cast<InnerProb*>(h->qProbs.h); pq.outs = reinterpret_cast<InnerOut*>(h->qOuts.h);
+    pq.order = reinterpret_cast<volatile unsigned*>(h->qOrder.h); pq.orderMask = ORDER - 1;
+    QueueDev qd; qd.probs = reinterpret_cast<const InnerProb*>(h->qProbs.d); qd.outs = reinterpret_cast<InnerOut*>(h->qOuts.d);
+    qd.order = reinterpret_cast<unsigned*>(h->qOrder.d); qd.orderMask = ORDER - 1; qd.claim = h->qClaim.as<unsigned>();
+    cudaEventRecord(h->main.ev0, h->stream);
+    CU(goicp_launch_inner_bnb_persistent(h->dPairs.as<PairDev>(), qd, h->qHeaps.as<HeapEnt>(), heapCap, ctas, h->qScratch.as<float>(), cfg.smemFloats,
+                                         cfg.NdP, cfg.NdQ, cfg.smemFloats, cfg.useSmem, h->exact_sums, cfg.threads, h->stream));
+    cudaEventRecord(h->main.ev1, h->stream);
+    g_no_device_alloc.store(true);
+    std::atomic<int> next(0);
+    std::vector<goicp_status> st(groups, GOICP_OK);
+    std::vector<std::thread> th;
+    const int per = NSLOT / groups;
+    for (int g = 0; g < groups; g++) {
+        WaveCtx* w = h->workers[g].get();
+        th.emplace_back([h, w, &pq, &next, &st, g, slots, per, &cfg]() { cudaSetDevice(h->device); st[g] = persistent_worker(h, *w, pq, next, slots, g * per, (g + 1) * per, cfg); });
+    }
+    for (auto& t : th) t.join();
+    for (int k = 0; k < ctas; k++) pq.publish(0xFFFFFFFFu);   // one shut-down marker per CTA
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    g_no_device_alloc.store(false);
+    if (e != cudaSuccess) return fail(h, GOICP_ERR_CUDA, "resident inner_bnb kernel: %s", cudaGetErrorString(e));
+    float ms = 0; cudaEventElapsedTime(&ms, h->main.ev0, h->main.ev1); h->main.ms[2] += ms; h->main.launches[2] += 1;
+    for (int g = 0; g < groups; g++) if (st[g]) return st[g];
+    for (int g = 0; g < groups; g++) {
+        WaveCtx* w = h->workers[g].get();
+        h->main.ms[3] += w->ms[3]; h->main.launches[3] += w->launches[3];
+        h->main.waves += w->waves; h->main.callsLaunched += w->callsLaunched;
     }
     return GOICP_OK;
 }
@@ -820,7 +1026,11 @@ static goicp_status register_all(Eng* h) {
         slots = h->slots > 0 ? h->slots : std::min(128, std::max(8, (np + groups - 1) / groups));
         groups = std::min(groups, (np + slots - 1) / slots);
     }
-    if (groups <= 1) {
+    { const char* e = getenv("GOICP_PERSISTENT"); if (e) h->persistent = atoi(e); }
+    if (np > 1 && h->persistent) {
+        if (h->slots <= 0) slots = std::min(512, std::max(8, (np + groups - 1) / groups));
+        if ((s = register_persistent(h, cfg, groups, slots))) return s;
+    } else if (groups <= 1) {
         h->main.ctaCap = 0;
         if ((s = register_group(h, h->main, cfg, next, slots))) return s;
     } else {
@@ -930,7 +1140,7 @@ void goicp_destroy(goicp_handle h) {
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->arenaIn, &h->arenaWork, &h->dPairs, &h->dTmp, &h->dTmp2, &h->dTmp3, &h->dSepBits, &h->dSepNx, &h->dSepNxy};
     for (DevBuf* b : bufs) b->release();
-    h->hStage.release(); h->hPairs.release();
+    h->hStage.release(); h->hPairs.release(); h->qProbs.release(); h->qOuts.release(); h->qOrder.release(); h->qClaim.release(); h->qHeaps.release(); h->qScratch.release();
     h->main.release();
     for (auto& w : h->workers) w->release();
     if (h->ownStream) cudaStreamDestroy(h->stream);

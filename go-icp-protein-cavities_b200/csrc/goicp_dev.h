@@ -69,6 +69,18 @@ struct InnerOut {
     int improved;
     int pops, subcubes;
     int status;             // 0 ok, 4 heap overflow
+    int done;               // persistent-queue mode: set (after a system fence) when the result is complete
+    int pad[2];
+};
+
+// Persistent-queue mode (batches): the host publishes requests by writing slot+1 into order[i % cap] (mapped host memory);
+// CTAs claim indices i from a device counter, wait for their cell, run the call and write outs[slot] + done flag.
+struct QueueDev {
+    const InnerProb* probs;   // mapped host memory, one per slot
+    InnerOut* outs;           // mapped host memory, one per slot
+    unsigned* order;          // mapped host memory ring: 0 = empty, 0xFFFFFFFF = shut down, else slot + 1
+    unsigned orderMask;       // ring capacity - 1 (power of two)
+    unsigned* claim;          // device counter
 };
 
 struct alignas(16) HeapEnt { float lb, w, x, y, z, pad0, pad1, pad2; };   // TRANSNODE without ub (never read, jly_goicp.h:75-87)

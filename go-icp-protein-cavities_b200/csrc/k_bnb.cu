@@ -100,14 +100,17 @@ struct BnbShared {
 //   phase B (warp 0)     the 16 sequential (ub, lb) sums [EXACT] or the fixed-order combine of per-chunk partial sums;
 //                        warp 1 does the 27 c-FPFH corner sums meanwhile; trimmed sums use warps 0..7;
 //   phase C (warp 0)     per-child corner min/max on 8 lanes, then lane 0: decisions, pushes and the next pop.
-template <bool EXACT>
+// PERSIST=false: the calls are probs[0..nprob), claimed through counter[0] (one launch per wave).
+// PERSIST=true : the kernel stays resident for a whole batch and serves the host's request ring `q` (see QueueDev).
+template <bool EXACT, bool PERSIST>
 __global__ void __launch_bounds__(BNB_MAX_THREADS, 2)
-inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* __restrict__ probs, InnerOut* __restrict__ outs,
+inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, InnerOut* outs,
                  int nprob, int* __restrict__ counter, HeapEnt* __restrict__ heaps, int heapCap,
-                 float* gscratch, size_t gstride, int NdP, int NdQ, int useSmem) {   // gscratch is exchanged between threads: no __restrict__
+                 float* gscratch, size_t gstride, int NdP, int NdQ, int useSmem, QueueDev q) {   // gscratch is exchanged between threads: no __restrict__
     extern __shared__ float4 dyn_smem4[];
     __shared__ BnbShared sh;
     __shared__ float4 sheap[2 * HEAP_SMEM];
+    __shared__ InnerProb s_pr;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = blockDim.x >> 5;
     float* base = useSmem ? reinterpret_cast<float*>(dyn_smem4) : gscratch + (size_t)blockIdx.x * gstride;
     float* tx = base; float* ty = tx + NdP; float* tz = ty + NdP; float* wgt = tz + NdP; float* mrd = wgt + NdP;
@@ -119,14 +122,38 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* __restrict_
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) sh.prob = atomicAdd(counter, 1);
+        if (tid == 0) {
+            if (!PERSIST) sh.prob = atomicAdd(counter, 1);
+            else {   // claim the next ring index and wait (with back-off) until the host has published it
+                const unsigned i = atomicAdd(q.claim, 1u);
+                volatile unsigned* cell = q.order + (i & q.orderMask);
+                unsigned v; unsigned backoff = 64;
+                unsigned long long t0 = 0, now;
+                while ((v = *cell) == 0u) {
+                    __nanosleep(backoff); if (backoff < 16384) backoff <<= 1;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                    if (t0 == 0) t0 = now;
+                    else if (now - t0 > 60000000000ull) { v = 0xFFFFFFFFu; break; }   // safety net: 60 s without work -> leave
+                }
+                if (v != 0xFFFFFFFFu) *cell = 0u;   // hand the cell back to the host (shut-down markers stay)
+                __threadfence_system();
+                sh.prob = (v == 0xFFFFFFFFu) ? -1 : (int)(v - 1u);
+            }
+        }
         __syncthreads();
         const int p = sh.prob;
-        if (p >= nprob) {   // the last CTA to leave re-arms the counters, so the host never has to memset them
+        if (PERSIST) { if (p < 0) return; }
+        else if (p >= nprob) {   // the last CTA to leave re-arms the counters, so the host never has to memset them
             if (tid == 0) { __threadfence(); if (atomicAdd(counter + 1, 1) == (int)gridDim.x - 1) { counter[0] = 0; counter[1] = 0; } }
             return;
         }
-        const InnerProb pr = probs[p];
+        // the request may live in mapped host memory: fetch it once per CTA (13 lanes, one 4-byte bus read each)
+        if (tid < (int)(sizeof(InnerProb) / 4)) {
+            const volatile int* src = reinterpret_cast<const volatile int*>((PERSIST ? q.probs : probs) + p);
+            reinterpret_cast<int*>(&s_pr)[tid] = src[tid];
+        }
+        __syncthreads();
+        const InnerProb pr = s_pr;
         const PairDev& P = pairs[pr.pair];
         const GridDev& g = P.g;
         const int Nd = P.Nd;
@@ -322,8 +349,12 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* __restrict_
         if (tid == 0) {
             InnerOut o;
             o.err = sh.optErrorT; o.node[0] = sh.best[0]; o.node[1] = sh.best[1]; o.node[2] = sh.best[2]; o.node[3] = sh.best[3];
-            o.improved = sh.improved; o.pops = sh.pops; o.subcubes = sh.subcubes; o.status = sh.status;
-            outs[p] = o;
+            o.improved = sh.improved; o.pops = sh.pops; o.subcubes = sh.subcubes; o.status = sh.status; o.done = 0; o.pad[0] = o.pad[1] = 0;
+            if (PERSIST) {
+                q.outs[p] = o;
+                __threadfence_system();
+                *reinterpret_cast<volatile int*>(&q.outs[p].done) = 1;
+            } else outs[p] = o;
         }
     }
 }
@@ -403,33 +434,48 @@ size_t goicp_bnb_smem_floats(int NdP, int NdQ, bool needMd, bool needFp) {
     return (size_t)5 * NdP + (size_t)(NdP >> 2) + (size_t)43 * (NdP >> 5) + (needMd ? (size_t)8 * NdQ : 0) + (needFp ? (size_t)27 * NdQ : 0);
 }
 
-static int g_bnb_attr_set[2] = {0, 0};
+static int g_bnb_attr_set[4] = {0, 0, 0, 0};
+typedef void (*bnb_kernel_t)(const PairDev*, const InnerProb*, InnerOut*, int, int*, HeapEnt*, int, float*, size_t, int, int, int, QueueDev);
+static bnb_kernel_t bnb_kernel(int exact, int persist) {
+    if (persist) return exact ? inner_bnb_kernel<true, true> : inner_bnb_kernel<false, true>;
+    return exact ? inner_bnb_kernel<true, false> : inner_bnb_kernel<false, false>;
+}
+static cudaError_t bnb_attr(int exact, int persist) {
+    const int k = (exact ? 1 : 0) + (persist ? 2 : 0);
+    if (g_bnb_attr_set[k]) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(bnb_kernel(exact, persist), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) g_bnb_attr_set[k] = 1;
+    return e;
+}
 
 cudaError_t goicp_launch_inner_bnb(const PairDev* pairs, const InnerProb* probs, InnerOut* outs, int nprob, int* counter,
                                    HeapEnt* heaps, int heapCap, int maxCtas, float* gscratch, size_t gstride,
                                    int NdP, int NdQ, size_t smemFloats, int useSmem, int exact, int threads, cudaStream_t st, int* ctasLaunched) {
     if (nprob <= 0) { if (ctasLaunched) *ctasLaunched = 0; return cudaSuccess; }
     const size_t smem = useSmem ? smemFloats * sizeof(float) : 0;
-    auto kern = exact ? inner_bnb_kernel<true> : inner_bnb_kernel<false>;
-    if (!g_bnb_attr_set[exact ? 1 : 0]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return e;
-        g_bnb_attr_set[exact ? 1 : 0] = 1;
-    }
+    cudaError_t e = bnb_attr(exact, 0);
+    if (e != cudaSuccess) return e;
     int grid = nprob < maxCtas ? nprob : maxCtas;
     if (ctasLaunched) *ctasLaunched = grid;
-    kern<<<grid, threads, smem, st>>>(pairs, probs, outs, nprob, counter, heaps, heapCap, gscratch, gstride, NdP, NdQ, useSmem);
+    QueueDev q{};
+    bnb_kernel(exact, 0)<<<grid, threads, smem, st>>>(pairs, probs, outs, nprob, counter, heaps, heapCap, gscratch, gstride, NdP, NdQ, useSmem, q);
+    return cudaGetLastError();
+}
+
+// the resident kernel of a batch: `ctas` CTAs serve the request ring until each has seen a shut-down marker
+cudaError_t goicp_launch_inner_bnb_persistent(const PairDev* pairs, const QueueDev& q, HeapEnt* heaps, int heapCap, int ctas, float* gscratch, size_t gstride,
+                                              int NdP, int NdQ, size_t smemFloats, int useSmem, int exact, int threads, cudaStream_t st) {
+    const size_t smem = useSmem ? smemFloats * sizeof(float) : 0;
+    cudaError_t e = bnb_attr(exact, 1);
+    if (e != cudaSuccess) return e;
+    bnb_kernel(exact, 1)<<<ctas, threads, smem, st>>>(pairs, nullptr, nullptr, 0, nullptr, heaps, heapCap, gscratch, gstride, NdP, NdQ, useSmem, q);
     return cudaGetLastError();
 }
 
 int goicp_inner_bnb_occupancy(size_t smemBytes, int exact, int threads) {
-    auto kern = exact ? inner_bnb_kernel<true> : inner_bnb_kernel<false>;
-    if (!g_bnb_attr_set[exact ? 1 : 0]) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return 1;
-        g_bnb_attr_set[exact ? 1 : 0] = 1;
-    }
+    if (bnb_attr(exact, 0) != cudaSuccess) return 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, smemBytes) != cudaSuccess || n < 1) n = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bnb_kernel(exact, 0), threads, smemBytes) != cudaSuccess || n < 1) n = 1;
     return n;
 }
 

@@ -307,7 +307,7 @@ icp_score_kernel(const PairDev* __restrict__ pairs, IcpState* __restrict__ state
 
 // ---- small problems: the whole GoICP::ICP call (begin, every ICP3D::Run iteration, DT re-score) in ONE launch, one CTA per
 //      request; the model cloud is tiled through shared memory for the exact nearest-neighbour pass ---------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)   // <= 64 registers: must fit beside the resident inner_bnb CTAs of a batch
 icp_fused_kernel(const PairDev* __restrict__ pairs, IcpState* states) {
     // `states` may live in mapped host memory: the request is staged in shared memory and written back once at the end
     __shared__ IcpState st;

@@ -10,6 +10,8 @@ int goicp_inner_bnb_occupancy(size_t smemBytes, int exact, int threads);
 cudaError_t goicp_launch_inner_bnb(const PairDev* pairs, const InnerProb* probs, InnerOut* outs, int nprob, int* counter,
                                    HeapEnt* heaps, int heapCap, int maxCtas, float* gscratch, size_t gstride,
                                    int NdP, int NdQ, size_t smemFloats, int useSmem, int exact, int threads, cudaStream_t st, int* ctasLaunched);
+cudaError_t goicp_launch_inner_bnb_persistent(const PairDev* pairs, const QueueDev& q, HeapEnt* heaps, int heapCap, int ctas, float* gscratch, size_t gstride,
+                                              int NdP, int NdQ, size_t smemFloats, int useSmem, int exact, int threads, cudaStream_t st);
 cudaError_t goicp_launch_eval_bounds(const PairDev* pairs, int pair, const float* Rs, const int* levels, const WaveCube* cubes,
                                      int nt, float* ub, float* lb, int* incomp_mm, int* fpfh_mm, float* scratch, int nwarps,
                                      cudaStream_t st);
