@@ -168,8 +168,9 @@ struct Problem {
     std::vector<PendReq> pend;
     std::unordered_set<unsigned long long> inflight;
     bool icpQueued = false;
+    int icpSlot[2] = {-1, -1};
     // ICP exchange
-    bool icpPending = false; int icpSlot[2] = {-1, -1};
+    bool icpPending = false;
     float icpErr = 0; double icpR[9], icpT[3]; int icpIncomp = 0, compatPose = 0; float initErr = 0;
 };
 
@@ -183,7 +184,7 @@ static void tracef(std::string& s, const char* fmt, ...) {
 // Everything one stream of waves needs: a worker thread of a batch owns one, the handle's own stream has `main`.
 struct WaveCtx {
     cudaStream_t stream = nullptr; bool ownStream = false;
-    DevBuf dCounter, dHeaps, dBnbScratch, dIcp;
+    DevBuf dCounter, dHeaps, dBnbScratch, dIcp, dMemo;
     PinBuf hIcp;
     MapBuf mProbs, mOuts, mIcp;
     bool counterReady = false;
@@ -209,7 +210,7 @@ struct WaveCtx {
         return cudaEventSynchronize(evDone);
     }
     void release() {
-        DevBuf* bufs[] = {&dCounter, &dHeaps, &dBnbScratch, &dIcp};
+        DevBuf* bufs[] = {&dCounter, &dHeaps, &dBnbScratch, &dIcp, &dMemo};
         for (DevBuf* b : bufs) b->release();
         hIcp.release(); mProbs.release(); mOuts.release(); mIcp.release();
         if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1); if (evDone) cudaEventDestroy(evDone);
@@ -230,7 +231,7 @@ struct goicp_handle_s {
     DevBuf arenaIn, arenaWork, dPairs, dTmp, dTmp2, dTmp3, dSepBits, dSepNx, dSepNxy;
     PinBuf hStage, hPairs;
     WaveCtx main;
-    MapBuf qProbs, qOuts, qOrder; DevBuf qClaim, qHeaps, qScratch;   // persistent-queue mode (batches)
+    MapBuf qProbs, qOuts, qOrder, qIcp; DevBuf qClaim, qHeaps, qScratch, qMemo, dGen;   // persistent-queue mode (batches)
     int persistent = 1;          // batches: 1 = resident kernel + request ring, 0 = one launch per wave
     std::vector<std::unique_ptr<WaveCtx>> workers;
     std::mutex errMutex;
@@ -484,7 +485,7 @@ static BnbCfg bnb_config(Eng* h) {
     const bool needMd = h->exact_sums || anyTrim, needFp = h->exact_sums && anyF;
     c.smemFloats = goicp_bnb_smem_floats(c.NdP, c.NdQ, needMd, needFp);
     const size_t smemBytes = c.smemFloats * sizeof(float);
-    c.useSmem = smemBytes <= 200 * 1024;
+    c.useSmem = smemBytes <= 180 * 1024;   // + ~32 KB static in the resident kernel
     c.threads = h->bnb_threads;
     c.perSM = goicp_inner_bnb_occupancy(c.useSmem ? smemBytes : 0, h->exact_sums, c.threads);
     return c;
@@ -507,12 +508,14 @@ static goicp_status run_inner(Eng* h, WaveCtx& c, const BnbCfg& cfg, std::vector
         const int ctas = std::min(m, maxCtas);
         CU(c.dHeaps.ensure(sizeof(HeapEnt) * (size_t)ctas * heapCap));
         if (!cfg.useSmem) CU(c.dBnbScratch.ensure(sizeof(float) * cfg.smemFloats * (size_t)ctas));
+        const int memoCap = 4096;
+        if (c.dMemo.cap < (size_t)32 * memoCap * ctas) { CU(c.dMemo.ensure((size_t)32 * memoCap * ctas)); CU(cudaMemsetAsync(c.dMemo.p, 0, c.dMemo.cap, c.stream)); }
         auto tq = clk::now();
         cudaEventRecord(c.ev0, c.stream);
         int launched = 0;
         CU(goicp_launch_inner_bnb(h->dPairs.as<PairDev>(), reinterpret_cast<const InnerProb*>(c.mProbs.d), reinterpret_cast<InnerOut*>(c.mOuts.d), m, c.dCounter.as<int>(),
                                   c.dHeaps.as<HeapEnt>(), heapCap, ctas, c.dBnbScratch.as<float>(), cfg.smemFloats, cfg.NdP, cfg.NdQ, cfg.smemFloats, cfg.useSmem,
-                                  h->exact_sums, cfg.threads, c.stream, &launched));
+                                  h->exact_sums, cfg.threads, c.dMemo.p, memoCap, h->dGen.as<unsigned>(), c.stream, &launched));
         cudaEventRecord(c.ev1, c.stream);
         c.tInnerEnq += secs_since(tq); tq = clk::now();
         CU(c.sync());
@@ -845,11 +848,11 @@ static goicp_status persistent_worker(Eng* h, WaveCtx& c, PQ& pq, std::atomic<in
     const int np = (int)h->probs.size();
     std::vector<int> freeSlots; freeSlots.reserve(slotHi - slotLo);
     for (int sidx = slotHi - 1; sidx >= slotLo; --sidx) freeSlots.push_back(sidx);
-    std::vector<int> active, icpWait, icpOwner;
+    std::vector<int> active;
     std::vector<Problem::PendReq> zombies;
-    std::vector<InnerProb> reqs; std::vector<ReqTag> tags; std::vector<IcpState> icps;
-    bool icpInFlight = false; int icpN = 0;
-    goicp_status s;
+    std::vector<InnerProb> reqs; std::vector<ReqTag> tags;
+    IcpState* icpHost = reinterpret_cast<IcpState*>(h->qIcp.h);
+    IcpState* icpDev = reinterpret_cast<IcpState*>(h->qIcp.d);
     Problem dummy;
     auto lastProgress = clk::now();
     auto harvest = [&](Problem& P, std::vector<Problem::PendReq>& pend, bool live) {
@@ -870,35 +873,65 @@ static goicp_status persistent_worker(Eng* h, WaveCtx& c, PQ& pq, std::atomic<in
         }
         return any;
     };
+    // GoICP::ICP requests of pair i: (initial error | updateCompatibilities) + ICP, two CTAs of the resident kernel
+    auto send_icp = [&](int i) -> bool {
+        Problem& P = h->probs[i];
+        if (freeSlots.size() < 2) return false;
+        const bool init = P.phase == PH_WAIT_INIT;
+        icpHost[2 * i] = make_icp_state(i, init ? 1 : 2, init ? nullptr : P.optR, init ? nullptr : P.optT);
+        icpHost[2 * i + 1] = make_icp_state(i, 0, P.optR, P.optT);
+        for (int k = 0; k < 2; k++) {
+            const int slot = freeSlots.back(); freeSlots.pop_back();
+            InnerProb ip; memset(&ip, 0, sizeof ip);
+            ip.pair = i; ip.level = GOICP_REQ_ICP; ip.optError = 0.f;
+            const unsigned long long ptr = (unsigned long long)(uintptr_t)(icpDev + 2 * i + k);
+            const unsigned lo = (unsigned)(ptr & 0xFFFFFFFFull), hi = (unsigned)(ptr >> 32);
+            memcpy(&ip.R[0], &lo, 4); memcpy(&ip.R[1], &hi, 4);
+            pq.probs[slot] = ip;
+            *reinterpret_cast<volatile int*>(&pq.outs[slot].done) = 0;
+            P.icpSlot[k] = slot;
+            pq.publish((unsigned)slot + 1u);
+        }
+        P.icpQueued = true;
+        c.launches[3] += 2;
+        return true;
+    };
     for (;;) {
         while ((int)active.size() < slots) { const int i = next.fetch_add(1); if (i >= np) break; reset_search(h->probs[i]); active.push_back(i); }
-        if (active.empty() && zombies.empty() && !icpInFlight) break;
+        if (active.empty() && zombies.empty()) break;
         bool progressed = false;
-        // ---- ICP batch of this thread finished? ----
-        if (icpInFlight && cudaEventQuery(c.evDone) == cudaSuccess) {
-            float ms = 0; cudaEventElapsedTime(&ms, c.ev0, c.ev1); c.ms[3] += ms; c.launches[3] += 1;
-            const IcpState* ms_ = reinterpret_cast<const IcpState*>(c.mIcp.h);
-            for (int k = 0; k < icpN; k++) { if (ms_[k].status != 0) return fail(h, GOICP_ERR_UNSUPPORTED, "ICP with trimming supports Nd <= 2048"); absorb_icp(h->probs[icpOwner[k]], ms_[k]); }
-            for (int k = 0; k < icpN; k += 2) { h->probs[icpOwner[k]].icpQueued = false; after_icp(h, icpOwner[k]); }
-            icpInFlight = false; progressed = true;
-        }
+        c.callsUsed++;   // loop iterations
+        auto tIter = clk::now();
         // ---- every active pair: harvest finished calls, advance, publish what it needs next ----
         for (int i : active) {
             Problem& P = h->probs[i];
             if (harvest(P, P.pend, true)) progressed = true;
             if (P.status) return fail(h, GOICP_ERR_OVERFLOW, "translation queue of a call exceeded the resident kernel's heap slab");
-            if (P.phase == PH_START) { P.phase = PH_WAIT_INIT; P.icpQueued = true; icpWait.push_back(i); progressed = true; continue; }
-            if (P.phase == PH_WAIT_INIT || P.phase == PH_WAIT_ICP) { if (!P.icpQueued) { P.icpQueued = true; icpWait.push_back(i); } continue; }
+            if (P.phase == PH_START) { P.phase = PH_WAIT_INIT; P.icpQueued = false; }
+            if (P.phase == PH_WAIT_INIT || P.phase == PH_WAIT_ICP) {
+                if (!P.icpQueued) { if (send_icp(i)) progressed = true; continue; }
+                const bool d0 = *reinterpret_cast<const volatile int*>(&pq.outs[P.icpSlot[0]].done) != 0, d1 = *reinterpret_cast<const volatile int*>(&pq.outs[P.icpSlot[1]].done) != 0;
+                if (!(d0 && d1)) continue;
+                std::atomic_thread_fence(std::memory_order_acquire);
+                freeSlots.push_back(P.icpSlot[0]); freeSlots.push_back(P.icpSlot[1]);
+                if (icpHost[2 * i].status != 0 || icpHost[2 * i + 1].status != 0) return fail(h, GOICP_ERR_UNSUPPORTED, "ICP with trimming supports Nd <= 2048");
+                absorb_icp(P, icpHost[2 * i]); absorb_icp(P, icpHost[2 * i + 1]);
+                P.icpQueued = false;
+                after_icp(h, i);
+                progressed = true;
+            }
             const Phase before = P.phase; const int jb = P.j; const int idb = P.par.id;
             advance(h, i);
             if (P.phase != before || P.j != jb || P.par.id != idb) progressed = true;
             if (P.phase == PH_DONE) { for (auto& r : P.pend) zombies.push_back(r); P.pend.clear(); P.inflight.clear(); continue; }
-            if (P.phase == PH_WAIT_ICP) { if (!P.icpQueued) { P.icpQueued = true; icpWait.push_back(i); } continue; }
+            if (P.phase == PH_WAIT_ICP) { P.icpQueued = false; if (send_icp(i)) progressed = true; continue; }
             // blocked on an InnerBnB result: is it already on its way?
             const unsigned long long need = call_key(P.par.id, P.j, P.phase == PH_CHILD_LB ? 1 : 0);
             if (P.inflight.count(need)) continue;
             reqs.clear(); tags.clear();
+            auto tg = clk::now();
             gather_requests(h, i, reqs, tags);
+            c.tLogic += secs_since(tg); tg = clk::now();
             for (size_t k = 0; k < reqs.size(); k++) {
                 if (freeSlots.empty()) break;   // out of slots: the rest is regathered later
                 const int slot = freeSlots.back(); freeSlots.pop_back();
@@ -909,45 +942,29 @@ static goicp_status persistent_worker(Eng* h, WaveCtx& c, PQ& pq, std::atomic<in
                 pq.publish((unsigned)slot + 1u);
                 c.callsLaunched++;
             }
+            c.tInnerEnq += secs_since(tg);
             if (!reqs.empty()) { progressed = true; c.waves++; }
         }
         active.erase(std::remove_if(active.begin(), active.end(), [&](int i) { return h->probs[i].phase == PH_DONE; }), active.end());
         // ---- results of calls whose pair has already finished (speculation): just recycle the slots ----
         if (!zombies.empty()) { if (harvest(dummy, zombies, false)) progressed = true; }
-        // ---- start the next ICP batch of this thread ----
-        if (!icpInFlight && !icpWait.empty()) {
-            icps.clear(); icpOwner.clear();
-            bool small = true;
-            for (int i : icpWait) {
-                Problem& P = h->probs[i];
-                icps.push_back(make_icp_state(i, P.phase == PH_WAIT_INIT ? 1 : 2, P.phase == PH_WAIT_INIT ? nullptr : P.optR, P.phase == PH_WAIT_INIT ? nullptr : P.optT)); icpOwner.push_back(i);
-                icps.push_back(make_icp_state(i, 0, P.optR, P.optT)); icpOwner.push_back(i);
-                if ((size_t)P.Nd * P.Nm > ((size_t)1 << 21) || (P.dev.doTrim && P.Nd > 2048)) small = false;
-            }
-            icpWait.clear();
-            icpN = (int)icps.size();
-            if (small) {
-                CU(c.mIcp.ensure(sizeof(IcpState) * icpN));
-                IcpState* ms_ = reinterpret_cast<IcpState*>(c.mIcp.h);
-                for (int k = 0; k < icpN; k++) ms_[k] = icps[k];
-                cudaEventRecord(c.ev0, c.stream);
-                CU(goicp_launch_icp_fused(h->dPairs.as<PairDev>(), reinterpret_cast<IcpState*>(c.mIcp.d), icpN, c.stream));
-                cudaEventRecord(c.ev1, c.stream);
-                CU(cudaEventRecord(c.evDone, c.stream));
-                icpInFlight = true;
-            } else {   // large clouds: the multi-kernel ICP path (blocks this thread only)
-                if ((s = run_icp(h, c, icps))) return s;
-                for (int k = 0; k < icpN; k++) absorb_icp(h->probs[icpOwner[k]], icps[k]);
-                for (int k = 0; k < icpN; k += 2) { h->probs[icpOwner[k]].icpQueued = false; after_icp(h, icpOwner[k]); }
-            }
-            progressed = true;
-        }
+        c.tIcp += secs_since(tIter);   // busy time of the loop body
         if (progressed) lastProgress = clk::now();
         else {
+            auto ts0 = clk::now();
+            static const bool dbg = getenv("GOICP_DEBUG") != nullptr;
+            if (dbg && secs_since(lastProgress) > 3.0) {
+                std::string m;
+                for (int i : active) { Problem& P = h->probs[i]; char b[160]; snprintf(b, sizeof b, " [pair %d ph %d j %d pend %zu infl %zu icpq %d]", i, (int)P.phase, P.j, P.pend.size(), P.inflight.size(), (int)P.icpQueued); m += b; }
+                fprintf(stderr, "main stream: %s; worker slots %d..%d: active %zu zombies %zu reserve %u free %zu%s\n", cudaGetErrorString(cudaStreamQuery(h->stream)), slotLo, slotHi, active.size(), zombies.size(), pq.reserve.load(), freeSlots.size(), m.c_str());
+                return fail(h, GOICP_ERR_CUDA, "persistent scheduler: debug stop");
+            }
             if (secs_since(lastProgress) > 45.0) return fail(h, GOICP_ERR_CUDA, "persistent scheduler: no progress for 45 s (device stalled?)");
             struct timespec ts = {0, 20000}; nanosleep(&ts, nullptr);
+            c.tInnerWait += secs_since(ts0);
         }
     }
+    (void)cfg; (void)c;
     return GOICP_OK;
 }
 
@@ -959,24 +976,25 @@ static goicp_status register_persistent(Eng* h, const BnbCfg& cfg, int groups, i
     CU(h->qOuts.ensure(sizeof(InnerOut) * (size_t)NSLOT));
     CU(h->qOrder.ensure(sizeof(unsigned) * (size_t)ORDER));
     CU(h->qClaim.ensure(sizeof(unsigned)));
-    const int perSM = std::max(1, std::min(cfg.perSM, 4) - 1);   // leave room on every SM for the ICP kernels of the side streams
-    const int ctas = h->numSM * perSM;
+    CU(h->qIcp.ensure(sizeof(IcpState) * 2 * (size_t)np));
+    int perSM = goicp_inner_bnb_persistent_occupancy(cfg.useSmem ? cfg.smemFloats * sizeof(float) : 0, h->exact_sums, cfg.threads);
+    const int ctas = h->numSM * perSM;   // the resident kernel owns the GPU for the batch: InnerBnB and ICP requests both run on its CTAs
     const int heapCap = 1 << 15;
     CU(h->qHeaps.ensure(sizeof(HeapEnt) * (size_t)ctas * heapCap));
     if (!cfg.useSmem) CU(h->qScratch.ensure(sizeof(float) * cfg.smemFloats * (size_t)ctas));
+    const int memoCap = 8192;
+    if (h->qMemo.cap < (size_t)32 * memoCap * ctas) { CU(h->qMemo.ensure((size_t)32 * memoCap * ctas)); CU(cudaMemsetAsync(h->qMemo.p, 0, h->qMemo.cap, h->stream)); }
     while ((int)h->workers.size() < groups) {
         std::unique_ptr<WaveCtx> w(new WaveCtx());
         if (w->init(true, nullptr) != GOICP_OK) return fail(h, GOICP_ERR_CUDA, "worker stream creation failed");
         h->workers.push_back(std::move(w));
     }
-    int maxStates = 2 * std::min(np, slots) + 2;
     for (int g = 0; g < groups; g++) {
         WaveCtx* w = h->workers[g].get();
-        CU(w->mIcp.ensure(sizeof(IcpState) * (size_t)maxStates));
-        CU(w->dIcp.ensure(sizeof(IcpState) * (size_t)maxStates)); CU(w->hIcp.ensure(sizeof(IcpState) * (size_t)maxStates));
         memset(w->ms, 0, sizeof w->ms); memset(w->launches, 0, sizeof w->launches); w->waves = w->callsLaunched = 0;
-        w->tLogic = w->tInnerEnq = w->tInnerWait = w->tIcp = 0;
+        w->tLogic = w->tInnerEnq = w->tInnerWait = w->tIcp = 0; w->callsUsed = 0;
     }
+    h->main.callsUsed = 0;
     memset(h->qOrder.h, 0, sizeof(unsigned) * (size_t)ORDER);
     CU(cudaMemsetAsync(h->qClaim.p, 0, sizeof(unsigned), h->stream));
     PQ pq; pq.probs = reinterpret_cast<InnerProb*>(h->qProbs.h); pq.outs = reinterpret_cast<InnerOut*>(h->qOuts.h);
@@ -985,7 +1003,7 @@ static goicp_status register_persistent(Eng* h, const BnbCfg& cfg, int groups, i
     qd.order = reinterpret_cast<unsigned*>(h->qOrder.d); qd.orderMask = ORDER - 1; qd.claim = h->qClaim.as<unsigned>();
     cudaEventRecord(h->main.ev0, h->stream);
     CU(goicp_launch_inner_bnb_persistent(h->dPairs.as<PairDev>(), qd, h->qHeaps.as<HeapEnt>(), heapCap, ctas, h->qScratch.as<float>(), cfg.smemFloats,
-                                         cfg.NdP, cfg.NdQ, cfg.smemFloats, cfg.useSmem, h->exact_sums, cfg.threads, h->stream));
+                                         cfg.NdP, cfg.NdQ, cfg.smemFloats, cfg.useSmem, h->exact_sums, cfg.threads, h->qMemo.p, memoCap, h->dGen.as<unsigned>(), h->stream));
     cudaEventRecord(h->main.ev1, h->stream);
     g_no_device_alloc.store(true);
     std::atomic<int> next(0);
@@ -1006,8 +1024,12 @@ static goicp_status register_persistent(Eng* h, const BnbCfg& cfg, int groups, i
     for (int g = 0; g < groups; g++) {
         WaveCtx* w = h->workers[g].get();
         h->main.ms[3] += w->ms[3]; h->main.launches[3] += w->launches[3];
-        h->main.waves += w->waves; h->main.callsLaunched += w->callsLaunched;
+        h->main.waves += w->waves; h->main.callsLaunched += w->callsLaunched; h->main.callsUsed += w->callsUsed;
+        h->main.tLogic += w->tLogic; h->main.tInnerEnq += w->tInnerEnq; h->main.tInnerWait += w->tInnerWait; h->main.tIcp += w->tIcp;
     }
+    { unsigned long long st8[8]; cudaMemcpy(st8, h->dGen.as<char>() + 8, sizeof st8, cudaMemcpyDeviceToHost); cudaMemset(h->dGen.as<char>() + 8, 0, 64);
+      fprintf(stderr, "[device] calls %llu pops %llu busy-cycles/pop %.0f corner-misses/pop %.2f busy CTA-seconds %.3f poll CTA-seconds %.3f (ctas %d)\n", st8[3], st8[1], (double)st8[0] / std::max<double>(1, st8[1]), (double)st8[2] / std::max<double>(1, st8[1]), st8[0] / 1.9e9, st8[4] / 1.9e9, ctas); }
+    fprintf(stderr, "[persistent] loops %lld gather %.3fs publish %.3fs idle-sleep %.3fs loop-busy %.3fs (summed over %d workers)\n", h->main.callsUsed, h->main.tLogic, h->main.tInnerEnq, h->main.tInnerWait, h->main.tIcp, groups);
     return GOICP_OK;
 }
 
@@ -1027,7 +1049,9 @@ static goicp_status register_all(Eng* h) {
         groups = std::min(groups, (np + slots - 1) / slots);
     }
     { const char* e = getenv("GOICP_PERSISTENT"); if (e) h->persistent = atoi(e); }
-    if (np > 1 && h->persistent) {
+    bool allSmall = true;
+    for (auto& P : h->probs) if ((size_t)P.Nd * P.Nm > ((size_t)1 << 21) || (P.dev.doTrim && P.Nd > 2048)) allSmall = false;
+    if (np > 1 && h->persistent && allSmall) {
         if (h->slots <= 0) slots = std::min(512, std::max(8, (np + groups - 1) / groups));
         if ((s = register_persistent(h, cfg, groups, slots))) return s;
     } else if (groups <= 1) {
@@ -1128,6 +1152,10 @@ goicp_status goicp_create(goicp_handle* out, int device, void* stream_or_null) {
     h->device = device; h->numSM = prop.multiProcessorCount;
     if (stream_or_null) { h->stream = (cudaStream_t)stream_or_null; h->ownStream = false; }
     else { if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete h; return fail(nullptr, GOICP_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); } h->ownStream = true; }
+    if ((e = goicp_preload_bnb()) != cudaSuccess || (e = goicp_preload_dt()) != cudaSuccess || (e = goicp_preload_icp()) != cudaSuccess || (e = goicp_preload_misc()) != cudaSuccess) {
+        delete h; return fail(nullptr, GOICP_ERR_CUDA, "kernel preload failed: %s (library built for sm_100a only)", cudaGetErrorString(e));
+    }
+    if (h->dGen.ensure(128) != cudaSuccess || cudaMemset(h->dGen.p, 0, 128) != cudaSuccess) { delete h; return fail(nullptr, GOICP_ERR_CUDA, "device allocation failed"); }
     if (h->main.init(false, h->stream) != GOICP_OK) { delete h; return fail(nullptr, GOICP_ERR_CUDA, "event creation failed"); }
     goicp_params_default(&h->params); h->haveParams = true;
     *out = h;
@@ -1140,7 +1168,7 @@ void goicp_destroy(goicp_handle h) {
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->arenaIn, &h->arenaWork, &h->dPairs, &h->dTmp, &h->dTmp2, &h->dTmp3, &h->dSepBits, &h->dSepNx, &h->dSepNxy};
     for (DevBuf* b : bufs) b->release();
-    h->hStage.release(); h->hPairs.release(); h->qProbs.release(); h->qOuts.release(); h->qOrder.release(); h->qClaim.release(); h->qHeaps.release(); h->qScratch.release();
+    h->hStage.release(); h->hPairs.release(); h->qProbs.release(); h->qOuts.release(); h->qOrder.release(); h->qIcp.release(); h->qClaim.release(); h->qHeaps.release(); h->qScratch.release(); h->qMemo.release(); h->dGen.release();
     h->main.release();
     for (auto& w : h->workers) w->release();
     if (h->ownStream) cudaStreamDestroy(h->stream);

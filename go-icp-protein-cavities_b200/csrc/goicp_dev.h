@@ -10,6 +10,7 @@
 #define GOICP_PI 3.1415926536              // jly_goicp.h:44
 #define GOICP_SQRT3 1.732050808            // jly_goicp.h:45
 #define GOICP_NN_EMPTY 0xFFFFFFFFFFFFFFFFull
+#define GOICP_REQ_ICP (-100)               // InnerProb.level of an ICP request in the resident batch kernel
 
 // DT3D (jly_3ddt.h:123-139) as laid out in HBM: structure-of-arrays, voxel index (z*S+y)*S+x.
 struct GridDev {

@@ -12,7 +12,7 @@
 //
 // The translation priority queue lives in global memory (one slab per CTA) and follows libstdc++'s
 // push_heap/pop_heap step for step so that ties between equal (lb, w) keys pop in the reference's order.
-#include "dev_common.cuh"
+#include "icp_device.cuh"
 #include "launch.h"
 
 namespace {
@@ -26,7 +26,17 @@ __device__ __forceinline__ bool node_less(const HeapEnt& a, const HeapEnt& b) {
 }
 // The translation queue: entries [0, HEAP_SMEM) live in shared memory (the levels every pop walks), the rest in the
 // CTA's global slab.  Only thread 0 touches it.
-constexpr int HEAP_SMEM = 256;
+constexpr int HEAP_SMEM = 128;
+// corner-memo hash: the coordinates are dyadic floats (long runs of trailing zero bits), so mix with rotations and take the
+// HIGH bits of a multiplicative hash
+__device__ __forceinline__ unsigned memo_hash(unsigned kx, unsigned ky, unsigned kz) {
+    unsigned h = kx * 0x9E3779B1u;
+    h = __funnelshift_l(h, h, 13) ^ (ky * 0x85EBCA77u);
+    h = __funnelshift_l(h, h, 11) ^ (kz * 0xC2B2AE3Du);
+    h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15;
+    return h * 0x846CA68Bu;
+}
+__device__ __forceinline__ unsigned memo_slot(unsigned h, int shift) { return h >> shift; }
 struct Heap {
     float4* s;       // shared: 2 x float4 per entry
     HeapEnt* g;      // global slab
@@ -93,6 +103,10 @@ struct BnbShared {
     int running, prob, heapN, status;
     int pops, subcubes, improved;
     float best[4];
+    int missList[27];
+    int nmiss, workCtr;
+    unsigned gen;
+    long long t0; int missTot;
 };
 
 // Per pop of the translation queue:
@@ -102,29 +116,34 @@ struct BnbShared {
 //   phase C (warp 0)     per-child corner min/max on 8 lanes, then lane 0: decisions, pushes and the next pop.
 // PERSIST=false: the calls are probs[0..nprob), claimed through counter[0] (one launch per wave).
 // PERSIST=true : the kernel stays resident for a whole batch and serves the host's request ring `q` (see QueueDev).
-template <bool EXACT, bool PERSIST>
+template <bool EXACT, bool PERSIST, bool SMEM>
 __global__ void __launch_bounds__(BNB_MAX_THREADS, 2)
 inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, InnerOut* outs,
                  int nprob, int* __restrict__ counter, HeapEnt* __restrict__ heaps, int heapCap,
-                 float* gscratch, size_t gstride, int NdP, int NdQ, int useSmem, QueueDev q) {   // gscratch is exchanged between threads: no __restrict__
+                 float* gscratch, size_t gstride, int NdP, int NdQ, int useSmem, QueueDev q,
+                 uint4* memoAll, int memoCap, unsigned* genCounter) {
+    unsigned long long* dstat = reinterpret_cast<unsigned long long*>(genCounter) + 1;   // [0] busy cycles [1] pops [2] corner misses [3] calls [4] poll cycles   // gscratch is exchanged between threads: no __restrict__
     extern __shared__ float4 dyn_smem4[];
     __shared__ BnbShared sh;
     __shared__ float4 sheap[2 * HEAP_SMEM];
     __shared__ InnerProb s_pr;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = blockDim.x >> 5;
-    float* base = useSmem ? reinterpret_cast<float*>(dyn_smem4) : gscratch + (size_t)blockIdx.x * gstride;
+    float* base = SMEM ? reinterpret_cast<float*>(dyn_smem4) : gscratch + (size_t)blockIdx.x * gstride;   // SMEM: address space known -> LDS/STS
     float* tx = base; float* ty = tx + NdP; float* tz = ty + NdP; float* wgt = tz + NdP; float* mrd = wgt + NdP;
     uint8_t* dprop_s = reinterpret_cast<uint8_t*>(mrd + NdP);   // [NdP] colour index of each data point
     float* part = mrd + NdP + (NdP >> 2);   // [8][nchunks][2] + [27][nchunks] per-chunk partial sums (tree-sum mode)
     float* md = part + 43 * (NdP >> 5);   // [8][NdQ]   (EXACT or trimmed)
     float* fp = md + 8 * NdQ;         // [27][NdQ]  (EXACT with the c-FPFH term)
     Heap heap; heap.s = sheap; heap.g = heaps + (size_t)blockIdx.x * heapCap;
+    uint4* memo = memoAll + 2 * (size_t)blockIdx.x * memoCap;
+    const int memoShift = 32 - (31 - __clz(memoCap));   // this CTA's corner memo: direct-mapped, 32 B entries, tagged with the call's generation
 
     for (;;) {
         __syncthreads();
         if (tid == 0) {
             if (!PERSIST) sh.prob = atomicAdd(counter, 1);
             else {   // claim the next ring index and wait (with back-off) until the host has published it
+                const long long tp0 = clock64();
                 const unsigned i = atomicAdd(q.claim, 1u);
                 volatile unsigned* cell = q.order + (i & q.orderMask);
                 unsigned v; unsigned backoff = 64;
@@ -137,6 +156,7 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
                 }
                 if (v != 0xFFFFFFFFu) *cell = 0u;   // hand the cell back to the host (shut-down markers stay)
                 __threadfence_system();
+                atomicAdd(dstat + 4, (unsigned long long)(clock64() - tp0));
                 sh.prob = (v == 0xFFFFFFFFu) ? -1 : (int)(v - 1u);
             }
         }
@@ -154,6 +174,13 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
         }
         __syncthreads();
         const InnerProb pr = s_pr;
+        if (PERSIST && pr.level == GOICP_REQ_ICP) {   // an ICP / scoring request (GoICP::ICP): state pointer packed into R[0..1]
+            IcpState* gst = reinterpret_cast<IcpState*>(((unsigned long long)__float_as_uint(pr.R[1]) << 32) | (unsigned long long)__float_as_uint(pr.R[0]));
+            icp_fused_body(pairs, gst);
+            __syncthreads();
+            if (tid == 0) { __threadfence_system(); *reinterpret_cast<volatile int*>(&q.outs[p].done) = 1; }
+            continue;
+        }
         const PairDev& P = pairs[pr.pair];
         const GridDev& g = P.g;
         const int Nd = P.Nd;
@@ -185,6 +212,7 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
         if (tid < 27) sh.cnt[tid] = 0;
         if (tid == 0) {
             sh.heapN = 0; sh.status = 0; sh.pops = 1; sh.subcubes = 0; sh.improved = 0;
+            sh.gen = atomicAdd(genCounter, 1u) + 1u; sh.nmiss = 0; sh.workCtr = 0; sh.t0 = clock64(); sh.missTot = 0;
             sh.optErrorT = pr.optError;                                              // :297
             sh.best[0] = sh.best[1] = sh.best[2] = sh.best[3] = 0.f;
             // the first pop is always the initial node (:300,:314) with lb = 0
@@ -205,76 +233,59 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
             const float wc = sh.wc, mtd = sh.mtd;
             const float half = wc / 2;
 
-            // ---- phase A ---------------------------------------------------------------------------------------
-            // item `it` = (row, chunk): rows 0..7 are the child cubes, rows 8..34 the lattice corners; (row, chunk) advance
-            // incrementally (no integer division in the loop)
+            // ---- phase A1: the cube.point bound evals (:343-382) on all warps; the last warp first looks the 27 lattice
+            //      corners up in the call's corner memo (the reference memoises corner terms per InnerBnB call too, :304-305) ---
+            if (corners && warp == nwarps - 1) {
+                bool miss = false;
+                if (lane < 27) {
+                    const int cz_ = lane / 9, cy_ = (lane - 9 * cz_) / 3, cx_ = lane - 9 * cz_ - 3 * cy_;
+                    const unsigned kx = __float_as_uint(sh.X[cx_]), ky = __float_as_uint(sh.Y[cy_]), kz = __float_as_uint(sh.Z[cz_]);
+                    const unsigned hsh = memo_hash(kx, ky, kz);
+                    const uint4* e = memo + 2 * (size_t)memo_slot(hsh, memoShift);
+                    const uint4 e0 = e[0], e1 = e[1];
+                    if (e0.x == kx && e0.y == ky && e0.z == kz && e0.w == sh.gen) { sh.cnt[lane] = (int)e1.x; sh.cf[lane] = __uint_as_float(e1.y); }
+                    else { miss = true; sh.cnt[lane] = 0; }
+                }
+                const unsigned mm = __ballot_sync(GOICP_FULL, miss);
+                if (miss) sh.missList[__popc(mm & ((1u << lane) - 1u))] = lane;
+                if (lane == 0) { sh.nmiss = __popc(mm); sh.workCtr = 0; sh.missTot += __popc(mm); }
+            }
             {
                 int row = 0, ch = warp;
                 while (ch >= nchunks) { ch -= nchunks; ++row; }
-                for (int it = warp; it < allItems; it += nwarps) {
+                for (int it = warp; it < evalItems; it += nwarps) {
                     const int i = (ch << 5) + lane;
-                    if (row < 8) {   // the cube.point bound evals (:343-382)
-                        const int c = row;
-                        const float transX = sh.X[c & 1] + half, transY = sh.Y[(c >> 1) & 1] + half, transZ = sh.Z[(c >> 2) & 1] + half;   // :331-333
-                        float su = 0.f, sl = 0.f;
-                        if (i < Nd) {
-                            float d = wgt[i] * dt_distance_v(S, gx0, gy0, gz0, gscale, dist, tx[i] + transX, ty[i] + transY, tz[i] + transZ);
-                            d = d - mrd[i];
-                            if (d < 0.f) d = 0.f;
-                            if (useMd) md[c * NdQ + i] = d;
-                            else {
-                                su = (norm == 2) ? d * d : d;
-                                const float dis = d - mtd;
-                                if (dis > 0.f) sl = (norm == 2) ? dis * dis : dis;
-                            }
+                    const int c = row;
+                    const float transX = sh.X[c & 1] + half, transY = sh.Y[(c >> 1) & 1] + half, transZ = sh.Z[(c >> 2) & 1] + half;   // :331-333
+                    float su = 0.f, sl = 0.f;
+                    if (i < Nd) {
+                        float d = wgt[i] * dt_distance_v(S, gx0, gy0, gz0, gscale, dist, tx[i] + transX, ty[i] + transY, tz[i] + transZ);
+                        d = d - mrd[i];
+                        if (d < 0.f) d = 0.f;
+                        if (useMd) md[c * NdQ + i] = d;
+                        else {
+                            su = (norm == 2) ? d * d : d;
+                            const float dis = d - mtd;
+                            if (dis > 0.f) sl = (norm == 2) ? dis * dis : dis;
                         }
-                        if (!useMd) {
-                            su = warp_sum(su); sl = warp_sum(sl);
-                            if (lane == 0) { part[2 * it] = su; part[2 * it + 1] = sl; }
-                        }
-                    } else {   // corner terms on the 3x3x3 lattice of child-cube corners (:431-550, checkCompatibilities :919,
-                               // sumFPFH :1689); pure functions of the corner, so the reference's memo is not needed
-                        const int c = row - 8;
-                        const int cz_ = c / 9, cy_ = (c - 9 * cz_) / 3, cx_ = c - 9 * cz_ - 3 * cy_;
-                        const float cx = sh.X[cx_], cy = sh.Y[cy_], cz = sh.Z[cz_];
-                        int bad = 0; float fv = 0.f;
-                        if (i < Nd) {
-                            const int cell = clamp_cell_v(S, gx0, gy0, gz0, gscale, vcell, tx[i] + cx, ty[i] + cy, tz[i] + cz);
-                            if (use_reg) bad = ((__ldg(cmask + cell) >> dprop_s[i]) & 1u) ? 0 : 1;
-                            if (use_fpfh) {
-                                fv = __ldg(fpfhD + (size_t)i * ncp1 + cell);
-                                if (EXACT) fp[c * NdQ + i] = fv;
-                            }
-                        }
-                        if (use_reg) { bad = warp_sum_i(bad); if (lane == 0 && bad) atomicAdd(&sh.cnt[c], bad); }
-                        if (!EXACT && use_fpfh) { fv = warp_sum(fv); if (lane == 0) part[16 * nchunks + (it - evalItems)] = fv; }
+                    }
+                    if (!useMd) {
+                        su = warp_sum(su); sl = warp_sum(sl);
+                        if (lane == 0) { part[2 * it] = su; part[2 * it + 1] = sl; }
                     }
                     ch += nwarps;
                     while (ch >= nchunks) { ch -= nchunks; ++row; }
                 }
             }
             __syncthreads();                                                         // (2)
-            // ---- phase B ---------------------------------------------------------------------------------------
+            // ---- phase A2: warp 0 sums the residuals while the other warps evaluate the corners the memo missed -----------
             if (P.doTrim) {   // radix select replaces intro_select (:384-390); one warp per child
                 for (int c = warp; c < 8; c += nwarps) {
                     float su, sl;
                     warp_trimmed_sums(md + c * NdQ, Nd, P.inlierNum, lane, norm, mtd, &su, &sl);
                     if (lane == 0) { sh.ub[c] = su; sh.lb[c] = sl; }
                 }
-                __syncthreads();
-            }
-            if (warp == 1 && P.use_fpfh) {
-                if (lane < 27) {
-                    float s_ = 0.f;
-                    if (EXACT) { const float* f = fp + lane * NdQ; for (int i = 0; i < Nd; ++i) s_ = s_ + f[i]; }   // sumFPFH :1692-1695
-                    else { const float* f = part + 16 * nchunks + lane * nchunks; for (int k = 0; k < nchunks; ++k) s_ = s_ + f[k]; }
-                    sh.cf[lane] = (float)(int)(s_ / (float)Nd);                       // :1696, int truncation :468,:495 (H7)
-                }
-                __syncwarp();
-                asm volatile("bar.sync 1, 64;" ::: "memory");
-            }
-            if (warp != 0) continue;
-            if (!P.doTrim && lane < 16) {
+            } else if (warp == 0 && lane < 16) {
                 const int c = lane >> 1;
                 float acc = 0.f;
                 if (EXACT) {   // sequential float sums in index order (:393-415): lane = (child, ub|lb); 16 independent chains
@@ -294,8 +305,54 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
                 }
                 if (lane & 1) sh.lb[c] = acc; else sh.ub[c] = acc;
             }
+            if (corners) {   // corner terms (:431-550, checkCompatibilities :919, sumFPFH :1689): (missed corner, 32-point chunk) items
+                const int nItems = sh.nmiss * nchunks;
+                for (;;) {
+                    int it = 0;
+                    if (lane == 0) it = atomicAdd(&sh.workCtr, 1);
+                    it = __shfl_sync(GOICP_FULL, it, 0);
+                    if (it >= nItems) break;
+                    const int m = it / nchunks, ch = it - m * nchunks, i = (ch << 5) + lane;
+                    const int c = sh.missList[m];
+                    const int cz_ = c / 9, cy_ = (c - 9 * cz_) / 3, cx_ = c - 9 * cz_ - 3 * cy_;
+                    const float cx = sh.X[cx_], cy = sh.Y[cy_], cz = sh.Z[cz_];
+                    int bad = 0; float fv = 0.f;
+                    if (i < Nd) {
+                        const int cell = clamp_cell_v(S, gx0, gy0, gz0, gscale, vcell, tx[i] + cx, ty[i] + cy, tz[i] + cz);
+                        if (use_reg) bad = ((__ldg(cmask + cell) >> dprop_s[i]) & 1u) ? 0 : 1;
+                        if (use_fpfh) {
+                            fv = __ldg(fpfhD + (size_t)i * ncp1 + cell);
+                            if (EXACT) fp[m * NdQ + i] = fv;
+                        }
+                    }
+                    if (use_reg) { bad = warp_sum_i(bad); if (lane == 0 && bad) atomicAdd(&sh.cnt[c], bad); }
+                    if (!EXACT && use_fpfh) { fv = warp_sum(fv); if (lane == 0) part[16 * nchunks + it] = fv; }
+                }
+            }
+            __syncthreads();                                                         // (3)
+            if (warp == 1 && use_fpfh) {   // c-FPFH sums of the missed corners, one chain per lane
+                if (lane < sh.nmiss) {
+                    float s_ = 0.f;
+                    if (EXACT) { const float* f = fp + lane * NdQ; for (int i = 0; i < Nd; ++i) s_ = s_ + f[i]; }   // sumFPFH :1692-1695
+                    else { const float* f = part + 16 * nchunks + lane * nchunks; for (int k = 0; k < nchunks; ++k) s_ = s_ + f[k]; }
+                    sh.cf[sh.missList[lane]] = (float)(int)(s_ / (float)Nd);          // :1696, int truncation :468,:495 (H7)
+                }
+                __syncwarp();
+                asm volatile("bar.sync 1, 64;" ::: "memory");
+            }
+            if (warp != 0) continue;
             __syncwarp();
-            if (P.use_fpfh) asm volatile("bar.sync 1, 64;" ::: "memory");
+            if (use_fpfh) asm volatile("bar.sync 1, 64;" ::: "memory");
+            __syncwarp();
+            if (corners && lane < sh.nmiss) {   // remember the freshly computed corners
+                const int c = sh.missList[lane];
+                const int cz_ = c / 9, cy_ = (c - 9 * cz_) / 3, cx_ = c - 9 * cz_ - 3 * cy_;
+                const unsigned kx = __float_as_uint(sh.X[cx_]), ky = __float_as_uint(sh.Y[cy_]), kz = __float_as_uint(sh.Z[cz_]);
+                const unsigned hsh = memo_hash(kx, ky, kz);
+                uint4* e = memo + 2 * (size_t)memo_slot(hsh, memoShift);
+                e[0] = make_uint4(kx, ky, kz, sh.gen);
+                e[1] = make_uint4((unsigned)sh.cnt[c], __float_as_uint(sh.cf[c]), 0u, 0u);
+            }
             // ---- phase C: corner min/max per child on 8 lanes (:431-550), then lane 0 alone -------------------------
             if (corners && lane < 8) {
                 const int j = lane, jx = j & 1, jy = (j >> 1) & 1, jz = (j >> 2) & 1;
@@ -311,7 +368,6 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
                 sh.ub[j] = ub; sh.lb[j] = lb;
             }
             __syncwarp();
-            if (lane < 27) sh.cnt[lane] = 0;                                         // re-armed for the next pop's atomics
             if (lane == 0) {   // decisions and pushes in child order (:417-575), then the next pop (:314-320)
                 float optErrorT = sh.optErrorT;
                 int heapN = sh.heapN;
@@ -347,6 +403,8 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
             }
         }
         if (tid == 0) {
+            atomicAdd(dstat + 0, (unsigned long long)(clock64() - sh.t0)); atomicAdd(dstat + 1, (unsigned long long)sh.pops);
+            atomicAdd(dstat + 2, (unsigned long long)sh.missTot); atomicAdd(dstat + 3, 1ull);
             InnerOut o;
             o.err = sh.optErrorT; o.node[0] = sh.best[0]; o.node[1] = sh.best[1]; o.node[2] = sh.best[2]; o.node[3] = sh.best[3];
             o.improved = sh.improved; o.pops = sh.pops; o.subcubes = sh.subcubes; o.status = sh.status; o.done = 0; o.pad[0] = o.pad[1] = 0;
@@ -434,44 +492,58 @@ size_t goicp_bnb_smem_floats(int NdP, int NdQ, bool needMd, bool needFp) {
     return (size_t)5 * NdP + (size_t)(NdP >> 2) + (size_t)43 * (NdP >> 5) + (needMd ? (size_t)8 * NdQ : 0) + (needFp ? (size_t)27 * NdQ : 0);
 }
 
-static int g_bnb_attr_set[4] = {0, 0, 0, 0};
-typedef void (*bnb_kernel_t)(const PairDev*, const InnerProb*, InnerOut*, int, int*, HeapEnt*, int, float*, size_t, int, int, int, QueueDev);
-static bnb_kernel_t bnb_kernel(int exact, int persist) {
-    if (persist) return exact ? inner_bnb_kernel<true, true> : inner_bnb_kernel<false, true>;
-    return exact ? inner_bnb_kernel<true, false> : inner_bnb_kernel<false, false>;
+static int g_bnb_attr_set[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+typedef void (*bnb_kernel_t)(const PairDev*, const InnerProb*, InnerOut*, int, int*, HeapEnt*, int, float*, size_t, int, int, int, QueueDev, uint4*, int, unsigned*);
+static bnb_kernel_t bnb_kernel(int exact, int persist, int smem = 1) {
+    if (smem) {
+        if (persist) return exact ? inner_bnb_kernel<true, true, true> : inner_bnb_kernel<false, true, true>;
+        return exact ? inner_bnb_kernel<true, false, true> : inner_bnb_kernel<false, false, true>;
+    }
+    if (persist) return exact ? inner_bnb_kernel<true, true, false> : inner_bnb_kernel<false, true, false>;
+    return exact ? inner_bnb_kernel<true, false, false> : inner_bnb_kernel<false, false, false>;
 }
-static cudaError_t bnb_attr(int exact, int persist) {
-    const int k = (exact ? 1 : 0) + (persist ? 2 : 0);
+static cudaError_t bnb_attr(int exact, int persist, int smem = 1) {
+    const int k = (exact ? 1 : 0) + (persist ? 2 : 0) + (smem ? 4 : 0);
     if (g_bnb_attr_set[k]) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(bnb_kernel(exact, persist), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, bnb_kernel(exact, persist, smem));
+    if (e != cudaSuccess) return e;
+    const int maxDyn = 227 * 1024 - (int)fa.sharedSizeBytes - 1024;   // static (queue top, ICP tiles) + dynamic <= 227 KB per CTA
+    e = cudaFuncSetAttribute(bnb_kernel(exact, persist, smem), cudaFuncAttributeMaxDynamicSharedMemorySize, maxDyn);
     if (e == cudaSuccess) g_bnb_attr_set[k] = 1;
     return e;
 }
 
 cudaError_t goicp_launch_inner_bnb(const PairDev* pairs, const InnerProb* probs, InnerOut* outs, int nprob, int* counter,
                                    HeapEnt* heaps, int heapCap, int maxCtas, float* gscratch, size_t gstride,
-                                   int NdP, int NdQ, size_t smemFloats, int useSmem, int exact, int threads, cudaStream_t st, int* ctasLaunched) {
+                                   int NdP, int NdQ, size_t smemFloats, int useSmem, int exact, int threads, void* memo, int memoCap, unsigned* genCounter, cudaStream_t st, int* ctasLaunched) {
     if (nprob <= 0) { if (ctasLaunched) *ctasLaunched = 0; return cudaSuccess; }
     const size_t smem = useSmem ? smemFloats * sizeof(float) : 0;
-    cudaError_t e = bnb_attr(exact, 0);
+    cudaError_t e = bnb_attr(exact, 0, useSmem);
     if (e != cudaSuccess) return e;
     int grid = nprob < maxCtas ? nprob : maxCtas;
     if (ctasLaunched) *ctasLaunched = grid;
     QueueDev q{};
-    bnb_kernel(exact, 0)<<<grid, threads, smem, st>>>(pairs, probs, outs, nprob, counter, heaps, heapCap, gscratch, gstride, NdP, NdQ, useSmem, q);
+    bnb_kernel(exact, 0, useSmem)<<<grid, threads, smem, st>>>(pairs, probs, outs, nprob, counter, heaps, heapCap, gscratch, gstride, NdP, NdQ, useSmem, q, (uint4*)memo, memoCap, genCounter);
     return cudaGetLastError();
 }
 
 // the resident kernel of a batch: `ctas` CTAs serve the request ring until each has seen a shut-down marker
 cudaError_t goicp_launch_inner_bnb_persistent(const PairDev* pairs, const QueueDev& q, HeapEnt* heaps, int heapCap, int ctas, float* gscratch, size_t gstride,
-                                              int NdP, int NdQ, size_t smemFloats, int useSmem, int exact, int threads, cudaStream_t st) {
+                                              int NdP, int NdQ, size_t smemFloats, int useSmem, int exact, int threads, void* memo, int memoCap, unsigned* genCounter, cudaStream_t st) {
     const size_t smem = useSmem ? smemFloats * sizeof(float) : 0;
-    cudaError_t e = bnb_attr(exact, 1);
+    cudaError_t e = bnb_attr(exact, 1, useSmem);
     if (e != cudaSuccess) return e;
-    bnb_kernel(exact, 1)<<<ctas, threads, smem, st>>>(pairs, nullptr, nullptr, 0, nullptr, heaps, heapCap, gscratch, gstride, NdP, NdQ, useSmem, q);
+    bnb_kernel(exact, 1, useSmem)<<<ctas, threads, smem, st>>>(pairs, nullptr, nullptr, 0, nullptr, heaps, heapCap, gscratch, gstride, NdP, NdQ, useSmem, q, (uint4*)memo, memoCap, genCounter);
     return cudaGetLastError();
 }
 
+int goicp_inner_bnb_persistent_occupancy(size_t smemBytes, int exact, int threads) {
+    if (bnb_attr(exact, 1) != cudaSuccess) return 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bnb_kernel(exact, 1), threads, smemBytes) != cudaSuccess || n < 1) n = 1;
+    return n;
+}
 int goicp_inner_bnb_occupancy(size_t smemBytes, int exact, int threads) {
     if (bnb_attr(exact, 0) != cudaSuccess) return 1;
     int n = 0;
@@ -486,4 +558,17 @@ cudaError_t goicp_launch_eval_bounds(const PairDev* pairs, int pair, const float
     const int blocks = (nwarps + 7) / 8;
     eval_bounds_kernel<<<blocks, 256, 0, st>>>(pairs, pair, Rs, levels, cubes, nt, ub, lb, incomp_mm, fpfh_mm, scratch);
     return cudaGetLastError();
+}
+
+// forces the (lazily loaded) kernels of this file into the context: a first launch while a resident kernel is spinning
+// would otherwise wait for that kernel (CUDA lazy module loading)
+cudaError_t goicp_preload_bnb() {
+    cudaFuncAttributes a; cudaError_t e;
+    if ((e = cudaFuncGetAttributes(&a, inner_bnb_kernel<true, true, true>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, inner_bnb_kernel<true, true, false>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, inner_bnb_kernel<false, true, true>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, inner_bnb_kernel<true, false, true>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, inner_bnb_kernel<false, false, true>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, eval_bounds_kernel)) != cudaSuccess) return e;
+    return cudaSuccess;
 }

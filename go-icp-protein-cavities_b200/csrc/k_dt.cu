@@ -302,3 +302,17 @@ cudaError_t goicp_launch_dt_distance(const PairDev* pairs, int pair, const doubl
     dt_distance_kernel<<<(n + 255) / 256, 256, 0, st>>>(pairs, pair, xyz, n, out, cell);
     return cudaGetLastError();
 }
+
+// forces the (lazily loaded) kernels of this file into the context: a first launch while a resident kernel is spinning
+// would otherwise wait for that kernel (CUDA lazy module loading)
+cudaError_t goicp_preload_dt() {
+    cudaFuncAttributes a; cudaError_t e;
+    if ((e = cudaFuncGetAttributes(&a, dt_replay_kernel)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, dt_sep_seed_kernel)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, dt_sep_x_kernel)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, dt_sep_y_kernel)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, dt_sep_z_kernel)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, dt_vcell_kernel)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, dt_distance_kernel)) != cudaSuccess) return e;
+    return cudaSuccess;
+}

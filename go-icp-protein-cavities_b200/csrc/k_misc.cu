@@ -168,3 +168,17 @@ cudaError_t goicp_launch_rmsd(const double* a, const double* b, int n, double* t
     rmsd_kernel<<<1, 256, 0, st>>>(a, b, n, terms, out);
     return cudaGetLastError();
 }
+
+// forces the (lazily loaded) kernels of this file into the context: a first launch while a resident kernel is spinning
+// would otherwise wait for that kernel (CUDA lazy module loading)
+cudaError_t goicp_preload_misc() {
+    cudaFuncAttributes a; cudaError_t e;
+    if ((e = cudaFuncGetAttributes(&a, initialize_kernel)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, fpfh_table_kernel)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, normalize_kernel)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, scale_kernel)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, apply_rigid_kernel)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, rescale_kernel)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, rmsd_kernel)) != cudaSuccess) return e;
+    return cudaSuccess;
+}

@@ -7,11 +7,12 @@
 // k_bnb.cu
 size_t goicp_bnb_smem_floats(int NdP, int NdQ, bool needMd, bool needFp);
 int goicp_inner_bnb_occupancy(size_t smemBytes, int exact, int threads);
+int goicp_inner_bnb_persistent_occupancy(size_t smemBytes, int exact, int threads);
 cudaError_t goicp_launch_inner_bnb(const PairDev* pairs, const InnerProb* probs, InnerOut* outs, int nprob, int* counter,
                                    HeapEnt* heaps, int heapCap, int maxCtas, float* gscratch, size_t gstride,
-                                   int NdP, int NdQ, size_t smemFloats, int useSmem, int exact, int threads, cudaStream_t st, int* ctasLaunched);
+                                   int NdP, int NdQ, size_t smemFloats, int useSmem, int exact, int threads, void* memo, int memoCap, unsigned* genCounter, cudaStream_t st, int* ctasLaunched);
 cudaError_t goicp_launch_inner_bnb_persistent(const PairDev* pairs, const QueueDev& q, HeapEnt* heaps, int heapCap, int ctas, float* gscratch, size_t gstride,
-                                              int NdP, int NdQ, size_t smemFloats, int useSmem, int exact, int threads, cudaStream_t st);
+                                              int NdP, int NdQ, size_t smemFloats, int useSmem, int exact, int threads, void* memo, int memoCap, unsigned* genCounter, cudaStream_t st);
 cudaError_t goicp_launch_eval_bounds(const PairDev* pairs, int pair, const float* Rs, const int* levels, const WaveCube* cubes,
                                      int nt, float* ub, float* lb, int* incomp_mm, int* fpfh_mm, float* scratch, int nwarps,
                                      cudaStream_t st);
@@ -33,3 +34,8 @@ cudaError_t goicp_launch_scale(double* xyz, int n, double scale, cudaStream_t st
 cudaError_t goicp_launch_apply_rigid(const double* xyz, int n, const double* Rt, double* out, cudaStream_t st);
 cudaError_t goicp_launch_rescale(const double* in19, double* out3, cudaStream_t st);
 cudaError_t goicp_launch_rmsd(const double* a, const double* b, int n, double* terms, float* out, cudaStream_t st);
+// lazy-loading guards (see k_*.cu)
+cudaError_t goicp_preload_bnb();
+cudaError_t goicp_preload_dt();
+cudaError_t goicp_preload_icp();
+cudaError_t goicp_preload_misc();
