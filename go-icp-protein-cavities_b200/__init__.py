@@ -214,6 +214,17 @@ class Engine:
                               _p(d, C.c_float), _p(dc, C.c_int32), _p(df, C.c_float), len(d), int(pr.get("nd", 0)))
         return arr, keep
 
+    def make_descs(self, pairs):
+        """goicp_pair_desc array over the callers' host buffers (kept alive by the returned object)"""
+        arr, keep = self._descs(pairs)
+        return dict(arr=arr, keep=keep, n=len(pairs))
+
+    def register_batch_descs(self, params, descs):
+        """goicp_register_batch on a prepared descriptor array: host buffers in, results out"""
+        res = (Result * descs["n"])()
+        self.check(self.L.goicp_register_batch(self.h, C.byref(params), descs["n"], descs["arr"], res))
+        return res
+
     def batch_upload(self, params, pairs):
         arr, keep = self._descs(pairs)
         self._npairs = len(pairs)

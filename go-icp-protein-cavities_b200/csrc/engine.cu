@@ -179,6 +179,16 @@ static void tracef(std::string& s, const char* fmt, ...) {
     if (n > 0) s.append(buf, std::min(n, (int)sizeof buf - 1));
 }
 
+// host-side parallel loop (pre-processing of a batch: voxelisation, cell lists, staging)
+template <class F> static void parallel_for(int n, F fn) {
+    const int nt = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), (unsigned)std::max(1, n / 16));
+    if (nt <= 1) { for (int i = 0; i < n; i++) fn(i); return; }
+    std::atomic<int> next(0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) th.emplace_back([&]() { for (;;) { const int i = next.fetch_add(1); if (i >= n) break; fn(i); } });
+    for (auto& t : th) t.join();
+}
+
 }  // namespace
 
 // Everything one stream of waves needs: a worker thread of a batch owns one, the handle's own stream has `main`.
@@ -356,7 +366,8 @@ static goicp_status upload_problems(Eng* h) {
     CU(h->hStage.ensure(inTot));
     char* stage = h->hStage.as<char>();
     char* dIn = h->arenaIn.as<char>(); char* dWork = h->arenaWork.as<char>();
-    for (auto& P : h->probs) {
+    parallel_for((int)h->probs.size(), [&](int pi) {
+        Problem& P = h->probs[pi];
         const int nc = P.info.ncells;
         size_t o = P.inOff;
         PairDev& D = P.dev;
@@ -392,7 +403,7 @@ static goicp_status upload_problems(Eng* h) {
         D.scratch = reinterpret_cast<float*>(dWork + w); w += al256(sizeof(float) * 8 * (size_t)std::max(P.NdAll, 1));
         D.g.S = S; D.g.ncells = nc; D.g.xMin = P.info.xMin; D.g.yMin = P.info.yMin; D.g.zMin = P.info.zMin; D.g.scale = P.info.scale;
         D.Nm = P.Nm; D.Nd = P.Nd;
-    }
+    });
     CU(cudaMemcpyAsync(dIn, stage, inTot, cudaMemcpyHostToDevice, h->stream));
     return GOICP_OK;
 }
@@ -1109,7 +1120,9 @@ static goicp_status ensure_single(Eng* h) {
 static goicp_status prepare_all(Eng* h) {
     if (!h->haveParams) return fail(h, GOICP_ERR_ARG, "goicp_set_params not called");
     goicp_status s;
-    for (auto& P : h->probs) if ((s = prepare_problem(h, P))) return s;
+    std::atomic<int> bad(0);
+    parallel_for((int)h->probs.size(), [&](int i) { goicp_status r = prepare_problem(h, h->probs[i]); if (r) bad.store((int)r); });
+    if (bad.load()) return (goicp_status)bad.load();
     if ((s = upload_problems(h))) return s;
     return GOICP_OK;
 }
@@ -1401,12 +1414,16 @@ goicp_status goicp_batch_upload(goicp_handle h, const goicp_params* p, int32_t n
     h->params = *p; h->haveParams = true;
     h->probs.clear(); h->probs.resize(npairs);
     for (int i = 0; i < npairs; i++) {
-        const goicp_pair_desc& d = pairs[i]; Problem& P = h->probs[i];
+        const goicp_pair_desc& d = pairs[i];
         if (!d.model_xyz || !d.data_xyz || d.Nm < 1 || d.NdAll < 1) return fail(h, GOICP_ERR_ARG, "pair %d: empty cloud", i);
-        set_cloud(P.mxyz, P.mc, P.mf, d.model_xyz, d.model_c, d.model_fpfh, d.Nm); P.Nm = d.Nm;
-        set_cloud(P.dxyz, P.dc, P.df, d.data_xyz, d.data_c, d.data_fpfh, d.NdAll); P.NdAll = d.NdAll;
-        P.Nd = (d.Nd > 0 && d.Nd <= d.NdAll) ? d.Nd : d.NdAll;
     }
+    const bool wantF = p->cfpfh != 0;   // descriptors are only copied when the configuration uses them
+    parallel_for(npairs, [&](int i) {
+        const goicp_pair_desc& d = pairs[i]; Problem& P = h->probs[i];
+        set_cloud(P.mxyz, P.mc, P.mf, d.model_xyz, d.model_c, wantF ? d.model_fpfh : nullptr, d.Nm); P.Nm = d.Nm;
+        set_cloud(P.dxyz, P.dc, P.df, d.data_xyz, d.data_c, wantF ? d.data_fpfh : nullptr, d.NdAll); P.NdAll = d.NdAll;
+        P.Nd = (d.Nd > 0 && d.Nd <= d.NdAll) ? d.Nd : d.NdAll;
+    });
     goicp_status s;
     if ((s = prepare_all(h))) return s;
     CU(cudaStreamSynchronize(h->stream));

@@ -190,7 +190,7 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
         const bool useMd = EXACT || P.doTrim;
         const int ncp1 = g.ncells + 1;
         const int norm = P.norm;
-        const int evalItems = 8 * nchunks, allItems = evalItems + (corners ? 27 * nchunks : 0);
+        const int G = min(nchunks, 8), ngroups = (nchunks + G - 1) / G;   // chunks per work item, items per row
         // per-problem constants in registers (the PairDev lives in global memory)
         const int S = g.S;
         const double gx0 = g.xMin, gy0 = g.yMin, gz0 = g.zMin, gscale = g.scale;
@@ -250,31 +250,26 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
                 if (miss) sh.missList[__popc(mm & ((1u << lane) - 1u))] = lane;
                 if (lane == 0) { sh.nmiss = __popc(mm); sh.workCtr = 0; sh.missTot += __popc(mm); }
             }
-            {
-                int row = 0, ch = warp;
-                while (ch >= nchunks) { ch -= nchunks; ++row; }
-                for (int it = warp; it < evalItems; it += nwarps) {
-                    const int i = (ch << 5) + lane;
-                    const int c = row;
-                    const float transX = sh.X[c & 1] + half, transY = sh.Y[(c >> 1) & 1] + half, transZ = sh.Z[(c >> 2) & 1] + half;   // :331-333
-                    float su = 0.f, sl = 0.f;
-                    if (i < Nd) {
-                        float d = wgt[i] * dt_distance_v(S, gx0, gy0, gz0, gscale, dist, tx[i] + transX, ty[i] + transY, tz[i] + transZ);
-                        d = d - mrd[i];
-                        if (d < 0.f) d = 0.f;
-                        if (useMd) md[c * NdQ + i] = d;
-                        else {
-                            su = (norm == 2) ? d * d : d;
-                            const float dis = d - mtd;
-                            if (dis > 0.f) sl = (norm == 2) ? dis * dis : dis;
-                        }
+            // item = (child cube, group of G 32-point chunks): the per-item overhead is paid once per G points of a lane
+            for (int it = warp; it < 8 * ngroups; it += nwarps) {
+                const int c = it / ngroups, gi = it - c * ngroups;
+                const float transX = sh.X[c & 1] + half, transY = sh.Y[(c >> 1) & 1] + half, transZ = sh.Z[(c >> 2) & 1] + half;   // :331-333
+                const int iEnd = min(Nd, (gi + 1) * G * 32);
+                float su = 0.f, sl = 0.f;
+                for (int i = gi * G * 32 + lane; i < iEnd; i += 32) {
+                    float d = wgt[i] * dt_distance_v(S, gx0, gy0, gz0, gscale, dist, tx[i] + transX, ty[i] + transY, tz[i] + transZ);
+                    d = d - mrd[i];
+                    if (d < 0.f) d = 0.f;
+                    if (useMd) md[c * NdQ + i] = d;
+                    else {
+                        su = su + ((norm == 2) ? d * d : d);
+                        const float dis = d - mtd;
+                        if (dis > 0.f) sl = sl + ((norm == 2) ? dis * dis : dis);
                     }
-                    if (!useMd) {
-                        su = warp_sum(su); sl = warp_sum(sl);
-                        if (lane == 0) { part[2 * it] = su; part[2 * it + 1] = sl; }
-                    }
-                    ch += nwarps;
-                    while (ch >= nchunks) { ch -= nchunks; ++row; }
+                }
+                if (!useMd) {
+                    su = warp_sum(su); sl = warp_sum(sl);
+                    if (lane == 0) { part[2 * it] = su; part[2 * it + 1] = sl; }
                 }
             }
             __syncthreads();                                                         // (2)
@@ -300,33 +295,34 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
                         for (int i = 0; i < n; ++i) { const float v = fmaxf(m[i] - off, 0.f); acc = acc + v; }
                     }
                 } else {
-                    const float* q = part + 2 * c * nchunks + (lane & 1);
-                    for (int k = 0; k < nchunks; ++k) acc = acc + q[2 * k];
+                    const float* q = part + 2 * c * ngroups + (lane & 1);
+                    for (int k = 0; k < ngroups; ++k) acc = acc + q[2 * k];
                 }
                 if (lane & 1) sh.lb[c] = acc; else sh.ub[c] = acc;
             }
             if (corners) {   // corner terms (:431-550, checkCompatibilities :919, sumFPFH :1689): (missed corner, 32-point chunk) items
-                const int nItems = sh.nmiss * nchunks;
+                const int nItems = sh.nmiss * ngroups;
                 for (;;) {
                     int it = 0;
                     if (lane == 0) it = atomicAdd(&sh.workCtr, 1);
                     it = __shfl_sync(GOICP_FULL, it, 0);
                     if (it >= nItems) break;
-                    const int m = it / nchunks, ch = it - m * nchunks, i = (ch << 5) + lane;
+                    const int m = it / ngroups, gi = it - m * ngroups;
                     const int c = sh.missList[m];
                     const int cz_ = c / 9, cy_ = (c - 9 * cz_) / 3, cx_ = c - 9 * cz_ - 3 * cy_;
                     const float cx = sh.X[cx_], cy = sh.Y[cy_], cz = sh.Z[cz_];
-                    int bad = 0; float fv = 0.f;
-                    if (i < Nd) {
+                    const int iEnd = min(Nd, (gi + 1) * G * 32);
+                    int bad = 0; float fs = 0.f;
+                    for (int i = gi * G * 32 + lane; i < iEnd; i += 32) {
                         const int cell = clamp_cell_v(S, gx0, gy0, gz0, gscale, vcell, tx[i] + cx, ty[i] + cy, tz[i] + cz);
-                        if (use_reg) bad = ((__ldg(cmask + cell) >> dprop_s[i]) & 1u) ? 0 : 1;
+                        if (use_reg) bad += ((__ldg(cmask + cell) >> dprop_s[i]) & 1u) ? 0 : 1;
                         if (use_fpfh) {
-                            fv = __ldg(fpfhD + (size_t)i * ncp1 + cell);
-                            if (EXACT) fp[m * NdQ + i] = fv;
+                            const float fv = __ldg(fpfhD + (size_t)i * ncp1 + cell);
+                            if (EXACT) fp[m * NdQ + i] = fv; else fs = fs + fv;
                         }
                     }
                     if (use_reg) { bad = warp_sum_i(bad); if (lane == 0 && bad) atomicAdd(&sh.cnt[c], bad); }
-                    if (!EXACT && use_fpfh) { fv = warp_sum(fv); if (lane == 0) part[16 * nchunks + it] = fv; }
+                    if (!EXACT && use_fpfh) { fs = warp_sum(fs); if (lane == 0) part[16 * ngroups + it] = fs; }
                 }
             }
             __syncthreads();                                                         // (3)
@@ -334,7 +330,7 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
                 if (lane < sh.nmiss) {
                     float s_ = 0.f;
                     if (EXACT) { const float* f = fp + lane * NdQ; for (int i = 0; i < Nd; ++i) s_ = s_ + f[i]; }   // sumFPFH :1692-1695
-                    else { const float* f = part + 16 * nchunks + lane * nchunks; for (int k = 0; k < nchunks; ++k) s_ = s_ + f[k]; }
+                    else { const float* f = part + 16 * ngroups + lane * ngroups; for (int k = 0; k < ngroups; ++k) s_ = s_ + f[k]; }
                     sh.cf[sh.missList[lane]] = (float)(int)(s_ / (float)Nd);          // :1696, int truncation :468,:495 (H7)
                 }
                 __syncwarp();
