@@ -66,9 +66,11 @@ ABI_SYMBOLS = [
     "goicp_dt_download", "goicp_dt_distance", "goicp_set_nd", "goicp_initialize", "goicp_get_weights", "goicp_get_maxrotdis",
     "goicp_get_thresholds", "goicp_eval_bounds", "goicp_inner_bnb", "goicp_icp", "goicp_register", "goicp_last_trace",
     "goicp_set_options", "goicp_register_batch", "goicp_batch_upload", "goicp_batch_run", "goicp_get_timings",
-    "goicp_set_batch_options", "goicp_get_stats",
+    "goicp_set_batch_options", "goicp_get_stats", "goicp_set_frontier_sharding", "goicp_test_exchange",
     "goicp_normalize_cloud", "goicp_scale_cloud", "goicp_rescale_translation", "goicp_apply_rigid", "goicp_rmsd",
 ]
+
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
 
 _lib = None
 
@@ -115,6 +117,8 @@ def lib():
     L.goicp_get_timings.argtypes = [vp, fp, C.POINTER(C.c_int64)]
     L.goicp_set_batch_options.argtypes = [vp, C.c_int32, C.c_int32]
     L.goicp_get_stats.argtypes = [vp, dp]
+    L.goicp_set_frontier_sharding.argtypes = [vp, C.c_int32, C.c_int32, ALLGATHER_FN, vp]
+    L.goicp_test_exchange.argtypes = [vp, vp, vp, C.c_int64]
     L.goicp_normalize_cloud.argtypes = [vp, dp, C.c_int32, dp, dp]
     L.goicp_scale_cloud.argtypes = [vp, dp, C.c_int32, C.c_double]
     L.goicp_rescale_translation.argtypes = [vp, C.c_double, dp, dp, dp, dp, dp]
@@ -187,6 +191,29 @@ class Engine:
         ln = (C.c_int64 * 5)()
         self.check(self.L.goicp_get_timings(self.h, ms, ln))
         return dict(ms=list(ms), launches=list(ln))
+
+    def set_frontier_sharding(self, rank, world, device=None):
+        """Shard the InnerBnB calls of every wave of ONE registration over `world` ranks (torch.distributed must be
+        initialised): results are all-gathered once per wave (NCCL when `device` is a cuda device, else gloo)."""
+        import torch
+        import torch.distributed as dist
+
+        def _allgather(send, recv, nbytes, user):
+            try:
+                src = np.ctypeslib.as_array(C.cast(send, C.POINTER(C.c_uint8)), shape=(nbytes,))
+                dst = np.ctypeslib.as_array(C.cast(recv, C.POINTER(C.c_uint8)), shape=(nbytes * world,))
+                t = torch.from_numpy(src.copy())
+                if device is not None:
+                    t = t.to(device)
+                out = torch.empty(nbytes * world, dtype=torch.uint8, device=t.device)
+                dist.all_gather_into_tensor(out, t)
+                dst[:] = out.cpu().numpy()
+                return 0
+            except Exception as exc:  # noqa: BLE001 - reported through the status code
+                print("all-gather callback failed:", exc)
+                return 1
+        self._ag = ALLGATHER_FN(_allgather)   # keep the callback alive
+        self.check(self.L.goicp_set_frontier_sharding(self.h, rank, world, self._ag, None))
 
     def stats(self):
         o = (C.c_double * 8)()

@@ -242,6 +242,8 @@ struct goicp_handle_s {
     PinBuf hStage, hPairs;
     WaveCtx main;
     MapBuf qProbs, qOuts, qOrder, qIcp; DevBuf qClaim, qHeaps, qScratch, qMemo, dGen;   // persistent-queue mode (batches)
+    int shardRank = 0, shardN = 1; goicp_allgather_fn allgather = nullptr; void* allgatherUser = nullptr;   // frontier sharding
+    std::vector<InnerOut> xSend, xRecv;
     int persistent = 1;          // batches: 1 = resident kernel + request ring, 0 = one launch per wave
     std::vector<std::unique_ptr<WaveCtx>> workers;
     std::mutex errMutex;
@@ -501,7 +503,26 @@ static BnbCfg bnb_config(Eng* h) {
     c.perSM = goicp_inner_bnb_occupancy(c.useSmem ? smemBytes : 0, h->exact_sums, c.threads);
     return c;
 }
+static goicp_status run_inner_local(Eng* h, WaveCtx& c, const BnbCfg& cfg, std::vector<InnerProb>& reqs, std::vector<InnerOut>& outs);
+// One wave of InnerBnB calls.  With frontier sharding the calls are dealt round-robin to the ranks, evaluated locally and
+// exchanged with one all-gather, so every rank continues with the complete, identical result set.
 static goicp_status run_inner(Eng* h, WaveCtx& c, const BnbCfg& cfg, std::vector<InnerProb>& reqs, std::vector<InnerOut>& outs) {
+    const int n = (int)reqs.size();
+    if (h->shardN <= 1 || !h->allgather) return run_inner_local(h, c, cfg, reqs, outs);
+    outs.resize(n);
+    const int N = h->shardN, r = h->shardRank, per = (n + N - 1) / N;
+    std::vector<InnerProb> mine; std::vector<InnerOut> mineOut;
+    for (int k = r; k < n; k += N) mine.push_back(reqs[k]);
+    goicp_status s = run_inner_local(h, c, cfg, mine, mineOut);
+    if (s) return s;
+    h->xSend.assign(std::max(per, 1), InnerOut{}); h->xRecv.assign((size_t)std::max(per, 1) * N, InnerOut{});
+    for (size_t k = 0; k < mineOut.size(); k++) h->xSend[k] = mineOut[k];
+    if (h->allgather(h->xSend.data(), h->xRecv.data(), (int64_t)sizeof(InnerOut) * std::max(per, 1), h->allgatherUser) != 0)
+        return fail(h, GOICP_ERR_ARG, "frontier sharding: the all-gather callback failed");
+    for (int k = 0; k < n; k++) outs[k] = h->xRecv[(size_t)(k % N) * std::max(per, 1) + k / N];
+    return GOICP_OK;
+}
+static goicp_status run_inner_local(Eng* h, WaveCtx& c, const BnbCfg& cfg, std::vector<InnerProb>& reqs, std::vector<InnerOut>& outs) {
     const int n = (int)reqs.size();
     outs.resize(n);
     if (n == 0) return GOICP_OK;
@@ -1445,6 +1466,15 @@ goicp_status goicp_register_batch(goicp_handle h, const goicp_params* p, int32_t
     goicp_status s;
     if ((s = goicp_batch_upload(h, p, npairs, pairs))) return s;
     return goicp_batch_run(h, results);
+}
+goicp_status goicp_set_frontier_sharding(goicp_handle h, int32_t rank, int32_t nranks, goicp_allgather_fn allgather, void* user) {
+    if (!h || nranks < 1 || rank < 0 || rank >= nranks || (nranks > 1 && !allgather)) return h ? fail(h, GOICP_ERR_ARG, "set_frontier_sharding: bad arguments") : GOICP_ERR_ARG;
+    h->shardRank = rank; h->shardN = nranks; h->allgather = allgather; h->allgatherUser = user;
+    return GOICP_OK;
+}
+goicp_status goicp_test_exchange(goicp_handle h, const void* send, void* recv, int64_t bytes_per_rank) {
+    if (!h || !send || !recv || bytes_per_rank < 1 || !h->allgather) return GOICP_ERR_ARG;
+    return h->allgather(send, recv, bytes_per_rank, h->allgatherUser) == 0 ? GOICP_OK : fail(h, GOICP_ERR_ARG, "all-gather callback failed");
 }
 goicp_status goicp_set_batch_options(goicp_handle h, int32_t groups, int32_t slots) {
     if (!h) return GOICP_ERR_ARG;

@@ -137,6 +137,17 @@ const char* goicp_last_trace(goicp_handle h);
  * speculatively per device launch (results are used only when the reference's order reaches them). */
 goicp_status goicp_set_options(goicp_handle h, int32_t exact_sums, int32_t spec_width, int32_t use_dt_replay);
 
+/* ---- one deep registration sharded over several GPUs (second shard) -------------------------------
+ * Every rank holds the same clouds / DT and runs the same (deterministic) rotation queue; each wave's InnerBnB calls are
+ * dealt round-robin to the ranks and the results are exchanged with ONE all-gather per wave, so every rank sees every
+ * bound (the best upper bound per wave is the min over the gathered results) and the search stays identical to the
+ * single-GPU one.  `allgather(send, recv, bytes_per_rank, user)` must fill recv[rank * bytes_per_rank ...] for all ranks
+ * (host buffers); the python binding implements it with torch.distributed (NCCL on GPUs, gloo in the CPU tests). */
+typedef int (*goicp_allgather_fn)(const void* send, void* recv, int64_t bytes_per_rank, void* user);
+goicp_status goicp_set_frontier_sharding(goicp_handle h, int32_t rank, int32_t nranks, goicp_allgather_fn allgather, void* user);
+/* test hook: runs the exchange on `bytes_per_rank` bytes (no device needed once the handle exists) */
+goicp_status goicp_test_exchange(goicp_handle h, const void* send, void* recv, int64_t bytes_per_rank);
+
 /* ---- batch of independent pairs (the dataset sweep of bo1_GoICP.py, one GPU) ------------------------- */
 /* BuildDT + Register for npairs pairs with shared params; pairs advance in lock-step waves on one device. */
 goicp_status goicp_register_batch(goicp_handle h, const goicp_params* p, int32_t npairs,

@@ -29,7 +29,7 @@ assert len(res) == n
 for i, r in enumerate(res):
     assert r["R"][0, 0] == i and r["t"][1] == i + 0.5 and r["optComp"] == i %% 7 and r["counters"][3] == i and r["optError"] == np.float32(i / 4), (i, r)
 lo, hi = sw.shard_range(n, rank, world)
-print("rank", rank, "block", lo, hi, "ok")
+sys.stdout.write("rank %d block %d %d ok\n" % (rank, lo, hi)); sys.stdout.flush()
 dist.destroy_process_group()
 """
 
@@ -57,3 +57,42 @@ def test_sweep_world2_gloo(tmp_path):
                           "--master-port", "29731", str(script)], capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "rank 0 block 0 6 ok" in out.stdout and "rank 1 block 6 11 ok" in out.stdout
+
+
+FRONTIER_WORKER = r"""
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, %r)
+import __graft_entry__ as ge
+g = ge.load_package()
+import ctypes as C
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+# the exchange of the frontier-sharded search (one all-gather of InnerOut records per wave), exercised without a device:
+# build the callback exactly as Engine.set_frontier_sharding does, but on a bare object (no goicp handle on a CPU box)
+class Fake(g.Engine):
+    def __init__(self): self.L = g.lib(); self.h = None
+    def check(self, st): assert st in (0, 2), st   # the C call refuses a NULL handle (status 2) -- only the callback is used here
+eng = Fake()
+eng.set_frontier_sharding(rank, world, None)
+nb = 48 * 5
+send = (np.arange(nb, dtype=np.uint8) + 7 * rank).astype(np.uint8)
+recv = np.zeros(nb * world, np.uint8)
+assert eng._ag(send.ctypes.data, recv.ctypes.data, nb, None) == 0
+for r in range(world):
+    assert np.array_equal(recv[r * nb:(r + 1) * nb], (np.arange(nb, dtype=np.uint8) + 7 * r).astype(np.uint8))
+sys.stdout.write("rank %d exchange ok\n" % rank); sys.stdout.flush()
+dist.destroy_process_group()
+"""
+
+
+def test_frontier_exchange_world2_gloo(tmp_path):
+    """the per-wave all-gather of the frontier-sharded registration over gloo, world_size 2"""
+    script = tmp_path / "fworker.py"
+    script.write_text(FRONTIER_WORKER % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29733", str(script)], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "rank 0 exchange ok" in out.stdout and "rank 1 exchange ok" in out.stdout
