@@ -29,7 +29,7 @@ assert len(res) == n
 for i, r in enumerate(res):
     assert r["R"][0, 0] == i and r["t"][1] == i + 0.5 and r["optComp"] == i %% 7 and r["counters"][3] == i and r["optError"] == np.float32(i / 4), (i, r)
 lo, hi = sw.shard_range(n, rank, world)
-sys.stdout.write("rank %d block %d %d ok\n" % (rank, lo, hi)); sys.stdout.flush()
+sys.stdout.write("rank %%d block %%d %%d ok\n" %% (rank, lo, hi)); sys.stdout.flush()
 dist.destroy_process_group()
 """
 
@@ -82,7 +82,7 @@ recv = np.zeros(nb * world, np.uint8)
 assert eng._ag(send.ctypes.data, recv.ctypes.data, nb, None) == 0
 for r in range(world):
     assert np.array_equal(recv[r * nb:(r + 1) * nb], (np.arange(nb, dtype=np.uint8) + 7 * r).astype(np.uint8))
-sys.stdout.write("rank %d exchange ok\n" % rank); sys.stdout.flush()
+sys.stdout.write("rank %%d exchange ok\n" %% rank); sys.stdout.flush()
 dist.destroy_process_group()
 """
 
