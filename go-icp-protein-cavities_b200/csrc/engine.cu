@@ -244,6 +244,7 @@ struct goicp_handle_s {
     MapBuf qProbs, qOuts, qOrder, qIcp; DevBuf qClaim, qHeaps, qScratch, qMemo, dGen;   // persistent-queue mode (batches)
     int shardRank = 0, shardN = 1; goicp_allgather_fn allgather = nullptr; void* allgatherUser = nullptr;   // frontier sharding
     std::vector<InnerOut> xSend, xRecv;
+    std::atomic<int> activePairs{0};   // pairs currently being searched (persistent scheduler): few left -> speculate wider
     int persistent = 1;          // batches: 1 = resident kernel + request ring, 0 = one launch per wave
     std::vector<std::unique_ptr<WaveCtx>> workers;
     std::mutex errMutex;
@@ -754,7 +755,7 @@ static void gather_requests(Eng* h, int pi, std::vector<InnerProb>& reqs, std::v
         want(P.par, j, 1, ch, R);
     }
     // the next queue nodes in pop order; width grows while the incumbent stays unchanged
-    const int specw = h->probs.size() > 1 ? std::min(h->spec_width, h->batch_spec_width) : h->spec_width;
+    const int specw = h->probs.size() > 1 ? std::min(h->spec_width, h->batch_spec_width) : h->spec_width;   // inside a batch the pairs themselves fill the GPU
     int width = std::min(specw, P.quiet < 30 ? (1 << std::min(P.quiet, 20)) - 1 : specw);
     if (width > 0 && !P.q.empty()) {
         std::vector<RNode> top(P.q);
@@ -929,7 +930,7 @@ static goicp_status persistent_worker(Eng* h, WaveCtx& c, PQ& pq, std::atomic<in
         return true;
     };
     for (;;) {
-        while ((int)active.size() < slots) { const int i = next.fetch_add(1); if (i >= np) break; reset_search(h->probs[i]); active.push_back(i); }
+        while ((int)active.size() < slots) { const int i = next.fetch_add(1); if (i >= np) break; reset_search(h->probs[i]); active.push_back(i); h->activePairs.fetch_add(1); }
         if (active.empty() && zombies.empty()) break;
         bool progressed = false;
         c.callsUsed++;   // loop iterations
@@ -955,7 +956,7 @@ static goicp_status persistent_worker(Eng* h, WaveCtx& c, PQ& pq, std::atomic<in
             const Phase before = P.phase; const int jb = P.j; const int idb = P.par.id;
             advance(h, i);
             if (P.phase != before || P.j != jb || P.par.id != idb) progressed = true;
-            if (P.phase == PH_DONE) { for (auto& r : P.pend) zombies.push_back(r); P.pend.clear(); P.inflight.clear(); continue; }
+            if (P.phase == PH_DONE) { for (auto& r : P.pend) zombies.push_back(r); P.pend.clear(); P.inflight.clear(); h->activePairs.fetch_sub(1); continue; }
             if (P.phase == PH_WAIT_ICP) { P.icpQueued = false; if (send_icp(i)) progressed = true; continue; }
             // blocked on an InnerBnB result: is it already on its way?
             const unsigned long long need = call_key(P.par.id, P.j, P.phase == PH_CHILD_LB ? 1 : 0);
@@ -1039,6 +1040,7 @@ static goicp_status register_persistent(Eng* h, const BnbCfg& cfg, int groups, i
     cudaEventRecord(h->main.ev1, h->stream);
     g_no_device_alloc.store(true);
     std::atomic<int> next(0);
+    h->activePairs.store(0);
     std::vector<goicp_status> st(groups, GOICP_OK);
     std::vector<std::thread> th;
     const int per = NSLOT / groups;
