@@ -245,6 +245,7 @@ struct goicp_handle_s {
     int shardRank = 0, shardN = 1; goicp_allgather_fn allgather = nullptr; void* allgatherUser = nullptr;   // frontier sharding
     std::vector<InnerOut> xSend, xRecv;
     std::atomic<int> activePairs{0};   // pairs currently being searched (persistent scheduler): few left -> speculate wider
+    int persistent_single = 1;   // single registrations of small clouds also go through the resident kernel (no launches per wave)
     int persistent = 1;          // batches: 1 = resident kernel + request ring, 0 = one launch per wave
     std::vector<std::unique_ptr<WaveCtx>> workers;
     std::mutex errMutex;
@@ -1082,10 +1083,10 @@ static goicp_status register_all(Eng* h) {
         slots = h->slots > 0 ? h->slots : std::min(128, std::max(8, (np + groups - 1) / groups));
         groups = std::min(groups, (np + slots - 1) / slots);
     }
-    { const char* e = getenv("GOICP_PERSISTENT"); if (e) h->persistent = atoi(e); }
+    { const char* e = getenv("GOICP_PERSISTENT"); if (e) { h->persistent = atoi(e) != 0; h->persistent_single = atoi(e) == 1; } }   // 0 off, 1 on, 2 batches only
     bool allSmall = true;
     for (auto& P : h->probs) if ((size_t)P.Nd * P.Nm > ((size_t)1 << 21) || (P.dev.doTrim && P.Nd > 2048)) allSmall = false;
-    if (np > 1 && h->persistent && allSmall) {
+    if (h->persistent && allSmall && h->shardN <= 1 && (np > 1 || h->persistent_single)) {
         if (h->slots <= 0) slots = std::min(512, std::max(8, (np + groups - 1) / groups));
         if ((s = register_persistent(h, cfg, groups, slots))) return s;
     } else if (groups <= 1) {
