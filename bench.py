@@ -234,9 +234,10 @@ def main():
     agg = total_evals / world * 4 / (dev_ms * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": "inner_bnb_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
             "traffic": None, "peak_source": peak_src, "achieved_aggregate": agg, "frac_aggregate": agg / peaks["hbm_gbs"],
-            "note": "4 algorithmic bytes per eval. `achieved` is the per-launch rate (evals x 4 B / summed CUDA-event time of the inner_bnb launches; the worker "
-                    "streams' launches overlap), `achieved_aggregate` = evals x 4 B / step time per GPU. S=20 grids are L1-resident (99 % L1 hit, <1 MB DRAM per "
-                    "launch): the binding limit is SM issue, not HBM -- see DESIGN.md section 4"}
+            "note": "4 algorithmic bytes per eval. `achieved` = evals x 4 B / CUDA-event time of the resident inner_bnb kernel (one launch per step serves every InnerBnB and "
+                    "ICP request of the batch), `achieved_aggregate` = evals x 4 B / step time per GPU. S=20 grids are L1-resident (98 % L1 hit): the binding limit is SM "
+                    "issue + the serial phases of each queue pop, not HBM -- see DESIGN.md section 4. `traffic` = DRAM bytes of one classic-mode launch of the same kernel "
+                    "(ncu cannot replay the resident kernel; profiles/README.md)"}
     prof = os.path.join(ROOT, "profiles", "r01_inner_bnb_traffic.json")
     if os.path.exists(prof):
         try:

@@ -216,10 +216,14 @@ class Engine:
         self.check(self.L.goicp_set_frontier_sharding(self.h, rank, world, self._ag, None))
 
     def stats(self):
-        o = (C.c_double * 8)()
+        o = (C.c_double * 16)()
         self.check(self.L.goicp_get_stats(self.h, o))
-        return dict(waves=int(o[0]), calls_launched=int(o[1]), calls_used=int(o[2]), streams=int(o[3]), host_seconds=o[4],
-                    stream_seconds=dict(inner_enqueue=o[5], inner_wait=o[6], icp=o[7]))
+        d = dict(rounds=int(o[0]), calls_launched=int(o[1]), calls_used=int(o[2]), host_threads=int(o[3]), host_seconds=o[4],
+                 host_thread_seconds=dict(build_requests=o[5], publish=o[6], wait=o[7]))
+        if o[13] > 0:
+            d["resident_kernel"] = dict(ctas=int(o[13]), calls=int(o[8]), pops=int(o[9]), busy_cycles_per_pop=o[10] / max(o[9], 1.0),
+                                        corner_misses_per_pop=o[11] / max(o[9], 1.0), busy_cycles=o[10], poll_cycles=o[12])
+        return d
 
     def set_options(self, exact_sums=-1, spec_width=-1, use_dt_replay=-1):
         self.check(self.L.goicp_set_options(self.h, exact_sums, spec_width, use_dt_replay))

@@ -251,7 +251,7 @@ struct goicp_handle_s {
     std::mutex errMutex;
     std::string err, trace;
     float ms[5] = {0, 0, 0, 0, 0}; long long launches[5] = {0, 0, 0, 0, 0};
-    double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // waves, calls launched, calls consumed, worker streams, host seconds
+    double stats[16] = {0};   // see goicp_get_stats
 };
 
 namespace {
@@ -1063,8 +1063,12 @@ static goicp_status register_persistent(Eng* h, const BnbCfg& cfg, int groups, i
         h->main.tLogic += w->tLogic; h->main.tInnerEnq += w->tInnerEnq; h->main.tInnerWait += w->tInnerWait; h->main.tIcp += w->tIcp;
     }
     { unsigned long long st8[8]; cudaMemcpy(st8, h->dGen.as<char>() + 8, sizeof st8, cudaMemcpyDeviceToHost); cudaMemset(h->dGen.as<char>() + 8, 0, 64);
-      fprintf(stderr, "[device] calls %llu pops %llu busy-cycles/pop %.0f corner-misses/pop %.2f busy CTA-seconds %.3f poll CTA-seconds %.3f (ctas %d)\n", st8[3], st8[1], (double)st8[0] / std::max<double>(1, st8[1]), (double)st8[2] / std::max<double>(1, st8[1]), st8[0] / 1.9e9, st8[4] / 1.9e9, ctas); }
-    fprintf(stderr, "[persistent] loops %lld gather %.3fs publish %.3fs idle-sleep %.3fs loop-busy %.3fs (summed over %d workers)\n", h->main.callsUsed, h->main.tLogic, h->main.tInnerEnq, h->main.tInnerWait, h->main.tIcp, groups);
+      h->stats[8] = (double)st8[3]; h->stats[9] = (double)st8[1]; h->stats[10] = (double)st8[0]; h->stats[11] = (double)st8[2]; h->stats[12] = (double)st8[4]; h->stats[13] = ctas;
+      h->stats[5] = h->main.tLogic; h->stats[6] = h->main.tInnerEnq; h->stats[7] = h->main.tInnerWait;
+      if (getenv("GOICP_DEBUG")) {
+          fprintf(stderr, "[device] calls %llu pops %llu busy-cycles/pop %.0f corner-misses/pop %.2f busy-cycles %.4g poll-cycles %.4g (ctas %d)\n", st8[3], st8[1], (double)st8[0] / std::max<double>(1, st8[1]), (double)st8[2] / std::max<double>(1, st8[1]), (double)st8[0], (double)st8[4], ctas);
+          fprintf(stderr, "[persistent] loops %lld gather %.3fs publish %.3fs idle-sleep %.3fs loop-busy %.3fs (summed over %d workers)\n", h->main.callsUsed, h->main.tLogic, h->main.tInnerEnq, h->main.tInnerWait, h->main.tIcp, groups);
+      } }
     return GOICP_OK;
 }
 
@@ -1121,7 +1125,7 @@ static goicp_status register_all(Eng* h) {
     for (auto& P : h->probs) P.t_reg = dt / std::max(1, np);
     long long used = 0; for (auto& P : h->probs) used += P.cnt[0];
     h->stats[0] = (double)h->main.waves; h->stats[1] = (double)h->main.callsLaunched; h->stats[2] = (double)used; h->stats[3] = groups; h->stats[4] = dt;
-    h->stats[5] = h->main.tInnerEnq; h->stats[6] = h->main.tInnerWait; h->stats[7] = h->main.tIcp;
+    if (!(h->persistent && allSmall && h->shardN <= 1 && (np > 1 || h->persistent_single))) { h->stats[5] = h->main.tLogic; h->stats[6] = h->main.tInnerEnq; h->stats[7] = h->main.tInnerWait; for (int k = 8; k < 16; k++) h->stats[k] = 0; }
     return GOICP_OK;
 }
 
@@ -1486,9 +1490,9 @@ goicp_status goicp_set_batch_options(goicp_handle h, int32_t groups, int32_t slo
     { const char* e = getenv("GOICP_BNB_THREADS"); if (e) { int t = atoi(e); if (t >= 64 && t <= 512 && t % 32 == 0) h->bnb_threads = t; } }
     return GOICP_OK;
 }
-goicp_status goicp_get_stats(goicp_handle h, double* out8) {
-    if (!h || !out8) return GOICP_ERR_ARG;
-    for (int k = 0; k < 8; k++) out8[k] = h->stats[k];
+goicp_status goicp_get_stats(goicp_handle h, double* out16) {
+    if (!h || !out16) return GOICP_ERR_ARG;
+    for (int k = 0; k < 16; k++) out16[k] = h->stats[k];
     return GOICP_OK;
 }
 goicp_status goicp_get_timings(goicp_handle h, float* ms5, int64_t* launches5) {

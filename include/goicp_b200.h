@@ -162,10 +162,12 @@ goicp_status goicp_get_timings(goicp_handle h, float* ms5, int64_t* launches5);
 /* batch scheduling: `groups` worker streams (0 = auto: one per host core, 4..32), each advancing `slots` pairs
  * (0 = auto: npairs / groups, 8..128) in lock-step waves and pulling the next pair from a shared counter when one finishes (bo1_GoICP.py:40-54 is serial). */
 goicp_status goicp_set_batch_options(goicp_handle h, int32_t groups, int32_t slots);
-/* search statistics of the last register / batch_run: out[0] waves, [1] InnerBnB calls launched (incl. speculative),
- * [2] InnerBnB calls the reference order consumed, [3] worker streams, [4] host seconds of the search,
- * [5..7] host seconds summed over worker streams: InnerBnB enqueue, InnerBnB wait, ICP launches */
-goicp_status goicp_get_stats(goicp_handle h, double* out8);
+/* search statistics of the last register / batch_run (16 doubles): [0] request rounds, [1] InnerBnB calls launched (incl.
+ * speculative), [2] InnerBnB calls the reference order consumed, [3] host worker threads, [4] host seconds of the search,
+ * [5..7] host seconds summed over workers: building requests, publishing / enqueueing, waiting;
+ * resident-kernel mode only: [8] calls served, [9] translation-queue pops, [10] CTA busy cycles, [11] corner evaluations the
+ * memo missed, [12] CTA cycles spent polling the request ring, [13] resident CTAs; [14..15] reserved */
+goicp_status goicp_get_stats(goicp_handle h, double* out16);
 
 /* ---- Transformation (transformation.cpp), per-pair pre/post-processing -------------------------------- */
 /* normalizeMolCloud (:311): centre in place (n x 3 doubles), returns mean[3] and the max norm. */
