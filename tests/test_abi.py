@@ -57,4 +57,4 @@ def test_product_never_touches_oracle():
 def test_cpp_dropin_builds(g):
     """the header-only C++ mirror of the reference classes compiles and links against the C-ABI library"""
     subprocess.check_call(["make", "-s", "-B", "-C", os.path.join(ROOT, "examples")])
-    assert os.path.exists(os.path.join(ROOT, "examples", "goicp_demo"))
+    assert os.path.exists(os.path.join(ROOT, "examples", "goicp_demo")) and os.path.exists(os.path.join(ROOT, "examples", "GoICP_b200"))

@@ -264,3 +264,31 @@ def test_cpp_dropin_demo(g, tmp_path):
     R = np.array([[float(v) for v in rows[i].split()] for i in (1, 2, 3)])
     t = np.array([float(rows[i]) for i in (4, 5, 6)])
     assert np.abs(R - z["exp64_R"]).max() < 1e-5 and np.abs(t - z["exp64_t"]).max() < 1e-5
+
+
+def test_cli_pair1_golden(tmp_path):
+    """examples/GoICP_b200 = the reference's command line (jly_main.cpp) on this engine: the same invocation as
+    bo1_GoICP.py:51 reproduces the files the reference ships for pair 1 byte for byte (except the Time: line):
+    cavitiesN/*_sim1N.xyz, output/similar1.txt (R, t, Error 8.45388, Compatibilities 133), output/similar1_rescaled.txt"""
+    import os
+    import shutil
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "examples", "GoICP_b200")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "examples")])
+    src = os.path.join(ROOT, "tests", "golden", "cli")
+    for d in ("cavities", "cfpfh"):
+        shutil.copytree(os.path.join(src, d), tmp_path / d)
+    shutil.copy(os.path.join(src, "config.txt"), tmp_path / "config.txt")
+    os.makedirs(tmp_path / "cavitiesN"); os.makedirs(tmp_path / "output")
+    out = subprocess.run([exe, "cavities/1eq2_6_cavity6.mol2", "cavities/2x86_3_cavity6.mol2", "238", "config.txt", "output/similar1.txt", "1"],
+                         cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    exp = os.path.join(src, "expected")
+    for f in ("1eq2_6_cavity6_sim1N.xyz", "2x86_3_cavity6_sim1N.xyz"):
+        assert open(tmp_path / "cavitiesN" / f, "rb").read() == open(os.path.join(exp, f), "rb").read(), f
+    for f in ("similar1.txt", "similar1_rescaled.txt"):
+        got = open(tmp_path / "output" / f).read().split("\n")
+        want = open(os.path.join(exp, f)).read().split("\n")
+        assert got[0].startswith("Time: ") and got[1:] == want[1:], (f, got, want)
