@@ -230,12 +230,16 @@ def main():
     except Exception:
         pass
     kern_evals_per_gpu = total_evals / world
-    achieved = kern_evals_per_gpu * 4 / (kern_ms * 1e-3) / 1e9
-    agg = total_evals / world * 4 / (dev_ms * 1e-3) / 1e9
+    # 4 B per cube.point eval (one DT voxel) + with regularization>0 27/8 corner evals x (4 B index map + 2 B
+    # property mask) = 20.25 B (+ 27/8 x 4 B of the per-cell c-FPFH table with the c-FPFH term)
+    bytes_per_eval = 4.0 + (20.25 if params.regularization > 0 else 0.0) + (13.5 if args.fpfh else 0.0)
+    achieved = kern_evals_per_gpu * bytes_per_eval / (kern_ms * 1e-3) / 1e9
+    agg = total_evals / world * bytes_per_eval / (dev_ms * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": "inner_bnb_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
             "traffic": None, "peak_source": peak_src, "achieved_aggregate": agg, "frac_aggregate": agg / peaks["hbm_gbs"],
-            "note": "4 algorithmic bytes per eval. `achieved` = evals x 4 B / CUDA-event time of the resident inner_bnb kernel (one launch per step serves every InnerBnB and "
-                    "ICP request of the batch), `achieved_aggregate` = evals x 4 B / step time per GPU. S=20 grids are L1-resident (98 % L1 hit): the binding limit is SM "
+            "algorithmic_bytes_per_eval": bytes_per_eval, "achieved_dt_gather_only": kern_evals_per_gpu * 4 / (kern_ms * 1e-3) / 1e9,
+            "note": "algorithmic bytes per eval per SURVEY 8(d): 4 B DT voxel + 20.25 B corner-term gathers when regularization>0. `achieved` = evals x bytes / CUDA-event time of the resident inner_bnb kernel (one launch per step serves every InnerBnB and "
+                    "ICP request of the batch), `achieved_aggregate` = evals x bytes / step time per GPU, `achieved_dt_gather_only` counts the 4 B DT voxel alone. S=20 grids are L1-resident (98 % L1 hit): the binding limit is SM "
                     "issue + the serial phases of each queue pop, not HBM -- see DESIGN.md section 4. `traffic` = DRAM bytes of one classic-mode launch of the same kernel "
                     "(ncu cannot replay the resident kernel; profiles/README.md)"}
     prof = os.path.join(ROOT, "profiles", "r01_inner_bnb_traffic.json")

@@ -61,6 +61,12 @@ __device__ void svd3(const double H[9], double U[9], double W[3], double V[9]) {
         W[j] = n;
         for (int k = 0; k < 3; k++) U[3 * k + j] = n > 0 ? A[3 * k + j] / n : 0;
     }
+    // order the singular triplets by descending singular value, as Matrix::svd does (matrix.cpp:770-800): the float `det`
+    // of jly_icp3d.hpp:291-297 then scales the same (smallest) direction as in the reference
+    for (int a = 0; a < 2; a++) for (int b = a + 1; b < 3; b++) if (W[b] > W[a]) {
+        double tw = W[a]; W[a] = W[b]; W[b] = tw;
+        for (int k = 0; k < 3; k++) { double tu = U[3 * k + a]; U[3 * k + a] = U[3 * k + b]; U[3 * k + b] = tu; double tv = V[3 * k + a]; V[3 * k + a] = V[3 * k + b]; V[3 * k + b] = tv; }
+    }
     for (int j = 0; j < 3; j++) if (W[j] <= 1e-300) {   // rank-deficient column: complete U to an orthonormal basis
         const int a = (j + 1) % 3, b = (j + 2) % 3;
         U[j] = U[3 + a] * U[6 + b] - U[6 + a] * U[3 + b];

@@ -160,7 +160,7 @@ def test_register_cavity_golden(g, name, fp, golden_err, compat):
     r = reg.Register()
     assert r["optError"] == float(z[pre + "optError"]) and abs(r["optError"] - golden_err) < 1e-4
     assert int(z["nd"]) - r["optComp"] == compat
-    assert np.abs(r["R"] - z[pre + "R"]).max() < 1e-6 and np.abs(r["t"] - z[pre + "t"]).max() < 1e-6
+    assert np.abs(r["R"] - z[pre + "R"]).max() < 1e-12 and np.abs(r["t"] - z[pre + "t"]).max() < 1e-12   # vs the reference itself
     assert r["counters"][:6] == z[pre + "counters"][:6].tolist()
     assert g.error_trace(r["trace"]) == list(z[pre + "trace"])
     reg.set_options(exact_sums=0)

@@ -42,7 +42,7 @@ def test_pair1_register_golden(po):
     r = o.register(int(z["nd"]))
     assert r["optError"] == float(z["exp_optError"]) and abs(r["optError"] - 8.45388) < 5e-6
     assert r["optComp"] == int(z["exp_optComp"]) == 238 - 133
-    assert np.abs(r["R"] - z["exp_R"]).max() < 1e-6 and np.abs(r["t"] - z["exp_t"]).max() < 1e-6
+    assert np.abs(r["R"] - z["exp_R"]).max() < 1e-12 and np.abs(r["t"] - z["exp_t"]).max() < 1e-12   # same SVD ordering as Matrix::svd
     golden_R = np.array([[0.2491547, 0.7601179, 0.6001184], [-0.7550769, -0.2355628, 0.6118569], [0.6064490, -0.6055829, 0.5152558]])
     assert np.abs(r["R"] - golden_R).max() < 1e-6
     assert r["counters"][:6] == z["exp_counters"][:6].tolist()
@@ -73,7 +73,7 @@ def test_bunny100_register(po):
     o = po.Oracle("port", z["model_xyz"], z["data_xyz"], po.upstream_config(distTransSize=100))
     r = o.register(int(z["nd"]))
     assert r["optError"] == float(z["exp100_optError"])
-    assert np.abs(r["R"] - z["exp100_R"]).max() < 1e-6 and np.abs(r["t"] - z["exp100_t"]).max() < 1e-6
+    assert np.abs(r["R"] - z["exp100_R"]).max() < 1e-12 and np.abs(r["t"] - z["exp100_t"]).max() < 1e-12
     assert r["counters"][:6] == z["exp100_counters"][:6].tolist()
 
 
@@ -134,4 +134,4 @@ def test_port_vs_reference_inner_calls(po):
             assert ea == eb and (level >= 0 or np.array_equal(ta, tb))
     ea, Ra, ta, ca = a.icp(np.eye(3), np.zeros(3))
     eb, Rb, tb, cb = b.icp(np.eye(3), np.zeros(3))
-    assert ea == eb and np.abs(Ra - Rb).max() < 1e-6 and np.array_equal(ca, cb)
+    assert ea == eb and np.abs(Ra - Rb).max() < 1e-12 and np.array_equal(ca, cb)
