@@ -57,6 +57,12 @@ __device__ __forceinline__ int clamp_cell_v(int S, double x0, double y0, double 
     return __ldg(vcell + ((z * S + y) * S + x));
 }
 
+__device__ __forceinline__ int clamp_vox_v(int S, double x0, double y0, double z0, double scale, float fx, float fy, float fz) {
+    int x = vox_round(fx, x0, scale), y = vox_round(fy, y0, scale), z = vox_round(fz, z0, scale);
+    x = min(max(x, 0), S - 1); y = min(max(y, 0), S - 1); z = min(max(z, 0), S - 1);
+    return (z * S + y) * S + x;
+}
+
 // checkCompatibility's voxel (jly_goicp.cpp:976-984): same rounding, clamped INTO the grid; returns the compact id
 // of the closest occupied cell (emptyCells), ncells if that voxel is unresolved.
 __device__ __forceinline__ int clamp_cell(const GridDev& g, float fx, float fy, float fz) {

@@ -241,9 +241,10 @@ struct goicp_handle_s {
     DevBuf arenaIn, arenaWork, dPairs, dTmp, dTmp2, dTmp3, dSepBits, dSepNx, dSepNxy;
     PinBuf hStage, hPairs;
     WaveCtx main;
-    MapBuf qProbs, qOuts, qOrder, qIcp; DevBuf qClaim, qHeaps, qScratch, qMemo, dGen;   // persistent-queue mode (batches)
+    MapBuf qOuts, qOrder, qIcp; DevBuf qClaim, qHeaps, qScratch, qMemo, dGen;   // persistent-queue mode (batches)
     int shardRank = 0, shardN = 1; goicp_allgather_fn allgather = nullptr; void* allgatherUser = nullptr;   // frontier sharding
     std::vector<InnerOut> xSend, xRecv;
+    std::atomic<int> outstanding{0};   // requests published and not yet harvested (persistent scheduler)
     std::atomic<int> activePairs{0};   // pairs currently being searched (persistent scheduler): few left -> speculate wider
     int persistent_single = 1;   // single registrations of small clouds also go through the resident kernel (no launches per wave)
     int persistent = 1;          // batches: 1 = resident kernel + request ring, 0 = one launch per wave
@@ -359,10 +360,11 @@ static goicp_status upload_problems(Eng* h) {
         in += al256(sizeof(int) * std::max(nc, 1)) + al256(sizeof(uint32_t) * (nc + 1)) + al256(sizeof(int) * (nc + 1)) + al256(sizeof(int) * P.Nm);
         P.inBytes = in; P.inOff = inTot; inTot += in;
         size_t w = 0;
-        w += al256(sizeof(float) * S3) + al256(sizeof(int) * S3) + (wantVcell ? al256(sizeof(int) * S3) : 0);
+        w += al256(sizeof(float) * S3) + al256(sizeof(int) * S3) + (wantVcell ? 2 * al256(sizeof(int) * S3) : 0);
         w += 2 * al256(sizeof(float) * P.NdAll) + al256(sizeof(float) * GOICP_MAXROTLEVEL * (size_t)P.NdAll);
         if (useF && p.regularizationFPFH > 0) w += al256(sizeof(float) * (size_t)P.NdAll * (nc + 1));
         w += al256(sizeof(unsigned long long) * P.NdAll) + al256(sizeof(int) * P.NdAll) + al256(sizeof(float) * 8 * (size_t)std::max(P.NdAll, 1));
+        if (!(p.trimFraction < 0.001)) w += al256(sizeof(unsigned long long) * 2048);
         P.workBytes = w; P.workOff = workTot; workTot += w;
     }
     CU(h->arenaIn.ensure(inTot));
@@ -397,7 +399,7 @@ static goicp_status upload_problems(Eng* h) {
         size_t w = P.workOff;
         D.g.dist = reinterpret_cast<float*>(dWork + w); w += al256(sizeof(float) * S3);
         D.g.vnear = reinterpret_cast<int*>(dWork + w); w += al256(sizeof(int) * S3);
-        if (wantVcell) { D.g.vcell = reinterpret_cast<int*>(dWork + w); w += al256(sizeof(int) * S3); }
+        if (wantVcell) { D.g.vcell = reinterpret_cast<int*>(dWork + w); w += al256(sizeof(int) * S3); D.g.vmask = reinterpret_cast<uint32_t*>(dWork + w); w += al256(sizeof(int) * S3); }
         D.normData = reinterpret_cast<float*>(dWork + w); w += al256(sizeof(float) * P.NdAll);
         D.weights = reinterpret_cast<float*>(dWork + w); w += al256(sizeof(float) * P.NdAll);
         D.maxRotDis = reinterpret_cast<float*>(dWork + w); w += al256(sizeof(float) * GOICP_MAXROTLEVEL * (size_t)P.NdAll);
@@ -405,6 +407,7 @@ static goicp_status upload_problems(Eng* h) {
         D.nn = reinterpret_cast<unsigned long long*>(dWork + w); w += al256(sizeof(unsigned long long) * P.NdAll);
         D.order = reinterpret_cast<int*>(dWork + w); w += al256(sizeof(int) * P.NdAll);
         D.scratch = reinterpret_cast<float*>(dWork + w); w += al256(sizeof(float) * 8 * (size_t)std::max(P.NdAll, 1));
+        if (!(p.trimFraction < 0.001)) { D.sortKeys = reinterpret_cast<unsigned long long*>(dWork + w); w += al256(sizeof(unsigned long long) * 2048); }
         D.g.S = S; D.g.ncells = nc; D.g.xMin = P.info.xMin; D.g.yMin = P.info.yMin; D.g.zMin = P.info.zMin; D.g.scale = P.info.scale;
         D.Nm = P.Nm; D.Nd = P.Nd;
     });
@@ -496,9 +499,9 @@ static BnbCfg bnb_config(Eng* h) {
     int maxNd = 1; bool anyTrim = false, anyF = false;
     for (auto& P : h->probs) { maxNd = std::max(maxNd, P.Nd); anyTrim |= P.dev.doTrim != 0; anyF |= P.dev.use_fpfh != 0; }
     BnbCfg c;
-    c.NdP = (maxNd + 31) & ~31; c.NdQ = c.NdP + 4;
+    c.NdP = (maxNd + 31) & ~31; c.NdQ = c.NdP + 2;   // row stride = 2 mod 32: the 16 chain lanes read 16 different banks
     const bool needMd = h->exact_sums || anyTrim, needFp = h->exact_sums && anyF;
-    c.smemFloats = goicp_bnb_smem_floats(c.NdP, c.NdQ, needMd, needFp);
+    c.smemFloats = goicp_bnb_smem_floats(c.NdP, c.NdQ, h->exact_sums != 0, needMd, needFp);
     const size_t smemBytes = c.smemFloats * sizeof(float);
     c.useSmem = smemBytes <= 180 * 1024;   // + ~32 KB static in the resident kernel
     c.threads = h->bnb_threads;
@@ -867,16 +870,25 @@ static goicp_status register_group(Eng* h, WaveCtx& c, const BnbCfg& cfg, std::a
 // keeps going as soon as the call its OuterBnB order waits for has completed, and sends ICP requests through its thread's
 // side stream.  A deep pair therefore delays nobody else, and the GPU always holds a mix of calls of hundreds of pairs.
 struct PQ {
-    InnerProb* probs; InnerOut* outs; volatile unsigned* order; unsigned orderMask;
+    QueueCell* cells; InnerOut* outs; unsigned cellMask, cellShift;
     std::atomic<unsigned> reserve{0};
-    void publish(unsigned value) {   // value = slot + 1, or the shut-down marker
+    // request words first, the two lap tags last (x86 stores are observed in program order; a 32-byte half of the cell that
+    // shows its tag therefore shows its request words too)
+    void publish(unsigned slot, const InnerProb* pr) {
         const unsigned idx = reserve.fetch_add(1);
-        volatile unsigned* cell = order + (idx & orderMask);
-        while (*cell != 0u) std::this_thread::yield();   // ring full: the GPU has not consumed the previous lap yet
+        QueueCell* c = cells + (idx & cellMask);
+        const unsigned tag = (idx >> cellShift) + 1u;
+        c->slot = slot;
+        if (pr) c->pr = *pr;
         std::atomic_thread_fence(std::memory_order_release);
-        *cell = value;
+        *reinterpret_cast<volatile unsigned*>(&c->seqA) = tag;
+        *reinterpret_cast<volatile unsigned*>(&c->seqB) = tag;
     }
 };
+static inline bool out_ready(const InnerOut& o) {
+    return *reinterpret_cast<const volatile unsigned*>(&o.seq0) == 1u && *reinterpret_cast<const volatile unsigned*>(&o.seq1) == 1u;
+}
+static inline void out_arm(InnerOut& o) { *reinterpret_cast<volatile unsigned*>(&o.seq0) = 0u; *reinterpret_cast<volatile unsigned*>(&o.seq1) = 0u; }
 
 static goicp_status persistent_worker(Eng* h, WaveCtx& c, PQ& pq, std::atomic<int>& next, int slots, int slotLo, int slotHi, const BnbCfg& cfg) {
     const int np = (int)h->probs.size();
@@ -889,11 +901,12 @@ static goicp_status persistent_worker(Eng* h, WaveCtx& c, PQ& pq, std::atomic<in
     IcpState* icpDev = reinterpret_cast<IcpState*>(h->qIcp.d);
     Problem dummy;
     auto lastProgress = clk::now();
+    const auto tStart = clk::now(); double nextSample = 0; const bool dbgTimeline = getenv("GOICP_TIMELINE") != nullptr;
     auto harvest = [&](Problem& P, std::vector<Problem::PendReq>& pend, bool live) {
         bool any = false;
         for (size_t k = 0; k < pend.size();) {
             const InnerOut& o = pq.outs[pend[k].slot];
-            if (*reinterpret_cast<const volatile int*>(&o.done) == 0) { ++k; continue; }
+            if (!out_ready(o)) { ++k; continue; }
             std::atomic_thread_fence(std::memory_order_acquire);
             if (o.status == 4) { P.status = GOICP_ERR_OVERFLOW; }
             if (live && pend[k].entryOpt == P.optError) {
@@ -903,6 +916,7 @@ static goicp_status persistent_worker(Eng* h, WaveCtx& c, PQ& pq, std::atomic<in
             }
             freeSlots.push_back(pend[k].slot);
             pend[k] = pend.back(); pend.pop_back();
+            h->outstanding.fetch_sub(1, std::memory_order_relaxed);
             any = true;
         }
         return any;
@@ -921,10 +935,9 @@ static goicp_status persistent_worker(Eng* h, WaveCtx& c, PQ& pq, std::atomic<in
             const unsigned long long ptr = (unsigned long long)(uintptr_t)(icpDev + 2 * i + k);
             const unsigned lo = (unsigned)(ptr & 0xFFFFFFFFull), hi = (unsigned)(ptr >> 32);
             memcpy(&ip.R[0], &lo, 4); memcpy(&ip.R[1], &hi, 4);
-            pq.probs[slot] = ip;
-            *reinterpret_cast<volatile int*>(&pq.outs[slot].done) = 0;
+            out_arm(pq.outs[slot]);
             P.icpSlot[k] = slot;
-            pq.publish((unsigned)slot + 1u);
+            pq.publish((unsigned)slot, &ip);
         }
         P.icpQueued = true;
         c.launches[3] += 2;
@@ -935,6 +948,7 @@ static goicp_status persistent_worker(Eng* h, WaveCtx& c, PQ& pq, std::atomic<in
         if (active.empty() && zombies.empty()) break;
         bool progressed = false;
         c.callsUsed++;   // loop iterations
+        if (slotLo == 0 && dbgTimeline) { const double tnow = secs_since(tStart); if (tnow >= nextSample) { fprintf(stderr, "[timeline] t=%.3f active_pairs=%d outstanding=%d\n", tnow, h->activePairs.load(), h->outstanding.load()); nextSample += 0.05; } }
         auto tIter = clk::now();
         // ---- every active pair: harvest finished calls, advance, publish what it needs next ----
         for (int i : active) {
@@ -944,7 +958,7 @@ static goicp_status persistent_worker(Eng* h, WaveCtx& c, PQ& pq, std::atomic<in
             if (P.phase == PH_START) { P.phase = PH_WAIT_INIT; P.icpQueued = false; }
             if (P.phase == PH_WAIT_INIT || P.phase == PH_WAIT_ICP) {
                 if (!P.icpQueued) { if (send_icp(i)) progressed = true; continue; }
-                const bool d0 = *reinterpret_cast<const volatile int*>(&pq.outs[P.icpSlot[0]].done) != 0, d1 = *reinterpret_cast<const volatile int*>(&pq.outs[P.icpSlot[1]].done) != 0;
+                const bool d0 = out_ready(pq.outs[P.icpSlot[0]]), d1 = out_ready(pq.outs[P.icpSlot[1]]);
                 if (!(d0 && d1)) continue;
                 std::atomic_thread_fence(std::memory_order_acquire);
                 freeSlots.push_back(P.icpSlot[0]); freeSlots.push_back(P.icpSlot[1]);
@@ -967,13 +981,13 @@ static goicp_status persistent_worker(Eng* h, WaveCtx& c, PQ& pq, std::atomic<in
             gather_requests(h, i, reqs, tags);
             c.tLogic += secs_since(tg); tg = clk::now();
             for (size_t k = 0; k < reqs.size(); k++) {
-                if (freeSlots.empty()) break;   // out of slots: the rest is regathered later
+                if (freeSlots.empty() || h->outstanding.load(std::memory_order_relaxed) > (int)(pq.cellMask >> 1)) break;   // out of slots / ring half full: the rest is regathered later
                 const int slot = freeSlots.back(); freeSlots.pop_back();
-                pq.probs[slot] = reqs[k];
-                *reinterpret_cast<volatile int*>(&pq.outs[slot].done) = 0;
+                out_arm(pq.outs[slot]);
                 P.pend.push_back(Problem::PendReq{slot, tags[k].key, tags[k].entryOpt});
                 P.inflight.insert(tags[k].key);
-                pq.publish((unsigned)slot + 1u);
+                pq.publish((unsigned)slot, &reqs[k]);
+                h->outstanding.fetch_add(1, std::memory_order_relaxed);
                 c.callsLaunched++;
             }
             c.tInnerEnq += secs_since(tg);
@@ -1003,12 +1017,11 @@ static goicp_status persistent_worker(Eng* h, WaveCtx& c, PQ& pq, std::atomic<in
 }
 
 static goicp_status register_persistent(Eng* h, const BnbCfg& cfg, int groups, int slots) {
-    const int NSLOT = 1 << 17, ORDER = 1 << 18;
+    const int NSLOT = 1 << 17, ORDER = 1 << 18;   // result slots; ring cells (> requests ever in flight)
     const int np = (int)h->probs.size();
     // everything is allocated BEFORE the resident kernel starts (cudaMalloc / cudaFree would wait for it forever)
-    CU(h->qProbs.ensure(sizeof(InnerProb) * (size_t)NSLOT));
     CU(h->qOuts.ensure(sizeof(InnerOut) * (size_t)NSLOT));
-    CU(h->qOrder.ensure(sizeof(unsigned) * (size_t)ORDER));
+    CU(h->qOrder.ensure(sizeof(QueueCell) * (size_t)ORDER));
     CU(h->qClaim.ensure(sizeof(unsigned)));
     CU(h->qIcp.ensure(sizeof(IcpState) * 2 * (size_t)np));
     int perSM = goicp_inner_bnb_persistent_occupancy(cfg.useSmem ? cfg.smemFloats * sizeof(float) : 0, h->exact_sums, cfg.threads);
@@ -1029,19 +1042,19 @@ static goicp_status register_persistent(Eng* h, const BnbCfg& cfg, int groups, i
         w->tLogic = w->tInnerEnq = w->tInnerWait = w->tIcp = 0; w->callsUsed = 0;
     }
     h->main.callsUsed = 0;
-    memset(h->qOrder.h, 0, sizeof(unsigned) * (size_t)ORDER);
+    memset(h->qOrder.h, 0, sizeof(QueueCell) * (size_t)ORDER);
     CU(cudaMemsetAsync(h->qClaim.p, 0, sizeof(unsigned), h->stream));
-    PQ pq; pq.probs = reinterpret_cast<InnerProb*>(h->qProbs.h); pq.outs = reinterpret_cast<InnerOut*>(h->qOuts.h);
-    pq.order = reinterpret_cast<volatile unsigned*>(h->qOrder.h); pq.orderMask = ORDER - 1;
-    QueueDev qd; qd.probs = reinterpret_cast<const InnerProb*>(h->qProbs.d); qd.outs = reinterpret_cast<InnerOut*>(h->qOuts.d);
-    qd.order = reinterpret_cast<unsigned*>(h->qOrder.d); qd.orderMask = ORDER - 1; qd.claim = h->qClaim.as<unsigned>();
+    PQ pq; pq.cells = reinterpret_cast<QueueCell*>(h->qOrder.h); pq.outs = reinterpret_cast<InnerOut*>(h->qOuts.h);
+    pq.cellMask = ORDER - 1; pq.cellShift = 18;
+    QueueDev qd; qd.cells = reinterpret_cast<const QueueCell*>(h->qOrder.d); qd.outs = reinterpret_cast<InnerOut*>(h->qOuts.d);
+    qd.cellMask = ORDER - 1; qd.cellShift = 18; qd.claim = h->qClaim.as<unsigned>();
     cudaEventRecord(h->main.ev0, h->stream);
     CU(goicp_launch_inner_bnb_persistent(h->dPairs.as<PairDev>(), qd, h->qHeaps.as<HeapEnt>(), heapCap, ctas, h->qScratch.as<float>(), cfg.smemFloats,
                                          cfg.NdP, cfg.NdQ, cfg.smemFloats, cfg.useSmem, h->exact_sums, cfg.threads, h->qMemo.p, memoCap, h->dGen.as<unsigned>(), h->stream));
     cudaEventRecord(h->main.ev1, h->stream);
     g_no_device_alloc.store(true);
     std::atomic<int> next(0);
-    h->activePairs.store(0);
+    h->activePairs.store(0); h->outstanding.store(0);
     std::vector<goicp_status> st(groups, GOICP_OK);
     std::vector<std::thread> th;
     const int per = NSLOT / groups;
@@ -1050,7 +1063,7 @@ static goicp_status register_persistent(Eng* h, const BnbCfg& cfg, int groups, i
         th.emplace_back([h, w, &pq, &next, &st, g, slots, per, &cfg]() { cudaSetDevice(h->device); st[g] = persistent_worker(h, *w, pq, next, slots, g * per, (g + 1) * per, cfg); });
     }
     for (auto& t : th) t.join();
-    for (int k = 0; k < ctas; k++) pq.publish(0xFFFFFFFFu);   // one shut-down marker per CTA
+    for (int k = 0; k < ctas; k++) pq.publish(0xFFFFFFFFu, nullptr);   // one shut-down marker per CTA
     cudaError_t e = cudaStreamSynchronize(h->stream);
     g_no_device_alloc.store(false);
     if (e != cudaSuccess) return fail(h, GOICP_ERR_CUDA, "resident inner_bnb kernel: %s", cudaGetErrorString(e));
@@ -1067,6 +1080,7 @@ static goicp_status register_persistent(Eng* h, const BnbCfg& cfg, int groups, i
       h->stats[5] = h->main.tLogic; h->stats[6] = h->main.tInnerEnq; h->stats[7] = h->main.tInnerWait;
       if (getenv("GOICP_DEBUG")) {
           fprintf(stderr, "[device] calls %llu pops %llu busy-cycles/pop %.0f corner-misses/pop %.2f busy-cycles %.4g poll-cycles %.4g (ctas %d)\n", st8[3], st8[1], (double)st8[0] / std::max<double>(1, st8[1]), (double)st8[2] / std::max<double>(1, st8[1]), (double)st8[0], (double)st8[4], ctas);
+          fprintf(stderr, "[device] claims that found their cell empty: %llu of %llu; cycles in cell hand-back + system fence per call: %.0f; poll cycles per call %.0f\n", st8[5], st8[3], (double)st8[6] / std::max<double>(1, st8[3]), (double)st8[4] / std::max<double>(1, st8[3]));
           fprintf(stderr, "[persistent] loops %lld gather %.3fs publish %.3fs idle-sleep %.3fs loop-busy %.3fs (summed over %d workers)\n", h->main.callsUsed, h->main.tLogic, h->main.tInnerEnq, h->main.tInnerWait, h->main.tIcp, groups);
       } }
     return GOICP_OK;
@@ -1209,7 +1223,7 @@ void goicp_destroy(goicp_handle h) {
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->arenaIn, &h->arenaWork, &h->dPairs, &h->dTmp, &h->dTmp2, &h->dTmp3, &h->dSepBits, &h->dSepNx, &h->dSepNxy};
     for (DevBuf* b : bufs) b->release();
-    h->hStage.release(); h->hPairs.release(); h->qProbs.release(); h->qOuts.release(); h->qOrder.release(); h->qIcp.release(); h->qClaim.release(); h->qHeaps.release(); h->qScratch.release(); h->qMemo.release(); h->dGen.release();
+    h->hStage.release(); h->hPairs.release(); h->qOuts.release(); h->qOrder.release(); h->qIcp.release(); h->qClaim.release(); h->qHeaps.release(); h->qScratch.release(); h->qMemo.release(); h->dGen.release();
     h->main.release();
     for (auto& w : h->workers) w->release();
     if (h->ownStream) cudaStreamDestroy(h->stream);
@@ -1235,6 +1249,7 @@ goicp_status goicp_set_data(goicp_handle h, const float* xyz, const int32_t* c, 
 goicp_status goicp_set_params(goicp_handle h, const goicp_params* p) {
     if (!h || !p) return GOICP_ERR_ARG;
     const bool gridChanged = !h->haveParams || p->distTransSize != h->params.distTransSize || p->distTransExpandFactor != h->params.distTransExpandFactor ||
+                             (p->trimFraction < 0.001) != (h->params.trimFraction < 0.001) ||
                              p->cfpfh != h->params.cfpfh || p->regularizationFPFH != h->params.regularizationFPFH;
     h->params = *p; h->haveParams = true;
     for (auto& P : h->probs) { P.initialized = false; if (gridChanged) P.prepared = P.dt_built = false; }

@@ -22,6 +22,7 @@ struct GridDev {
     int* vcell;              // S^3   compact id of that cell (ncells if the voxel points at an empty cell)
     int* cell_vox;           // ncells   voxel of each occupied cell, ascending
     uint32_t* cmask;         // ncells+1   bit k set <=> a source point of colour index k is compatible (checkProperty)
+    uint32_t* vmask;         // S^3   cmask of the voxel's closest cell (one gather for the incompatibility term)
 };
 
 // GoICP state after Initialize (jly_goicp.cpp:180-267) for one pair.
@@ -55,7 +56,8 @@ struct PairDev {
     // ICP workspace (written by the ICP kernels)
     unsigned long long* nn;              // Nd packed (float bits of squared distance << 32 | model index)
     int* order;                          // Nd: id_data of points[i] (identity unless trimmed, jly_icp3d.hpp:252)
-    float* scratch;                      // 2*max(Nd,Nm) floats
+    float* scratch;                      // 8*Nd floats
+    unsigned long long* sortKeys;        // 2048 keys for the trimmed-ICP sort (NULL unless trimming)
 };
 
 struct InnerProb {          // one GoICP::InnerBnB call (jly_goicp.cpp:286)
@@ -64,23 +66,34 @@ struct InnerProb {          // one GoICP::InnerBnB call (jly_goicp.cpp:286)
     float optError;
     float R[9];
 };
-struct InnerOut {
-    float err;              // optErrorT
-    float node[4];          // best translation node x,y,z,w (valid if improved)
+struct alignas(64) InnerOut {   // one 64-byte record: it leaves the SM as a single coalesced warp store
+    unsigned seq0;          // resident-queue mode: both flags equal the request's tag once the record is complete (each 32-byte
+    float err;              // optErrorT                                   half of the record carries one flag, so a reader that
+    float node[4];          // best translation node x,y,z,w               sees both has seen every word -- no system fence needed)
     int improved;
-    int pops, subcubes;
+    int pops;
+    int subcubes;
     int status;             // 0 ok, 4 heap overflow
-    int done;               // persistent-queue mode: set (after a system fence) when the result is complete
-    int pad[2];
+    int pad[5];
+    unsigned seq1;
 };
 
-// Persistent-queue mode (batches): the host publishes requests by writing slot+1 into order[i % cap] (mapped host memory);
-// CTAs claim indices i from a device counter, wait for their cell, run the call and write outs[slot] + done flag.
+// Resident-queue mode (batches): the host publishes requests into a ring of 64-byte cells in mapped host memory; CTAs claim
+// ring indices from a device counter, wait until BOTH flags of their cell carry the tag of that lap (the request words in
+// between are then complete), run the call and write outs[slot].  Cells are never handed back: the host keeps fewer requests
+// in flight than the ring has cells, and claims are sequential, so a cell is consumed before its index comes round again.
+struct alignas(64) QueueCell {
+    unsigned seqA;          // lap tag (ring index / capacity + 1)
+    unsigned slot;          // result slot; 0xFFFFFFFF = shut down
+    InnerProb pr;           // 48 bytes
+    unsigned pad;
+    unsigned seqB;
+};
 struct QueueDev {
-    const InnerProb* probs;   // mapped host memory, one per slot
+    const QueueCell* cells;   // mapped host memory ring
     InnerOut* outs;           // mapped host memory, one per slot
-    unsigned* order;          // mapped host memory ring: 0 = empty, 0xFFFFFFFF = shut down, else slot + 1
-    unsigned orderMask;       // ring capacity - 1 (power of two)
+    unsigned cellMask;        // ring capacity - 1 (power of two)
+    unsigned cellShift;       // log2(capacity)
     unsigned* claim;          // device counter
 };
 

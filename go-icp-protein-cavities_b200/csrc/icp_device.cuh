@@ -81,15 +81,15 @@ constexpr int SORT_CAP = 2048;
 __device__ __forceinline__ bool icp_update_part(const PairDev& P, IcpState& st) {
     const int n = P.Nd, num = P.inlierNum, tid = threadIdx.x;
     const int iter0 = st.iter;   // st.iter is only written by thread 0 after the last barrier below
-    __shared__ unsigned long long keys[SORT_CAP];
     __shared__ double s_mu[6];
     __shared__ double s_H[9];
     __shared__ float s_err;
     __shared__ int s_done;
     float* T = P.scratch;   // [7][n]: p_m xyz, p_d xyz, dis  (positions follow `order`)
 
-    if (P.doTrim) {   // qsort of POINTREF by dis (:252-255); ties keep index order
-        if (n > SORT_CAP) { if (tid == 0) { st.status = 3; st.done = 1; } return true; }
+    if (P.doTrim) {   // qsort of POINTREF by dis (:252-255); ties keep index order.  Bitonic sort in the pair's global scratch
+        unsigned long long* keys = P.sortKeys;
+        if (n > SORT_CAP || keys == nullptr) { if (tid == 0) { st.status = 3; st.done = 1; } return true; }
         for (int i = tid; i < SORT_CAP; i += blockDim.x)
             keys[i] = (i < n) ? (((P.nn[i] >> 32) << 32) | (unsigned)i) : GOICP_NN_EMPTY;
         __syncthreads();

@@ -127,58 +127,65 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
     __shared__ BnbShared sh;
     __shared__ float4 sheap[2 * HEAP_SMEM];
     __shared__ InnerProb s_pr;
+    __shared__ InnerOut s_out;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = blockDim.x >> 5;
     float* base = SMEM ? reinterpret_cast<float*>(dyn_smem4) : gscratch + (size_t)blockIdx.x * gstride;   // SMEM: address space known -> LDS/STS
     float* tx = base; float* ty = tx + NdP; float* tz = ty + NdP; float* wgt = tz + NdP; float* mrd = wgt + NdP;
     uint8_t* dprop_s = reinterpret_cast<uint8_t*>(mrd + NdP);   // [NdP] colour index of each data point
     float* part = mrd + NdP + (NdP >> 2);   // [8][nchunks][2] + [27][nchunks] per-chunk partial sums (tree-sum mode)
-    float* md = part + 43 * (NdP >> 5);   // [8][NdQ]   (EXACT or trimmed)
-    float* fp = md + 8 * NdQ;         // [27][NdQ]  (EXACT with the c-FPFH term)
+    float* md = part + 43 * (NdP >> 5);   // EXACT: [16][NdQ] sum terms (ub, lb per child); trimmed: [8][NdQ] residuals
+    float* fp = md + (EXACT ? 16 : 8) * NdQ;   // [27][NdQ]  (EXACT with the c-FPFH term)
     Heap heap; heap.s = sheap; heap.g = heaps + (size_t)blockIdx.x * heapCap;
     uint4* memo = memoAll + 2 * (size_t)blockIdx.x * memoCap;
     const int memoShift = 32 - (31 - __clz(memoCap));   // this CTA's corner memo: direct-mapped, 32 B entries, tagged with the call's generation
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) {
-            if (!PERSIST) sh.prob = atomicAdd(counter, 1);
-            else {   // claim the next ring index and wait (with back-off) until the host has published it
-                const long long tp0 = clock64();
-                const unsigned i = atomicAdd(q.claim, 1u);
-                volatile unsigned* cell = q.order + (i & q.orderMask);
-                unsigned v; unsigned backoff = 64;
-                unsigned long long t0 = 0, now;
-                while ((v = *cell) == 0u) {
-                    __nanosleep(backoff); if (backoff < 16384) backoff <<= 1;
-                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-                    if (t0 == 0) t0 = now;
-                    else if (now - t0 > 60000000000ull) { v = 0xFFFFFFFFu; break; }   // safety net: 60 s without work -> leave
-                }
-                if (v != 0xFFFFFFFFu) *cell = 0u;   // hand the cell back to the host (shut-down markers stay)
-                __threadfence_system();
-                atomicAdd(dstat + 4, (unsigned long long)(clock64() - tp0));
-                sh.prob = (v == 0xFFFFFFFFu) ? -1 : (int)(v - 1u);
+        if (!PERSIST) {
+            if (tid == 0) sh.prob = atomicAdd(counter, 1);
+            __syncthreads();
+            if (sh.prob >= nprob) {   // the last CTA to leave re-arms the counters, so the host never has to memset them
+                if (tid == 0) { __threadfence(); if (atomicAdd(counter + 1, 1) == (int)gridDim.x - 1) { counter[0] = 0; counter[1] = 0; } }
+                return;
+            }
+            if (tid < (int)(sizeof(InnerProb) / 4)) reinterpret_cast<int*>(&s_pr)[tid] = reinterpret_cast<const volatile int*>(probs + sh.prob)[tid];
+        } else if (warp == 0) {
+            // claim the next ring index; the 16 lanes read the 64-byte cell with one load until both lap tags are there
+            unsigned i = 0;
+            const long long tp0 = clock64();
+            if (lane == 0) i = atomicAdd(q.claim, 1u);
+            i = __shfl_sync(GOICP_FULL, i, 0);
+            const unsigned want = (i >> q.cellShift) + 1u;
+            const volatile unsigned* cell = reinterpret_cast<const volatile unsigned*>(q.cells + (i & q.cellMask));
+            unsigned w = 0, backoff = 64; unsigned long long t0 = 0, now; int notReady = 0; bool dead = false;
+            for (;;) {
+                if (lane < 16) w = cell[lane];
+                const unsigned a = __shfl_sync(GOICP_FULL, w, 0), b = __shfl_sync(GOICP_FULL, w, 15);
+                if (a == want && b == want) break;
+                notReady = 1;
+                __nanosleep(backoff); if (backoff < 16384) backoff <<= 1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 60000000000ull) { dead = true; break; }   // safety net: 60 s without work -> leave
+            }
+            const unsigned slot = __shfl_sync(GOICP_FULL, w, 1);
+            if (lane >= 2 && lane < 14) reinterpret_cast<unsigned*>(&s_pr)[lane - 2] = w;
+            if (lane == 0) {
+                sh.prob = (dead || slot == 0xFFFFFFFFu) ? -1 : (int)slot;
+                atomicAdd(dstat + 4, (unsigned long long)(clock64() - tp0)); atomicAdd(dstat + 5, (unsigned long long)notReady);
             }
         }
         __syncthreads();
         const int p = sh.prob;
-        if (PERSIST) { if (p < 0) return; }
-        else if (p >= nprob) {   // the last CTA to leave re-arms the counters, so the host never has to memset them
-            if (tid == 0) { __threadfence(); if (atomicAdd(counter + 1, 1) == (int)gridDim.x - 1) { counter[0] = 0; counter[1] = 0; } }
-            return;
-        }
-        // the request may live in mapped host memory: fetch it once per CTA (13 lanes, one 4-byte bus read each)
-        if (tid < (int)(sizeof(InnerProb) / 4)) {
-            const volatile int* src = reinterpret_cast<const volatile int*>((PERSIST ? q.probs : probs) + p);
-            reinterpret_cast<int*>(&s_pr)[tid] = src[tid];
-        }
-        __syncthreads();
+        if (PERSIST && p < 0) return;
         const InnerProb pr = s_pr;
         if (PERSIST && pr.level == GOICP_REQ_ICP) {   // an ICP / scoring request (GoICP::ICP): state pointer packed into R[0..1]
             IcpState* gst = reinterpret_cast<IcpState*>(((unsigned long long)__float_as_uint(pr.R[1]) << 32) | (unsigned long long)__float_as_uint(pr.R[0]));
             icp_fused_body(pairs, gst);
             __syncthreads();
-            if (tid == 0) { __threadfence_system(); *reinterpret_cast<volatile int*>(&q.outs[p].done) = 1; }
+            if (warp == 0) {
+                if (lane < 16) reinterpret_cast<unsigned*>(q.outs + p)[lane] = (lane == 0 || lane == 15) ? 1u : 0u;
+            }
             continue;
         }
         const PairDev& P = pairs[pr.pair];
@@ -187,7 +194,8 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
         const int nchunks = (Nd + 31) >> 5;
         const float* __restrict__ dist = g.dist;
         const bool corners = P.use_reg || P.use_fpfh;
-        const bool useMd = EXACT || P.doTrim;
+        const bool doTrim = P.doTrim != 0;
+        const bool useMd = EXACT || doTrim;
         const int ncp1 = g.ncells + 1;
         const int norm = P.norm;
         const int G = min(nchunks, 8), ngroups = (nchunks + G - 1) / G;   // chunks per work item, items per row
@@ -196,6 +204,7 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
         const double gx0 = g.xMin, gy0 = g.yMin, gz0 = g.zMin, gscale = g.scale;
         const int* __restrict__ vcell = g.vcell;
         const uint32_t* __restrict__ cmask = g.cmask;
+        const uint32_t* __restrict__ vmask = g.vmask;
         const float* __restrict__ fpfhD = P.fpfhD;
         const bool use_reg = P.use_reg != 0, use_fpfh = P.use_fpfh != 0;
 
@@ -260,7 +269,11 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
                     float d = wgt[i] * dt_distance_v(S, gx0, gy0, gz0, gscale, dist, tx[i] + transX, ty[i] + transY, tz[i] + transZ);
                     d = d - mrd[i];
                     if (d < 0.f) d = 0.f;
-                    if (useMd) md[c * NdQ + i] = d;
+                    if (EXACT && !doTrim) {   // the two sum terms of this point (:393-415), summed in index order by the chain lanes
+                        const float dis = fmaxf(d - mtd, 0.f);
+                        md[(2 * c) * NdQ + i] = (norm == 2) ? d * d : d;
+                        md[(2 * c + 1) * NdQ + i] = (norm == 2) ? dis * dis : dis;
+                    } else if (useMd) md[c * NdQ + i] = d;
                     else {
                         su = su + ((norm == 2) ? d * d : d);
                         const float dis = d - mtd;
@@ -284,16 +297,10 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
                 const int c = lane >> 1;
                 float acc = 0.f;
                 if (EXACT) {   // sequential float sums in index order (:393-415): lane = (child, ub|lb); 16 independent chains
-                    const float off = (lane & 1) ? mtd : 0.f;
-                    const float* m = md + c * NdQ;
+                    const float* m = md + lane * NdQ;
                     const int n = P.inlierNum;
-                    if (norm == 2) {
-#pragma unroll 4
-                        for (int i = 0; i < n; ++i) { const float v = fmaxf(m[i] - off, 0.f); acc = acc + v * v; }
-                    } else {
-#pragma unroll 4
-                        for (int i = 0; i < n; ++i) { const float v = fmaxf(m[i] - off, 0.f); acc = acc + v; }
-                    }
+#pragma unroll 8
+                    for (int i = 0; i < n; ++i) acc = acc + m[i];
                 } else {
                     const float* q = part + 2 * c * ngroups + (lane & 1);
                     for (int k = 0; k < ngroups; ++k) acc = acc + q[2 * k];
@@ -314,9 +321,11 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
                     const int iEnd = min(Nd, (gi + 1) * G * 32);
                     int bad = 0; float fs = 0.f;
                     for (int i = gi * G * 32 + lane; i < iEnd; i += 32) {
-                        const int cell = clamp_cell_v(S, gx0, gy0, gz0, gscale, vcell, tx[i] + cx, ty[i] + cy, tz[i] + cz);
-                        if (use_reg) bad += ((__ldg(cmask + cell) >> dprop_s[i]) & 1u) ? 0 : 1;
-                        if (use_fpfh) {
+                        const int vox = clamp_vox_v(S, gx0, gy0, gz0, gscale, tx[i] + cx, ty[i] + cy, tz[i] + cz);
+                        if (!use_fpfh) bad += ((__ldg(vmask + vox) >> dprop_s[i]) & 1u) ? 0 : 1;   // per-voxel mask of the closest cell: one gather
+                        else {
+                            const int cell = __ldg(vcell + vox);
+                            if (use_reg) bad += ((__ldg(cmask + cell) >> dprop_s[i]) & 1u) ? 0 : 1;
                             const float fv = __ldg(fpfhD + (size_t)i * ncp1 + cell);
                             if (EXACT) fp[m * NdQ + i] = fv; else fs = fs + fv;
                         }
@@ -403,12 +412,14 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
             atomicAdd(dstat + 2, (unsigned long long)sh.missTot); atomicAdd(dstat + 3, 1ull);
             InnerOut o;
             o.err = sh.optErrorT; o.node[0] = sh.best[0]; o.node[1] = sh.best[1]; o.node[2] = sh.best[2]; o.node[3] = sh.best[3];
-            o.improved = sh.improved; o.pops = sh.pops; o.subcubes = sh.subcubes; o.status = sh.status; o.done = 0; o.pad[0] = o.pad[1] = 0;
-            if (PERSIST) {
-                q.outs[p] = o;
-                __threadfence_system();
-                *reinterpret_cast<volatile int*>(&q.outs[p].done) = 1;
-            } else outs[p] = o;
+            o.improved = sh.improved; o.pops = sh.pops; o.subcubes = sh.subcubes; o.status = sh.status;
+            o.seq0 = o.seq1 = 1u; for (int k = 0; k < 5; k++) o.pad[k] = 0;
+            s_out = o;
+        }
+        if (warp == 0) {   // the record leaves the SM as ONE coalesced 64-byte store (it may live in mapped host memory)
+            __syncwarp();
+            InnerOut* dst = PERSIST ? q.outs + p : outs + p;
+            if (lane < 16) reinterpret_cast<unsigned*>(dst)[lane] = reinterpret_cast<const unsigned*>(&s_out)[lane];
         }
     }
 }
@@ -484,8 +495,8 @@ eval_bounds_kernel(const PairDev* __restrict__ pairs, int pair, const float* __r
 }  // namespace
 
 // ---- launchers ---------------------------------------------------------------------------------------------
-size_t goicp_bnb_smem_floats(int NdP, int NdQ, bool needMd, bool needFp) {
-    return (size_t)5 * NdP + (size_t)(NdP >> 2) + (size_t)43 * (NdP >> 5) + (needMd ? (size_t)8 * NdQ : 0) + (needFp ? (size_t)27 * NdQ : 0);
+size_t goicp_bnb_smem_floats(int NdP, int NdQ, bool exact, bool needMd, bool needFp) {
+    return (size_t)5 * NdP + (size_t)(NdP >> 2) + (size_t)43 * (NdP >> 5) + (needMd ? (size_t)(exact ? 16 : 8) * NdQ : 0) + (needFp ? (size_t)27 * NdQ : 0);
 }
 
 static int g_bnb_attr_set[8] = {0, 0, 0, 0, 0, 0, 0, 0};

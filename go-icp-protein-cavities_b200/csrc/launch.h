@@ -5,7 +5,7 @@
 #include "goicp_dev.h"
 
 // k_bnb.cu
-size_t goicp_bnb_smem_floats(int NdP, int NdQ, bool needMd, bool needFp);
+size_t goicp_bnb_smem_floats(int NdP, int NdQ, bool exact, bool needMd, bool needFp);
 int goicp_inner_bnb_occupancy(size_t smemBytes, int exact, int threads);
 int goicp_inner_bnb_persistent_occupancy(size_t smemBytes, int exact, int threads);
 cudaError_t goicp_launch_inner_bnb(const PairDev* pairs, const InnerProb* probs, InnerOut* outs, int nprob, int* counter,
