@@ -820,15 +820,15 @@ static void reset_search(Problem& P) {
 
 // One stream of lock-step waves over up to `slots` problems at a time; finished problems are replaced from the shared
 // counter `next` (so a deep pair never stalls more than its own stream).  GoICP::OuterBnB (jly_goicp.cpp:582) per problem.
-static goicp_status register_group(Eng* h, WaveCtx& c, const BnbCfg& cfg, std::atomic<int>& next, int slots) {
+static goicp_status register_group(Eng* h, WaveCtx& c, const BnbCfg& cfg, std::atomic<int>& next, int slots, const std::vector<int>* subset = nullptr) {
     const goicp_params& p = h->params;
-    const int np = (int)h->probs.size();
+    const int np = subset ? (int)subset->size() : (int)h->probs.size();
     std::vector<int> active;
     std::vector<InnerProb> reqs; std::vector<ReqTag> tags; std::vector<InnerOut> outs; std::vector<IcpState> icps; std::vector<int> icpOwner;
     goicp_status s;
     auto tl = clk::now();
     for (;;) {
-        while ((int)active.size() < slots) { const int i = next.fetch_add(1); if (i >= np) break; reset_search(h->probs[i]); active.push_back(i); }
+        while ((int)active.size() < slots) { const int k = next.fetch_add(1); if (k >= np) break; const int i = subset ? (*subset)[k] : k; reset_search(h->probs[i]); active.push_back(i); }
         if (active.empty()) break;
         reqs.clear(); tags.clear(); icps.clear(); icpOwner.clear();
         for (int i : active) {
@@ -908,7 +908,7 @@ static goicp_status persistent_worker(Eng* h, WaveCtx& c, PQ& pq, std::atomic<in
             const InnerOut& o = pq.outs[pend[k].slot];
             if (!out_ready(o)) { ++k; continue; }
             std::atomic_thread_fence(std::memory_order_acquire);
-            if (o.status == 4) { P.status = GOICP_ERR_OVERFLOW; }
+            if (o.status == 4 && live) P.status = GOICP_ERR_OVERFLOW;   // queue outgrew the CTA's slab: the pair is re-run by the wave scheduler
             if (live && pend[k].entryOpt == P.optError) {
                 CallRes r; r.entryOpt = pend[k].entryOpt; r.err = o.err; memcpy(r.tn, (const void*)o.node, sizeof r.tn); r.pops = o.pops; r.subcubes = o.subcubes;
                 P.cache[pend[k].key] = r;
@@ -954,7 +954,13 @@ static goicp_status persistent_worker(Eng* h, WaveCtx& c, PQ& pq, std::atomic<in
         for (int i : active) {
             Problem& P = h->probs[i];
             if (harvest(P, P.pend, true)) progressed = true;
-            if (P.status) return fail(h, GOICP_ERR_OVERFLOW, "translation queue of a call exceeded the resident kernel's heap slab");
+            if (P.status == GOICP_ERR_OVERFLOW) {   // abandon the pair here; register_persistent re-runs it with growing queues
+                for (auto& r : P.pend) zombies.push_back(r);
+                P.pend.clear(); P.inflight.clear(); P.cache.clear();
+                if (P.icpQueued) { zombies.push_back(Problem::PendReq{P.icpSlot[0], 0ull, 0.f}); zombies.push_back(Problem::PendReq{P.icpSlot[1], 0ull, 0.f}); P.icpQueued = false; }
+                P.phase = PH_DONE; h->activePairs.fetch_sub(1); progressed = true;
+                continue;
+            }
             if (P.phase == PH_START) { P.phase = PH_WAIT_INIT; P.icpQueued = false; }
             if (P.phase == PH_WAIT_INIT || P.phase == PH_WAIT_ICP) {
                 if (!P.icpQueued) { if (send_icp(i)) progressed = true; continue; }
@@ -1026,7 +1032,8 @@ static goicp_status register_persistent(Eng* h, const BnbCfg& cfg, int groups, i
     CU(h->qIcp.ensure(sizeof(IcpState) * 2 * (size_t)np));
     int perSM = goicp_inner_bnb_persistent_occupancy(cfg.useSmem ? cfg.smemFloats * sizeof(float) : 0, h->exact_sums, cfg.threads);
     const int ctas = h->numSM * perSM;   // the resident kernel owns the GPU for the batch: InnerBnB and ICP requests both run on its CTAs
-    const int heapCap = 1 << 15;
+    int heapCap = 1 << 15;
+    { const char* e = getenv("GOICP_HEAPCAP"); if (e && atoi(e) >= 129) heapCap = atoi(e); }   // test hook: force the overflow pool
     CU(h->qHeaps.ensure(sizeof(HeapEnt) * (size_t)ctas * heapCap));
     if (!cfg.useSmem) CU(h->qScratch.ensure(sizeof(float) * cfg.smemFloats * (size_t)ctas));
     const int memoCap = 8192;
@@ -1054,7 +1061,7 @@ static goicp_status register_persistent(Eng* h, const BnbCfg& cfg, int groups, i
     cudaEventRecord(h->main.ev1, h->stream);
     g_no_device_alloc.store(true);
     std::atomic<int> next(0);
-    h->activePairs.store(0); h->outstanding.store(0);
+    h->activePairs.store(0); h->outstanding.store(0); h->stats[14] = 0;
     std::vector<goicp_status> st(groups, GOICP_OK);
     std::vector<std::thread> th;
     const int per = NSLOT / groups;
@@ -1069,6 +1076,18 @@ static goicp_status register_persistent(Eng* h, const BnbCfg& cfg, int groups, i
     if (e != cudaSuccess) return fail(h, GOICP_ERR_CUDA, "resident inner_bnb kernel: %s", cudaGetErrorString(e));
     float ms = 0; cudaEventElapsedTime(&ms, h->main.ev0, h->main.ev1); h->main.ms[2] += ms; h->main.launches[2] += 1;
     for (int g = 0; g < groups; g++) if (st[g]) return st[g];
+    {   // pairs whose translation queue outgrew the resident kernel's per-CTA slab: re-run them with the wave scheduler,
+        // which grows the queue slabs on demand (the resident kernel cannot: no device allocation while it runs)
+        std::vector<int> redo;
+        for (int i = 0; i < np; i++) if (h->probs[i].status == GOICP_ERR_OVERFLOW) redo.push_back(i);
+        if (!redo.empty()) {
+            std::atomic<int> nx(0);
+            h->main.ctaCap = 0;
+            goicp_status s2 = register_group(h, h->main, cfg, nx, std::min<int>(64, (int)redo.size()), &redo);
+            if (s2) return s2;
+            h->stats[14] = (double)redo.size();
+        }
+    }
     for (int g = 0; g < groups; g++) {
         WaveCtx* w = h->workers[g].get();
         h->main.ms[3] += w->ms[3]; h->main.launches[3] += w->launches[3];

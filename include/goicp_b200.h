@@ -166,7 +166,8 @@ goicp_status goicp_set_batch_options(goicp_handle h, int32_t groups, int32_t slo
  * speculative), [2] InnerBnB calls the reference order consumed, [3] host worker threads, [4] host seconds of the search,
  * [5..7] host seconds summed over workers: building requests, publishing / enqueueing, waiting;
  * resident-kernel mode only: [8] calls served, [9] translation-queue pops, [10] CTA busy cycles, [11] corner evaluations the
- * memo missed, [12] CTA cycles spent polling the request ring, [13] resident CTAs; [14..15] reserved */
+ * memo missed, [12] CTA cycles spent polling the request ring, [13] resident CTAs, [14] pairs re-run by the wave scheduler
+ * because a translation queue outgrew the resident kernel's slab; [15] reserved */
 goicp_status goicp_get_stats(goicp_handle h, double* out16);
 
 /* ---- Transformation (transformation.cpp), per-pair pre/post-processing -------------------------------- */

@@ -292,3 +292,15 @@ def test_cli_pair1_golden(tmp_path):
         got = open(tmp_path / "output" / f).read().split("\n")
         want = open(os.path.join(exp, f)).read().split("\n")
         assert got[0].startswith("Time: ") and got[1:] == want[1:], (f, got, want)
+
+
+def test_deep_queue_overflow_rerun(g, monkeypatch):
+    """a translation queue that outgrows the resident kernel's per-CTA slab: the pair is re-run by the wave scheduler
+    (growing slabs); forcing a tiny slab (160 entries) must not change anything about pair 2's search (2.6 M sub-cubes)"""
+    monkeypatch.setenv("GOICP_HEAPCAP", "160")
+    z = golden("pair2")
+    reg = g.GoICP(z["model_xyz"], z["data_xyz"], g.shipped_config(), **pair_clouds(z))
+    reg.BuildDT(); reg.set_nd(int(z["nd"]))
+    r = reg.Register()
+    assert r["optError"] == float(z["exp_optError"]) and r["counters"][:6] == z["exp_counters"][:6].tolist()
+    assert g.error_trace(r["trace"]) == list(z["exp_trace"])
