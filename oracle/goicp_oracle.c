@@ -36,6 +36,7 @@ struct orc_ctx {
     int* nearest;    /* S^3*3 : emptyCells cx,cy,cz */
     int* cellc;      /* S^3 : CELL.c  (-2 empty, -1 mixed, else uniform colour) */
     int *cell_start, *cell_pts; /* CSR of cellPoints[].points in insertion (index) order */
+    int *nbD, *nbM;             /* POINT3D.neighbors of the data / model points (assignNeighbors, jly_goicp.cpp:1213-1248) */
     int dt_built;
     /* Initialize */
     float *normData, *minDis, *maxRotDis, *weights;
@@ -122,7 +123,7 @@ void orc_destroy(orc_ctx* c) {
     free_init(c);
     free(c->mx); free(c->my); free(c->mz); free(c->mc); free(c->mf);
     free(c->dx); free(c->dy); free(c->dz); free(c->dc); free(c->df);
-    free(c->A); free(c->nearest); free(c->cellc); free(c->cell_start); free(c->cell_pts); free(c->memo); free(c->trace);
+    free(c->A); free(c->nearest); free(c->cellc); free(c->cell_start); free(c->cell_pts); free(c->memo); free(c->trace); free(c->nbD); free(c->nbM);
     free(c);
 }
 void orc_set_nd(orc_ctx* c, int nd) { c->Nd = nd; }
@@ -280,6 +281,15 @@ double orc_build_dt(orc_ctx* c) {
         int prop = c->mc[c->cell_pts[b]]; c->cellc[v] = prop;
         for (int k = b + 1; k < e; k++) if (c->mc[c->cell_pts[k]] != prop) { c->cellc[v] = -1; break; }
     }
+    if (c->p.regularizationNeighbors > 0) { /* assignNeighbors jly_goicp.cpp:1213-1248 (BuildDT :94): Nd is still ALL source points here */
+        free(c->nbD); free(c->nbM);
+        c->nbD = (int*)calloc(c->NdAll, sizeof(int)); c->nbM = (int*)calloc(c->Nm, sizeof(int));
+        const double thr = (double)sqrtf(0.050f); /* isNeighbor :1097-1103: sqrt(float radius) is the float overload */
+        for (int i = 0; i < c->NdAll; i++) { int n = 0; for (int j = 0; j < c->NdAll; j++) { if (j == i) continue;
+            double d = sqrt(pow((double)(c->dx[j] - c->dx[i]), 2) + pow((double)(c->dy[j] - c->dy[i]), 2) + pow((double)(c->dz[j] - c->dz[i]), 2)); if (d < thr) n++; } c->nbD[i] = n; }
+        for (int i = 0; i < c->Nm; i++) { int n = 0; for (int j = 0; j < c->Nm; j++) { if (j == i) continue;
+            double d = sqrt(pow((double)(c->mx[j] - c->mx[i]), 2) + pow((double)(c->my[j] - c->my[i]), 2) + pow((double)(c->mz[j] - c->mz[i]), 2)); if (d < thr) n++; } c->nbM[i] = n; }
+    }
     c->dt_built = 1;
     return now_s() - t0;
 }
@@ -369,6 +379,23 @@ static float sum_fpfh(const orc_ctx* c, float x, float y, float z) {
     float sum = 0;
     for (int i = 0; i < c->Nd; i++) sum += fpfh_diff_bnb(c, i, c->tx[i] + x, c->ty[i] + y, c->tz[i] + z);
     return sum / c->Nd;
+}
+/* nearestNeighbor :1200-1211 + compareNeighbors(false,...) :1250-1288: per point the closest model point INSIDE the closest
+ * occupied cell (index 0 if that cell is empty), |neighbour-count difference| summed */
+static int compare_neighbors_bnb(const orc_ctx* c, float x, float y, float z) {
+    int sum = 0;
+    for (int i = 0; i < c->Nd; i++) {
+        const float ax = c->tx[i] + x, ay = c->ty[i] + y, az = c->tz[i] + z;
+        const size_t cell = clamp_cell(c, ax, ay, az);
+        double minD = 100; int ind = 0;
+        for (int k = c->cell_start[cell]; k < c->cell_start[cell + 1]; k++) {
+            const int p = c->cell_pts[k];
+            const double d = sqrt(pow((double)(ax - c->mx[p]), 2) + pow((double)(ay - c->my[p]), 2) + pow((double)(az - c->mz[p]), 2));
+            if (d < minD) { ind = p; minD = d; }
+        }
+        sum += abs(c->nbD[i] - c->nbM[ind]);
+    }
+    return sum;
 }
 /* countCompatibilities :890-914 over ICP correspondences */
 static int count_compat_corr(const orc_ctx* c, const int* model_of) {
@@ -505,14 +532,16 @@ static leaf_t eval_leaf(orc_ctx* c, const float* maxRotDisL, float nx, float ny,
     }
     float reg = c->p.regularization, regF = c->p.regularizationFPFH;
     if (reg > 0 || c->p.regularizationNeighbors > 0 || (regF > 0 && c->p.cfpfh != 0)) { /* :436 */
-        int minI = 0, maxI = 0; float minF = 0, maxF = 0; /* floats holding int-truncated values (H7) */
+        int minI = 0, maxI = 0, minN = 0, maxN = 0; float minF = 0, maxF = 0; /* floats holding int-truncated values (H7) */
+        const float regN = c->p.regularizationNeighbors;
         for (int k = 0; k < 8; k++) { /* :437-439,:486-488 */
             float xI = nx + (k & 1) * nw, yI = ny + (k >> 1 & 1) * nw, zI = nz + (k >> 2 & 1) * nw;
             if (regF > 0) { int f = (int)corner_fpfh(c, xI, yI, zI); if (k == 0) { minF = maxF = (float)f; } else { if (f > maxF) maxF = (float)f; if (f < minF) minF = (float)f; } }
             if (reg > 0) { int n = corner_comp(c, xI, yI, zI); if (k == 0) { minI = maxI = n; } else { if (n > maxI) maxI = n; if (n < minI) minI = n; } }
+            if (regN > 0) { int n = compare_neighbors_bnb(c, xI, yI, zI); if (k == 0) { minN = maxN = n; } else { if (n > maxN) maxN = n; if (n < minN) minN = n; } } /* :462-466,:489-493, not memoised */
         }
         if (reg > 0) { ub += reg * (maxI * maxI); lb += reg * (minI * minI); }       /* :536-538 */
-        /* regularizationNeighbors (:542-545) is SURVEY 8f row N2 ("next"); not restated */
+        if (regN > 0) { ub += regN * (maxN * maxN); lb += regN * (minN * minN); }   /* :542-545 */
         if (regF > 0) { ub += regF * (maxF * maxF); lb += regF * (minF * minF); }    /* :546-549 */
         r.minIncomp = minI; r.maxIncomp = maxI; r.minFPFH = minF; r.maxFPFH = maxF;
     }
@@ -702,6 +731,11 @@ static float goicp_icp(orc_ctx* c, double* R, double* t) {
     fpfh = fpfh / Nd; /* :147 */
     /* correspondences per DATA index (countCompatibilities :890-914 sums over all pairs, order-free) */
     for (int i = 0; i < Nd; i++) c->icp_model[points[i].id_data] = points[i].id_model;
+    if (c->p.regularizationNeighbors > 0) { /* :149-153 compareNeighbors(true): over the correspondences */
+        int nb = 0;
+        for (int i = 0; i < Nd; i++) nb += abs(c->nbD[points[i].id_data] - c->nbM[points[i].id_model]);
+        error += c->p.regularizationNeighbors * (nb * nb);
+    }
     if (c->p.regularization > 0) { /* :154-159 countCompatibilities(true) */
         int incomp = 0;
         for (int i = 0; i < Nd; i++) { int s = c->dc[points[i].id_data], tt = c->mc[points[i].id_model]; if (!(known_prop(s) && s == tt)) incomp++; }

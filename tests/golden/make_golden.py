@@ -111,6 +111,9 @@ def make_pair(name, tgt, src, nd, tmp, fpfh_variant=False):
     if fpfh_variant:
         expf = run_ref(m_xyz, d_xyz, po.shipped_config(cfpfh=1, regularizationFPFH=0.000005), nd, **clouds)
         fx.update({"expf_" + k: v for k, v in expf.items() if not k.startswith("dt_")})
+        # neighbour-count term (regularizationNeighbors, jly_goicp.cpp:1200-1288)
+        expn = run_ref(m_xyz, d_xyz, po.shipped_config(regularizationNeighbors=0.00001), nd, **clouds)
+        fx.update({"expn_" + k: v for k, v in expn.items() if not k.startswith("dt_")})
     fx.update(protein_fixture(src, tgt, exp, scale, S["mean"], T["mean"]))
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **fx)
 

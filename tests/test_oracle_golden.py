@@ -135,3 +135,14 @@ def test_port_vs_reference_inner_calls(po):
     ea, Ra, ta, ca = a.icp(np.eye(3), np.zeros(3))
     eb, Rb, tb, cb = b.icp(np.eye(3), np.zeros(3))
     assert ea == eb and np.abs(Ra - Rb).max() < 1e-12 and np.array_equal(ca, cb)
+
+
+def test_pair1_neighbours_term(po):
+    """regularizationNeighbors = 1e-5 (assignNeighbors / nearestNeighbor / compareNeighbors, jly_goicp.cpp:1200-1288):
+    the restatement equals the reference run frozen in the fixture"""
+    z = golden("pair1")
+    o = _oracle(po, z, po.shipped_config(regularizationNeighbors=0.00001))
+    r = o.register(int(z["nd"]))
+    assert r["optError"] == float(z["expn_optError"]) and r["optComp"] == int(z["expn_optComp"])
+    assert r["counters"][:6] == z["expn_counters"][:6].tolist() and po.error_trace(r["trace"]) == list(z["expn_trace"])
+    assert np.abs(r["R"] - z["expn_R"]).max() < 1e-12
