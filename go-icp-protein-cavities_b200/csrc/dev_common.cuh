@@ -41,15 +41,16 @@ __device__ __forceinline__ float dt_distance_d(const GridDev& g, double dx, doub
 }
 
 // register-argument forms of the two lookups for the hot loop (grid constants hoisted out of the PairDev)
-__device__ __forceinline__ float dt_distance_v(int S, double x0, double y0, double z0, double scale, const float* __restrict__ dist, float fx, float fy, float fz) {
+template <bool LDG = true>
+__device__ __forceinline__ float dt_distance_v(int S, double x0, double y0, double z0, double scale, const float* dist, float fx, float fy, float fz) {
     int x = vox_round(fx, x0, scale), y = vox_round(fy, y0, scale), z = vox_round(fz, z0, scale);
     if ((unsigned)x < (unsigned)S && (unsigned)y < (unsigned)S && (unsigned)z < (unsigned)S)
-        return __ldg(dist + ((z * S + y) * S + x));
+        return LDG ? __ldg(dist + ((z * S + y) * S + x)) : dist[(z * S + y) * S + x];
     float a = 0.f, b = 0.f, c = 0.f;
     if (x < 0) { a = (float)x; x = 0; } else if (x >= S) { a = (float)(x - S + 1); x = S - 1; }
     if (y < 0) { b = (float)y; y = 0; } else if (y >= S) { b = (float)(y - S + 1); y = S - 1; }
     if (z < 0) { c = (float)z; z = 0; } else if (z >= S) { c = (float)(z - S + 1); z = S - 1; }
-    return (float)((double)sqrtf(a * a + b * b + c * c) / scale + (double)__ldg(dist + ((z * S + y) * S + x)));
+    return (float)((double)sqrtf(a * a + b * b + c * c) / scale + (double)(LDG ? __ldg(dist + ((z * S + y) * S + x)) : dist[(z * S + y) * S + x]));
 }
 __device__ __forceinline__ int clamp_cell_v(int S, double x0, double y0, double z0, double scale, const int* __restrict__ vcell, float fx, float fy, float fz) {
     int x = vox_round(fx, x0, scale), y = vox_round(fy, y0, scale), z = vox_round(fz, z0, scale);
@@ -70,6 +71,21 @@ __device__ __forceinline__ int clamp_cell(const GridDev& g, float fx, float fy, 
     int x = vox_round(fx, g.xMin, g.scale), y = vox_round(fy, g.yMin, g.scale), z = vox_round(fz, g.zMin, g.scale);
     x = min(max(x, 0), S - 1); y = min(max(y, 0), S - 1); z = min(max(z, 0), S - 1);
     return __ldg(g.vcell + ((z * S + y) * S + x));
+}
+
+// FP32 fast path of the voxel index (GridDev.vf*): kx,ky,kz = bit patterns of fma(p, vfScale, C) with
+// C = (float)((trans - min)*scale + vfMagic).  Returns the linear voxel index, or -1 when any axis lies in the
+// ambiguity zone of a rounding boundary or outside the grid (the caller then runs the exact FP64 form).
+struct VoxFast { float sc; int sh; unsigned bias, mask, zone; double magic; };
+__device__ __forceinline__ VoxFast vox_fast_of(const GridDev& g) { VoxFast v; v.sc = g.vfScale; v.sh = g.vfShift; v.bias = g.vfBias; v.mask = g.vfMask; v.zone = g.vfZone; v.magic = g.vfMagic; return v; }
+__device__ __forceinline__ float vox_fast_c(const VoxFast& vf, float trans, double mn, double scale) { return (float)(((double)trans - mn) * scale + vf.magic); }
+__device__ __forceinline__ int vox_fast(const VoxFast& vf, int S, float px, float py, float pz, float Cx, float Cy, float Cz) {
+    const unsigned kx = __float_as_uint(__fmaf_rn(px, vf.sc, Cx)), ky = __float_as_uint(__fmaf_rn(py, vf.sc, Cy)), kz = __float_as_uint(__fmaf_rn(pz, vf.sc, Cz));
+    const unsigned x = (kx >> vf.sh) - vf.bias, y = (ky >> vf.sh) - vf.bias, z = (kz >> vf.sh) - vf.bias;
+    const unsigned fr = min(min(kx & vf.mask, ky & vf.mask), kz & vf.mask);
+    const unsigned mx = max(max(x, y), z);
+    if (fr < vf.zone || mx >= (unsigned)S) return -1;
+    return (int)((z * S + y) * S + x);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -11,6 +11,7 @@
 // There is no CPU fallback anywhere in this file: every numeric result comes from a kernel.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <cmath>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -139,7 +140,7 @@ enum Phase { PH_START, PH_WAIT_INIT, PH_POP, PH_CHILD_UB, PH_WAIT_ICP, PH_CHILD_
 
 struct Problem {
     // ---- inputs (host copies) ----
-    int Nm = 0, NdAll = 0, Nd = 0;
+    int Nm = 0, NdAll = 0, Nd = 0, ncolours = 1;
     std::vector<float> mxyz, dxyz;       // AoS as given
     std::vector<int> mc, dc;
     std::vector<float> mf, df;           // N x 41 or empty
@@ -308,6 +309,7 @@ static goicp_status prepare_problem(Eng* h, Problem& P) {
     for (int i = 0; i < P.NdAll; i++) dict.emplace(P.dc.empty() ? 0 : P.dc[i], 0);
     if (dict.size() > 32) return fail(h, GOICP_ERR_UNSUPPORTED, "more than 32 distinct colour codes in one pair (%zu)", dict.size());
     { int k = 0; for (auto& kv : dict) kv.second = k++; }
+    P.ncolours = (int)dict.size();
     P.mprop.resize(num); P.dprop.resize(P.NdAll); P.dknown.resize(P.NdAll);
     for (int i = 0; i < num; i++) P.mprop[i] = (uint8_t)dict[P.mc.empty() ? 0 : P.mc[i]];
     for (int i = 0; i < P.NdAll; i++) { int c = P.dc.empty() ? 0 : P.dc[i]; P.dprop[i] = (uint8_t)dict[c]; P.dknown[i] = known_prop(c) ? 1 : 0; }
@@ -360,7 +362,7 @@ static goicp_status upload_problems(Eng* h) {
         in += al256(sizeof(int) * std::max(nc, 1)) + al256(sizeof(uint32_t) * (nc + 1)) + al256(sizeof(int) * (nc + 1)) + al256(sizeof(int) * P.Nm);
         P.inBytes = in; P.inOff = inTot; inTot += in;
         size_t w = 0;
-        w += al256(sizeof(float) * S3) + al256(sizeof(int) * S3) + (wantVcell ? 2 * al256(sizeof(int) * S3) : 0);
+        w += al256(sizeof(float) * S3) + al256(sizeof(int) * S3) + (wantVcell ? 2 * al256(sizeof(int) * S3) + al256(S3 + 16) : 0);
         w += 2 * al256(sizeof(float) * P.NdAll) + al256(sizeof(float) * GOICP_MAXROTLEVEL * (size_t)P.NdAll);
         if (useF && p.regularizationFPFH > 0) w += al256(sizeof(float) * (size_t)P.NdAll * (nc + 1));
         w += al256(sizeof(unsigned long long) * P.NdAll) + al256(sizeof(int) * P.NdAll) + al256(sizeof(float) * 8 * (size_t)std::max(P.NdAll, 1));
@@ -399,7 +401,7 @@ static goicp_status upload_problems(Eng* h) {
         size_t w = P.workOff;
         D.g.dist = reinterpret_cast<float*>(dWork + w); w += al256(sizeof(float) * S3);
         D.g.vnear = reinterpret_cast<int*>(dWork + w); w += al256(sizeof(int) * S3);
-        if (wantVcell) { D.g.vcell = reinterpret_cast<int*>(dWork + w); w += al256(sizeof(int) * S3); D.g.vmask = reinterpret_cast<uint32_t*>(dWork + w); w += al256(sizeof(int) * S3); }
+        if (wantVcell) { D.g.vcell = reinterpret_cast<int*>(dWork + w); w += al256(sizeof(int) * S3); D.g.vmask = reinterpret_cast<uint32_t*>(dWork + w); w += al256(sizeof(int) * S3); D.g.vmask8 = reinterpret_cast<uint8_t*>(dWork + w); w += al256(S3 + 16); }
         D.normData = reinterpret_cast<float*>(dWork + w); w += al256(sizeof(float) * P.NdAll);
         D.weights = reinterpret_cast<float*>(dWork + w); w += al256(sizeof(float) * P.NdAll);
         D.maxRotDis = reinterpret_cast<float*>(dWork + w); w += al256(sizeof(float) * GOICP_MAXROTLEVEL * (size_t)P.NdAll);
@@ -433,6 +435,28 @@ static goicp_status upload_pairdevs(Eng* h) {
         D.MSEThresh = p.MSEThresh; D.trimFraction = p.trimFraction;
         D.SSEThresh = p.MSEThresh * D.inlierNum;                                     // :266
         D.tMinX = p.transMinX; D.tMinY = p.transMinY; D.tMinZ = p.transMinZ; D.tWidth = p.transWidth;
+        {   // FP32 fast path of the voxel index (goicp_dev.h: GridDev.vf*): fraction bits kept and the ambiguity zone around
+            // each rounding boundary, from a bound on the float evaluation error of (v - min) * scale + 0.5 inside the grid
+            GridDev& g = D.g;
+            const int S = g.S;
+            int lg = 0; while ((1 << lg) < S + 2) lg++;
+            const int f = std::min(16, 22 - lg);
+            const double ulp = std::ldexp(1.0, -f);
+            const double ext = (double)S / g.scale + 1.0 / g.scale;
+            const double A = std::max({std::fabs(g.xMin), std::fabs(g.xMin + ext), std::fabs(g.yMin), std::fabs(g.yMin + ext), std::fabs(g.zMin), std::fabs(g.zMin + ext)});
+            const double T = std::max({std::fabs((double)p.transMinX), std::fabs((double)p.transMinX + p.transWidth), std::fabs((double)p.transMinY), std::fabs((double)p.transMinY + p.transWidth),
+                                       std::fabs((double)p.transMinZ), std::fabs((double)p.transMinZ + p.transWidth)});
+            // |v| <= A for an in-grid voxel, |p| = |v - trans| <= A + T; terms: float rounding of v = p + trans, of the scale, of C and of the fma
+            const double err = g.scale * std::ldexp(1.0, -24) * (2 * A + T) * 1.25 + ulp + 1e-9;
+            const int E = (int)std::ceil(err / ulp) + 1;
+            g.vfScale = (float)g.scale; g.vfShift = f; g.vfMask = (1u << f) - 1u;
+            const float magic = (float)std::ldexp(1.5, 23 - f);
+            unsigned mb; memcpy(&mb, &magic, 4);
+            g.vfBias = mb >> f;
+            g.vfMagic = (double)magic + 0.5 + E * ulp;
+            g.vfZone = (f >= 8 && (2 * E + 1) * 64 < (1 << f) && std::isfinite(err)) ? (unsigned)(2 * E + 1) : 0xFFFFFFFFu;
+            if (getenv("GOICP_NO_VOXFAST")) g.vfZone = 0xFFFFFFFFu;
+        }
         for (int l = 0; l < GOICP_MAXROTLEVEL; l++) {                                // :195-204, host libm as the reference
             float sigma = (float)(p.rotWidth / pow(2.0, l) / 2.0);
             float maxAngle = (float)(GOICP_SQRT3 * sigma);
@@ -494,18 +518,27 @@ static goicp_status initialize_all(Eng* h) {
 }
 
 // ---- one launch of InnerBnB calls (handles heap overflow by re-running the overflowed calls with larger heaps) -------
-struct BnbCfg { int NdP, NdQ; size_t smemFloats; int useSmem, perSM, threads; };
+struct BnbCfg { int NdP, NdQ; size_t smemFloats, smemBytes; int useSmem, perSM, threads, gridOff, S3p; };
 static BnbCfg bnb_config(Eng* h) {
-    int maxNd = 1; bool anyTrim = false, anyF = false;
-    for (auto& P : h->probs) { maxNd = std::max(maxNd, P.Nd); anyTrim |= P.dev.doTrim != 0; anyF |= P.dev.use_fpfh != 0; }
+    int maxNd = 1, maxCol = 1; bool anyTrim = false, anyF = false;
+    for (auto& P : h->probs) { maxNd = std::max(maxNd, P.Nd); anyTrim |= P.dev.doTrim != 0; anyF |= P.dev.use_fpfh != 0; maxCol = std::max(maxCol, P.ncolours); }
     BnbCfg c;
     c.NdP = (maxNd + 31) & ~31; c.NdQ = c.NdP + 2;   // row stride = 2 mod 32: the 16 chain lanes read 16 different banks
     const bool needMd = h->exact_sums || anyTrim, needFp = h->exact_sums && anyF;
     c.smemFloats = goicp_bnb_smem_floats(c.NdP, c.NdQ, h->exact_sums != 0, needMd, needFp);
-    const size_t smemBytes = c.smemFloats * sizeof(float);
-    c.useSmem = smemBytes <= 180 * 1024;   // + ~32 KB static in the resident kernel
+    c.smemBytes = c.smemFloats * sizeof(float);
+    c.useSmem = c.smemBytes <= 180 * 1024;   // + ~32 KB static in the resident kernel
+    c.gridOff = 0; c.S3p = 0;
+    // small volumes (cavity grids, 20^3): distances + one colour-mask byte per voxel are staged in shared memory per call
+    const int S = h->params.distTransSize; const size_t S3 = (size_t)S * S * S;
+    const size_t S3p = (S3 + 15) & ~(size_t)15;
+    if (c.useSmem && maxCol <= 8 && !getenv("GOICP_NO_GRID_SMEM") && ((c.smemFloats + 3) & ~(size_t)3) * 4 + S3p * 5 <= 100 * 1024) {
+        c.gridOff = (int)((c.smemFloats + 3) & ~(size_t)3); c.S3p = (int)S3p;
+        c.smemBytes = (size_t)c.gridOff * 4 + S3p * 5;
+        c.useSmem = 2;
+    }
     c.threads = h->bnb_threads;
-    c.perSM = goicp_inner_bnb_occupancy(c.useSmem ? smemBytes : 0, h->exact_sums, c.threads);
+    c.perSM = goicp_inner_bnb_occupancy(c.smemBytes, h->exact_sums, c.threads, c.useSmem);
     return c;
 }
 static goicp_status run_inner_local(Eng* h, WaveCtx& c, const BnbCfg& cfg, std::vector<InnerProb>& reqs, std::vector<InnerOut>& outs);
@@ -551,7 +584,7 @@ static goicp_status run_inner_local(Eng* h, WaveCtx& c, const BnbCfg& cfg, std::
         cudaEventRecord(c.ev0, c.stream);
         int launched = 0;
         CU(goicp_launch_inner_bnb(h->dPairs.as<PairDev>(), reinterpret_cast<const InnerProb*>(c.mProbs.d), reinterpret_cast<InnerOut*>(c.mOuts.d), m, c.dCounter.as<int>(),
-                                  c.dHeaps.as<HeapEnt>(), heapCap, ctas, c.dBnbScratch.as<float>(), cfg.smemFloats, cfg.NdP, cfg.NdQ, cfg.smemFloats, cfg.useSmem,
+                                  c.dHeaps.as<HeapEnt>(), heapCap, ctas, c.dBnbScratch.as<float>(), cfg.smemFloats, cfg.NdP, cfg.NdQ, cfg.smemBytes, cfg.useSmem, cfg.gridOff, cfg.S3p,
                                   h->exact_sums, cfg.threads, c.dMemo.p, memoCap, h->dGen.as<unsigned>(), c.stream, &launched));
         cudaEventRecord(c.ev1, c.stream);
         c.tInnerEnq += secs_since(tq); tq = clk::now();
@@ -1030,7 +1063,8 @@ static goicp_status register_persistent(Eng* h, const BnbCfg& cfg, int groups, i
     CU(h->qOrder.ensure(sizeof(QueueCell) * (size_t)ORDER));
     CU(h->qClaim.ensure(sizeof(unsigned)));
     CU(h->qIcp.ensure(sizeof(IcpState) * 2 * (size_t)np));
-    int perSM = goicp_inner_bnb_persistent_occupancy(cfg.useSmem ? cfg.smemFloats * sizeof(float) : 0, h->exact_sums, cfg.threads);
+    int perSM = goicp_inner_bnb_persistent_occupancy(cfg.smemBytes, h->exact_sums, cfg.threads, cfg.useSmem);
+    { const char* e = getenv("GOICP_CTAS_PER_SM"); if (e && atoi(e) >= 1) perSM = std::min(perSM, atoi(e)); }
     const int ctas = h->numSM * perSM;   // the resident kernel owns the GPU for the batch: InnerBnB and ICP requests both run on its CTAs
     int heapCap = 1 << 15;
     { const char* e = getenv("GOICP_HEAPCAP"); if (e && atoi(e) >= 129) heapCap = atoi(e); }   // test hook: force the overflow pool
@@ -1057,7 +1091,7 @@ static goicp_status register_persistent(Eng* h, const BnbCfg& cfg, int groups, i
     qd.cellMask = ORDER - 1; qd.cellShift = 18; qd.claim = h->qClaim.as<unsigned>();
     cudaEventRecord(h->main.ev0, h->stream);
     CU(goicp_launch_inner_bnb_persistent(h->dPairs.as<PairDev>(), qd, h->qHeaps.as<HeapEnt>(), heapCap, ctas, h->qScratch.as<float>(), cfg.smemFloats,
-                                         cfg.NdP, cfg.NdQ, cfg.smemFloats, cfg.useSmem, h->exact_sums, cfg.threads, h->qMemo.p, memoCap, h->dGen.as<unsigned>(), h->stream));
+                                         cfg.NdP, cfg.NdQ, cfg.smemBytes, cfg.useSmem, cfg.gridOff, cfg.S3p, h->exact_sums, cfg.threads, h->qMemo.p, memoCap, h->dGen.as<unsigned>(), h->stream));
     cudaEventRecord(h->main.ev1, h->stream);
     g_no_device_alloc.store(true);
     std::atomic<int> next(0);
@@ -1094,7 +1128,8 @@ static goicp_status register_persistent(Eng* h, const BnbCfg& cfg, int groups, i
         h->main.waves += w->waves; h->main.callsLaunched += w->callsLaunched; h->main.callsUsed += w->callsUsed;
         h->main.tLogic += w->tLogic; h->main.tInnerEnq += w->tInnerEnq; h->main.tInnerWait += w->tInnerWait; h->main.tIcp += w->tIcp;
     }
-    { unsigned long long st8[8]; cudaMemcpy(st8, h->dGen.as<char>() + 8, sizeof st8, cudaMemcpyDeviceToHost); cudaMemset(h->dGen.as<char>() + 8, 0, 64);
+    { unsigned long long st8[14]; cudaMemcpy(st8, h->dGen.as<char>() + 8, sizeof st8, cudaMemcpyDeviceToHost); cudaMemset(h->dGen.as<char>() + 8, 0, 112);
+      if (getenv("GOICP_DEBUG") && st8[8]) fprintf(stderr, "[phases] cycles per pop: stage(per call) %.0f  A1 %.0f  A2 %.0f (chain on warp 0: %.0f)  C %.0f\n", (double)st8[8] / std::max<double>(1, st8[3]), (double)st8[9] / std::max<double>(1, st8[1]), (double)st8[10] / std::max<double>(1, st8[1]), (double)st8[12] / std::max<double>(1, st8[1]), (double)st8[11] / std::max<double>(1, st8[1]));
       h->stats[8] = (double)st8[3]; h->stats[9] = (double)st8[1]; h->stats[10] = (double)st8[0]; h->stats[11] = (double)st8[2]; h->stats[12] = (double)st8[4]; h->stats[13] = ctas;
       h->stats[5] = h->main.tLogic; h->stats[6] = h->main.tInnerEnq; h->stats[7] = h->main.tInnerWait;
       if (getenv("GOICP_DEBUG")) {

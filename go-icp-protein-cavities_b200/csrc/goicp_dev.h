@@ -23,6 +23,14 @@ struct GridDev {
     int* cell_vox;           // ncells   voxel of each occupied cell, ascending
     uint32_t* cmask;         // ncells+1   bit k set <=> a source point of colour index k is compatible (checkProperty)
     uint32_t* vmask;         // S^3   cmask of the voxel's closest cell (one gather for the incompatibility term)
+    uint8_t* vmask8;         // S^3 (padded to 16)   low byte of vmask: the form staged in shared memory when a pair has <= 8 colours
+    // FP32 fast path of ROUND((v-min)*scale) (dev_common.cuh:vox_fast): t = fma(p, vfScale, C) + magic keeps vfShift
+    // fractional bits of the voxel coordinate in the float's mantissa; a coordinate closer than the float error bound to a
+    // rounding boundary (fraction bits < vfZone) or outside the grid takes the exact FP64 path instead.
+    double vfMagic;          // 1.5*2^(23-vfShift) + 0.5 + E*2^-vfShift
+    float vfScale;
+    int vfShift;
+    unsigned vfBias, vfMask, vfZone;   // vfZone = 0xFFFFFFFF disables the fast path
 };
 
 // GoICP state after Initialize (jly_goicp.cpp:180-267) for one pair.

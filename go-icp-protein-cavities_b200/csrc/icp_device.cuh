@@ -253,7 +253,7 @@ __device__ __forceinline__ void icp_score_part(const PairDev& P, IcpState& st) {
 //      request; the model cloud is tiled through shared memory for the exact nearest-neighbour pass ---------------------
 // Runs on one CTA (any multiple of 32 threads).  `gstate` may live in mapped host memory: the request is staged in shared memory and
 // written back once at the end.
-__device__ __forceinline__ void icp_fused_body(const PairDev* __restrict__ pairs, IcpState* gstate) {
+__device__ __forceinline__ void icp_fused_body(const PairDev* __restrict__ pairs, IcpState* gstate, float* tile /* shared, 3*NN_TILE floats */) {
     __shared__ IcpState st;
     const int tid = threadIdx.x, nthr = blockDim.x;
     __syncthreads();
@@ -261,7 +261,7 @@ __device__ __forceinline__ void icp_fused_body(const PairDev* __restrict__ pairs
     __syncthreads();
     const PairDev& P = pairs[st.pair];
     const int Nd = P.Nd, Nm = P.Nm;
-    __shared__ float sx[NN_TILE], sy[NN_TILE], sz[NN_TILE];
+    float* sx = tile; float* sy = tile + NN_TILE; float* sz = tile + 2 * NN_TILE;
     icp_begin_part(P, st);
     __syncthreads();
     if (st.mode == 2) { if (tid == 0) *gstate = st; return; }

@@ -19,6 +19,25 @@ namespace {
 
 constexpr int BNB_MAX_THREADS = 512;
 
+// ---- 1-D TMA (cp.async.bulk) global -> shared with mbarrier completion: the S<=~26 DT volume of a call is staged in shared
+//      memory by the copy engine while the CTA rotates the cloud ----------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile("{\n .reg .pred p;\n WAIT_LOOP:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra.uni WAIT_DONE;\n bra.uni WAIT_LOOP;\n WAIT_DONE:\n}"
+                 ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
 // TRANSNODE operator< (jly_goicp.h:79-86)
 __device__ __forceinline__ bool node_less(const HeapEnt& a, const HeapEnt& b) {
     if (a.lb != b.lb) return a.lb > b.lb;
@@ -107,6 +126,9 @@ struct BnbShared {
     int nmiss, workCtr;
     unsigned gen;
     long long t0; int missTot;
+#ifdef GOICP_PHASE_TIMING
+    long long tp[6]; long long tmark;
+#endif
 };
 
 // Per pop of the translation queue:
@@ -116,18 +138,21 @@ struct BnbShared {
 //   phase C (warp 0)     per-child corner min/max on 8 lanes, then lane 0: decisions, pushes and the next pop.
 // PERSIST=false: the calls are probs[0..nprob), claimed through counter[0] (one launch per wave).
 // PERSIST=true : the kernel stays resident for a whole batch and serves the host's request ring `q` (see QueueDev).
-template <bool EXACT, bool PERSIST, bool SMEM>
+// GS=true (needs SMEM): the call's DT volume (float distances + one colour-mask byte per voxel) is staged in shared memory by
+// TMA, so the per-point gathers are LDS instead of L1/L2 sector gathers (S^3 * 5 bytes at dynamic-smem offset gridOff).
+template <bool EXACT, bool PERSIST, bool SMEM, bool GS>
 __global__ void __launch_bounds__(BNB_MAX_THREADS, 2)
 inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, InnerOut* outs,
                  int nprob, int* __restrict__ counter, HeapEnt* __restrict__ heaps, int heapCap,
                  float* gscratch, size_t gstride, int NdP, int NdQ, int useSmem, QueueDev q,
-                 uint4* memoAll, int memoCap, unsigned* genCounter) {
+                 uint4* memoAll, int memoCap, unsigned* genCounter, int gridOff, int S3p) {
     unsigned long long* dstat = reinterpret_cast<unsigned long long*>(genCounter) + 1;   // [0] busy cycles [1] pops [2] corner misses [3] calls [4] poll cycles   // gscratch is exchanged between threads: no __restrict__
     extern __shared__ float4 dyn_smem4[];
     __shared__ BnbShared sh;
     __shared__ float4 sheap[2 * HEAP_SMEM];
     __shared__ InnerProb s_pr;
     __shared__ InnerOut s_out;
+    __shared__ unsigned long long s_gbar;   // mbarrier of the DT staging copies
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = blockDim.x >> 5;
     float* base = SMEM ? reinterpret_cast<float*>(dyn_smem4) : gscratch + (size_t)blockIdx.x * gstride;   // SMEM: address space known -> LDS/STS
     float* tx = base; float* ty = tx + NdP; float* tz = ty + NdP; float* wgt = tz + NdP; float* mrd = wgt + NdP;
@@ -138,6 +163,12 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
     Heap heap; heap.s = sheap; heap.g = heaps + (size_t)blockIdx.x * heapCap;
     uint4* memo = memoAll + 2 * (size_t)blockIdx.x * memoCap;
     const int memoShift = 32 - (31 - __clz(memoCap));   // this CTA's corner memo: direct-mapped, 32 B entries, tagged with the call's generation
+    float* sdist = reinterpret_cast<float*>(dyn_smem4) + gridOff;                     // GS: [S3p] DT distances
+    uint8_t* svm = reinterpret_cast<uint8_t*>(sdist + S3p);                          // GS: [S3p] colour mask of the voxel's closest cell
+    float* icpTile;   // model tile of an ICP request: aliases the staging arrays (the dynamic region holds >= 3*NN_TILE floats)
+    if constexpr (SMEM) icpTile = reinterpret_cast<float*>(dyn_smem4); else { __shared__ float s_tile[3 * NN_TILE]; icpTile = s_tile; }
+    unsigned gphase = 0; int gpair = -1;                                              // mbarrier parity; pair whose volume is staged
+    if (GS) { if (tid == 0) mbar_init(&s_gbar, 1); __syncthreads(); }
 
     for (;;) {
         __syncthreads();
@@ -181,7 +212,7 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
         const InnerProb pr = s_pr;
         if (PERSIST && pr.level == GOICP_REQ_ICP) {   // an ICP / scoring request (GoICP::ICP): state pointer packed into R[0..1]
             IcpState* gst = reinterpret_cast<IcpState*>(((unsigned long long)__float_as_uint(pr.R[1]) << 32) | (unsigned long long)__float_as_uint(pr.R[0]));
-            icp_fused_body(pairs, gst);
+            icp_fused_body(pairs, gst, icpTile);
             __syncthreads();
             if (warp == 0) {
                 if (lane < 16) reinterpret_cast<unsigned*>(q.outs + p)[lane] = (lane == 0 || lane == 15) ? 1u : 0u;
@@ -190,6 +221,12 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
         }
         const PairDev& P = pairs[pr.pair];
         const GridDev& g = P.g;
+        const bool gload = GS && gpair != pr.pair;   // (the __syncthreads at the top of the loop ordered the last reads of the old volume)
+        if (gload && tid == 0) {
+            mbar_expect_tx(&s_gbar, (unsigned)S3p * 5u);
+            tma_bulk_g2s(sdist, g.dist, (unsigned)S3p * 4u, &s_gbar);
+            tma_bulk_g2s(svm, g.vmask8, (unsigned)S3p, &s_gbar);
+        }
         const int Nd = P.Nd;
         const int nchunks = (Nd + 31) >> 5;
         const float* __restrict__ dist = g.dist;
@@ -207,6 +244,7 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
         const uint32_t* __restrict__ vmask = g.vmask;
         const float* __restrict__ fpfhD = P.fpfhD;
         const bool use_reg = P.use_reg != 0, use_fpfh = P.use_fpfh != 0;
+        const VoxFast vf = vox_fast_of(g);
 
         // ---- stage the rotated cloud (jly_goicp.cpp:750-756), weights and rotation radii ---------------------
         for (int i = tid; i < Nd; i += nthreads) {
@@ -222,6 +260,9 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
         if (tid == 0) {
             sh.heapN = 0; sh.status = 0; sh.pops = 1; sh.subcubes = 0; sh.improved = 0;
             sh.gen = atomicAdd(genCounter, 1u) + 1u; sh.nmiss = 0; sh.workCtr = 0; sh.t0 = clock64(); sh.missTot = 0;
+#ifdef GOICP_PHASE_TIMING
+            for (int k = 0; k < 6; k++) sh.tp[k] = 0; sh.tmark = clock64();
+#endif
             sh.optErrorT = pr.optError;                                              // :297
             sh.best[0] = sh.best[1] = sh.best[2] = sh.best[3] = 0.f;
             // the first pop is always the initial node (:300,:314) with lb = 0
@@ -236,8 +277,12 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
             }
         }
 
+        if (gload) { mbar_wait(&s_gbar, gphase); gphase ^= 1u; gpair = pr.pair; }
         for (;;) {
             __syncthreads();                                                         // (1) the popped node is visible
+#ifdef GOICP_PHASE_TIMING
+            if (tid == 0) { const long long n_ = clock64(); sh.tp[sh.pops == 1 && sh.subcubes == 0 ? 0 : 3] += n_ - sh.tmark; sh.tmark = n_; }
+#endif
             if (!sh.running) break;
             const float wc = sh.wc, mtd = sh.mtd;
             const float half = wc / 2;
@@ -264,9 +309,15 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
                 const int c = it / ngroups, gi = it - c * ngroups;
                 const float transX = sh.X[c & 1] + half, transY = sh.Y[(c >> 1) & 1] + half, transZ = sh.Z[(c >> 2) & 1] + half;   // :331-333
                 const int iEnd = min(Nd, (gi + 1) * G * 32);
+                const float Cx = vox_fast_c(vf, transX, gx0, gscale), Cy = vox_fast_c(vf, transY, gy0, gscale), Cz = vox_fast_c(vf, transZ, gz0, gscale);
                 float su = 0.f, sl = 0.f;
                 for (int i = gi * G * 32 + lane; i < iEnd; i += 32) {
-                    float d = wgt[i] * dt_distance_v(S, gx0, gy0, gz0, gscale, dist, tx[i] + transX, ty[i] + transY, tz[i] + transZ);
+                    const float px = tx[i], py = ty[i], pz = tz[i];
+                    const int vox = vox_fast(vf, S, px, py, pz, Cx, Cy, Cz);
+                    float dv;
+                    if (vox >= 0) dv = GS ? sdist[vox] : __ldg(dist + vox);
+                    else dv = dt_distance_v<!GS>(S, gx0, gy0, gz0, gscale, GS ? sdist : dist, px + transX, py + transY, pz + transZ);
+                    float d = wgt[i] * dv;
                     d = d - mrd[i];
                     if (d < 0.f) d = 0.f;
                     if (EXACT && !doTrim) {   // the two sum terms of this point (:393-415), summed in index order by the chain lanes
@@ -286,6 +337,9 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
                 }
             }
             __syncthreads();                                                         // (2)
+#ifdef GOICP_PHASE_TIMING
+            if (tid == 0) { const long long n_ = clock64(); sh.tp[1] += n_ - sh.tmark; sh.tmark = n_; }
+#endif
             // ---- phase A2: warp 0 sums the residuals while the other warps evaluate the corners the memo missed -----------
             if (P.doTrim) {   // radix select replaces intro_select (:384-390); one warp per child
                 for (int c = warp; c < 8; c += nwarps) {
@@ -306,6 +360,9 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
                     for (int k = 0; k < ngroups; ++k) acc = acc + q[2 * k];
                 }
                 if (lane & 1) sh.lb[c] = acc; else sh.ub[c] = acc;
+#ifdef GOICP_PHASE_TIMING
+                if (tid == 0) sh.tp[4] += clock64() - sh.tmark;
+#endif
             }
             if (corners) {   // corner terms (:431-550, checkCompatibilities :919, sumFPFH :1689): (missed corner, 32-point chunk) items
                 const int nItems = sh.nmiss * ngroups;
@@ -319,10 +376,13 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
                     const int cz_ = c / 9, cy_ = (c - 9 * cz_) / 3, cx_ = c - 9 * cz_ - 3 * cy_;
                     const float cx = sh.X[cx_], cy = sh.Y[cy_], cz = sh.Z[cz_];
                     const int iEnd = min(Nd, (gi + 1) * G * 32);
+                    const float Cx = vox_fast_c(vf, cx, gx0, gscale), Cy = vox_fast_c(vf, cy, gy0, gscale), Cz = vox_fast_c(vf, cz, gz0, gscale);
                     int bad = 0; float fs = 0.f;
                     for (int i = gi * G * 32 + lane; i < iEnd; i += 32) {
-                        const int vox = clamp_vox_v(S, gx0, gy0, gz0, gscale, tx[i] + cx, ty[i] + cy, tz[i] + cz);
-                        if (!use_fpfh) bad += ((__ldg(vmask + vox) >> dprop_s[i]) & 1u) ? 0 : 1;   // per-voxel mask of the closest cell: one gather
+                        const float px = tx[i], py = ty[i], pz = tz[i];
+                        int vox = vox_fast(vf, S, px, py, pz, Cx, Cy, Cz);
+                        if (vox < 0) vox = clamp_vox_v(S, gx0, gy0, gz0, gscale, px + cx, py + cy, pz + cz);
+                        if (!use_fpfh) bad += ((((GS ? (unsigned)svm[vox] : __ldg(vmask + vox))) >> dprop_s[i]) & 1u) ? 0 : 1;   // per-voxel mask of the closest cell: one gather
                         else {
                             const int cell = __ldg(vcell + vox);
                             if (use_reg) bad += ((__ldg(cmask + cell) >> dprop_s[i]) & 1u) ? 0 : 1;
@@ -335,6 +395,9 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
                 }
             }
             __syncthreads();                                                         // (3)
+#ifdef GOICP_PHASE_TIMING
+            if (tid == 0) { const long long n_ = clock64(); sh.tp[2] += n_ - sh.tmark; sh.tmark = n_; }
+#endif
             if (warp == 1 && use_fpfh) {   // c-FPFH sums of the missed corners, one chain per lane
                 if (lane < sh.nmiss) {
                     float s_ = 0.f;
@@ -410,6 +473,9 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
         if (tid == 0) {
             atomicAdd(dstat + 0, (unsigned long long)(clock64() - sh.t0)); atomicAdd(dstat + 1, (unsigned long long)sh.pops);
             atomicAdd(dstat + 2, (unsigned long long)sh.missTot); atomicAdd(dstat + 3, 1ull);
+#ifdef GOICP_PHASE_TIMING
+            for (int k = 0; k < 5; k++) atomicAdd(dstat + 8 + k, (unsigned long long)sh.tp[k]);
+#endif
             InnerOut o;
             o.err = sh.optErrorT; o.node[0] = sh.best[0]; o.node[1] = sh.best[1]; o.node[2] = sh.best[2]; o.node[3] = sh.best[3];
             o.improved = sh.improved; o.pops = sh.pops; o.subcubes = sh.subcubes; o.status = sh.status;
@@ -496,21 +562,26 @@ eval_bounds_kernel(const PairDev* __restrict__ pairs, int pair, const float* __r
 
 // ---- launchers ---------------------------------------------------------------------------------------------
 size_t goicp_bnb_smem_floats(int NdP, int NdQ, bool exact, bool needMd, bool needFp) {
-    return (size_t)5 * NdP + (size_t)(NdP >> 2) + (size_t)43 * (NdP >> 5) + (needMd ? (size_t)(exact ? 16 : 8) * NdQ : 0) + (needFp ? (size_t)27 * NdQ : 0);
+    const size_t n = (size_t)5 * NdP + (size_t)(NdP >> 2) + (size_t)43 * (NdP >> 5) + (needMd ? (size_t)(exact ? 16 : 8) * NdQ : 0) + (needFp ? (size_t)27 * NdQ : 0);
+    return n > 3 * 512 ? n : 3 * 512;   // an ICP request tiles the model cloud through the same region (icp_device.cuh NN_TILE)
 }
 
-static int g_bnb_attr_set[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-typedef void (*bnb_kernel_t)(const PairDev*, const InnerProb*, InnerOut*, int, int*, HeapEnt*, int, float*, size_t, int, int, int, QueueDev, uint4*, int, unsigned*);
+static int g_bnb_attr_set[16] = {0};
+typedef void (*bnb_kernel_t)(const PairDev*, const InnerProb*, InnerOut*, int, int*, HeapEnt*, int, float*, size_t, int, int, int, QueueDev, uint4*, int, unsigned*, int, int);
 static bnb_kernel_t bnb_kernel(int exact, int persist, int smem = 1) {
-    if (smem) {
-        if (persist) return exact ? inner_bnb_kernel<true, true, true> : inner_bnb_kernel<false, true, true>;
-        return exact ? inner_bnb_kernel<true, false, true> : inner_bnb_kernel<false, false, true>;
+    if (smem == 2) {   // staging arrays AND the DT volume in shared memory
+        if (persist) return exact ? inner_bnb_kernel<true, true, true, true> : inner_bnb_kernel<false, true, true, true>;
+        return exact ? inner_bnb_kernel<true, false, true, true> : inner_bnb_kernel<false, false, true, true>;
     }
-    if (persist) return exact ? inner_bnb_kernel<true, true, false> : inner_bnb_kernel<false, true, false>;
-    return exact ? inner_bnb_kernel<true, false, false> : inner_bnb_kernel<false, false, false>;
+    if (smem) {
+        if (persist) return exact ? inner_bnb_kernel<true, true, true, false> : inner_bnb_kernel<false, true, true, false>;
+        return exact ? inner_bnb_kernel<true, false, true, false> : inner_bnb_kernel<false, false, true, false>;
+    }
+    if (persist) return exact ? inner_bnb_kernel<true, true, false, false> : inner_bnb_kernel<false, true, false, false>;
+    return exact ? inner_bnb_kernel<true, false, false, false> : inner_bnb_kernel<false, false, false, false>;
 }
 static cudaError_t bnb_attr(int exact, int persist, int smem = 1) {
-    const int k = (exact ? 1 : 0) + (persist ? 2 : 0) + (smem ? 4 : 0);
+    const int k = (exact ? 1 : 0) + (persist ? 2 : 0) + 4 * smem;
     if (g_bnb_attr_set[k]) return cudaSuccess;
     cudaFuncAttributes fa;
     cudaError_t e = cudaFuncGetAttributes(&fa, bnb_kernel(exact, persist, smem));
@@ -523,38 +594,38 @@ static cudaError_t bnb_attr(int exact, int persist, int smem = 1) {
 
 cudaError_t goicp_launch_inner_bnb(const PairDev* pairs, const InnerProb* probs, InnerOut* outs, int nprob, int* counter,
                                    HeapEnt* heaps, int heapCap, int maxCtas, float* gscratch, size_t gstride,
-                                   int NdP, int NdQ, size_t smemFloats, int useSmem, int exact, int threads, void* memo, int memoCap, unsigned* genCounter, cudaStream_t st, int* ctasLaunched) {
+                                   int NdP, int NdQ, size_t smemBytes, int useSmem, int gridOff, int S3p, int exact, int threads, void* memo, int memoCap, unsigned* genCounter, cudaStream_t st, int* ctasLaunched) {
     if (nprob <= 0) { if (ctasLaunched) *ctasLaunched = 0; return cudaSuccess; }
-    const size_t smem = useSmem ? smemFloats * sizeof(float) : 0;
+    const size_t smem = useSmem ? smemBytes : 0;
     cudaError_t e = bnb_attr(exact, 0, useSmem);
     if (e != cudaSuccess) return e;
     int grid = nprob < maxCtas ? nprob : maxCtas;
     if (ctasLaunched) *ctasLaunched = grid;
     QueueDev q{};
-    bnb_kernel(exact, 0, useSmem)<<<grid, threads, smem, st>>>(pairs, probs, outs, nprob, counter, heaps, heapCap, gscratch, gstride, NdP, NdQ, useSmem, q, (uint4*)memo, memoCap, genCounter);
+    bnb_kernel(exact, 0, useSmem)<<<grid, threads, smem, st>>>(pairs, probs, outs, nprob, counter, heaps, heapCap, gscratch, gstride, NdP, NdQ, useSmem, q, (uint4*)memo, memoCap, genCounter, gridOff, S3p);
     return cudaGetLastError();
 }
 
 // the resident kernel of a batch: `ctas` CTAs serve the request ring until each has seen a shut-down marker
 cudaError_t goicp_launch_inner_bnb_persistent(const PairDev* pairs, const QueueDev& q, HeapEnt* heaps, int heapCap, int ctas, float* gscratch, size_t gstride,
-                                              int NdP, int NdQ, size_t smemFloats, int useSmem, int exact, int threads, void* memo, int memoCap, unsigned* genCounter, cudaStream_t st) {
-    const size_t smem = useSmem ? smemFloats * sizeof(float) : 0;
+                                              int NdP, int NdQ, size_t smemBytes, int useSmem, int gridOff, int S3p, int exact, int threads, void* memo, int memoCap, unsigned* genCounter, cudaStream_t st) {
+    const size_t smem = useSmem ? smemBytes : 0;
     cudaError_t e = bnb_attr(exact, 1, useSmem);
     if (e != cudaSuccess) return e;
-    bnb_kernel(exact, 1, useSmem)<<<ctas, threads, smem, st>>>(pairs, nullptr, nullptr, 0, nullptr, heaps, heapCap, gscratch, gstride, NdP, NdQ, useSmem, q, (uint4*)memo, memoCap, genCounter);
+    bnb_kernel(exact, 1, useSmem)<<<ctas, threads, smem, st>>>(pairs, nullptr, nullptr, 0, nullptr, heaps, heapCap, gscratch, gstride, NdP, NdQ, useSmem, q, (uint4*)memo, memoCap, genCounter, gridOff, S3p);
     return cudaGetLastError();
 }
 
-int goicp_inner_bnb_persistent_occupancy(size_t smemBytes, int exact, int threads) {
-    if (bnb_attr(exact, 1) != cudaSuccess) return 1;
+int goicp_inner_bnb_persistent_occupancy(size_t smemBytes, int exact, int threads, int useSmem) {
+    if (bnb_attr(exact, 1, useSmem) != cudaSuccess) return 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bnb_kernel(exact, 1), threads, smemBytes) != cudaSuccess || n < 1) n = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bnb_kernel(exact, 1, useSmem), threads, useSmem ? smemBytes : 0) != cudaSuccess || n < 1) n = 1;
     return n;
 }
-int goicp_inner_bnb_occupancy(size_t smemBytes, int exact, int threads) {
-    if (bnb_attr(exact, 0) != cudaSuccess) return 1;
+int goicp_inner_bnb_occupancy(size_t smemBytes, int exact, int threads, int useSmem) {
+    if (bnb_attr(exact, 0, useSmem) != cudaSuccess) return 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bnb_kernel(exact, 0), threads, smemBytes) != cudaSuccess || n < 1) n = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bnb_kernel(exact, 0, useSmem), threads, useSmem ? smemBytes : 0) != cudaSuccess || n < 1) n = 1;
     return n;
 }
 
@@ -571,11 +642,15 @@ cudaError_t goicp_launch_eval_bounds(const PairDev* pairs, int pair, const float
 // would otherwise wait for that kernel (CUDA lazy module loading)
 cudaError_t goicp_preload_bnb() {
     cudaFuncAttributes a; cudaError_t e;
-    if ((e = cudaFuncGetAttributes(&a, inner_bnb_kernel<true, true, true>)) != cudaSuccess) return e;
-    if ((e = cudaFuncGetAttributes(&a, inner_bnb_kernel<true, true, false>)) != cudaSuccess) return e;
-    if ((e = cudaFuncGetAttributes(&a, inner_bnb_kernel<false, true, true>)) != cudaSuccess) return e;
-    if ((e = cudaFuncGetAttributes(&a, inner_bnb_kernel<true, false, true>)) != cudaSuccess) return e;
-    if ((e = cudaFuncGetAttributes(&a, inner_bnb_kernel<false, false, true>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, inner_bnb_kernel<true, true, true, true>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, inner_bnb_kernel<false, true, true, true>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, inner_bnb_kernel<true, false, true, true>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, inner_bnb_kernel<false, false, true, true>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, inner_bnb_kernel<true, true, true, false>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, inner_bnb_kernel<true, true, false, false>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, inner_bnb_kernel<false, true, true, false>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, inner_bnb_kernel<true, false, true, false>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, inner_bnb_kernel<false, false, true, false>)) != cudaSuccess) return e;
     if ((e = cudaFuncGetAttributes(&a, eval_bounds_kernel)) != cudaSuccess) return e;
     return cudaSuccess;
 }

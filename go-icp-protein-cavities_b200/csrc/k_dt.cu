@@ -163,7 +163,7 @@ dt_replay_kernel(PairDev* __restrict__ pairs, int first) {
             int lo = 0, hi = g.ncells - 1, id = g.ncells;
             while (lo <= hi) { const int mid = (lo + hi) >> 1; const int v = g.cell_vox[mid]; if (v == vn) { id = mid; break; } if (v < vn) lo = mid + 1; else hi = mid - 1; }
             g.vcell[i] = id;
-            if (g.vmask) g.vmask[i] = g.cmask[id];
+            if (g.vmask) { g.vmask[i] = g.cmask[id]; g.vmask8[i] = (uint8_t)g.cmask[id]; }
         }
     }
 }
@@ -243,7 +243,7 @@ dt_sep_z_kernel(const unsigned* __restrict__ nxy, GridDev g) {
             int lo = 0, hi = g.ncells - 1, id = g.ncells;
             while (lo <= hi) { const int mid = (lo + hi) >> 1; const int v = __ldg(g.cell_vox + mid); if (v == vn) { id = mid; break; } if (v < vn) lo = mid + 1; else hi = mid - 1; }
             g.vcell[i] = id;
-            if (g.vmask) g.vmask[i] = g.cmask[id];
+            if (g.vmask) { g.vmask[i] = g.cmask[id]; g.vmask8[i] = (uint8_t)g.cmask[id]; }
         }
     }
 }
@@ -256,7 +256,7 @@ __global__ void dt_vcell_kernel(GridDev g) {
         int lo = 0, hi = g.ncells - 1, id = g.ncells;
         while (lo <= hi) { const int mid = (lo + hi) >> 1; const int v = __ldg(g.cell_vox + mid); if (v == vn) { id = mid; break; } if (v < vn) lo = mid + 1; else hi = mid - 1; }
         g.vcell[i] = id;
-        if (g.vmask) g.vmask[i] = g.cmask[id];
+        if (g.vmask) { g.vmask[i] = g.cmask[id]; g.vmask8[i] = (uint8_t)g.cmask[id]; }
     }
 }
 

@@ -72,7 +72,7 @@ icp_score_kernel(const PairDev* __restrict__ pairs, IcpState* __restrict__ state
 }
 
 __global__ void __launch_bounds__(256, 4)
-icp_fused_kernel(const PairDev* __restrict__ pairs, IcpState* states) { icp_fused_body(pairs, states + blockIdx.x); }
+icp_fused_kernel(const PairDev* __restrict__ pairs, IcpState* states) { __shared__ float s_tile[3 * NN_TILE]; icp_fused_body(pairs, states + blockIdx.x, s_tile); }
 
 }  // namespace
 
