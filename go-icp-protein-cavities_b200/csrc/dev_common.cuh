@@ -88,6 +88,20 @@ __device__ __forceinline__ int vox_fast(const VoxFast& vf, int S, float px, floa
     return (int)((z * S + y) * S + x);
 }
 
+// Second tier: a position up to GOICP_OVLIM voxels outside the grid.  Returns the clamped linear index and the squared
+// voxel overshoot a^2+b^2+c^2 of DT3D::Distance (jly_3ddt.cpp:1150-1190); false when the position is in the ambiguity zone or
+// further out (the caller then runs the exact FP64 form).  GridDev.ovl[s] = (double)sqrtf(s) / scale.
+__device__ __forceinline__ bool vox_near(const VoxFast& vf, int S, float px, float py, float pz, float Cx, float Cy, float Cz, int* idx, int* s2) {
+    const unsigned kx = __float_as_uint(__fmaf_rn(px, vf.sc, Cx)), ky = __float_as_uint(__fmaf_rn(py, vf.sc, Cy)), kz = __float_as_uint(__fmaf_rn(pz, vf.sc, Cz));
+    const int xi = (int)(kx >> vf.sh) - (int)vf.bias, yi = (int)(ky >> vf.sh) - (int)vf.bias, zi = (int)(kz >> vf.sh) - (int)vf.bias;
+    const unsigned fr = min(min(kx & vf.mask, ky & vf.mask), kz & vf.mask);
+    const int cx = min(max(xi, 0), S - 1), cy = min(max(yi, 0), S - 1), cz = min(max(zi, 0), S - 1);
+    const int ax = xi - cx, ay = yi - cy, az = zi - cz;
+    *s2 = ax * ax + ay * ay + az * az;
+    *idx = (cz * S + cy) * S + cx;
+    return fr >= vf.zone && max(max(ax, ay), az) <= GOICP_OVLIM && min(min(ax, ay), az) >= -GOICP_OVLIM;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = v + __shfl_xor_sync(GOICP_FULL, v, o);

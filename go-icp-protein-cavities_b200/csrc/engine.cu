@@ -362,7 +362,7 @@ static goicp_status upload_problems(Eng* h) {
         in += al256(sizeof(int) * std::max(nc, 1)) + al256(sizeof(uint32_t) * (nc + 1)) + al256(sizeof(int) * (nc + 1)) + al256(sizeof(int) * P.Nm);
         P.inBytes = in; P.inOff = inTot; inTot += in;
         size_t w = 0;
-        w += al256(sizeof(float) * S3) + al256(sizeof(int) * S3) + (wantVcell ? 2 * al256(sizeof(int) * S3) + al256(S3 + 16) : 0);
+        w += al256(sizeof(float) * S3) + al256(sizeof(int) * S3) + (wantVcell ? 2 * al256(sizeof(int) * S3) + al256(S3 + 16) : 0) + al256(sizeof(double) * GOICP_OVN);
         w += 2 * al256(sizeof(float) * P.NdAll) + al256(sizeof(float) * GOICP_MAXROTLEVEL * (size_t)P.NdAll);
         if (useF && p.regularizationFPFH > 0) w += al256(sizeof(float) * (size_t)P.NdAll * (nc + 1));
         w += al256(sizeof(unsigned long long) * P.NdAll) + al256(sizeof(int) * P.NdAll) + al256(sizeof(float) * 8 * (size_t)std::max(P.NdAll, 1));
@@ -402,6 +402,7 @@ static goicp_status upload_problems(Eng* h) {
         D.g.dist = reinterpret_cast<float*>(dWork + w); w += al256(sizeof(float) * S3);
         D.g.vnear = reinterpret_cast<int*>(dWork + w); w += al256(sizeof(int) * S3);
         if (wantVcell) { D.g.vcell = reinterpret_cast<int*>(dWork + w); w += al256(sizeof(int) * S3); D.g.vmask = reinterpret_cast<uint32_t*>(dWork + w); w += al256(sizeof(int) * S3); D.g.vmask8 = reinterpret_cast<uint8_t*>(dWork + w); w += al256(S3 + 16); }
+        D.g.ovl = reinterpret_cast<double*>(dWork + w); w += al256(sizeof(double) * GOICP_OVN);
         D.normData = reinterpret_cast<float*>(dWork + w); w += al256(sizeof(float) * P.NdAll);
         D.weights = reinterpret_cast<float*>(dWork + w); w += al256(sizeof(float) * P.NdAll);
         D.maxRotDis = reinterpret_cast<float*>(dWork + w); w += al256(sizeof(float) * GOICP_MAXROTLEVEL * (size_t)P.NdAll);
@@ -439,14 +440,14 @@ static goicp_status upload_pairdevs(Eng* h) {
             // each rounding boundary, from a bound on the float evaluation error of (v - min) * scale + 0.5 inside the grid
             GridDev& g = D.g;
             const int S = g.S;
-            int lg = 0; while ((1 << lg) < S + 2) lg++;
+            int lg = 0; while ((1 << lg) < S + GOICP_OVLIM + 2) lg++;
             const int f = std::min(16, 22 - lg);
             const double ulp = std::ldexp(1.0, -f);
-            const double ext = (double)S / g.scale + 1.0 / g.scale;
-            const double A = std::max({std::fabs(g.xMin), std::fabs(g.xMin + ext), std::fabs(g.yMin), std::fabs(g.yMin + ext), std::fabs(g.zMin), std::fabs(g.zMin + ext)});
+            const double ext = (double)(S + GOICP_OVLIM + 1) / g.scale, lo = (double)(GOICP_OVLIM + 1) / g.scale;
+            const double A = std::max({std::fabs(g.xMin - lo), std::fabs(g.xMin + ext), std::fabs(g.yMin - lo), std::fabs(g.yMin + ext), std::fabs(g.zMin - lo), std::fabs(g.zMin + ext)});
             const double T = std::max({std::fabs((double)p.transMinX), std::fabs((double)p.transMinX + p.transWidth), std::fabs((double)p.transMinY), std::fabs((double)p.transMinY + p.transWidth),
                                        std::fabs((double)p.transMinZ), std::fabs((double)p.transMinZ + p.transWidth)});
-            // |v| <= A for an in-grid voxel, |p| = |v - trans| <= A + T; terms: float rounding of v = p + trans, of the scale, of C and of the fma
+            // |v| <= A for a voxel at most GOICP_OVLIM outside the grid, |p| = |v - trans| <= A + T; terms: float rounding of v = p + trans, of the scale, of C and of the fma
             const double err = g.scale * std::ldexp(1.0, -24) * (2 * A + T) * 1.25 + ulp + 1e-9;
             const int E = (int)std::ceil(err / ulp) + 1;
             g.vfScale = (float)g.scale; g.vfShift = f; g.vfMask = (1u << f) - 1u;
@@ -523,7 +524,7 @@ static BnbCfg bnb_config(Eng* h) {
     int maxNd = 1, maxCol = 1; bool anyTrim = false, anyF = false;
     for (auto& P : h->probs) { maxNd = std::max(maxNd, P.Nd); anyTrim |= P.dev.doTrim != 0; anyF |= P.dev.use_fpfh != 0; maxCol = std::max(maxCol, P.ncolours); }
     BnbCfg c;
-    c.NdP = (maxNd + 31) & ~31; c.NdQ = c.NdP + 2;   // row stride = 2 mod 32: the 16 chain lanes read 16 different banks
+    c.NdP = (maxNd + 31) & ~31; c.NdQ = c.NdP + 4;   // row stride = 4 mod 32: the chain lanes' float4 reads of the 8 rows hit 8 different bank quads
     const bool needMd = h->exact_sums || anyTrim, needFp = h->exact_sums && anyF;
     c.smemFloats = goicp_bnb_smem_floats(c.NdP, c.NdQ, h->exact_sums != 0, needMd, needFp);
     c.smemBytes = c.smemFloats * sizeof(float);
@@ -1128,8 +1129,10 @@ static goicp_status register_persistent(Eng* h, const BnbCfg& cfg, int groups, i
         h->main.waves += w->waves; h->main.callsLaunched += w->callsLaunched; h->main.callsUsed += w->callsUsed;
         h->main.tLogic += w->tLogic; h->main.tInnerEnq += w->tInnerEnq; h->main.tInnerWait += w->tInnerWait; h->main.tIcp += w->tIcp;
     }
-    { unsigned long long st8[14]; cudaMemcpy(st8, h->dGen.as<char>() + 8, sizeof st8, cudaMemcpyDeviceToHost); cudaMemset(h->dGen.as<char>() + 8, 0, 112);
+    { unsigned long long st8[20]; cudaMemcpy(st8, h->dGen.as<char>() + 8, sizeof st8, cudaMemcpyDeviceToHost); cudaMemset(h->dGen.as<char>() + 8, 0, 160);
       if (getenv("GOICP_DEBUG") && st8[8]) fprintf(stderr, "[phases] cycles per pop: stage(per call) %.0f  A1 %.0f  A2 %.0f (chain on warp 0: %.0f)  C %.0f\n", (double)st8[8] / std::max<double>(1, st8[3]), (double)st8[9] / std::max<double>(1, st8[1]), (double)st8[10] / std::max<double>(1, st8[1]), (double)st8[12] / std::max<double>(1, st8[1]), (double)st8[11] / std::max<double>(1, st8[1]));
+      if (getenv("GOICP_DEBUG") && st8[8]) fprintf(stderr, "[detail] A1 items with a fix-up per pop %.2f; corner items per pop %.2f of which with a fix-up %.2f; C: decisions %.0f  +pushes %.0f  +pop %.0f cycles (cumulative from barrier 3)\n", (double)st8[14] / std::max<double>(1, st8[1]), (double)(st8[15] & 0xFFFFFFFFull) / std::max<double>(1, st8[1]), (double)(st8[15] >> 32) / std::max<double>(1, st8[1]), (double)st8[16] / std::max<double>(1, st8[1]), (double)st8[17] / std::max<double>(1, st8[1]), (double)st8[18] / std::max<double>(1, st8[1]));
+      if (getenv("GOICP_DEBUG") && st8[8]) fprintf(stderr, "[queue] pops with more than 1024 entries queued: %.1f %%; mean queue length at pop %.0f\n", 100.0 * (double)(st8[13] >> 38) / std::max<double>(1, st8[1]), 16.0 * (double)(st8[13] & ((1ull << 38) - 1)) / std::max<double>(1, st8[1]));
       h->stats[8] = (double)st8[3]; h->stats[9] = (double)st8[1]; h->stats[10] = (double)st8[0]; h->stats[11] = (double)st8[2]; h->stats[12] = (double)st8[4]; h->stats[13] = ctas;
       h->stats[5] = h->main.tLogic; h->stats[6] = h->main.tInnerEnq; h->stats[7] = h->main.tInnerWait;
       if (getenv("GOICP_DEBUG")) {
@@ -1264,7 +1267,7 @@ goicp_status goicp_create(goicp_handle* out, int device, void* stream_or_null) {
     if ((e = goicp_preload_bnb()) != cudaSuccess || (e = goicp_preload_dt()) != cudaSuccess || (e = goicp_preload_icp()) != cudaSuccess || (e = goicp_preload_misc()) != cudaSuccess) {
         delete h; return fail(nullptr, GOICP_ERR_CUDA, "kernel preload failed: %s (library built for sm_100a only)", cudaGetErrorString(e));
     }
-    if (h->dGen.ensure(128) != cudaSuccess || cudaMemset(h->dGen.p, 0, 128) != cudaSuccess) { delete h; return fail(nullptr, GOICP_ERR_CUDA, "device allocation failed"); }
+    if (h->dGen.ensure(256) != cudaSuccess || cudaMemset(h->dGen.p, 0, 256) != cudaSuccess) { delete h; return fail(nullptr, GOICP_ERR_CUDA, "device allocation failed"); }
     if (h->main.init(false, h->stream) != GOICP_OK) { delete h; return fail(nullptr, GOICP_ERR_CUDA, "event creation failed"); }
     goicp_params_default(&h->params); h->haveParams = true;
     *out = h;
@@ -1556,7 +1559,7 @@ goicp_status goicp_set_batch_options(goicp_handle h, int32_t groups, int32_t slo
     if (!h) return GOICP_ERR_ARG;
     if (groups >= 0) h->groups = groups;
     if (slots >= 0) h->slots = slots;
-    { const char* e = getenv("GOICP_BNB_THREADS"); if (e) { int t = atoi(e); if (t >= 64 && t <= 512 && t % 32 == 0) h->bnb_threads = t; } }
+    { const char* e = getenv("GOICP_BNB_THREADS"); if (e) { int t = atoi(e); if (t >= 64 && t <= 256 && t % 32 == 0) h->bnb_threads = t; } }
     return GOICP_OK;
 }
 goicp_status goicp_get_stats(goicp_handle h, double* out16) {

@@ -10,6 +10,8 @@
 #define GOICP_PI 3.1415926536              // jly_goicp.h:44
 #define GOICP_SQRT3 1.732050808            // jly_goicp.h:45
 #define GOICP_NN_EMPTY 0xFFFFFFFFFFFFFFFFull
+#define GOICP_OVLIM 24                      // voxels outside the grid served by the overshoot table GridDev.ovl
+#define GOICP_OVN (3 * GOICP_OVLIM * GOICP_OVLIM + 1)
 #define GOICP_REQ_ICP (-100)               // InnerProb.level of an ICP request in the resident batch kernel
 
 // DT3D (jly_3ddt.h:123-139) as laid out in HBM: structure-of-arrays, voxel index (z*S+y)*S+x.
@@ -24,6 +26,7 @@ struct GridDev {
     uint32_t* cmask;         // ncells+1   bit k set <=> a source point of colour index k is compatible (checkProperty)
     uint32_t* vmask;         // S^3   cmask of the voxel's closest cell (one gather for the incompatibility term)
     uint8_t* vmask8;         // S^3 (padded to 16)   low byte of vmask: the form staged in shared memory when a pair has <= 8 colours
+    double* ovl;             // GOICP_OVN   (double)sqrtf(s) / scale for a squared voxel overshoot s (DT3D::Distance outside the grid)
     // FP32 fast path of ROUND((v-min)*scale) (dev_common.cuh:vox_fast): t = fma(p, vfScale, C) + magic keeps vfShift
     // fractional bits of the voxel coordinate in the float's mantissa; a coordinate closer than the float error bound to a
     // rounding boundary (fraction bits < vfZone) or outside the grid takes the exact FP64 path instead.

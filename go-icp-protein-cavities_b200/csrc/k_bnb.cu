@@ -17,11 +17,17 @@
 
 namespace {
 
-constexpr int BNB_MAX_THREADS = 512;
+constexpr int BNB_MAX_THREADS = 256;
 
 // ---- 1-D TMA (cp.async.bulk) global -> shared with mbarrier completion: the S<=~26 DT volume of a call is staged in shared
 //      memory by the copy engine while the CTA rotates the cloud ----------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+// plain shared-memory atomics (nvcc wraps atomicAdd in ~30 instructions of warp-aggregation code; the callers below already
+// elect one lane)
+__device__ __forceinline__ int smem_fetch_add(int* p, int v) {
+    int old; asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory"); return old;
+}
+__device__ __forceinline__ void smem_red_add(int* p, int v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory"); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -38,14 +44,21 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
                  ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
-// TRANSNODE operator< (jly_goicp.h:79-86)
-__device__ __forceinline__ bool node_less(const HeapEnt& a, const HeapEnt& b) {
-    if (a.lb != b.lb) return a.lb > b.lb;
-    return a.w < b.w;
+// The translation queue.  A node is a 64-bit key {lb, (level << 26) | slot} plus a payload slot {x, y, z}: only the keys move
+// when the heap is sifted.  The node width is tWidth / 2^level exactly (every level halves it, jly_goicp.cpp:322), so
+// TRANSNODE operator< (jly_goicp.h:79-86: larger lb is "less"; equal lb: smaller w is "less") compares levels instead of
+// widths.  Keys [0, HK_SMEM) and payload slots [0, HP_SMEM) live in shared memory, the rest in the CTA's global slab.
+// Only lane 0 of warp 0 touches the queue; it follows libstdc++'s push_heap / pop_heap step for step, so ties between equal
+// (lb, w) keys pop in the reference's order.
+constexpr int HK_SMEM = 1024;
+constexpr int HP_SMEM = 256;
+constexpr int HF_SMEM = 256;
+constexpr int MAX_TLEVEL = 64;
+__device__ __forceinline__ bool key_less(const uint2 a, const uint2 b) {
+    const float la = __uint_as_float(a.x), lb = __uint_as_float(b.x);
+    if (la != lb) return la > lb;
+    return (a.y >> 26) > (b.y >> 26);
 }
-// The translation queue: entries [0, HEAP_SMEM) live in shared memory (the levels every pop walks), the rest in the
-// CTA's global slab.  Only thread 0 touches it.
-constexpr int HEAP_SMEM = 128;
 // corner-memo hash: the coordinates are dyadic floats (long runs of trailing zero bits), so mix with rotations and take the
 // HIGH bits of a multiplicative hash
 __device__ __forceinline__ unsigned memo_hash(unsigned kx, unsigned ky, unsigned kz) {
@@ -57,57 +70,89 @@ __device__ __forceinline__ unsigned memo_hash(unsigned kx, unsigned ky, unsigned
 }
 __device__ __forceinline__ unsigned memo_slot(unsigned h, int shift) { return h >> shift; }
 struct Heap {
-    float4* s;       // shared: 2 x float4 per entry
-    HeapEnt* g;      // global slab
-    __device__ __forceinline__ void store(int i, const HeapEnt& e) const {
-        float4* p = (i < HEAP_SMEM) ? s + 2 * i : reinterpret_cast<float4*>(g + i);
-        p[0] = make_float4(e.lb, e.w, e.x, e.y);
-        p[1] = make_float4(e.z, 0.f, 0.f, 0.f);
-    }
-    __device__ __forceinline__ HeapEnt load(int i) const {
-        const float4* p = (i < HEAP_SMEM) ? s + 2 * i : reinterpret_cast<const float4*>(g + i);
-        const float4 a = p[0], b = p[1];
-        HeapEnt e; e.lb = a.x; e.w = a.y; e.x = a.z; e.y = a.w; e.z = b.x; e.pad0 = e.pad1 = e.pad2 = 0.f;
-        return e;
-    }
+    uint2* ks;       // shared keys
+    uint2* kg;       // global keys (slab)
+    float4* ps;      // shared payload slots
+    float4* pg;      // global payload slots
+    __device__ __forceinline__ uint2 key(int i) const { return (i < HK_SMEM) ? ks[i] : kg[i]; }
+    __device__ __forceinline__ void setkey(int i, const uint2 k) const { if (i < HK_SMEM) ks[i] = k; else kg[i] = k; }
+    __device__ __forceinline__ float4 pay(int sl) const { return (sl < HP_SMEM) ? ps[sl] : pg[sl]; }
+    __device__ __forceinline__ void setpay(int sl, const float4 v) const { if (sl < HP_SMEM) ps[sl] = v; else pg[sl] = v; }
 };
-// std::push_heap (__push_heap) on h[0..n) + val
-__device__ __forceinline__ void heap_push(const Heap& h, int& n, const HeapEnt& val) {
-    int hole = n++;
-    int parent = (hole - 1) / 2;
-    while (hole > 0) {
-        const HeapEnt pe = h.load(parent);
-        if (!node_less(pe, val)) break;
-        h.store(hole, pe);
-        hole = parent; parent = (hole - 1) / 2;
-    }
-    h.store(hole, val);
+// shared-memory-only, warp-cooperative forms (queue shorter than HK_SMEM: the common case).  Called by all 32 lanes.
+// __push_heap from position `hole` with value `val`: lane l reads the l-th ancestor; val stops below the first ancestor that is
+// not "less" than it; the ancestors it passes each move down one step.  Same final layout as the sequential loop.
+__device__ __forceinline__ void heap_siftup_w(uint2* ks, int hole, const uint2 val, int lane) {
+    const int anc = ((hole + 1) >> min(lane + 1, 31)) - 1;           // parent^(lane+1)(hole); -1 above the root
+    const uint2 pe = ks[max(anc, 0)];
+    const unsigned m = __ballot_sync(GOICP_FULL, anc >= 0 && key_less(pe, val));
+    const int moves = __ffs(~m) - 1;                                 // leading ancestors that are "less" than val
+    if (lane < moves) ks[lane == 0 ? hole : ((hole + 1) >> lane) - 1] = pe;
+    if (lane == 0) ks[moves == 0 ? hole : ((hole + 1) >> moves) - 1] = val;
+    __syncwarp();
 }
-// std::pop_heap (__adjust_heap to the bottom, then __push_heap of the former last element)
-__device__ __forceinline__ HeapEnt heap_pop(const Heap& h, int& n) {
-    const HeapEnt top = h.load(0);
-    const int len = --n;
+// std::pop_heap: __adjust_heap walks the hole to the bottom along the "not less" children (every lane follows the same path,
+// lane 0 stores), then the former last element is sifted up from there.  n = size before the pop; returns the former top.
+__device__ __forceinline__ uint2 heap_pop_w(uint2* ks, int n, int lane) {
+    const uint2 top = ks[0];
+    const int len = n - 1;
     if (len > 0) {
-        const HeapEnt val = h.load(len);
+        const uint2 val = ks[len];
         int hole = 0, child = 0;
         while (child < (len - 1) / 2) {
             child = 2 * (child + 1);
-            HeapEnt c1 = h.load(child); const HeapEnt c0 = h.load(child - 1);
-            if (node_less(c1, c0)) { child--; c1 = c0; }
-            h.store(hole, c1); hole = child;
+            uint2 c1 = ks[child]; const uint2 c0 = ks[child - 1];
+            if (key_less(c1, c0)) { child--; c1 = c0; }
+            if (lane == 0) ks[hole] = c1;
+            hole = child;
         }
         if ((len & 1) == 0 && child == (len - 2) / 2) {
             child = 2 * (child + 1);
-            h.store(hole, h.load(child - 1)); hole = child - 1;
+            if (lane == 0) ks[hole] = ks[child - 1];
+            hole = child - 1;
         }
-        int parent = (hole - 1) / 2;
+        __syncwarp();
+        heap_siftup_w(ks, hole, val, lane);
+    }
+    return top;
+}
+// std::push_heap (__push_heap) on h[0..n) + val
+__device__ __forceinline__ void heap_push(const Heap& h, int& n, const uint2 val) {
+    int hole = n++;
+    while (hole > 0) {
+        const int parent = (hole - 1) >> 1;
+        const uint2 pe = h.key(parent);
+        if (!key_less(pe, val)) break;
+        h.setkey(hole, pe);
+        hole = parent;
+    }
+    h.setkey(hole, val);
+}
+// std::pop_heap (__adjust_heap to the bottom, then __push_heap of the former last element); returns the former top
+__device__ __forceinline__ uint2 heap_pop(const Heap& h, int& n) {
+    const uint2 top = h.key(0);
+    const int len = --n;
+    if (len > 0) {
+        const uint2 val = h.key(len);
+        int hole = 0, child = 0;
+        while (child < (len - 1) / 2) {
+            child = 2 * (child + 1);
+            uint2 c1 = h.key(child); const uint2 c0 = h.key(child - 1);
+            if (key_less(c1, c0)) { child--; c1 = c0; }
+            h.setkey(hole, c1); hole = child;
+        }
+        if ((len & 1) == 0 && child == (len - 2) / 2) {
+            child = 2 * (child + 1);
+            h.setkey(hole, h.key(child - 1)); hole = child - 1;
+        }
         while (hole > 0) {
-            const HeapEnt pe = h.load(parent);
-            if (!node_less(pe, val)) break;
-            h.store(hole, pe);
-            hole = parent; parent = (hole - 1) / 2;
+            const int parent = (hole - 1) >> 1;
+            const uint2 pe = h.key(parent);
+            if (!key_less(pe, val)) break;
+            h.setkey(hole, pe);
+            hole = parent;
         }
-        h.store(hole, val);
+        h.setkey(hole, val);
     }
     return top;
 }
@@ -116,40 +161,55 @@ struct BnbShared {
     float ub[8], lb[8];
     int cnt[27];
     float cf[27];
-    float X[3], Y[3], Z[3];
+    float X[9];                    // corner lattice of the popped node: X[0..2] x, X[3..5] y, X[6..8] z (child origins = the first two of each)
+    float CX[9];                   // vox_fast constants of the lattice coordinates (corner terms), same layout
+    float HX[6];                   // child-centre translations X[k] + w/2 (:331-333): [0..1] x, [2..3] y, [4..5] z ...
+    float DX[6];                   // ... and their vox_fast constants
+    float wtab[MAX_TLEVEL];        // node width per level: tWidth halved level times (:322)
     float wc, mtd;
     float optErrorT;
-    int running, prob, heapN, status;
+    int level;                     // level of the children being evaluated
+    int running, prob, status;
     int pops, subcubes, improved;
     float best[4];
     int missList[27];
-    int nmiss, workCtr;
+    int cntM[27];                  // incompatibility counts of the missed corners, in missList order
+    float mC[81];                  // vox_fast constants of the missed corners: [m] x, [27+m] y, [54+m] z
+    int nmiss, workCtr, workA;
     unsigned gen;
     long long t0; int missTot;
 #ifdef GOICP_PHASE_TIMING
-    long long tp[6]; long long tmark;
+    long long tp[12]; long long tmark;
 #endif
 };
 
-// Per pop of the translation queue:
-//   phase A (all warps)  flat list of (child cube | lattice corner) x 32-point chunks, dealt round-robin to the warps;
-//   phase B (warp 0)     the 16 sequential (ub, lb) sums [EXACT] or the fixed-order combine of per-chunk partial sums;
-//                        warp 1 does the 27 c-FPFH corner sums meanwhile; trimmed sums use warps 0..7;
-//   phase C (warp 0)     per-child corner min/max on 8 lanes, then lane 0: decisions, pushes and the next pop.
+// Per pop of the translation queue (three CTA barriers):
+//   phase A1 (all warps)  work items (32-point chunk, 4 child cubes): a lane loads its point once and evaluates the four
+//                         cubes as independent chains (translate -> voxel -> DT gather -> weight, radius, clamp); warp 0 then
+//                         files the corner-memo look-ups it issued at the end of the previous pop;
+//   phase A2              warp 0 lanes 0..15: the sixteen sequential (ub, lb) sums [EXACT] or the fixed-order combine of the
+//                         per-chunk partial sums; all other warps (then warp 0 too): the corners the memo missed, work items
+//                         (32-point chunk, 4 corners); trimmed sums: one warp per child;
+//   phase C (warp 0)      c-FPFH corner sums, memo update, per-child corner min/max on 8 lanes, the eight decisions as a warp
+//                         prefix-min, then lane 0: pushes and the next pop; lanes 0..14 derive the next node's voxel constants
+//                         and lanes 0..26 issue its memo look-ups.
 // PERSIST=false: the calls are probs[0..nprob), claimed through counter[0] (one launch per wave).
 // PERSIST=true : the kernel stays resident for a whole batch and serves the host's request ring `q` (see QueueDev).
 // GS=true (needs SMEM): the call's DT volume (float distances + one colour-mask byte per voxel) is staged in shared memory by
 // TMA, so the per-point gathers are LDS instead of L1/L2 sector gathers (S^3 * 5 bytes at dynamic-smem offset gridOff).
 template <bool EXACT, bool PERSIST, bool SMEM, bool GS>
-__global__ void __launch_bounds__(BNB_MAX_THREADS, 2)
+__global__ void __launch_bounds__(BNB_MAX_THREADS, 3)
 inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, InnerOut* outs,
                  int nprob, int* __restrict__ counter, HeapEnt* __restrict__ heaps, int heapCap,
                  float* gscratch, size_t gstride, int NdP, int NdQ, int useSmem, QueueDev q,
                  uint4* memoAll, int memoCap, unsigned* genCounter, int gridOff, int S3p) {
-    unsigned long long* dstat = reinterpret_cast<unsigned long long*>(genCounter) + 1;   // [0] busy cycles [1] pops [2] corner misses [3] calls [4] poll cycles   // gscratch is exchanged between threads: no __restrict__
+    unsigned long long* dstat = reinterpret_cast<unsigned long long*>(genCounter) + 1;   // [0] busy cycles [1] pops [2] corner misses [3] calls [4] poll cycles
     extern __shared__ float4 dyn_smem4[];
     __shared__ BnbShared sh;
-    __shared__ float4 sheap[2 * HEAP_SMEM];
+    __shared__ uint2 s_hkey[HK_SMEM];
+    __shared__ float4 s_hpay[HP_SMEM];
+    __shared__ int s_free[HF_SMEM];   // recycled payload slots (stack)
+    __shared__ uint2 s_pk[8];         // keys of the children being pushed
     __shared__ InnerProb s_pr;
     __shared__ InnerOut s_out;
     __shared__ unsigned long long s_gbar;   // mbarrier of the DT staging copies
@@ -157,10 +217,15 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
     float* base = SMEM ? reinterpret_cast<float*>(dyn_smem4) : gscratch + (size_t)blockIdx.x * gstride;   // SMEM: address space known -> LDS/STS
     float* tx = base; float* ty = tx + NdP; float* tz = ty + NdP; float* wgt = tz + NdP; float* mrd = wgt + NdP;
     uint8_t* dprop_s = reinterpret_cast<uint8_t*>(mrd + NdP);   // [NdP] colour index of each data point
-    float* part = mrd + NdP + (NdP >> 2);   // [8][nchunks][2] + [27][nchunks] per-chunk partial sums (tree-sum mode)
-    float* md = part + 43 * (NdP >> 5);   // EXACT: [16][NdQ] sum terms (ub, lb per child); trimmed: [8][NdQ] residuals
-    float* fp = md + (EXACT ? 16 : 8) * NdQ;   // [27][NdQ]  (EXACT with the c-FPFH term)
-    Heap heap; heap.s = sheap; heap.g = heaps + (size_t)blockIdx.x * heapCap;
+    float* part = mrd + NdP + (NdP >> 2);                       // [8][nchunks][2] + [27][nchunks] per-chunk partial sums (tree-sum mode)
+    float* md = part + ((43 * (NdP >> 5) + 3) & ~3);            // [8][NdQ] clamped residuals d of the 8 child cubes (EXACT / trimmed); rows 16-byte aligned
+    float* fp = md + 8 * NdQ;                                   // [27][NdQ]  (EXACT with the c-FPFH term)
+    Heap heap;
+    {
+        char* slab = reinterpret_cast<char*>(heaps + (size_t)blockIdx.x * heapCap);      // 32 bytes per queue entry: 8 key + 16 payload used
+        heap.ks = s_hkey; heap.kg = reinterpret_cast<uint2*>(slab);
+        heap.ps = s_hpay; heap.pg = reinterpret_cast<float4*>(slab + (size_t)heapCap * 8);
+    }
     uint4* memo = memoAll + 2 * (size_t)blockIdx.x * memoCap;
     const int memoShift = 32 - (31 - __clz(memoCap));   // this CTA's corner memo: direct-mapped, 32 B entries, tagged with the call's generation
     float* sdist = reinterpret_cast<float*>(dyn_smem4) + gridOff;                     // GS: [S3p] DT distances
@@ -227,23 +292,24 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
             tma_bulk_g2s(sdist, g.dist, (unsigned)S3p * 4u, &s_gbar);
             tma_bulk_g2s(svm, g.vmask8, (unsigned)S3p, &s_gbar);
         }
+        // per-problem constants in registers (the PairDev lives in global memory)
         const int Nd = P.Nd;
         const int nchunks = (Nd + 31) >> 5;
         const float* __restrict__ dist = g.dist;
-        const bool corners = P.use_reg || P.use_fpfh;
         const bool doTrim = P.doTrim != 0;
         const bool useMd = EXACT || doTrim;
         const int ncp1 = g.ncells + 1;
         const int norm = P.norm;
-        const int G = min(nchunks, 8), ngroups = (nchunks + G - 1) / G;   // chunks per work item, items per row
-        // per-problem constants in registers (the PairDev lives in global memory)
+        const int inlierNum = P.inlierNum;
         const int S = g.S;
         const double gx0 = g.xMin, gy0 = g.yMin, gz0 = g.zMin, gscale = g.scale;
         const int* __restrict__ vcell = g.vcell;
         const uint32_t* __restrict__ cmask = g.cmask;
         const uint32_t* __restrict__ vmask = g.vmask;
         const float* __restrict__ fpfhD = P.fpfhD;
+        const double* __restrict__ ovl = g.ovl;
         const bool use_reg = P.use_reg != 0, use_fpfh = P.use_fpfh != 0;
+        const bool corners = use_reg || use_fpfh;
         const VoxFast vf = vox_fast_of(g);
 
         // ---- stage the rotated cloud (jly_goicp.cpp:750-756), weights and rotation radii ---------------------
@@ -258,140 +324,254 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
         }
         if (tid < 27) sh.cnt[tid] = 0;
         if (tid == 0) {
-            sh.heapN = 0; sh.status = 0; sh.pops = 1; sh.subcubes = 0; sh.improved = 0;
-            sh.gen = atomicAdd(genCounter, 1u) + 1u; sh.nmiss = 0; sh.workCtr = 0; sh.t0 = clock64(); sh.missTot = 0;
+            sh.status = 0; sh.pops = 1; sh.subcubes = 0; sh.improved = 0;
+            sh.gen = atomicAdd(genCounter, 1u) + 1u; sh.nmiss = 0; sh.workCtr = 0; sh.workA = 0; sh.t0 = clock64(); sh.missTot = 0;
 #ifdef GOICP_PHASE_TIMING
-            for (int k = 0; k < 6; k++) sh.tp[k] = 0; sh.tmark = clock64();
+            for (int k = 0; k < 12; k++) sh.tp[k] = 0; sh.tmark = clock64();
 #endif
             sh.optErrorT = pr.optError;                                              // :297
             sh.best[0] = sh.best[1] = sh.best[2] = sh.best[3] = 0.f;
+            { float w = P.tWidth; for (int l = 0; l < MAX_TLEVEL; l++) { sh.wtab[l] = w; w = w / 2; } }   // :322
             // the first pop is always the initial node (:300,:314) with lb = 0
             if (pr.optError - 0.f < P.SSEThresh) sh.running = 0;                     // :317
             else {
                 sh.running = 1;
                 const float wc = P.tWidth / 2;
-                sh.wc = wc; sh.mtd = (float)(GOICP_SQRT3 / 2.0 * wc);
+                sh.wc = wc; sh.mtd = (float)(GOICP_SQRT3 / 2.0 * wc); sh.level = 1;
                 sh.X[0] = P.tMinX; sh.X[1] = P.tMinX + wc; sh.X[2] = sh.X[1] + wc;
-                sh.Y[0] = P.tMinY; sh.Y[1] = P.tMinY + wc; sh.Y[2] = sh.Y[1] + wc;
-                sh.Z[0] = P.tMinZ; sh.Z[1] = P.tMinZ + wc; sh.Z[2] = sh.Z[1] + wc;
+                sh.X[3 + (0)] = P.tMinY; sh.X[3 + (1)] = P.tMinY + wc; sh.X[3 + (2)] = sh.X[3 + (1)] + wc;
+                sh.X[6 + (0)] = P.tMinZ; sh.X[6 + (1)] = P.tMinZ + wc; sh.X[6 + (2)] = sh.X[6 + (1)] + wc;
             }
         }
-
+        __syncthreads();
+        // voxel-index constants of the first node (lanes 0..14 of warp 0, as after every later pop)
+        if (warp == 0 && sh.running) {
+            const float half = sh.wc / 2;
+            if (lane < 9) { const int a = lane / 3; sh.CX[lane] = vox_fast_c(vf, sh.X[lane], a == 0 ? gx0 : a == 1 ? gy0 : gz0, gscale); }
+            else if (lane < 15) { const int a = (lane - 9) >> 1, k = (lane - 9) & 1; const float t = sh.X[3 * a + k] + half;   // :331-333
+                                  sh.HX[2 * a + k] = t; sh.DX[2 * a + k] = vox_fast_c(vf, t, a == 0 ? gx0 : a == 1 ? gy0 : gz0, gscale); }
+        }
+        uint4 me0 = make_uint4(0u, 0u, 0u, 0u), me1 = make_uint4(0u, 0u, 0u, 0u);   // warp 0, lanes 0..26: this pop's memo look-ups (gen 0 never matches)
+        // search state of the call, warp-uniform registers of warp 0 (the only warp that runs phase C)
+        float optT = pr.optError;                                                    // :297
+        int heapN = 0, freeTop = 0, bump = 0, sh_pops = 1, sh_subcubes = 0;
+        int dNpush = 0, dPop = 0, predSlot = -1, intErr = 0;                        // queue update deferred past barrier 1
+        const float SSE = P.SSEThresh, regW = P.reg, regFW = P.regF;
         if (gload) { mbar_wait(&s_gbar, gphase); gphase ^= 1u; gpair = pr.pair; }
+
         for (;;) {
-            __syncthreads();                                                         // (1) the popped node is visible
+            __syncthreads();                                                         // (1) the popped node and its constants are visible
 #ifdef GOICP_PHASE_TIMING
-            if (tid == 0) { const long long n_ = clock64(); sh.tp[sh.pops == 1 && sh.subcubes == 0 ? 0 : 3] += n_ - sh.tmark; sh.tmark = n_; }
+            if (tid == 0) { const long long n_ = clock64(); sh.tp[sh_subcubes == 0 ? 0 : 3] += n_ - sh.tmark; sh.tmark = n_; }
 #endif
             if (!sh.running) break;
-            const float wc = sh.wc, mtd = sh.mtd;
-            const float half = wc / 2;
+            const float mtd = sh.mtd;
 
-            // ---- phase A1: the cube.point bound evals (:343-382) on all warps; the last warp first looks the 27 lattice
-            //      corners up in the call's corner memo (the reference memoises corner terms per InnerBnB call too, :304-305) ---
-            if (corners && warp == nwarps - 1) {
+            // warp 0 first brings the queue up to date: the pushes and the pop decided at the end of the previous pop
+            if (warp == 0 && dPop) {
+                uint2 top = make_uint2(0u, 0u);
+                if (heapN + dNpush <= HK_SMEM) {
+                    for (int r2 = 0; r2 < dNpush; ++r2) heap_siftup_w(s_hkey, heapN + r2, s_pk[r2], lane);
+                    top = heap_pop_w(s_hkey, heapN + dNpush, lane);
+                } else if (lane == 0) {
+                    int n2 = heapN;
+                    for (int r2 = 0; r2 < dNpush; ++r2) heap_push(heap, n2, s_pk[r2]);
+                    top = heap_pop(heap, n2);
+                }
+                heapN += dNpush - 1;
+                const int sl = (int)(__shfl_sync(GOICP_FULL, top.y, 0) & 0x3FFFFFFu);
+                if (sl != predSlot) intErr = 1;                                      // cannot happen (see phase C)
+                if (freeTop < HF_SMEM) { if (lane == 0) s_free[freeTop] = sl; freeTop++; }   // (a full stack leaks the slot: `bump` then runs into heapCap and the call is re-run)
+                dPop = 0; dNpush = 0;
+#ifdef GOICP_PHASE_TIMING
+                if (lane == 0) sh.tp[5] += ((heapN > HK_SMEM) ? (1ll << 38) : 0ll) + (heapN >> 4);
+                if (tid == 0) sh.tp[10] += clock64() - sh.tmark;
+#endif
+            }
+            // ---- phase A1: the cube.point bound evals (:343-382).  Item = (chunk of 32 points, 4 child cubes), dealt dynamically ----
+            for (;;) {
+                int it = 0;
+                if (lane == 0) it = smem_fetch_add(&sh.workA, 1);
+                it = __shfl_sync(GOICP_FULL, it, 0);
+                if (it >= 2 * nchunks) break;
+                const int ch = it >> 1, q4 = (it & 1) * 4;
+                const int i = ch * 32 + lane;
+                const bool valid = i < Nd;
+                const float px = valid ? tx[i] : 0.f, py = valid ? ty[i] : 0.f, pz = valid ? tz[i] : 0.f;
+                const float w_i = valid ? wgt[i] : 0.f, r_i = valid ? mrd[i] : 0.f;
+                const float dzc = sh.DX[4 + (q4 >> 2)], hz = sh.HX[4 + (q4 >> 2)];
+                float dres[4]; int vox[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) vox[k] = vox_fast(vf, S, px, py, pz, sh.DX[k & 1], sh.DX[2 + (k >> 1)], dzc);
+                unsigned flags = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { dres[k] = GS ? sdist[max(vox[k], 0)] : __ldg(dist + max(vox[k], 0)); flags |= (vox[k] < 0 ? 1u : 0u) << k; }
+                unsigned any = __reduce_or_sync(GOICP_FULL, flags);
+                while (any) {   // some lane is outside the grid or on a rounding boundary (rare): overshoot table, else the exact form
+                    const int k = __ffs(any) - 1; any &= any - 1;
+                    if (flags & (1u << k)) {
+                        int idx, s2;
+                        if (vox_near(vf, S, px, py, pz, sh.DX[k & 1], sh.DX[2 + ((k >> 1) & 1)], dzc, &idx, &s2)) {
+                            const float d0 = GS ? sdist[idx] : __ldg(dist + idx);
+                            const float dn = (s2 == 0) ? d0 : (float)(__ldg(ovl + s2) + (double)d0);
+                            if (k == 0) dres[0] = dn; else if (k == 1) dres[1] = dn; else if (k == 2) dres[2] = dn; else dres[3] = dn;
+                        } else {
+                            const float dn = dt_distance_v<!GS>(S, gx0, gy0, gz0, gscale, GS ? sdist : dist, px + sh.HX[k & 1], py + sh.HX[2 + ((k >> 1) & 1)], pz + hz);
+                            if (k == 0) dres[0] = dn; else if (k == 1) dres[1] = dn; else if (k == 2) dres[2] = dn; else dres[3] = dn;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float d = w_i * dres[k];
+                    d = d - r_i;
+                    if (d < 0.f) d = 0.f;
+                    dres[k] = d;
+                }
+                if (useMd) {
+                    if (valid) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) md[(q4 + k) * NdQ + i] = dres[k];
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float d = valid ? dres[k] : 0.f;
+                        float su = (norm == 2) ? d * d : d;
+                        const float dis = d - mtd;
+                        float sl = (dis > 0.f) ? ((norm == 2) ? dis * dis : dis) : 0.f;
+                        su = warp_sum(su); sl = warp_sum(sl);
+                        if (lane == 0) { part[2 * ((q4 + k) * nchunks + ch)] = su; part[2 * ((q4 + k) * nchunks + ch) + 1] = sl; }
+                    }
+                }
+            }
+            // warp 0 files the memo look-ups issued at the end of the previous pop (the reference memoises corner terms per
+            // InnerBnB call too, :304-305)
+            if (corners && warp == 0) {
                 bool miss = false;
                 if (lane < 27) {
                     const int cz_ = lane / 9, cy_ = (lane - 9 * cz_) / 3, cx_ = lane - 9 * cz_ - 3 * cy_;
-                    const unsigned kx = __float_as_uint(sh.X[cx_]), ky = __float_as_uint(sh.Y[cy_]), kz = __float_as_uint(sh.Z[cz_]);
-                    const unsigned hsh = memo_hash(kx, ky, kz);
-                    const uint4* e = memo + 2 * (size_t)memo_slot(hsh, memoShift);
-                    const uint4 e0 = e[0], e1 = e[1];
-                    if (e0.x == kx && e0.y == ky && e0.z == kz && e0.w == sh.gen) { sh.cnt[lane] = (int)e1.x; sh.cf[lane] = __uint_as_float(e1.y); }
+                    const unsigned kx = __float_as_uint(sh.X[cx_]), ky = __float_as_uint(sh.X[3 + (cy_)]), kz = __float_as_uint(sh.X[6 + (cz_)]);
+                    if (me0.x == kx && me0.y == ky && me0.z == kz && me0.w == sh.gen) { sh.cnt[lane] = (int)me1.x; sh.cf[lane] = __uint_as_float(me1.y); }
                     else { miss = true; sh.cnt[lane] = 0; }
                 }
                 const unsigned mm = __ballot_sync(GOICP_FULL, miss);
-                if (miss) sh.missList[__popc(mm & ((1u << lane) - 1u))] = lane;
+                if (miss) {   // compact list of the corners to evaluate, with their voxel constants
+                    const int m = __popc(mm & ((1u << lane) - 1u));
+                    const int cz_ = lane / 9, cy_ = (lane - 9 * cz_) / 3, cx_ = lane - 9 * cz_ - 3 * cy_;
+                    sh.missList[m] = lane;
+                    sh.mC[m] = sh.CX[cx_]; sh.mC[27 + m] = sh.CX[3 + cy_]; sh.mC[54 + m] = sh.CX[6 + cz_];
+                }
+                if (lane < 27) sh.cntM[lane] = 0;
                 if (lane == 0) { sh.nmiss = __popc(mm); sh.workCtr = 0; sh.missTot += __popc(mm); }
-            }
-            // item = (child cube, group of G 32-point chunks): the per-item overhead is paid once per G points of a lane
-            for (int it = warp; it < 8 * ngroups; it += nwarps) {
-                const int c = it / ngroups, gi = it - c * ngroups;
-                const float transX = sh.X[c & 1] + half, transY = sh.Y[(c >> 1) & 1] + half, transZ = sh.Z[(c >> 2) & 1] + half;   // :331-333
-                const int iEnd = min(Nd, (gi + 1) * G * 32);
-                const float Cx = vox_fast_c(vf, transX, gx0, gscale), Cy = vox_fast_c(vf, transY, gy0, gscale), Cz = vox_fast_c(vf, transZ, gz0, gscale);
-                float su = 0.f, sl = 0.f;
-                for (int i = gi * G * 32 + lane; i < iEnd; i += 32) {
-                    const float px = tx[i], py = ty[i], pz = tz[i];
-                    const int vox = vox_fast(vf, S, px, py, pz, Cx, Cy, Cz);
-                    float dv;
-                    if (vox >= 0) dv = GS ? sdist[vox] : __ldg(dist + vox);
-                    else dv = dt_distance_v<!GS>(S, gx0, gy0, gz0, gscale, GS ? sdist : dist, px + transX, py + transY, pz + transZ);
-                    float d = wgt[i] * dv;
-                    d = d - mrd[i];
-                    if (d < 0.f) d = 0.f;
-                    if (EXACT && !doTrim) {   // the two sum terms of this point (:393-415), summed in index order by the chain lanes
-                        const float dis = fmaxf(d - mtd, 0.f);
-                        md[(2 * c) * NdQ + i] = (norm == 2) ? d * d : d;
-                        md[(2 * c + 1) * NdQ + i] = (norm == 2) ? dis * dis : dis;
-                    } else if (useMd) md[c * NdQ + i] = d;
-                    else {
-                        su = su + ((norm == 2) ? d * d : d);
-                        const float dis = d - mtd;
-                        if (dis > 0.f) sl = sl + ((norm == 2) ? dis * dis : dis);
-                    }
-                }
-                if (!useMd) {
-                    su = warp_sum(su); sl = warp_sum(sl);
-                    if (lane == 0) { part[2 * it] = su; part[2 * it + 1] = sl; }
-                }
             }
             __syncthreads();                                                         // (2)
 #ifdef GOICP_PHASE_TIMING
             if (tid == 0) { const long long n_ = clock64(); sh.tp[1] += n_ - sh.tmark; sh.tmark = n_; }
 #endif
             // ---- phase A2: warp 0 sums the residuals while the other warps evaluate the corners the memo missed -----------
-            if (P.doTrim) {   // radix select replaces intro_select (:384-390); one warp per child
+            if (doTrim) {   // radix select replaces intro_select (:384-390); one warp per child
                 for (int c = warp; c < 8; c += nwarps) {
                     float su, sl;
-                    warp_trimmed_sums(md + c * NdQ, Nd, P.inlierNum, lane, norm, mtd, &su, &sl);
+                    warp_trimmed_sums(md + c * NdQ, Nd, inlierNum, lane, norm, mtd, &su, &sl);
                     if (lane == 0) { sh.ub[c] = su; sh.lb[c] = sl; }
                 }
             } else if (warp == 0 && lane < 16) {
                 const int c = lane >> 1;
                 float acc = 0.f;
                 if (EXACT) {   // sequential float sums in index order (:393-415): lane = (child, ub|lb); 16 independent chains
-                    const float* m = md + lane * NdQ;
-                    const int n = P.inlierNum;
-#pragma unroll 8
-                    for (int i = 0; i < n; ++i) acc = acc + m[i];
+                    const float sub = (lane & 1) ? mtd : 0.f;   // d - 0 == d and max(d, 0) == d: one code path for both sums
+                    const float* m = md + c * NdQ;
+                    const float4* m4 = reinterpret_cast<const float4*>(m);
+                    const int n4 = inlierNum >> 2;
+                    float4 cur = m4[0];
+                    for (int k = 0; k < n4; ++k) {
+                        const float4 nxt = m4[k + 1];   // rows are padded: the read-ahead stays inside the row
+                        float t;
+                        t = fmaxf(cur.x - sub, 0.f); acc = acc + ((norm == 2) ? t * t : t);
+                        t = fmaxf(cur.y - sub, 0.f); acc = acc + ((norm == 2) ? t * t : t);
+                        t = fmaxf(cur.z - sub, 0.f); acc = acc + ((norm == 2) ? t * t : t);
+                        t = fmaxf(cur.w - sub, 0.f); acc = acc + ((norm == 2) ? t * t : t);
+                        cur = nxt;
+                    }
+                    for (int i = n4 * 4; i < inlierNum; ++i) { const float t = fmaxf(m[i] - sub, 0.f); acc = acc + ((norm == 2) ? t * t : t); }
                 } else {
-                    const float* q = part + 2 * c * ngroups + (lane & 1);
-                    for (int k = 0; k < ngroups; ++k) acc = acc + q[2 * k];
+                    const float* qd = part + 2 * c * nchunks + (lane & 1);
+                    for (int k = 0; k < nchunks; ++k) acc = acc + qd[2 * k];
                 }
                 if (lane & 1) sh.lb[c] = acc; else sh.ub[c] = acc;
 #ifdef GOICP_PHASE_TIMING
                 if (tid == 0) sh.tp[4] += clock64() - sh.tmark;
 #endif
             }
-            if (corners) {   // corner terms (:431-550, checkCompatibilities :919, sumFPFH :1689): (missed corner, 32-point chunk) items
-                const int nItems = sh.nmiss * ngroups;
+            if (corners) {   // corner terms (:431-550, checkCompatibilities :919, sumFPFH :1689): item = (chunk, half of the missed corners)
+                const int nmiss = sh.nmiss;
+                const int ngrp = (nmiss + 3) >> 2, ghalf = (ngrp + 1) >> 1;
                 for (;;) {
                     int it = 0;
-                    if (lane == 0) it = atomicAdd(&sh.workCtr, 1);
+                    if (lane == 0) it = smem_fetch_add(&sh.workCtr, 1);
                     it = __shfl_sync(GOICP_FULL, it, 0);
-                    if (it >= nItems) break;
-                    const int m = it / ngroups, gi = it - m * ngroups;
-                    const int c = sh.missList[m];
-                    const int cz_ = c / 9, cy_ = (c - 9 * cz_) / 3, cx_ = c - 9 * cz_ - 3 * cy_;
-                    const float cx = sh.X[cx_], cy = sh.Y[cy_], cz = sh.Z[cz_];
-                    const int iEnd = min(Nd, (gi + 1) * G * 32);
-                    const float Cx = vox_fast_c(vf, cx, gx0, gscale), Cy = vox_fast_c(vf, cy, gy0, gscale), Cz = vox_fast_c(vf, cz, gz0, gscale);
-                    int bad = 0; float fs = 0.f;
-                    for (int i = gi * G * 32 + lane; i < iEnd; i += 32) {
-                        const float px = tx[i], py = ty[i], pz = tz[i];
-                        int vox = vox_fast(vf, S, px, py, pz, Cx, Cy, Cz);
-                        if (vox < 0) vox = clamp_vox_v(S, gx0, gy0, gz0, gscale, px + cx, py + cy, pz + cz);
-                        if (!use_fpfh) bad += ((((GS ? (unsigned)svm[vox] : __ldg(vmask + vox))) >> dprop_s[i]) & 1u) ? 0 : 1;   // per-voxel mask of the closest cell: one gather
-                        else {
-                            const int cell = __ldg(vcell + vox);
-                            if (use_reg) bad += ((__ldg(cmask + cell) >> dprop_s[i]) & 1u) ? 0 : 1;
-                            const float fv = __ldg(fpfhD + (size_t)i * ncp1 + cell);
-                            if (EXACT) fp[m * NdQ + i] = fv; else fs = fs + fv;
+                    if (it >= 2 * nchunks) break;
+                    const int ch = it >> 1;
+                    const int g0 = (it & 1) * ghalf, g1 = min(ngrp, g0 + ghalf);
+                    const int i = ch * 32 + lane;
+                    const bool valid = i < Nd;
+                    const float px = valid ? tx[i] : 0.f, py = valid ? ty[i] : 0.f, pz = valid ? tz[i] : 0.f;
+                    const unsigned dp = valid ? dprop_s[i] : 0u;
+                    for (int gq = g0; gq < g1; ++gq) {
+                        if (!use_fpfh) {   // incompatibility counts only: four independent chains, one packed warp reduction
+                            int vox[4];
+                            unsigned flags = 0;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const int m = min(gq * 4 + k, nmiss - 1);
+                                vox[k] = vox_fast(vf, S, px, py, pz, sh.mC[m], sh.mC[27 + m], sh.mC[54 + m]);
+                                flags |= (vox[k] < 0 ? 1u : 0u) << k;
+                            }
+                            unsigned any = __reduce_or_sync(GOICP_FULL, flags);
+                            while (any) {   // clamped INTO the grid (checkCompatibility :976-984): near table, else the exact form
+                                const int k = __ffs(any) - 1; any &= any - 1;
+                                if (flags & (1u << k)) {
+                                    const int m = min(gq * 4 + k, nmiss - 1);
+                                    const int c = sh.missList[m];
+                                    const int cz_ = c / 9, cy_ = (c - 9 * cz_) / 3, cx_ = c - 9 * cz_ - 3 * cy_;
+                                    int idx, s2;
+                                    if (!vox_near(vf, S, px, py, pz, sh.mC[m], sh.mC[27 + m], sh.mC[54 + m], &idx, &s2))
+                                        idx = clamp_vox_v(S, gx0, gy0, gz0, gscale, px + sh.X[cx_], py + sh.X[3 + cy_], pz + sh.X[6 + cz_]);
+                                    if (k == 0) vox[0] = idx; else if (k == 1) vox[1] = idx; else if (k == 2) vox[2] = idx; else vox[3] = idx;
+                                }
+                            }
+                            unsigned packed = 0;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const unsigned mk = GS ? (unsigned)svm[vox[k]] : __ldg(vmask + vox[k]);   // per-voxel mask of the closest cell: one gather
+                                packed |= (((mk >> dp) & 1u) ^ 1u) << (8 * k);
+                            }
+                            packed = __reduce_add_sync(GOICP_FULL, valid ? packed : 0u);   // <= 32 per byte field
+                            if (lane < 4 && gq * 4 + lane < nmiss) {
+                                const unsigned bad = (packed >> (8 * lane)) & 0xFFu;
+                                if (bad) smem_red_add(&sh.cntM[gq * 4 + lane], (int)bad);
+                            }
+                        } else {
+                            for (int k = 0; k < 4; ++k) {
+                                const int m = gq * 4 + k;
+                                if (m >= nmiss) break;
+                                const int c = sh.missList[m];
+                                const int cz_ = c / 9, cy_ = (c - 9 * cz_) / 3, cx_ = c - 9 * cz_ - 3 * cy_;
+                                int vox = vox_fast(vf, S, px, py, pz, sh.mC[m], sh.mC[27 + m], sh.mC[54 + m]);
+                                if (vox < 0) vox = clamp_vox_v(S, gx0, gy0, gz0, gscale, px + sh.X[cx_], py + sh.X[3 + cy_], pz + sh.X[6 + cz_]);
+                                const int cell = __ldg(vcell + vox);
+                                const float fv = valid ? __ldg(fpfhD + (size_t)i * ncp1 + cell) : 0.f;
+                                if (EXACT) { if (valid) fp[m * NdQ + i] = fv; }
+                                else { const float fs = warp_sum(fv); if (lane == 0) part[16 * nchunks + m * nchunks + ch] = fs; }
+                                if (use_reg) {
+                                    int bad = ((__ldg(cmask + cell) >> dp) & 1u) ? 0 : 1;
+                                    bad = warp_sum_i(valid ? bad : 0);
+                                    if (lane == 0 && bad) smem_red_add(&sh.cntM[m], bad);
+                                }
+                            }
                         }
                     }
-                    if (use_reg) { bad = warp_sum_i(bad); if (lane == 0 && bad) atomicAdd(&sh.cnt[c], bad); }
-                    if (!EXACT && use_fpfh) { fs = warp_sum(fs); if (lane == 0) part[16 * ngroups + it] = fs; }
                 }
             }
             __syncthreads();                                                         // (3)
@@ -402,7 +582,7 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
                 if (lane < sh.nmiss) {
                     float s_ = 0.f;
                     if (EXACT) { const float* f = fp + lane * NdQ; for (int i = 0; i < Nd; ++i) s_ = s_ + f[i]; }   // sumFPFH :1692-1695
-                    else { const float* f = part + 16 * ngroups + lane * ngroups; for (int k = 0; k < ngroups; ++k) s_ = s_ + f[k]; }
+                    else { const float* f = part + 16 * nchunks + lane * nchunks; for (int k = 0; k < nchunks; ++k) s_ = s_ + f[k]; }
                     sh.cf[sh.missList[lane]] = (float)(int)(s_ / (float)Nd);          // :1696, int truncation :468,:495 (H7)
                 }
                 __syncwarp();
@@ -412,69 +592,139 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
             __syncwarp();
             if (use_fpfh) asm volatile("bar.sync 1, 64;" ::: "memory");
             __syncwarp();
+            if (corners && lane < sh.nmiss) sh.cnt[sh.missList[lane]] = sh.cntM[lane];
+            __syncwarp();
             if (corners && lane < sh.nmiss) {   // remember the freshly computed corners
                 const int c = sh.missList[lane];
                 const int cz_ = c / 9, cy_ = (c - 9 * cz_) / 3, cx_ = c - 9 * cz_ - 3 * cy_;
-                const unsigned kx = __float_as_uint(sh.X[cx_]), ky = __float_as_uint(sh.Y[cy_]), kz = __float_as_uint(sh.Z[cz_]);
+                const unsigned kx = __float_as_uint(sh.X[cx_]), ky = __float_as_uint(sh.X[3 + (cy_)]), kz = __float_as_uint(sh.X[6 + (cz_)]);
                 const unsigned hsh = memo_hash(kx, ky, kz);
                 uint4* e = memo + 2 * (size_t)memo_slot(hsh, memoShift);
                 e[0] = make_uint4(kx, ky, kz, sh.gen);
                 e[1] = make_uint4((unsigned)sh.cnt[c], __float_as_uint(sh.cf[c]), 0u, 0u);
             }
-            // ---- phase C: corner min/max per child on 8 lanes (:431-550), then lane 0 alone -------------------------
-            if (corners && lane < 8) {
-                const int j = lane, jx = j & 1, jy = (j >> 1) & 1, jz = (j >> 2) & 1;
-                float ub = sh.ub[j], lb = sh.lb[j];
-                int minI = 0, maxI = 0; float minF = 0.f, maxF = 0.f;
-                for (int k = 0; k < 8; ++k) {
-                    const int c = (jx + (k & 1)) + 3 * (jy + ((k >> 1) & 1)) + 9 * (jz + ((k >> 2) & 1));
-                    if (P.use_fpfh) { const float f = sh.cf[c]; if (k == 0) { minF = maxF = f; } else { if (f > maxF) maxF = f; if (f < minF) minF = f; } }
-                    if (P.use_reg) { const int n = sh.cnt[c]; if (k == 0) { minI = maxI = n; } else { if (n > maxI) maxI = n; if (n < minI) minI = n; } }
-                }
-                if (P.use_reg) { ub = ub + P.reg * (float)(maxI * maxI); lb = lb + P.reg * (float)(minI * minI); }      // :536-538
-                if (P.use_fpfh) { ub = ub + P.regF * (maxF * maxF); lb = lb + P.regF * (minF * minF); }                  // :546-549
-                sh.ub[j] = ub; sh.lb[j] = lb;
-            }
-            __syncwarp();
-            if (lane == 0) {   // decisions and pushes in child order (:417-575), then the next pop (:314-320)
-                float optErrorT = sh.optErrorT;
-                int heapN = sh.heapN;
-                for (int j = 0; j < 8; ++j) {
-                    const float ub = sh.ub[j], lb = sh.lb[j];
-                    const float nx = sh.X[j & 1], ny = sh.Y[(j >> 1) & 1], nz = sh.Z[(j >> 2) & 1];
-                    if (ub < optErrorT) {                                                                                         // :554-566
-                        optErrorT = ub; sh.improved = 1;
-                        sh.best[0] = nx; sh.best[1] = ny; sh.best[2] = nz; sh.best[3] = wc;
+            // ---- phase C: corner min/max per child on 8 lanes (:431-550), the eight decisions (:554-572) as a prefix-min ----
+            const float INF = __int_as_float(0x7f800000);
+            const int jx = lane & 1, jy = (lane >> 1) & 1, jz = (lane >> 2) & 1;
+            float ubj = INF, lbj = INF;
+            if (lane < 8) {
+                float ub = sh.ub[lane], lb = sh.lb[lane];
+                if (corners) {
+                    int minI = 0, maxI = 0; float minF = 0.f, maxF = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int c = (jx + (k & 1)) + 3 * (jy + ((k >> 1) & 1)) + 9 * (jz + ((k >> 2) & 1));
+                        if (use_fpfh) { const float f = sh.cf[c]; if (k == 0) { minF = maxF = f; } else { if (f > maxF) maxF = f; if (f < minF) minF = f; } }
+                        if (use_reg) { const int n = sh.cnt[c]; if (k == 0) { minI = maxI = n; } else { if (n > maxI) maxI = n; if (n < minI) minI = n; } }
                     }
-                    if (lb >= optErrorT) continue;                                                                                // :568-572
-                    if (heapN >= heapCap) { sh.status = 4; break; }
-                    HeapEnt e; e.lb = lb; e.w = wc; e.x = nx; e.y = ny; e.z = nz; e.pad0 = e.pad1 = e.pad2 = 0.f;
-                    heap_push(heap, heapN, e);
+                    if (use_reg) { ub = ub + regW * (float)(maxI * maxI); lb = lb + regW * (float)(minI * minI); }      // :536-538
+                    if (use_fpfh) { ub = ub + regFW * (maxF * maxF); lb = lb + regFW * (minF * minF); }                  // :546-549
                 }
-                sh.subcubes += 8;
-                sh.optErrorT = optErrorT;
-                if (heapN == 0 || sh.status != 0) sh.running = 0;
+                ubj = ub; lbj = lb;
+            }
+            // optErrorT after child j = min(optErrorT, ub_0..ub_j) (:554-566 takes a strictly smaller ub); child j is pushed
+            // unless lb_j >= that value (:568-572)
+            float run = ubj;
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) { const float v = __shfl_up_sync(GOICP_FULL, run, o); if (lane >= o) run = fminf(run, v); }
+            const float optj = fminf(optT, run);
+            float optPrev = __shfl_up_sync(GOICP_FULL, optj, 1); if (lane == 0) optPrev = optT;
+            const unsigned impMask = __ballot_sync(GOICP_FULL, lane < 8 && ubj < optPrev);
+            const unsigned pushMask = __ballot_sync(GOICP_FULL, lane < 8 && !(lbj >= optj));
+            optT = __shfl_sync(GOICP_FULL, optj, 7);
+#ifdef GOICP_PHASE_TIMING
+            if (tid == 0) sh.tp[8] += clock64() - sh.tmark;
+#endif
+            // the node's own lattice origin and width (lane j < 8: origin of child j)
+            const float ox = sh.X[jx], oy = sh.X[3 + (jy)], oz = sh.X[6 + (jz)];
+            const float wc = sh.wc;
+            const int lvl = sh.level;
+            if (impMask) {   // the last child that lowered optErrorT holds the final value
+                const int jb = 31 - __clz(impMask);
+                if (lane == jb) { sh.improved = 1; sh.best[0] = ox; sh.best[1] = oy; sh.best[2] = oz; sh.best[3] = wc; }
+            }
+            // every pushed child takes a payload slot and stages its key.  The queue itself is updated later (after barrier 1,
+            // while the other warps already evaluate the next node): the node popped next is known without touching the queue.
+            // It is the queue's top T unless a pushed child is strictly better than T, and then the first such child with the
+            // smallest lb: __push_heap moves a key up only past strictly worse ancestors, so equal keys stay below older ones.
+            const int npush = __popc(pushMask);
+            int status = 0, running = 1;
+            sh_subcubes += 8;
+#ifdef GOICP_PHASE_TIMING
+            if (tid == 0) sh.tp[9] += clock64() - sh.tmark;
+#endif
+            if (heapN + npush > heapCap || bump + npush > heapCap) { status = 4; running = 0; }
+            else {
+                const bool pushed = (pushMask >> lane) & 1u;
+                const int r = __popc(pushMask & ((1u << lane) - 1u));
+                int mySlot = 0;
+                if (pushed) {
+                    mySlot = (r < freeTop) ? s_free[freeTop - 1 - r] : bump + (r - freeTop);
+                    heap.setpay(mySlot, make_float4(ox, oy, oz, 0.f));
+                    s_pk[r] = make_uint2(__float_as_uint(lbj), ((unsigned)lvl << 26) | (unsigned)mySlot);
+                }
+                const int fromFree = min(npush, freeTop);
+                freeTop -= fromFree; bump += npush - fromFree;
+                const unsigned minBits = __reduce_min_sync(GOICP_FULL, pushed ? __float_as_uint(lbj) : 0xFFFFFFFFu);   // lb >= +0: bit order = value order
+                const uint2 T = s_hkey[0];
+                const bool childBetter = npush > 0 && (heapN == 0 || key_less(T, make_uint2(minBits, (unsigned)lvl << 26)));
+                if (!childBetter && heapN == 0) running = 0;                         // queue empty (:314)
                 else {
-                    const HeapEnt par = heap_pop(heap, heapN);
-                    sh.pops++;
-                    if (optErrorT - par.lb < P.SSEThresh) sh.running = 0;            // :317
+                    float nlb, nx, ny, nz; int plev;
+                    if (childBetter) {
+                        const int a = __ffs(__ballot_sync(GOICP_FULL, pushed && __float_as_uint(lbj) == minBits)) - 1;
+                        nlb = __uint_as_float(minBits); plev = lvl;
+                        nx = __shfl_sync(GOICP_FULL, ox, a); ny = __shfl_sync(GOICP_FULL, oy, a); nz = __shfl_sync(GOICP_FULL, oz, a);
+                        predSlot = __shfl_sync(GOICP_FULL, mySlot, a);
+                    } else {
+                        nlb = __uint_as_float(T.x); plev = min((int)(T.y >> 26), MAX_TLEVEL - 1);
+                        predSlot = (int)(T.y & 0x3FFFFFFu);
+                        const float4 pp = heap.pay(predSlot);
+                        nx = pp.x; ny = pp.y; nz = pp.z;
+                    }
+                    sh_pops++;
+                    dNpush = npush; dPop = 1;
+                    if (optT - nlb < SSE) running = 0;   // :317
                     else {
-                        const float w2 = par.w / 2;                                  // :322
-                        sh.wc = w2;
-                        sh.mtd = (float)(GOICP_SQRT3 / 2.0 * w2);                    // :323
-                        sh.X[0] = par.x; sh.X[1] = par.x + w2; sh.X[2] = sh.X[1] + w2;   // child / corner lattice
-                        sh.Y[0] = par.y; sh.Y[1] = par.y + w2; sh.Y[2] = sh.Y[1] + w2;
-                        sh.Z[0] = par.z; sh.Z[1] = par.z + w2; sh.Z[2] = sh.Z[1] + w2;
+                        const float w2 = sh.wtab[plev] / 2;                          // :322
+                        // child / corner lattice, voxel-index constants: lane = 3 * axis + k (9 lanes), child-centre forms on lanes 9..14
+                        const int a = lane < 9 ? lane / 3 : (lane - 9) >> 1, k = lane < 9 ? lane - 3 * a : (lane - 9) & 1;
+                        const float o = a == 0 ? nx : a == 1 ? ny : nz;
+                        const double mn = a == 0 ? gx0 : a == 1 ? gy0 : gz0;
+                        float t = o; if (k >= 1) t = o + w2; if (k == 2) t = t + w2;   // X[1] = x + w, X[2] = X[1] + w
+                        if (lane < 9) {
+                            sh.X[3 * a + k] = t;                                     // X, Y, Z are contiguous
+                            sh.CX[3 * a + k] = vox_fast_c(vf, t, mn, gscale);
+                        } else if (lane < 15) {
+                            const float th = t + w2 / 2;                             // :331-333
+                            sh.HX[2 * a + k] = th;
+                            sh.DX[2 * a + k] = vox_fast_c(vf, th, mn, gscale);
+                        } else if (lane == 15) {
+                            sh.wc = w2; sh.level = min(plev + 1, MAX_TLEVEL - 1);
+                            sh.mtd = (float)(GOICP_SQRT3 / 2.0 * w2);                // :323
+                            sh.workA = 0;
+                        }
+                        if (corners && lane < 27) {   // corner-memo look-ups of the next node, consumed after its phase A1
+                            const int cz_ = lane / 9, cy_ = (lane - 9 * cz_) / 3, cx_ = lane - 9 * cz_ - 3 * cy_;
+                            float cxv = nx; if (cx_ >= 1) cxv = nx + w2; if (cx_ == 2) cxv = cxv + w2;
+                            float cyv = ny; if (cy_ >= 1) cyv = ny + w2; if (cy_ == 2) cyv = cyv + w2;
+                            float czv = nz; if (cz_ >= 1) czv = nz + w2; if (cz_ == 2) czv = czv + w2;
+                            const unsigned hsh = memo_hash(__float_as_uint(cxv), __float_as_uint(cyv), __float_as_uint(czv));
+                            const uint4* e = memo + 2 * (size_t)memo_slot(hsh, memoShift);
+                            me0 = e[0]; me1 = e[1];
+                        }
                     }
                 }
-                sh.heapN = heapN;
             }
+            if (lane == 0) { sh.running = running; sh.status = status; }
         }
+        if (tid == 0) { sh.optErrorT = optT; sh.pops = sh_pops; sh.subcubes = sh_subcubes; if (intErr) sh.status = 6; }
+        __syncwarp();
         if (tid == 0) {
             atomicAdd(dstat + 0, (unsigned long long)(clock64() - sh.t0)); atomicAdd(dstat + 1, (unsigned long long)sh.pops);
             atomicAdd(dstat + 2, (unsigned long long)sh.missTot); atomicAdd(dstat + 3, 1ull);
 #ifdef GOICP_PHASE_TIMING
-            for (int k = 0; k < 5; k++) atomicAdd(dstat + 8 + k, (unsigned long long)sh.tp[k]);
+            for (int k = 0; k < 12; k++) atomicAdd(dstat + 8 + k, (unsigned long long)sh.tp[k]);
 #endif
             InnerOut o;
             o.err = sh.optErrorT; o.node[0] = sh.best[0]; o.node[1] = sh.best[1]; o.node[2] = sh.best[2]; o.node[3] = sh.best[3];
@@ -562,7 +812,7 @@ eval_bounds_kernel(const PairDev* __restrict__ pairs, int pair, const float* __r
 
 // ---- launchers ---------------------------------------------------------------------------------------------
 size_t goicp_bnb_smem_floats(int NdP, int NdQ, bool exact, bool needMd, bool needFp) {
-    const size_t n = (size_t)5 * NdP + (size_t)(NdP >> 2) + (size_t)43 * (NdP >> 5) + (needMd ? (size_t)(exact ? 16 : 8) * NdQ : 0) + (needFp ? (size_t)27 * NdQ : 0);
+    const size_t n = (size_t)5 * NdP + (size_t)(NdP >> 2) + (size_t)((43 * (NdP >> 5) + 3) & ~3) + (needMd ? (size_t)8 * NdQ : 0) + (needFp ? (size_t)27 * NdQ : 0);
     return n > 3 * 512 ? n : 3 * 512;   // an ICP request tiles the model cloud through the same region (icp_device.cuh NN_TILE)
 }
 

@@ -18,6 +18,7 @@ initialize_kernel(PairDev* __restrict__ pairs, int first) {
         for (int l = 0; l < GOICP_MAXROTLEVEL; ++l) P.maxRotDis[(size_t)l * Nd + i] = P.s2[l] * nrm;   // :205
         P.weights[i] = 1.f;
     }
+    for (int s = tid; s < GOICP_OVN; s += blockDim.x) P.g.ovl[s] = (double)sqrtf((float)s) / P.g.scale;   // jly_3ddt.cpp:1190 for every near overshoot
     if (P.ponderation != 1) return;
     if (tid == 0) { s_max = 0; s_min = 100; }
     __syncthreads();
