@@ -173,6 +173,7 @@ struct BnbShared {
     int pops, subcubes, improved;
     float best[4];
     int missList[27];
+    unsigned mSlot[27], mChk[27];  // memo slot and key checksum of the missed corners
     int cntM[27];                  // incompatibility counts of the missed corners, in missList order
     float mC[81];                  // vox_fast constants of the missed corners: [m] x, [27+m] y, [54+m] z
     int nmiss, workCtr, workA;
@@ -230,6 +231,7 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
     const int memoShift = 32 - (31 - __clz(memoCap));   // this CTA's corner memo: direct-mapped, 32 B entries, tagged with the call's generation
     float* sdist = reinterpret_cast<float*>(dyn_smem4) + gridOff;                     // GS: [S3p] DT distances
     uint8_t* svm = reinterpret_cast<uint8_t*>(sdist + S3p);                          // GS: [S3p] colour mask of the voxel's closest cell
+    const int chainWarp = nwarps > 1 ? 1 : 0;
     float* icpTile;   // model tile of an ICP request: aliases the staging arrays (the dynamic region holds >= 3*NN_TILE floats)
     if constexpr (SMEM) icpTile = reinterpret_cast<float*>(dyn_smem4); else { __shared__ float s_tile[3 * NN_TILE]; icpTile = s_tile; }
     unsigned gphase = 0; int gpair = -1;                                              // mbarrier parity; pair whose volume is staged
@@ -367,27 +369,6 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
             if (!sh.running) break;
             const float mtd = sh.mtd;
 
-            // warp 0 first brings the queue up to date: the pushes and the pop decided at the end of the previous pop
-            if (warp == 0 && dPop) {
-                uint2 top = make_uint2(0u, 0u);
-                if (heapN + dNpush <= HK_SMEM) {
-                    for (int r2 = 0; r2 < dNpush; ++r2) heap_siftup_w(s_hkey, heapN + r2, s_pk[r2], lane);
-                    top = heap_pop_w(s_hkey, heapN + dNpush, lane);
-                } else if (lane == 0) {
-                    int n2 = heapN;
-                    for (int r2 = 0; r2 < dNpush; ++r2) heap_push(heap, n2, s_pk[r2]);
-                    top = heap_pop(heap, n2);
-                }
-                heapN += dNpush - 1;
-                const int sl = (int)(__shfl_sync(GOICP_FULL, top.y, 0) & 0x3FFFFFFu);
-                if (sl != predSlot) intErr = 1;                                      // cannot happen (see phase C)
-                if (freeTop < HF_SMEM) { if (lane == 0) s_free[freeTop] = sl; freeTop++; }   // (a full stack leaks the slot: `bump` then runs into heapCap and the call is re-run)
-                dPop = 0; dNpush = 0;
-#ifdef GOICP_PHASE_TIMING
-                if (lane == 0) sh.tp[5] += ((heapN > HK_SMEM) ? (1ll << 38) : 0ll) + (heapN >> 4);
-                if (tid == 0) sh.tp[10] += clock64() - sh.tmark;
-#endif
-            }
             // ---- phase A1: the cube.point bound evals (:343-382).  Item = (chunk of 32 points, 4 child cubes), dealt dynamically ----
             for (;;) {
                 int it = 0;
@@ -449,10 +430,12 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
             // InnerBnB call too, :304-305)
             if (corners && warp == 0) {
                 bool miss = false;
+                unsigned mkx = 0, mky = 0, mkz = 0;
                 if (lane < 27) {
                     const int cz_ = lane / 9, cy_ = (lane - 9 * cz_) / 3, cx_ = lane - 9 * cz_ - 3 * cy_;
                     const unsigned kx = __float_as_uint(sh.X[cx_]), ky = __float_as_uint(sh.X[3 + (cy_)]), kz = __float_as_uint(sh.X[6 + (cz_)]);
-                    if (me0.x == kx && me0.y == ky && me0.z == kz && me0.w == sh.gen) { sh.cnt[lane] = (int)me1.x; sh.cf[lane] = __uint_as_float(me1.y); }
+                    mkx = kx; mky = ky; mkz = kz;
+                    if (me0.x == kx && me0.y == ky && me0.z == kz && me0.w == sh.gen && me1.z == (kx ^ __funnelshift_l(ky, ky, 11) ^ __funnelshift_l(kz, kz, 22))) { sh.cnt[lane] = (int)me1.x; sh.cf[lane] = __uint_as_float(me1.y); }
                     else { miss = true; sh.cnt[lane] = 0; }
                 }
                 const unsigned mm = __ballot_sync(GOICP_FULL, miss);
@@ -460,6 +443,9 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
                     const int m = __popc(mm & ((1u << lane) - 1u));
                     const int cz_ = lane / 9, cy_ = (lane - 9 * cz_) / 3, cx_ = lane - 9 * cz_ - 3 * cy_;
                     sh.missList[m] = lane;
+                    const unsigned slot = memo_slot(memo_hash(mkx, mky, mkz), memoShift);   // the entry's key half is written now, its value half after phase A2
+                    memo[2 * (size_t)slot] = make_uint4(mkx, mky, mkz, sh.gen);
+                    sh.mSlot[m] = slot; sh.mChk[m] = mkx ^ __funnelshift_l(mky, mky, 11) ^ __funnelshift_l(mkz, mkz, 22);
                     sh.mC[m] = sh.CX[cx_]; sh.mC[27 + m] = sh.CX[3 + cy_]; sh.mC[54 + m] = sh.CX[6 + cz_];
                 }
                 if (lane < 27) sh.cntM[lane] = 0;
@@ -469,6 +455,28 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
 #ifdef GOICP_PHASE_TIMING
             if (tid == 0) { const long long n_ = clock64(); sh.tp[1] += n_ - sh.tmark; sh.tmark = n_; }
 #endif
+            // warp 0 brings the queue up to date (the pushes and the pop decided at the end of the previous pop) while warp 1 sums
+            // the residuals and the other warps start on the corners
+            if (warp == 0 && dPop) {
+                uint2 top = make_uint2(0u, 0u);
+                if (heapN + dNpush <= HK_SMEM) {
+                    for (int r2 = 0; r2 < dNpush; ++r2) heap_siftup_w(s_hkey, heapN + r2, s_pk[r2], lane);
+                    top = heap_pop_w(s_hkey, heapN + dNpush, lane);
+                } else if (lane == 0) {
+                    int n2 = heapN;
+                    for (int r2 = 0; r2 < dNpush; ++r2) heap_push(heap, n2, s_pk[r2]);
+                    top = heap_pop(heap, n2);
+                }
+                heapN += dNpush - 1;
+                const int sl = (int)(__shfl_sync(GOICP_FULL, top.y, 0) & 0x3FFFFFFu);
+                if (sl != predSlot) intErr = 1;                                      // cannot happen (see phase C)
+                if (freeTop < HF_SMEM) { if (lane == 0) s_free[freeTop] = sl; freeTop++; }   // (a full stack leaks the slot: `bump` then runs into heapCap and the call is re-run)
+                dPop = 0; dNpush = 0;
+#ifdef GOICP_PHASE_TIMING
+                if (lane == 0) sh.tp[5] += ((heapN > HK_SMEM) ? (1ll << 38) : 0ll) + (heapN >> 4);
+                if (tid == 0) sh.tp[10] += clock64() - sh.tmark;
+#endif
+            }
             // ---- phase A2: warp 0 sums the residuals while the other warps evaluate the corners the memo missed -----------
             if (doTrim) {   // radix select replaces intro_select (:384-390); one warp per child
                 for (int c = warp; c < 8; c += nwarps) {
@@ -476,7 +484,7 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
                     warp_trimmed_sums(md + c * NdQ, Nd, inlierNum, lane, norm, mtd, &su, &sl);
                     if (lane == 0) { sh.ub[c] = su; sh.lb[c] = sl; }
                 }
-            } else if (warp == 0 && lane < 16) {
+            } else if (warp == chainWarp && lane < 16) {
                 const int c = lane >> 1;
                 float acc = 0.f;
                 if (EXACT) {   // sequential float sums in index order (:393-415): lane = (child, ub|lb); 16 independent chains
@@ -501,7 +509,7 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
                 }
                 if (lane & 1) sh.lb[c] = acc; else sh.ub[c] = acc;
 #ifdef GOICP_PHASE_TIMING
-                if (tid == 0) sh.tp[4] += clock64() - sh.tmark;
+                if (lane == 0) sh.tp[4] += clock64() - sh.tmark;
 #endif
             }
             if (corners) {   // corner terms (:431-550, checkCompatibilities :919, sumFPFH :1689): item = (chunk, half of the missed corners)
@@ -592,17 +600,13 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
             __syncwarp();
             if (use_fpfh) asm volatile("bar.sync 1, 64;" ::: "memory");
             __syncwarp();
-            if (corners && lane < sh.nmiss) sh.cnt[sh.missList[lane]] = sh.cntM[lane];
-            __syncwarp();
-            if (corners && lane < sh.nmiss) {   // remember the freshly computed corners
+            if (corners && lane < sh.nmiss) {   // scatter the fresh counts to their lattice corners and complete their memo entries
                 const int c = sh.missList[lane];
-                const int cz_ = c / 9, cy_ = (c - 9 * cz_) / 3, cx_ = c - 9 * cz_ - 3 * cy_;
-                const unsigned kx = __float_as_uint(sh.X[cx_]), ky = __float_as_uint(sh.X[3 + (cy_)]), kz = __float_as_uint(sh.X[6 + (cz_)]);
-                const unsigned hsh = memo_hash(kx, ky, kz);
-                uint4* e = memo + 2 * (size_t)memo_slot(hsh, memoShift);
-                e[0] = make_uint4(kx, ky, kz, sh.gen);
-                e[1] = make_uint4((unsigned)sh.cnt[c], __float_as_uint(sh.cf[c]), 0u, 0u);
+                const int n = sh.cntM[lane];
+                sh.cnt[c] = n;
+                memo[2 * (size_t)sh.mSlot[lane] + 1] = make_uint4((unsigned)n, use_fpfh ? __float_as_uint(sh.cf[c]) : 0u, sh.mChk[lane], 0u);
             }
+            __syncwarp();
             // ---- phase C: corner min/max per child on 8 lanes (:431-550), the eight decisions (:554-572) as a prefix-min ----
             const float INF = __int_as_float(0x7f800000);
             const int jx = lane & 1, jy = (lane >> 1) & 1, jz = (lane >> 2) & 1;
