@@ -88,6 +88,19 @@ __device__ __forceinline__ int vox_fast(const VoxFast& vf, int S, float px, floa
     return (int)((z * S + y) * S + x);
 }
 
+// nearestNeighbor (jly_goicp.cpp:1200-1211) inside compact cell `cell` + one term of compareNeighbors(false, ...) (:1250-1288):
+// |neighbours of data point i - neighbours of the closest model point of the cell| (model point 0 if the cell is empty).
+__device__ __forceinline__ int nb_diff(const PairDev& P, int cell, int i, float ax, float ay, float az) {
+    double minD = 100.0; int ind = 0;
+    for (int k = cell < P.g.ncells ? __ldg(P.cell_start + cell) : 0, e = cell < P.g.ncells ? __ldg(P.cell_start + cell + 1) : 0; k < e; ++k) {
+        const int p = __ldg(P.cell_pts + k);
+        const double a = (double)(ax - __ldg(P.mx + p)), b = (double)(ay - __ldg(P.my + p)), c = (double)(az - __ldg(P.mz + p));
+        const double d = sqrt(a * a + b * b + c * c);
+        if (d < minD) { ind = p; minD = d; }
+    }
+    return abs(__ldg(P.nbD + i) - __ldg(P.nbM + ind));
+}
+
 // Second tier: a position up to GOICP_OVLIM voxels outside the grid.  Returns the clamped linear index and the squared
 // voxel overshoot a^2+b^2+c^2 of DT3D::Distance (jly_3ddt.cpp:1150-1190); false when the position is in the ambiguity zone or
 // further out (the caller then runs the exact FP64 form).  GridDev.ovl[s] = (double)sqrtf(s) / scale.

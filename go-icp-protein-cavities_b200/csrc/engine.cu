@@ -343,7 +343,7 @@ static goicp_status prepare_problem(Eng* h, Problem& P) {
     return GOICP_OK;
 }
 
-static bool need_corner_terms(const goicp_params& p) { return p.regularization > 0 || (p.regularizationFPFH > 0 && p.cfpfh != 0); }
+static bool need_corner_terms(const goicp_params& p) { return p.regularization > 0 || p.regularizationNeighbors > 0 || (p.regularizationFPFH > 0 && p.cfpfh != 0); }
 
 // ---- device layout + upload of all problems ----------------------------------------------------------------------
 static goicp_status upload_problems(Eng* h) {
@@ -365,6 +365,7 @@ static goicp_status upload_problems(Eng* h) {
         w += al256(sizeof(float) * S3) + al256(sizeof(int) * S3) + (wantVcell ? 2 * al256(sizeof(int) * S3) + al256(S3 + 16) : 0) + al256(sizeof(double) * GOICP_OVN);
         w += 2 * al256(sizeof(float) * P.NdAll) + al256(sizeof(float) * GOICP_MAXROTLEVEL * (size_t)P.NdAll);
         if (useF && p.regularizationFPFH > 0) w += al256(sizeof(float) * (size_t)P.NdAll * (nc + 1));
+        if (p.regularizationNeighbors > 0) w += al256(sizeof(int) * P.NdAll) + al256(sizeof(int) * P.Nm);
         w += al256(sizeof(unsigned long long) * P.NdAll) + al256(sizeof(int) * P.NdAll) + al256(sizeof(float) * 8 * (size_t)std::max(P.NdAll, 1));
         if (!(p.trimFraction < 0.001)) w += al256(sizeof(unsigned long long) * 2048);
         P.workBytes = w; P.workOff = workTot; workTot += w;
@@ -407,12 +408,13 @@ static goicp_status upload_problems(Eng* h) {
         D.weights = reinterpret_cast<float*>(dWork + w); w += al256(sizeof(float) * P.NdAll);
         D.maxRotDis = reinterpret_cast<float*>(dWork + w); w += al256(sizeof(float) * GOICP_MAXROTLEVEL * (size_t)P.NdAll);
         if (useF && p.regularizationFPFH > 0) { D.fpfhD = reinterpret_cast<float*>(dWork + w); w += al256(sizeof(float) * (size_t)P.NdAll * (nc + 1)); }
+        if (p.regularizationNeighbors > 0) { D.nbD = reinterpret_cast<int*>(dWork + w); w += al256(sizeof(int) * P.NdAll); D.nbM = reinterpret_cast<int*>(dWork + w); w += al256(sizeof(int) * P.Nm); }
         D.nn = reinterpret_cast<unsigned long long*>(dWork + w); w += al256(sizeof(unsigned long long) * P.NdAll);
         D.order = reinterpret_cast<int*>(dWork + w); w += al256(sizeof(int) * P.NdAll);
         D.scratch = reinterpret_cast<float*>(dWork + w); w += al256(sizeof(float) * 8 * (size_t)std::max(P.NdAll, 1));
         if (!(p.trimFraction < 0.001)) { D.sortKeys = reinterpret_cast<unsigned long long*>(dWork + w); w += al256(sizeof(unsigned long long) * 2048); }
         D.g.S = S; D.g.ncells = nc; D.g.xMin = P.info.xMin; D.g.yMin = P.info.yMin; D.g.zMin = P.info.zMin; D.g.scale = P.info.scale;
-        D.Nm = P.Nm; D.Nd = P.Nd;
+        D.Nm = P.Nm; D.Nd = P.Nd; D.NdAll = P.NdAll;
     });
     CU(cudaMemcpyAsync(dIn, stage, inTot, cudaMemcpyHostToDevice, h->stream));
     return GOICP_OK;
@@ -432,7 +434,8 @@ static goicp_status upload_pairdevs(Eng* h) {
         if (p.cfpfh == 1) D.fpfh_e = 41; else if (p.cfpfh == 2) D.fpfh_e = 33; else if (p.cfpfh == 3) { D.fpfh_b = 33; D.fpfh_e = 41; }
         D.use_reg = p.regularization > 0 ? 1 : 0;
         D.use_fpfh = (p.regularizationFPFH > 0 && p.cfpfh != 0) ? 1 : 0;
-        D.reg = p.regularization; D.regF = p.regularizationFPFH;
+        D.use_nb = p.regularizationNeighbors > 0 ? 1 : 0;
+        D.reg = p.regularization; D.regF = p.regularizationFPFH; D.regN = p.regularizationNeighbors;
         D.MSEThresh = p.MSEThresh; D.trimFraction = p.trimFraction;
         D.SSEThresh = p.MSEThresh * D.inlierNum;                                     // :266
         D.tMinX = p.transMinX; D.tMinY = p.transMinY; D.tMinZ = p.transMinZ; D.tWidth = p.transWidth;
@@ -512,6 +515,10 @@ static goicp_status initialize_all(Eng* h) {
     int nl = 1;
     CU(goicp_launch_initialize(h->dPairs.as<PairDev>(), 0, (int)h->probs.size(), h->stream));
     if (p.regularizationFPFH > 0 && p.cfpfh != 0) { CU(goicp_launch_fpfh_table(h->dPairs.as<PairDev>(), 0, (int)h->probs.size(), 32, h->stream)); nl++; }
+    if (p.regularizationNeighbors > 0) {   // assignNeighbors (BuildDT :94); both clouds, every source point
+        int maxN = 1; for (auto& P : h->probs) maxN = std::max(maxN, P.NdAll + P.Nm);
+        CU(goicp_launch_assign_neighbors(h->dPairs.as<PairDev>(), 0, (int)h->probs.size(), std::min(64, (maxN + 255) / 256), h->stream)); nl++;
+    }
     tm.stop(nl);
     CU(cudaGetLastError());
     for (auto& P : h->probs) P.initialized = true;

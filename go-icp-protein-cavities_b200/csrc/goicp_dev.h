@@ -40,14 +40,16 @@ struct GridDev {
 struct PairDev {
     GridDev g;
     int Nd, Nm;
+    int NdAll;               // every source point given (Nd = the first Nd of them, READMEGo-ICP.md:50)
     int inlierNum;
     int norm;                // 1 or 2
     int doTrim;
     int cfpfh;               // config key; 0 = descriptors unused
     int fpfh_b, fpfh_e;      // c-FPFH bin range selected by `cfpfh` (jly_goicp.cpp:1660-1674)
     int use_reg, use_fpfh;   // regularization > 0 ; regularizationFPFH > 0 && cfpfh != 0 (corner terms, :436)
+    int use_nb;              // regularizationNeighbors > 0 (neighbour-count term, :462-466,:489-493,:542-545)
     int ponderation;
-    float reg, regF;
+    float reg, regF, regN;
     float SSEThresh, MSEThresh, trimFraction;
     float tMinX, tMinY, tMinZ, tWidth;   // initNodeTrans
     float s2[GOICP_MAXROTLEVEL];         // 2*sinf(maxAngle/2) per rotation level, computed on the host (glibc sinf)
@@ -64,6 +66,8 @@ struct PairDev {
     int* cell_start;                     // ncells+1 CSR of cellPoints[].points (insertion = index order)
     int* cell_pts;                       // Nm
     float* fpfhD;                        // Nd x (ncells+1): min over the cell's points of the L1 descriptor distance
+    int* nbD;                            // NdAll: POINT3D.neighbors of the data points (assignNeighbors :1213-1248); NULL unless use_nb
+    int* nbM;                            // Nm
     // ICP workspace (written by the ICP kernels)
     unsigned long long* nn;              // Nd packed (float bits of squared distance << 32 | model index)
     int* order;                          // Nd: id_data of points[i] (identity unless trimmed, jly_icp3d.hpp:252)

@@ -190,11 +190,11 @@ __device__ __forceinline__ void icp_score_part(const PairDev& P, IcpState& st) {
     const int Nd = P.Nd, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float* val = P.scratch + (st.mode == 1 ? 7 * Nd : 0);   // Nd: per data index; mode 1 may run beside a mode-0 state whose update uses [0, 7 Nd)
     float* fd = P.scratch + Nd;        // Nd: per position of `order`
-    __shared__ int s_bad;
+    __shared__ int s_bad, s_nb;
     __shared__ float s_geom, s_fpfh, s_trim;
-    if (tid == 0) { s_bad = 0; s_geom = 0.f; s_fpfh = 0.f; s_trim = 0.f; }
+    if (tid == 0) { s_bad = 0; s_nb = 0; s_geom = 0.f; s_fpfh = 0.f; s_trim = 0.f; }
     __syncthreads();
-    int bad = 0;
+    int bad = 0, nb = 0;
     for (int i = tid; i < Nd; i += blockDim.x) {
         float x, y, z;
         if (st.mode == 1) { x = P.dx[i]; y = P.dy[i]; z = P.dz[i]; }
@@ -215,9 +215,10 @@ __device__ __forceinline__ void icp_score_part(const PairDev& P, IcpState& st) {
                 fd[i] = d;
             }
             bad += (P.dknown[idd] && P.dprop[idd] == P.mprop[idm]) ? 0 : 1;   // countCompatibilities :890-914
+            if (P.use_nb) nb += abs(P.nbD[idd] - P.nbM[idm]);                  // compareNeighbors(true) :1250-1288
         }
     }
-    if (st.mode == 0) { bad = warp_sum_i(bad); if (lane == 0) atomicAdd(&s_bad, bad); }
+    if (st.mode == 0) { bad = warp_sum_i(bad); nb = warp_sum_i(nb); if (lane == 0) { atomicAdd(&s_bad, bad); atomicAdd(&s_nb, nb); } }
     __syncthreads();
     if (!P.doTrim) {
         if (tid == 0) {   // sequential float sum in index order
@@ -240,6 +241,7 @@ __device__ __forceinline__ void icp_score_part(const PairDev& P, IcpState& st) {
     if (tid == 0) {
         float error = s_geom;
         if (st.mode == 0) {
+            if (P.use_nb) error = error + P.regN * (float)(s_nb * s_nb);              // :149-153
             if (P.use_reg) error = error + P.reg * (float)(s_bad * s_bad);            // :154-159
             if (P.regF > 0.f) error = error + P.regF * (s_fpfh * s_fpfh);             // :160-163
         }

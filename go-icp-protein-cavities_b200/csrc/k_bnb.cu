@@ -160,6 +160,7 @@ __device__ __forceinline__ uint2 heap_pop(const Heap& h, int& n) {
 struct BnbShared {
     float ub[8], lb[8];
     int cnt[27];
+    int cntN[27];                  // neighbour-count term per lattice corner (compareNeighbors :1250-1288)
     float cf[27];
     float X[9];                    // corner lattice of the popped node: X[0..2] x, X[3..5] y, X[6..8] z (child origins = the first two of each)
     float CX[9];                   // vox_fast constants of the lattice coordinates (corner terms), same layout
@@ -174,6 +175,7 @@ struct BnbShared {
     float best[4];
     int missList[27];
     unsigned mSlot[27], mChk[27];  // memo slot and key checksum of the missed corners
+    int cntNM[27];                 // neighbour-count terms of the missed corners, in missList order
     int cntM[27];                  // incompatibility counts of the missed corners, in missList order
     float mC[81];                  // vox_fast constants of the missed corners: [m] x, [27+m] y, [54+m] z
     int nmiss, workCtr, workA;
@@ -310,8 +312,8 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
         const uint32_t* __restrict__ vmask = g.vmask;
         const float* __restrict__ fpfhD = P.fpfhD;
         const double* __restrict__ ovl = g.ovl;
-        const bool use_reg = P.use_reg != 0, use_fpfh = P.use_fpfh != 0;
-        const bool corners = use_reg || use_fpfh;
+        const bool use_reg = P.use_reg != 0, use_fpfh = P.use_fpfh != 0, use_nb = P.use_nb != 0;
+        const bool corners = use_reg || use_fpfh || use_nb;
         const VoxFast vf = vox_fast_of(g);
 
         // ---- stage the rotated cloud (jly_goicp.cpp:750-756), weights and rotation radii ---------------------
@@ -358,7 +360,7 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
         float optT = pr.optError;                                                    // :297
         int heapN = 0, freeTop = 0, bump = 0, sh_pops = 1, sh_subcubes = 0;
         int dNpush = 0, dPop = 0, predSlot = -1, intErr = 0;                        // queue update deferred past barrier 1
-        const float SSE = P.SSEThresh, regW = P.reg, regFW = P.regF;
+        const float SSE = P.SSEThresh, regW = P.reg, regFW = P.regF, regNW = P.regN;
         if (gload) { mbar_wait(&s_gbar, gphase); gphase ^= 1u; gpair = pr.pair; }
 
         for (;;) {
@@ -435,7 +437,7 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
                     const int cz_ = lane / 9, cy_ = (lane - 9 * cz_) / 3, cx_ = lane - 9 * cz_ - 3 * cy_;
                     const unsigned kx = __float_as_uint(sh.X[cx_]), ky = __float_as_uint(sh.X[3 + (cy_)]), kz = __float_as_uint(sh.X[6 + (cz_)]);
                     mkx = kx; mky = ky; mkz = kz;
-                    if (me0.x == kx && me0.y == ky && me0.z == kz && me0.w == sh.gen && me1.z == (kx ^ __funnelshift_l(ky, ky, 11) ^ __funnelshift_l(kz, kz, 22))) { sh.cnt[lane] = (int)me1.x; sh.cf[lane] = __uint_as_float(me1.y); }
+                    if (me0.x == kx && me0.y == ky && me0.z == kz && me0.w == sh.gen && me1.z == (kx ^ __funnelshift_l(ky, ky, 11) ^ __funnelshift_l(kz, kz, 22))) { sh.cnt[lane] = (int)me1.x; sh.cf[lane] = __uint_as_float(me1.y); sh.cntN[lane] = (int)me1.w; }
                     else { miss = true; sh.cnt[lane] = 0; }
                 }
                 const unsigned mm = __ballot_sync(GOICP_FULL, miss);
@@ -448,7 +450,7 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
                     sh.mSlot[m] = slot; sh.mChk[m] = mkx ^ __funnelshift_l(mky, mky, 11) ^ __funnelshift_l(mkz, mkz, 22);
                     sh.mC[m] = sh.CX[cx_]; sh.mC[27 + m] = sh.CX[3 + cy_]; sh.mC[54 + m] = sh.CX[6 + cz_];
                 }
-                if (lane < 27) sh.cntM[lane] = 0;
+                if (lane < 27) { sh.cntM[lane] = 0; sh.cntNM[lane] = 0; }
                 if (lane == 0) { sh.nmiss = __popc(mm); sh.workCtr = 0; sh.missTot += __popc(mm); }
             }
             __syncthreads();                                                         // (2)
@@ -527,7 +529,7 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
                     const float px = valid ? tx[i] : 0.f, py = valid ? ty[i] : 0.f, pz = valid ? tz[i] : 0.f;
                     const unsigned dp = valid ? dprop_s[i] : 0u;
                     for (int gq = g0; gq < g1; ++gq) {
-                        if (!use_fpfh) {   // incompatibility counts only: four independent chains, one packed warp reduction
+                        if (!use_fpfh && !use_nb) {   // incompatibility counts only: four independent chains, one packed warp reduction
                             int vox[4];
                             unsigned flags = 0;
 #pragma unroll
@@ -569,9 +571,16 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
                                 int vox = vox_fast(vf, S, px, py, pz, sh.mC[m], sh.mC[27 + m], sh.mC[54 + m]);
                                 if (vox < 0) vox = clamp_vox_v(S, gx0, gy0, gz0, gscale, px + sh.X[cx_], py + sh.X[3 + cy_], pz + sh.X[6 + cz_]);
                                 const int cell = __ldg(vcell + vox);
-                                const float fv = valid ? __ldg(fpfhD + (size_t)i * ncp1 + cell) : 0.f;
-                                if (EXACT) { if (valid) fp[m * NdQ + i] = fv; }
-                                else { const float fs = warp_sum(fv); if (lane == 0) part[16 * nchunks + m * nchunks + ch] = fs; }
+                                if (use_fpfh) {
+                                    const float fv = valid ? __ldg(fpfhD + (size_t)i * ncp1 + cell) : 0.f;
+                                    if (EXACT) { if (valid) fp[m * NdQ + i] = fv; }
+                                    else { const float fs = warp_sum(fv); if (lane == 0) part[16 * nchunks + m * nchunks + ch] = fs; }
+                                }
+                                if (use_nb) {   // nearestNeighbor inside the closest cell + compareNeighbors (:1200-1211, :1250-1288)
+                                    int dn = valid ? nb_diff(P, cell, i, px + sh.X[cx_], py + sh.X[3 + cy_], pz + sh.X[6 + cz_]) : 0;
+                                    dn = warp_sum_i(dn);
+                                    if (lane == 0 && dn) smem_red_add(&sh.cntNM[m], dn);
+                                }
                                 if (use_reg) {
                                     int bad = ((__ldg(cmask + cell) >> dp) & 1u) ? 0 : 1;
                                     bad = warp_sum_i(valid ? bad : 0);
@@ -603,8 +612,9 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
             if (corners && lane < sh.nmiss) {   // scatter the fresh counts to their lattice corners and complete their memo entries
                 const int c = sh.missList[lane];
                 const int n = sh.cntM[lane];
-                sh.cnt[c] = n;
-                memo[2 * (size_t)sh.mSlot[lane] + 1] = make_uint4((unsigned)n, use_fpfh ? __float_as_uint(sh.cf[c]) : 0u, sh.mChk[lane], 0u);
+                const int nn = sh.cntNM[lane];
+                sh.cnt[c] = n; sh.cntN[c] = nn;
+                memo[2 * (size_t)sh.mSlot[lane] + 1] = make_uint4((unsigned)n, use_fpfh ? __float_as_uint(sh.cf[c]) : 0u, sh.mChk[lane], (unsigned)nn);
             }
             __syncwarp();
             // ---- phase C: corner min/max per child on 8 lanes (:431-550), the eight decisions (:554-572) as a prefix-min ----
@@ -614,14 +624,16 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
             if (lane < 8) {
                 float ub = sh.ub[lane], lb = sh.lb[lane];
                 if (corners) {
-                    int minI = 0, maxI = 0; float minF = 0.f, maxF = 0.f;
+                    int minI = 0, maxI = 0, minN = 0, maxN = 0; float minF = 0.f, maxF = 0.f;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         const int c = (jx + (k & 1)) + 3 * (jy + ((k >> 1) & 1)) + 9 * (jz + ((k >> 2) & 1));
+                        if (use_nb) { const int n = sh.cntN[c]; if (k == 0) { minN = maxN = n; } else { if (n > maxN) maxN = n; if (n < minN) minN = n; } }
                         if (use_fpfh) { const float f = sh.cf[c]; if (k == 0) { minF = maxF = f; } else { if (f > maxF) maxF = f; if (f < minF) minF = f; } }
                         if (use_reg) { const int n = sh.cnt[c]; if (k == 0) { minI = maxI = n; } else { if (n > maxI) maxI = n; if (n < minI) minI = n; } }
                     }
                     if (use_reg) { ub = ub + regW * (float)(maxI * maxI); lb = lb + regW * (float)(minI * minI); }      // :536-538
+                    if (use_nb) { ub = ub + regNW * (float)(maxN * maxN); lb = lb + regNW * (float)(minN * minN); }      // :542-545
                     if (use_fpfh) { ub = ub + regFW * (maxF * maxF); lb = lb + regFW * (minF * minF); }                  // :546-549
                 }
                 ubj = ub; lbj = lb;
@@ -769,6 +781,7 @@ eval_bounds_kernel(const PairDev* __restrict__ pairs, int pair, const float* __r
         const float mtd = (float)(GOICP_SQRT3 / 2.0 * cb.w);
         float su = 0.f, sl = 0.f;
         int bad[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int nbs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         float fs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int i = lane; i < Nd; i += 32) {
             const float x = P.dx[i], y = P.dy[i], z = P.dz[i];
@@ -782,26 +795,29 @@ eval_bounds_kernel(const PairDev* __restrict__ pairs, int pair, const float* __r
                 const float dis = d - mtd;
                 if (dis > 0.f) sl += (P.norm == 2) ? dis * dis : dis;
             }
-            if (P.use_reg || P.use_fpfh) {
+            if (P.use_reg || P.use_fpfh || P.use_nb) {
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const float cx = cb.x + (float)(c & 1) * cb.w, cy = cb.y + (float)((c >> 1) & 1) * cb.w, cz = cb.z + (float)((c >> 2) & 1) * cb.w;
                     const int cell = clamp_cell(g, px + cx, py + cy, pz + cz);
                     if (P.use_reg) bad[c] += ((__ldg(g.cmask + cell) >> P.dprop[i]) & 1u) ? 0 : 1;
                     if (P.use_fpfh) fs[c] += __ldg(P.fpfhD + (size_t)i * ncp1 + cell);
+                    if (P.use_nb) nbs[c] += nb_diff(P, cell, i, px + cx, py + cy, pz + cz);
                 }
             }
         }
         if (P.doTrim) { __syncwarp(); warp_trimmed_sums(md, Nd, P.inlierNum, lane, P.norm, mtd, &su, &sl); __syncwarp(); }
         else { su = warp_sum(su); sl = warp_sum(sl); }
-        int minI = 0, maxI = 0; float minF = 0.f, maxF = 0.f;
-        if (P.use_reg || P.use_fpfh) {
+        int minI = 0, maxI = 0, minN = 0, maxN = 0; float minF = 0.f, maxF = 0.f;
+        if (P.use_reg || P.use_fpfh || P.use_nb) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 if (P.use_fpfh) { const float f = (float)(int)(warp_sum(fs[c]) / (float)Nd); if (c == 0) { minF = maxF = f; } else { maxF = fmaxf(maxF, f); minF = fminf(minF, f); } }
                 if (P.use_reg) { const int n = warp_sum_i(bad[c]); if (c == 0) { minI = maxI = n; } else { maxI = max(maxI, n); minI = min(minI, n); } }
+                if (P.use_nb) { const int n = warp_sum_i(nbs[c]); if (c == 0) { minN = maxN = n; } else { maxN = max(maxN, n); minN = min(minN, n); } }
             }
             if (P.use_reg) { su = su + P.reg * (float)(maxI * maxI); sl = sl + P.reg * (float)(minI * minI); }
+            if (P.use_nb) { su = su + P.regN * (float)(maxN * maxN); sl = sl + P.regN * (float)(minN * minN); }
             if (P.use_fpfh) { su = su + P.regF * (maxF * maxF); sl = sl + P.regF * (minF * minF); }
         }
         if (lane == 0) {

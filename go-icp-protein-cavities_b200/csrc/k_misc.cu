@@ -142,6 +142,32 @@ cudaError_t goicp_launch_initialize(PairDev* pairs, int first, int count, cudaSt
     initialize_kernel<<<count, 256, 0, st>>>(pairs, first);
     return cudaGetLastError();
 }
+// assignNeighbors (jly_goicp.cpp:1213-1248, called from BuildDT :94 while Nd is still every source point): per point the
+// number of other points of its own cloud closer than sqrt(float 0.050) (isNeighbor :1097-1103, double distance)
+__global__ void __launch_bounds__(256)
+assign_neighbors_kernel(PairDev* __restrict__ pairs, int first) {
+    const PairDev& P = pairs[first + blockIdx.y];
+    const double thr = (double)sqrtf(0.050f);
+    const int nD = P.NdAll, nM = P.Nm;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nD + nM; t += gridDim.x * blockDim.x) {
+        const bool isD = t < nD;
+        const int i = isD ? t : t - nD, n = isD ? nD : nM;
+        const float* X = isD ? P.dx : P.mx; const float* Y = isD ? P.dy : P.my; const float* Z = isD ? P.dz : P.mz;
+        const float xi = X[i], yi = Y[i], zi = Z[i];
+        int cnt = 0;
+        for (int j = 0; j < n; ++j) {
+            if (j == i) continue;
+            const double a = (double)(X[j] - xi), b = (double)(Y[j] - yi), c = (double)(Z[j] - zi);
+            if (sqrt(a * a + b * b + c * c) < thr) cnt++;
+        }
+        (isD ? P.nbD : P.nbM)[i] = cnt;
+    }
+}
+cudaError_t goicp_launch_assign_neighbors(PairDev* pairs, int first, int count, int blocksPerPair, cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
+    assign_neighbors_kernel<<<dim3(blocksPerPair, count), 256, 0, st>>>(pairs, first);
+    return cudaGetLastError();
+}
 cudaError_t goicp_launch_fpfh_table(PairDev* pairs, int first, int count, int blocksPerPair, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
     fpfh_table_kernel<<<dim3(blocksPerPair, count), 256, 0, st>>>(pairs, first);
@@ -176,6 +202,7 @@ cudaError_t goicp_preload_misc() {
     cudaFuncAttributes a; cudaError_t e;
     if ((e = cudaFuncGetAttributes(&a, initialize_kernel)) != cudaSuccess) return e;
     if ((e = cudaFuncGetAttributes(&a, fpfh_table_kernel)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, assign_neighbors_kernel)) != cudaSuccess) return e;
     if ((e = cudaFuncGetAttributes(&a, normalize_kernel)) != cudaSuccess) return e;
     if ((e = cudaFuncGetAttributes(&a, scale_kernel)) != cudaSuccess) return e;
     if ((e = cudaFuncGetAttributes(&a, apply_rigid_kernel)) != cudaSuccess) return e;

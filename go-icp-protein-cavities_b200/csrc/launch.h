@@ -30,6 +30,7 @@ cudaError_t goicp_launch_icp_score(const PairDev* pairs, IcpState* states, int n
 // k_misc.cu
 cudaError_t goicp_launch_initialize(PairDev* pairs, int first, int count, cudaStream_t st);
 cudaError_t goicp_launch_fpfh_table(PairDev* pairs, int first, int count, int blocksPerPair, cudaStream_t st);
+cudaError_t goicp_launch_assign_neighbors(PairDev* pairs, int first, int count, int blocksPerPair, cudaStream_t st);
 cudaError_t goicp_launch_normalize(double* xyz, int n, double* out4, cudaStream_t st);
 cudaError_t goicp_launch_scale(double* xyz, int n, double scale, cudaStream_t st);
 cudaError_t goicp_launch_apply_rigid(const double* xyz, int n, const double* Rt, double* out, cudaStream_t st);

@@ -79,11 +79,11 @@ def test_initialize_bit_exact(g, po, name):
     assert reg.thresholds() == (o.ssethresh(), o.inliernum())
 
 
-@pytest.mark.parametrize("fp", [False, True])
+@pytest.mark.parametrize("fp", [False, True, "nb"])
 def test_leaf_bounds(g, po, fp):
     """every rotation cube x translation sub-cube x point bound in one launch: (ub, lb) within 1e-5, corner
     incompatibility counts and truncated c-FPFH means (point-inclusion counts) bit-exact"""
-    kw = dict(cfpfh=1, regularizationFPFH=0.000005) if fp else {}
+    kw = dict(regularizationNeighbors=0.00001) if fp == "nb" else dict(cfpfh=1, regularizationFPFH=0.000005) if fp else {}
     z, reg, o = _pair(g, po, "pair1", **kw)
     reg.BuildDT(); o.build_dt(); reg.set_nd(int(z["nd"])); o.set_nd(int(z["nd"])); reg.Initialize(); o.initialize()
     rng = np.random.default_rng(2)
@@ -113,11 +113,11 @@ def test_leaf_bounds_multi_rotation_wave(g, po):
         assert np.array_equal(inc[sel], oinc)
 
 
-@pytest.mark.parametrize("name,fp", [("pair1", False), ("pair1", True), ("pair2", False)])
+@pytest.mark.parametrize("name,fp", [("pair1", False), ("pair1", True), ("pair2", False), ("pair1", "nb")])
 def test_inner_bnb(g, po, name, fp):
     """GoICP::InnerBnB calls as OuterBnB makes them: exact-sum mode is bit-identical (value, best node, pop count);
     tree-sum mode within 1e-5"""
-    kw = dict(cfpfh=1, regularizationFPFH=0.000005) if fp else {}
+    kw = dict(regularizationNeighbors=0.00001) if fp == "nb" else dict(cfpfh=1, regularizationFPFH=0.000005) if fp else {}
     z, reg, o = _pair(g, po, name, **kw)
     reg.BuildDT(); o.build_dt(); reg.set_nd(int(z["nd"])); o.set_nd(int(z["nd"])); reg.Initialize(); o.initialize()
     rng = np.random.default_rng(4)
@@ -167,6 +167,19 @@ def test_register_cavity_golden(g, name, fp, golden_err, compat):
     r2 = reg.Register()
     assert abs(r2["optError"] - r["optError"]) <= REL * r["optError"]
     assert np.abs(r2["R"] - r["R"]).max() < 1e-5 and np.abs(r2["t"] - r["t"]).max() < 1e-5
+
+
+def test_register_neighbours_term(g):
+    """regularizationNeighbors = 1e-5 (assignNeighbors / nearestNeighbor / compareNeighbors, jly_goicp.cpp:1200-1288): the full
+    Register equals the reference run frozen in the fixture -- optimum, compatibilities, R, counters and improvement trace"""
+    z = golden("pair1")
+    reg = g.GoICP(z["model_xyz"], z["data_xyz"], g.shipped_config(regularizationNeighbors=0.00001), **pair_clouds(z))
+    reg.BuildDT(); reg.set_nd(int(z["nd"]))
+    r = reg.Register()
+    assert r["optError"] == float(z["expn_optError"]) and r["optComp"] == int(z["expn_optComp"])
+    assert np.abs(r["R"] - z["expn_R"]).max() < 1e-12 and np.abs(r["t"] - z["expn_t"]).max() < 1e-12
+    assert r["counters"][:6] == z["expn_counters"][:6].tolist()
+    assert g.error_trace(r["trace"]) == list(z["expn_trace"])
 
 
 def test_register_rand_trim(g):
