@@ -307,6 +307,34 @@ def test_cli_pair1_golden(tmp_path):
         assert got[0].startswith("Time: ") and got[1:] == want[1:], (f, got, want)
 
 
+def test_cli_sweep_batch(tmp_path):
+    """examples/GoICP_b200_sweep = bo1_GoICP.py's loop as one in-process batch: a pair list (TSV, columns 3/4) in, the
+    per-pair files of the reference out -- byte-identical to the shipped pair-1 files (except the Time: line) for every row"""
+    import os
+    import shutil
+    import subprocess
+    from conftest import ROOT
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "examples")])
+    exe = os.path.join(ROOT, "examples", "GoICP_b200_sweep")
+    src = os.path.join(ROOT, "tests", "golden", "cli")
+    for d in ("cavities", "cfpfh"):
+        shutil.copytree(os.path.join(src, d), tmp_path / d)
+    shutil.copy(os.path.join(src, "config.txt"), tmp_path / "config.txt")
+    os.makedirs(tmp_path / "cavitiesN"); os.makedirs(tmp_path / "output")
+    (tmp_path / "pairs.tsv").write_text("P67911\tP67910\t2x86_3\t1eq2_6\t0.8638\tIsomerase\tcluster_2\n" * 3 + "\nignored after the blank line\n")
+    out = subprocess.run([exe, "pairs.tsv", "config.txt"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    exp = os.path.join(src, "expected")
+    for k in (1, 2, 3):
+        for f in ("1eq2_6_cavity6_sim%dN.xyz", "2x86_3_cavity6_sim%dN.xyz"):
+            assert open(tmp_path / "cavitiesN" / (f % k), "rb").read() == open(os.path.join(exp, f % 1), "rb").read(), f % k
+        for f in ("similar%d.txt", "similar%d_rescaled.txt"):
+            got = open(tmp_path / "output" / (f % k)).read().split("\n")
+            want = open(os.path.join(exp, f % 1)).read().split("\n")
+            assert got[0].startswith("Time: ") and got[1:] == want[1:], (f % k, got, want)
+    assert not os.path.exists(tmp_path / "output" / "similar4.txt")
+
+
 def test_deep_queue_overflow_rerun(g, monkeypatch):
     """a translation queue that outgrows the resident kernel's per-CTA slab: the pair is re-run by the wave scheduler
     (growing slabs); forcing a tiny slab (160 entries) must not change anything about pair 2's search (2.6 M sub-cubes)"""
