@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgoicp_b200.so")
+LIB_PATH = os.environ.get("GOICP_LIB") or os.path.join(_HERE, "libgoicp_b200.so")   # GOICP_LIB: development A/B builds
 
 
 class GoICPError(RuntimeError):

@@ -76,9 +76,9 @@ __device__ __forceinline__ int clamp_cell(const GridDev& g, float fx, float fy, 
 // FP32 fast path of the voxel index (GridDev.vf*): kx,ky,kz = bit patterns of fma(p, vfScale, C) with
 // C = (float)((trans - min)*scale + vfMagic).  Returns the linear voxel index, or -1 when any axis lies in the
 // ambiguity zone of a rounding boundary or outside the grid (the caller then runs the exact FP64 form).
-struct VoxFast { float sc; int sh; unsigned bias, mask, zone; double magic; };
-__device__ __forceinline__ VoxFast vox_fast_of(const GridDev& g) { VoxFast v; v.sc = g.vfScale; v.sh = g.vfShift; v.bias = g.vfBias; v.mask = g.vfMask; v.zone = g.vfZone; v.magic = g.vfMagic; return v; }
-__device__ __forceinline__ float vox_fast_c(const VoxFast& vf, float trans, double mn, double scale) { return (float)(((double)trans - mn) * scale + vf.magic); }
+struct VoxFast { float sc; int sh; unsigned bias, mask, zone; };
+__device__ __forceinline__ VoxFast vox_fast_of(const GridDev& g) { VoxFast v; v.sc = g.vfScale; v.sh = g.vfShift; v.bias = g.vfBias; v.mask = g.vfMask; v.zone = g.vfZone; return v; }
+__device__ __forceinline__ float vox_fast_c(double magic, float trans, double mn, double scale) { return (float)(((double)trans - mn) * scale + magic); }
 __device__ __forceinline__ int vox_fast(const VoxFast& vf, int S, float px, float py, float pz, float Cx, float Cy, float Cz) {
     const unsigned kx = __float_as_uint(__fmaf_rn(px, vf.sc, Cx)), ky = __float_as_uint(__fmaf_rn(py, vf.sc, Cy)), kz = __float_as_uint(__fmaf_rn(pz, vf.sc, Cz));
     const unsigned x = (kx >> vf.sh) - vf.bias, y = (ky >> vf.sh) - vf.bias, z = (kz >> vf.sh) - vf.bias;

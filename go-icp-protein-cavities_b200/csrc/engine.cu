@@ -165,7 +165,7 @@ struct Problem {
     int status = 0;
     double t_dt = 0, t_reg = 0;
     // persistent-queue mode: requests in flight
-    struct PendReq { int slot; unsigned long long key; float entryOpt; };
+    struct PendReq { int slot; unsigned long long key; float entryOpt; bool both; };   // both: key is the upper-bound call, key | 1 the lower-bound call of the same request
     std::vector<PendReq> pend;
     std::unordered_set<unsigned long long> inflight;
     bool icpQueued = false;
@@ -237,6 +237,7 @@ struct goicp_handle_s {
     int exact_sums = 1, spec_width = 32, use_dt_replay = 1;
     int groups = 0, slots = 0;   // 0 = auto
     int batch_spec_width = 4;    // speculation width inside a batch (pairs already fill the GPU)
+    bool merge_calls = true;   // resident scheduler: one request per rotation cube carries its upper- and lower-bound InnerBnB calls
     int bnb_threads = 256;   // threads per InnerBnB CTA (64..512): more threads = shorter pops, fewer resident calls   // batch: worker streams (0 = auto) and pairs advanced in lock-step per stream
     std::vector<Problem> probs;
     DevBuf arenaIn, arenaWork, dPairs, dTmp, dTmp2, dTmp3, dSepBits, dSepNx, dSepNxy;
@@ -526,11 +527,12 @@ static goicp_status initialize_all(Eng* h) {
 }
 
 // ---- one launch of InnerBnB calls (handles heap overflow by re-running the overflowed calls with larger heaps) -------
-struct BnbCfg { int NdP, NdQ; size_t smemFloats, smemBytes; int useSmem, perSM, threads, gridOff, S3p; };
+struct BnbCfg { int NdP, NdQ; size_t smemFloats, smemBytes; int useSmem, perSM, threads, gridOff, S3p, ct; };
 static BnbCfg bnb_config(Eng* h) {
-    int maxNd = 1, maxCol = 1; bool anyTrim = false, anyF = false;
-    for (auto& P : h->probs) { maxNd = std::max(maxNd, P.Nd); anyTrim |= P.dev.doTrim != 0; anyF |= P.dev.use_fpfh != 0; maxCol = std::max(maxCol, P.ncolours); }
+    int maxNd = 1, maxCol = 1; bool anyTrim = false, anyF = false, anyNb = false;
+    for (auto& P : h->probs) { maxNd = std::max(maxNd, P.Nd); anyTrim |= P.dev.doTrim != 0; anyF |= P.dev.use_fpfh != 0; anyNb |= P.dev.use_nb != 0; maxCol = std::max(maxCol, P.ncolours); }
     BnbCfg c;
+    c.ct = (anyF || anyNb) ? 1 : 0;
     c.NdP = (maxNd + 31) & ~31; c.NdQ = c.NdP + 4;   // row stride = 4 mod 32: the chain lanes' float4 reads of the 8 rows hit 8 different bank quads
     const bool needMd = h->exact_sums || anyTrim, needFp = h->exact_sums && anyF;
     c.smemFloats = goicp_bnb_smem_floats(c.NdP, c.NdQ, h->exact_sums != 0, needMd, needFp);
@@ -546,7 +548,7 @@ static BnbCfg bnb_config(Eng* h) {
         c.useSmem = 2;
     }
     c.threads = h->bnb_threads;
-    c.perSM = goicp_inner_bnb_occupancy(c.smemBytes, h->exact_sums, c.threads, c.useSmem);
+    c.perSM = goicp_inner_bnb_occupancy(c.smemBytes, h->exact_sums, c.threads, c.useSmem, c.ct);
     return c;
 }
 static goicp_status run_inner_local(Eng* h, WaveCtx& c, const BnbCfg& cfg, std::vector<InnerProb>& reqs, std::vector<InnerOut>& outs);
@@ -593,7 +595,7 @@ static goicp_status run_inner_local(Eng* h, WaveCtx& c, const BnbCfg& cfg, std::
         int launched = 0;
         CU(goicp_launch_inner_bnb(h->dPairs.as<PairDev>(), reinterpret_cast<const InnerProb*>(c.mProbs.d), reinterpret_cast<InnerOut*>(c.mOuts.d), m, c.dCounter.as<int>(),
                                   c.dHeaps.as<HeapEnt>(), heapCap, ctas, c.dBnbScratch.as<float>(), cfg.smemFloats, cfg.NdP, cfg.NdQ, cfg.smemBytes, cfg.useSmem, cfg.gridOff, cfg.S3p,
-                                  h->exact_sums, cfg.threads, c.dMemo.p, memoCap, h->dGen.as<unsigned>(), c.stream, &launched));
+                                  h->exact_sums, cfg.ct, cfg.threads, c.dMemo.p, memoCap, h->dGen.as<unsigned>(), c.stream, &launched));
         cudaEventRecord(c.ev1, c.stream);
         c.tInnerEnq += secs_since(tq); tq = clk::now();
         CU(c.sync());
@@ -699,7 +701,7 @@ static inline RNode child_of(const RNode& par, int j) {
 }
 static inline unsigned long long call_key(int nodeId, int j, int kind) { return ((unsigned long long)(unsigned)nodeId << 4) | (unsigned)(j << 1) | (unsigned)kind; }
 
-struct ReqTag { int prob; unsigned long long key; float entryOpt; };
+struct ReqTag { int prob; unsigned long long key; float entryOpt; bool both; };
 
 // Advance one problem's OuterBnB as far as cached results allow; on return P.phase tells what it waits for.
 static void advance(Eng* h, int pi) {
@@ -777,7 +779,7 @@ static void finish_improvement(Eng* h, int pi) {
 }
 
 // Requests of one blocked problem: the blocking call first, then speculation in the reference's expected order.
-static void gather_requests(Eng* h, int pi, std::vector<InnerProb>& reqs, std::vector<ReqTag>& tags) {
+static void gather_requests(Eng* h, int pi, std::vector<InnerProb>& reqs, std::vector<ReqTag>& tags, bool merge = false) {
     Problem& P = h->probs[pi];
     const float SSE = P.dev.SSEThresh;
     std::unordered_set<unsigned long long> seen;
@@ -788,9 +790,16 @@ static void gather_requests(Eng* h, int pi, std::vector<InnerProb>& reqs, std::v
         if (P.inflight.count(key)) return;
         if (!seen.insert(key).second) return;
         // Q2: the reference indexes maxRotDis[level] without a bound check (undefined beyond level 19); we clamp.
-        InnerProb ip; ip.pair = pi; ip.level = kind ? std::min(ch.l, GOICP_MAXROTLEVEL - 1) : -1; ip.optError = P.optError;
+        const int lbLevel = std::min(ch.l, GOICP_MAXROTLEVEL - 1);
+        // resident-kernel scheduler: the lower-bound call of a cube rides on the request of its upper-bound call (one CTA runs
+        // both, sharing the staged cloud and the corner memo; the second is skipped if the first improves the incumbent)
+        if (merge && kind == 1 && !tags.empty() && tags.back().prob == pi && tags.back().key == call_key(par.id, j, 0) && !tags.back().both) {
+            reqs.back().level = GOICP_REQ_BOTH + lbLevel; tags.back().both = true;
+            return;
+        }
+        InnerProb ip; ip.pair = pi; ip.level = kind ? lbLevel : -1; ip.optError = P.optError;
         memcpy(ip.R, R, sizeof ip.R);
-        reqs.push_back(ip); tags.push_back(ReqTag{pi, key, P.optError});
+        reqs.push_back(ip); tags.push_back(ReqTag{pi, key, P.optError, false});
     };
     // current parent, from the blocking call on
     for (int j = P.j; j < 8; j++) {
@@ -954,6 +963,10 @@ static goicp_status persistent_worker(Eng* h, WaveCtx& c, PQ& pq, std::atomic<in
                 CallRes r; r.entryOpt = pend[k].entryOpt; r.err = o.err; memcpy(r.tn, (const void*)o.node, sizeof r.tn); r.pops = o.pops; r.subcubes = o.subcubes;
                 P.cache[pend[k].key] = r;
                 P.inflight.erase(pend[k].key);
+                if (pend[k].both) {
+                    if (o.ran2) { CallRes r2; r2.entryOpt = pend[k].entryOpt; r2.err = o.err2; memset(r2.tn, 0, sizeof r2.tn); r2.pops = o.pops2; r2.subcubes = o.subcubes2; P.cache[pend[k].key | 1ull] = r2; }
+                    P.inflight.erase(pend[k].key | 1ull);
+                }
             }
             freeSlots.push_back(pend[k].slot);
             pend[k] = pend.back(); pend.pop_back();
@@ -998,7 +1011,7 @@ static goicp_status persistent_worker(Eng* h, WaveCtx& c, PQ& pq, std::atomic<in
             if (P.status == GOICP_ERR_OVERFLOW) {   // abandon the pair here; register_persistent re-runs it with growing queues
                 for (auto& r : P.pend) zombies.push_back(r);
                 P.pend.clear(); P.inflight.clear(); P.cache.clear();
-                if (P.icpQueued) { zombies.push_back(Problem::PendReq{P.icpSlot[0], 0ull, 0.f}); zombies.push_back(Problem::PendReq{P.icpSlot[1], 0ull, 0.f}); P.icpQueued = false; }
+                if (P.icpQueued) { zombies.push_back(Problem::PendReq{P.icpSlot[0], 0ull, 0.f, false}); zombies.push_back(Problem::PendReq{P.icpSlot[1], 0ull, 0.f, false}); P.icpQueued = false; }
                 P.phase = PH_DONE; h->activePairs.fetch_sub(1); progressed = true;
                 continue;
             }
@@ -1025,14 +1038,15 @@ static goicp_status persistent_worker(Eng* h, WaveCtx& c, PQ& pq, std::atomic<in
             if (P.inflight.count(need)) continue;
             reqs.clear(); tags.clear();
             auto tg = clk::now();
-            gather_requests(h, i, reqs, tags);
+            gather_requests(h, i, reqs, tags, h->merge_calls);
             c.tLogic += secs_since(tg); tg = clk::now();
             for (size_t k = 0; k < reqs.size(); k++) {
                 if (freeSlots.empty() || h->outstanding.load(std::memory_order_relaxed) > (int)(pq.cellMask >> 1)) break;   // out of slots / ring half full: the rest is regathered later
                 const int slot = freeSlots.back(); freeSlots.pop_back();
                 out_arm(pq.outs[slot]);
-                P.pend.push_back(Problem::PendReq{slot, tags[k].key, tags[k].entryOpt});
+                P.pend.push_back(Problem::PendReq{slot, tags[k].key, tags[k].entryOpt, tags[k].both});
                 P.inflight.insert(tags[k].key);
+                if (tags[k].both) { P.inflight.insert(tags[k].key | 1ull); c.callsLaunched++; }
                 pq.publish((unsigned)slot, &reqs[k]);
                 h->outstanding.fetch_add(1, std::memory_order_relaxed);
                 c.callsLaunched++;
@@ -1071,7 +1085,7 @@ static goicp_status register_persistent(Eng* h, const BnbCfg& cfg, int groups, i
     CU(h->qOrder.ensure(sizeof(QueueCell) * (size_t)ORDER));
     CU(h->qClaim.ensure(sizeof(unsigned)));
     CU(h->qIcp.ensure(sizeof(IcpState) * 2 * (size_t)np));
-    int perSM = goicp_inner_bnb_persistent_occupancy(cfg.smemBytes, h->exact_sums, cfg.threads, cfg.useSmem);
+    int perSM = goicp_inner_bnb_persistent_occupancy(cfg.smemBytes, h->exact_sums, cfg.threads, cfg.useSmem, cfg.ct);
     { const char* e = getenv("GOICP_CTAS_PER_SM"); if (e && atoi(e) >= 1) perSM = std::min(perSM, atoi(e)); }
     const int ctas = h->numSM * perSM;   // the resident kernel owns the GPU for the batch: InnerBnB and ICP requests both run on its CTAs
     int heapCap = 1 << 15;
@@ -1099,7 +1113,7 @@ static goicp_status register_persistent(Eng* h, const BnbCfg& cfg, int groups, i
     qd.cellMask = ORDER - 1; qd.cellShift = 18; qd.claim = h->qClaim.as<unsigned>();
     cudaEventRecord(h->main.ev0, h->stream);
     CU(goicp_launch_inner_bnb_persistent(h->dPairs.as<PairDev>(), qd, h->qHeaps.as<HeapEnt>(), heapCap, ctas, h->qScratch.as<float>(), cfg.smemFloats,
-                                         cfg.NdP, cfg.NdQ, cfg.smemBytes, cfg.useSmem, cfg.gridOff, cfg.S3p, h->exact_sums, cfg.threads, h->qMemo.p, memoCap, h->dGen.as<unsigned>(), h->stream));
+                                         cfg.NdP, cfg.NdQ, cfg.smemBytes, cfg.useSmem, cfg.gridOff, cfg.S3p, h->exact_sums, cfg.ct, cfg.threads, h->qMemo.p, memoCap, h->dGen.as<unsigned>(), h->stream));
     cudaEventRecord(h->main.ev1, h->stream);
     g_no_device_alloc.store(true);
     std::atomic<int> next(0);
@@ -1566,6 +1580,7 @@ goicp_status goicp_set_batch_options(goicp_handle h, int32_t groups, int32_t slo
     if (!h) return GOICP_ERR_ARG;
     if (groups >= 0) h->groups = groups;
     if (slots >= 0) h->slots = slots;
+    { const char* e = getenv("GOICP_MERGE_CALLS"); if (e) h->merge_calls = atoi(e) != 0; }
     { const char* e = getenv("GOICP_BNB_THREADS"); if (e) { int t = atoi(e); if (t >= 64 && t <= 256 && t % 32 == 0) h->bnb_threads = t; } }
     return GOICP_OK;
 }

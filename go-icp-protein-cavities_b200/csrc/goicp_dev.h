@@ -12,6 +12,7 @@
 #define GOICP_NN_EMPTY 0xFFFFFFFFFFFFFFFFull
 #define GOICP_OVLIM 24                      // voxels outside the grid served by the overshoot table GridDev.ovl
 #define GOICP_OVN (3 * GOICP_OVLIM * GOICP_OVLIM + 1)
+#define GOICP_REQ_BOTH 0x100               // InnerProb.level = GOICP_REQ_BOTH + level: upper-bound call, then the lower-bound call at `level`
 #define GOICP_REQ_ICP (-100)               // InnerProb.level of an ICP request in the resident batch kernel
 
 // DT3D (jly_3ddt.h:123-139) as laid out in HBM: structure-of-arrays, voxel index (z*S+y)*S+x.
@@ -89,7 +90,10 @@ struct alignas(64) InnerOut {   // one 64-byte record: it leaves the SM as a sin
     int pops;
     int subcubes;
     int status;             // 0 ok, 4 heap overflow
-    int pad[5];
+    float err2;             // GOICP_REQ_BOTH: optErrorT, pops and sub-cubes of the lower-bound call; ran2 = 0 if the upper-bound
+    int pops2, subcubes2;   // call improved the incumbent (the lower-bound call is then not made)
+    int ran2;
+    int pad;
     unsigned seq1;
 };
 

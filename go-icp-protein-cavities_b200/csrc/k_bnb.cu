@@ -200,7 +200,8 @@ struct BnbShared {
 // PERSIST=true : the kernel stays resident for a whole batch and serves the host's request ring `q` (see QueueDev).
 // GS=true (needs SMEM): the call's DT volume (float distances + one colour-mask byte per voxel) is staged in shared memory by
 // TMA, so the per-point gathers are LDS instead of L1/L2 sector gathers (S^3 * 5 bytes at dynamic-smem offset gridOff).
-template <bool EXACT, bool PERSIST, bool SMEM, bool GS>
+// CT=false: no c-FPFH / neighbour-count corner terms in any pair of the launch (their code and registers drop out).
+template <bool EXACT, bool PERSIST, bool SMEM, bool GS, bool CT>
 __global__ void __launch_bounds__(BNB_MAX_THREADS, 3)
 inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, InnerOut* outs,
                  int nprob, int* __restrict__ counter, HeapEnt* __restrict__ heaps, int heapCap,
@@ -278,7 +279,7 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
         __syncthreads();
         const int p = sh.prob;
         if (PERSIST && p < 0) return;
-        const InnerProb pr = s_pr;
+        const InnerProb& pr = s_pr;   // (stays in shared memory: R is only read while staging)
         if (PERSIST && pr.level == GOICP_REQ_ICP) {   // an ICP / scoring request (GoICP::ICP): state pointer packed into R[0..1]
             IcpState* gst = reinterpret_cast<IcpState*>(((unsigned long long)__float_as_uint(pr.R[1]) << 32) | (unsigned long long)__float_as_uint(pr.R[0]));
             icp_fused_body(pairs, gst, icpTile);
@@ -299,39 +300,47 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
         // per-problem constants in registers (the PairDev lives in global memory)
         const int Nd = P.Nd;
         const int nchunks = (Nd + 31) >> 5;
-        const float* __restrict__ dist = g.dist;
         const bool doTrim = P.doTrim != 0;
         const bool useMd = EXACT || doTrim;
         const int ncp1 = g.ncells + 1;
         const int norm = P.norm;
         const int inlierNum = P.inlierNum;
         const int S = g.S;
-        const double gx0 = g.xMin, gy0 = g.yMin, gz0 = g.zMin, gscale = g.scale;
-        const int* __restrict__ vcell = g.vcell;
-        const uint32_t* __restrict__ cmask = g.cmask;
-        const uint32_t* __restrict__ vmask = g.vmask;
-        const float* __restrict__ fpfhD = P.fpfhD;
-        const double* __restrict__ ovl = g.ovl;
-        const bool use_reg = P.use_reg != 0, use_fpfh = P.use_fpfh != 0, use_nb = P.use_nb != 0;
+        const bool use_reg = P.use_reg != 0, use_fpfh = CT && P.use_fpfh != 0, use_nb = CT && P.use_nb != 0;
         const bool corners = use_reg || use_fpfh || use_nb;
         const VoxFast vf = vox_fast_of(g);
 
+        // A request may ask for both InnerBnB calls OuterBnB makes for one rotation cube (jly_goicp.cpp:768 and :856): the upper-
+        // bound call (no rotation radii) and, unless that one improves the incumbent, the lower-bound call at the cube's level.
+        // The two searches share the staged cloud, the DT volume and the corner memo (corner terms do not depend on the level).
+        const bool both = pr.level >= GOICP_REQ_BOTH;
+        const int nparts = both ? 2 : 1;
+        for (int cpart = 0; cpart < nparts; ++cpart) {
+        const int level = both ? (cpart == 0 ? -1 : pr.level - GOICP_REQ_BOTH) : pr.level;
+        if (cpart == 1) {
+            __syncthreads();
+            if (s_out.err < pr.optError || s_out.status != 0) break;   // the upper bound improved: OuterBnB runs ICP before the next call (:771-840)
+        }
         // ---- stage the rotated cloud (jly_goicp.cpp:750-756), weights and rotation radii ---------------------
         for (int i = tid; i < Nd; i += nthreads) {
-            const float x = P.dx[i], y = P.dy[i], z = P.dz[i];
-            tx[i] = pr.R[0] * x + pr.R[1] * y + pr.R[2] * z;
-            ty[i] = pr.R[3] * x + pr.R[4] * y + pr.R[5] * z;
-            tz[i] = pr.R[6] * x + pr.R[7] * y + pr.R[8] * z;
-            wgt[i] = P.weights[i];
-            mrd[i] = pr.level >= 0 ? P.maxRotDis[(size_t)pr.level * Nd + i] : 0.f;   // d - 0 == d
-            dprop_s[i] = P.dprop[i];
+            if (cpart == 0) {
+                const float x = P.dx[i], y = P.dy[i], z = P.dz[i];
+                tx[i] = pr.R[0] * x + pr.R[1] * y + pr.R[2] * z;
+                ty[i] = pr.R[3] * x + pr.R[4] * y + pr.R[5] * z;
+                tz[i] = pr.R[6] * x + pr.R[7] * y + pr.R[8] * z;
+                wgt[i] = P.weights[i];
+                dprop_s[i] = P.dprop[i];
+            }
+            mrd[i] = level >= 0 ? P.maxRotDis[(size_t)level * Nd + i] : 0.f;   // d - 0 == d
         }
         if (tid < 27) sh.cnt[tid] = 0;
         if (tid == 0) {
             sh.status = 0; sh.pops = 1; sh.subcubes = 0; sh.improved = 0;
-            sh.gen = atomicAdd(genCounter, 1u) + 1u; sh.nmiss = 0; sh.workCtr = 0; sh.workA = 0; sh.t0 = clock64(); sh.missTot = 0;
+            if (cpart == 0) { sh.gen = atomicAdd(genCounter, 1u) + 1u; sh.t0 = clock64(); sh.missTot = 0; }
+            sh.nmiss = 0; sh.workCtr = 0; sh.workA = 0;
 #ifdef GOICP_PHASE_TIMING
-            for (int k = 0; k < 12; k++) sh.tp[k] = 0; sh.tmark = clock64();
+            if (cpart == 0) for (int k = 0; k < 12; k++) sh.tp[k] = 0;
+            sh.tmark = clock64();
 #endif
             sh.optErrorT = pr.optError;                                              // :297
             sh.best[0] = sh.best[1] = sh.best[2] = sh.best[3] = 0.f;
@@ -351,9 +360,9 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
         // voxel-index constants of the first node (lanes 0..14 of warp 0, as after every later pop)
         if (warp == 0 && sh.running) {
             const float half = sh.wc / 2;
-            if (lane < 9) { const int a = lane / 3; sh.CX[lane] = vox_fast_c(vf, sh.X[lane], a == 0 ? gx0 : a == 1 ? gy0 : gz0, gscale); }
+            if (lane < 9) { const int a = lane / 3; sh.CX[lane] = vox_fast_c(g.vfMagic, sh.X[lane], a == 0 ? g.xMin : a == 1 ? g.yMin : g.zMin, g.scale); }
             else if (lane < 15) { const int a = (lane - 9) >> 1, k = (lane - 9) & 1; const float t = sh.X[3 * a + k] + half;   // :331-333
-                                  sh.HX[2 * a + k] = t; sh.DX[2 * a + k] = vox_fast_c(vf, t, a == 0 ? gx0 : a == 1 ? gy0 : gz0, gscale); }
+                                  sh.HX[2 * a + k] = t; sh.DX[2 * a + k] = vox_fast_c(g.vfMagic, t, a == 0 ? g.xMin : a == 1 ? g.yMin : g.zMin, g.scale); }
         }
         uint4 me0 = make_uint4(0u, 0u, 0u, 0u), me1 = make_uint4(0u, 0u, 0u, 0u);   // warp 0, lanes 0..26: this pop's memo look-ups (gen 0 never matches)
         // search state of the call, warp-uniform registers of warp 0 (the only warp that runs phase C)
@@ -361,7 +370,7 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
         int heapN = 0, freeTop = 0, bump = 0, sh_pops = 1, sh_subcubes = 0;
         int dNpush = 0, dPop = 0, predSlot = -1, intErr = 0;                        // queue update deferred past barrier 1
         const float SSE = P.SSEThresh, regW = P.reg, regFW = P.regF, regNW = P.regN;
-        if (gload) { mbar_wait(&s_gbar, gphase); gphase ^= 1u; gpair = pr.pair; }
+        if (gload && cpart == 0) { mbar_wait(&s_gbar, gphase); gphase ^= 1u; gpair = pr.pair; }
 
         for (;;) {
             __syncthreads();                                                         // (1) the popped node and its constants are visible
@@ -388,18 +397,18 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
                 for (int k = 0; k < 4; ++k) vox[k] = vox_fast(vf, S, px, py, pz, sh.DX[k & 1], sh.DX[2 + (k >> 1)], dzc);
                 unsigned flags = 0;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) { dres[k] = GS ? sdist[max(vox[k], 0)] : __ldg(dist + max(vox[k], 0)); flags |= (vox[k] < 0 ? 1u : 0u) << k; }
+                for (int k = 0; k < 4; ++k) { dres[k] = GS ? sdist[max(vox[k], 0)] : __ldg(g.dist + max(vox[k], 0)); flags |= (vox[k] < 0 ? 1u : 0u) << k; }
                 unsigned any = __reduce_or_sync(GOICP_FULL, flags);
                 while (any) {   // some lane is outside the grid or on a rounding boundary (rare): overshoot table, else the exact form
                     const int k = __ffs(any) - 1; any &= any - 1;
                     if (flags & (1u << k)) {
                         int idx, s2;
                         if (vox_near(vf, S, px, py, pz, sh.DX[k & 1], sh.DX[2 + ((k >> 1) & 1)], dzc, &idx, &s2)) {
-                            const float d0 = GS ? sdist[idx] : __ldg(dist + idx);
-                            const float dn = (s2 == 0) ? d0 : (float)(__ldg(ovl + s2) + (double)d0);
+                            const float d0 = GS ? sdist[idx] : __ldg(g.dist + idx);
+                            const float dn = (s2 == 0) ? d0 : (float)(__ldg(g.ovl + s2) + (double)d0);
                             if (k == 0) dres[0] = dn; else if (k == 1) dres[1] = dn; else if (k == 2) dres[2] = dn; else dres[3] = dn;
                         } else {
-                            const float dn = dt_distance_v<!GS>(S, gx0, gy0, gz0, gscale, GS ? sdist : dist, px + sh.HX[k & 1], py + sh.HX[2 + ((k >> 1) & 1)], pz + hz);
+                            const float dn = dt_distance_v<!GS>(S, g.xMin, g.yMin, g.zMin, g.scale, GS ? sdist : g.dist, px + sh.HX[k & 1], py + sh.HX[2 + ((k >> 1) & 1)], pz + hz);
                             if (k == 0) dres[0] = dn; else if (k == 1) dres[1] = dn; else if (k == 2) dres[2] = dn; else dres[3] = dn;
                         }
                     }
@@ -547,14 +556,14 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
                                     const int cz_ = c / 9, cy_ = (c - 9 * cz_) / 3, cx_ = c - 9 * cz_ - 3 * cy_;
                                     int idx, s2;
                                     if (!vox_near(vf, S, px, py, pz, sh.mC[m], sh.mC[27 + m], sh.mC[54 + m], &idx, &s2))
-                                        idx = clamp_vox_v(S, gx0, gy0, gz0, gscale, px + sh.X[cx_], py + sh.X[3 + cy_], pz + sh.X[6 + cz_]);
+                                        idx = clamp_vox_v(S, g.xMin, g.yMin, g.zMin, g.scale, px + sh.X[cx_], py + sh.X[3 + cy_], pz + sh.X[6 + cz_]);
                                     if (k == 0) vox[0] = idx; else if (k == 1) vox[1] = idx; else if (k == 2) vox[2] = idx; else vox[3] = idx;
                                 }
                             }
                             unsigned packed = 0;
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                const unsigned mk = GS ? (unsigned)svm[vox[k]] : __ldg(vmask + vox[k]);   // per-voxel mask of the closest cell: one gather
+                                const unsigned mk = GS ? (unsigned)svm[vox[k]] : __ldg(g.vmask + vox[k]);   // per-voxel mask of the closest cell: one gather
                                 packed |= (((mk >> dp) & 1u) ^ 1u) << (8 * k);
                             }
                             packed = __reduce_add_sync(GOICP_FULL, valid ? packed : 0u);   // <= 32 per byte field
@@ -569,10 +578,10 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
                                 const int c = sh.missList[m];
                                 const int cz_ = c / 9, cy_ = (c - 9 * cz_) / 3, cx_ = c - 9 * cz_ - 3 * cy_;
                                 int vox = vox_fast(vf, S, px, py, pz, sh.mC[m], sh.mC[27 + m], sh.mC[54 + m]);
-                                if (vox < 0) vox = clamp_vox_v(S, gx0, gy0, gz0, gscale, px + sh.X[cx_], py + sh.X[3 + cy_], pz + sh.X[6 + cz_]);
-                                const int cell = __ldg(vcell + vox);
+                                if (vox < 0) vox = clamp_vox_v(S, g.xMin, g.yMin, g.zMin, g.scale, px + sh.X[cx_], py + sh.X[3 + cy_], pz + sh.X[6 + cz_]);
+                                const int cell = __ldg(g.vcell + vox);
                                 if (use_fpfh) {
-                                    const float fv = valid ? __ldg(fpfhD + (size_t)i * ncp1 + cell) : 0.f;
+                                    const float fv = valid ? __ldg(P.fpfhD + (size_t)i * ncp1 + cell) : 0.f;
                                     if (EXACT) { if (valid) fp[m * NdQ + i] = fv; }
                                     else { const float fs = warp_sum(fv); if (lane == 0) part[16 * nchunks + m * nchunks + ch] = fs; }
                                 }
@@ -582,7 +591,7 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
                                     if (lane == 0 && dn) smem_red_add(&sh.cntNM[m], dn);
                                 }
                                 if (use_reg) {
-                                    int bad = ((__ldg(cmask + cell) >> dp) & 1u) ? 0 : 1;
+                                    int bad = ((__ldg(g.cmask + cell) >> dp) & 1u) ? 0 : 1;
                                     bad = warp_sum_i(valid ? bad : 0);
                                     if (lane == 0 && bad) smem_red_add(&sh.cntM[m], bad);
                                 }
@@ -706,15 +715,15 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
                         // child / corner lattice, voxel-index constants: lane = 3 * axis + k (9 lanes), child-centre forms on lanes 9..14
                         const int a = lane < 9 ? lane / 3 : (lane - 9) >> 1, k = lane < 9 ? lane - 3 * a : (lane - 9) & 1;
                         const float o = a == 0 ? nx : a == 1 ? ny : nz;
-                        const double mn = a == 0 ? gx0 : a == 1 ? gy0 : gz0;
+                        const double mn = a == 0 ? g.xMin : a == 1 ? g.yMin : g.zMin;
                         float t = o; if (k >= 1) t = o + w2; if (k == 2) t = t + w2;   // X[1] = x + w, X[2] = X[1] + w
                         if (lane < 9) {
                             sh.X[3 * a + k] = t;                                     // X, Y, Z are contiguous
-                            sh.CX[3 * a + k] = vox_fast_c(vf, t, mn, gscale);
+                            sh.CX[3 * a + k] = vox_fast_c(g.vfMagic, t, mn, g.scale);
                         } else if (lane < 15) {
                             const float th = t + w2 / 2;                             // :331-333
                             sh.HX[2 * a + k] = th;
-                            sh.DX[2 * a + k] = vox_fast_c(vf, th, mn, gscale);
+                            sh.DX[2 * a + k] = vox_fast_c(g.vfMagic, th, mn, g.scale);
                         } else if (lane == 15) {
                             sh.wc = w2; sh.level = min(plev + 1, MAX_TLEVEL - 1);
                             sh.mtd = (float)(GOICP_SQRT3 / 2.0 * w2);                // :323
@@ -734,19 +743,25 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
             }
             if (lane == 0) { sh.running = running; sh.status = status; }
         }
-        if (tid == 0) { sh.optErrorT = optT; sh.pops = sh_pops; sh.subcubes = sh_subcubes; if (intErr) sh.status = 6; }
-        __syncwarp();
         if (tid == 0) {
-            atomicAdd(dstat + 0, (unsigned long long)(clock64() - sh.t0)); atomicAdd(dstat + 1, (unsigned long long)sh.pops);
-            atomicAdd(dstat + 2, (unsigned long long)sh.missTot); atomicAdd(dstat + 3, 1ull);
+            if (intErr) sh.status = 6;
+            if (cpart == 0) {
+                InnerOut o;
+                o.err = optT; o.node[0] = sh.best[0]; o.node[1] = sh.best[1]; o.node[2] = sh.best[2]; o.node[3] = sh.best[3];
+                o.improved = sh.improved; o.pops = sh_pops; o.subcubes = sh_subcubes; o.status = sh.status;
+                o.seq0 = o.seq1 = 1u; o.err2 = 0.f; o.pops2 = 0; o.subcubes2 = 0; o.ran2 = 0; o.pad = 0;
+                s_out = o;
+            } else {
+                s_out.err2 = optT; s_out.pops2 = sh_pops; s_out.subcubes2 = sh_subcubes; s_out.ran2 = 1; s_out.status = sh.status;
+            }
+            atomicAdd(dstat + 1, (unsigned long long)sh_pops); atomicAdd(dstat + 3, 1ull);
+        }
+        }   // cpart
+        if (tid == 0) {
+            atomicAdd(dstat + 0, (unsigned long long)(clock64() - sh.t0)); atomicAdd(dstat + 2, (unsigned long long)sh.missTot);
 #ifdef GOICP_PHASE_TIMING
             for (int k = 0; k < 12; k++) atomicAdd(dstat + 8 + k, (unsigned long long)sh.tp[k]);
 #endif
-            InnerOut o;
-            o.err = sh.optErrorT; o.node[0] = sh.best[0]; o.node[1] = sh.best[1]; o.node[2] = sh.best[2]; o.node[3] = sh.best[3];
-            o.improved = sh.improved; o.pops = sh.pops; o.subcubes = sh.subcubes; o.status = sh.status;
-            o.seq0 = o.seq1 = 1u; for (int k = 0; k < 5; k++) o.pad[k] = 0;
-            s_out = o;
         }
         if (warp == 0) {   // the record leaves the SM as ONE coalesced 64-byte store (it may live in mapped host memory)
             __syncwarp();
@@ -836,66 +851,65 @@ size_t goicp_bnb_smem_floats(int NdP, int NdQ, bool exact, bool needMd, bool nee
     return n > 3 * 512 ? n : 3 * 512;   // an ICP request tiles the model cloud through the same region (icp_device.cuh NN_TILE)
 }
 
-static int g_bnb_attr_set[16] = {0};
 typedef void (*bnb_kernel_t)(const PairDev*, const InnerProb*, InnerOut*, int, int*, HeapEnt*, int, float*, size_t, int, int, int, QueueDev, uint4*, int, unsigned*, int, int);
-static bnb_kernel_t bnb_kernel(int exact, int persist, int smem = 1) {
-    if (smem == 2) {   // staging arrays AND the DT volume in shared memory
-        if (persist) return exact ? inner_bnb_kernel<true, true, true, true> : inner_bnb_kernel<false, true, true, true>;
-        return exact ? inner_bnb_kernel<true, false, true, true> : inner_bnb_kernel<false, false, true, true>;
-    }
-    if (smem) {
-        if (persist) return exact ? inner_bnb_kernel<true, true, true, false> : inner_bnb_kernel<false, true, true, false>;
-        return exact ? inner_bnb_kernel<true, false, true, false> : inner_bnb_kernel<false, false, true, false>;
-    }
-    if (persist) return exact ? inner_bnb_kernel<true, true, false, false> : inner_bnb_kernel<false, true, false, false>;
-    return exact ? inner_bnb_kernel<true, false, false, false> : inner_bnb_kernel<false, false, false, false>;
+template <bool SMEM, bool GS, bool CT>
+static bnb_kernel_t bnb_kernel_sel(int exact, int persist) {
+    if (persist) return exact ? inner_bnb_kernel<true, true, SMEM, GS, CT> : inner_bnb_kernel<false, true, SMEM, GS, CT>;
+    return exact ? inner_bnb_kernel<true, false, SMEM, GS, CT> : inner_bnb_kernel<false, false, SMEM, GS, CT>;
 }
-static cudaError_t bnb_attr(int exact, int persist, int smem = 1) {
-    const int k = (exact ? 1 : 0) + (persist ? 2 : 0) + 4 * smem;
+// smem: 0 staging arrays in a global slab, 1 in shared memory, 2 shared memory incl. the DT volume; ct: generic corner terms
+static bnb_kernel_t bnb_kernel(int exact, int persist, int smem, int ct) {
+    if (smem == 2) return ct ? bnb_kernel_sel<true, true, true>(exact, persist) : bnb_kernel_sel<true, true, false>(exact, persist);
+    if (smem == 1) return ct ? bnb_kernel_sel<true, false, true>(exact, persist) : bnb_kernel_sel<true, false, false>(exact, persist);
+    return ct ? bnb_kernel_sel<false, false, true>(exact, persist) : bnb_kernel_sel<false, false, false>(exact, persist);
+}
+static int g_bnb_attr_set[32] = {0};
+static cudaError_t bnb_attr(int exact, int persist, int smem, int ct) {
+    const int k = (exact ? 1 : 0) + (persist ? 2 : 0) + 4 * smem + 16 * (ct ? 1 : 0);
     if (g_bnb_attr_set[k]) return cudaSuccess;
     cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, bnb_kernel(exact, persist, smem));
+    cudaError_t e = cudaFuncGetAttributes(&fa, bnb_kernel(exact, persist, smem, ct));
     if (e != cudaSuccess) return e;
     const int maxDyn = 227 * 1024 - (int)fa.sharedSizeBytes - 1024;   // static (queue top, ICP tiles) + dynamic <= 227 KB per CTA
-    e = cudaFuncSetAttribute(bnb_kernel(exact, persist, smem), cudaFuncAttributeMaxDynamicSharedMemorySize, maxDyn);
+    e = cudaFuncSetAttribute(bnb_kernel(exact, persist, smem, ct), cudaFuncAttributeMaxDynamicSharedMemorySize, maxDyn);
     if (e == cudaSuccess) g_bnb_attr_set[k] = 1;
     return e;
 }
 
 cudaError_t goicp_launch_inner_bnb(const PairDev* pairs, const InnerProb* probs, InnerOut* outs, int nprob, int* counter,
                                    HeapEnt* heaps, int heapCap, int maxCtas, float* gscratch, size_t gstride,
-                                   int NdP, int NdQ, size_t smemBytes, int useSmem, int gridOff, int S3p, int exact, int threads, void* memo, int memoCap, unsigned* genCounter, cudaStream_t st, int* ctasLaunched) {
+                                   int NdP, int NdQ, size_t smemBytes, int useSmem, int gridOff, int S3p, int exact, int ct, int threads, void* memo, int memoCap, unsigned* genCounter, cudaStream_t st, int* ctasLaunched) {
     if (nprob <= 0) { if (ctasLaunched) *ctasLaunched = 0; return cudaSuccess; }
     const size_t smem = useSmem ? smemBytes : 0;
-    cudaError_t e = bnb_attr(exact, 0, useSmem);
+    cudaError_t e = bnb_attr(exact, 0, useSmem, ct);
     if (e != cudaSuccess) return e;
     int grid = nprob < maxCtas ? nprob : maxCtas;
     if (ctasLaunched) *ctasLaunched = grid;
     QueueDev q{};
-    bnb_kernel(exact, 0, useSmem)<<<grid, threads, smem, st>>>(pairs, probs, outs, nprob, counter, heaps, heapCap, gscratch, gstride, NdP, NdQ, useSmem, q, (uint4*)memo, memoCap, genCounter, gridOff, S3p);
+    bnb_kernel(exact, 0, useSmem, ct)<<<grid, threads, smem, st>>>(pairs, probs, outs, nprob, counter, heaps, heapCap, gscratch, gstride, NdP, NdQ, useSmem, q, (uint4*)memo, memoCap, genCounter, gridOff, S3p);
     return cudaGetLastError();
 }
 
 // the resident kernel of a batch: `ctas` CTAs serve the request ring until each has seen a shut-down marker
 cudaError_t goicp_launch_inner_bnb_persistent(const PairDev* pairs, const QueueDev& q, HeapEnt* heaps, int heapCap, int ctas, float* gscratch, size_t gstride,
-                                              int NdP, int NdQ, size_t smemBytes, int useSmem, int gridOff, int S3p, int exact, int threads, void* memo, int memoCap, unsigned* genCounter, cudaStream_t st) {
+                                              int NdP, int NdQ, size_t smemBytes, int useSmem, int gridOff, int S3p, int exact, int ct, int threads, void* memo, int memoCap, unsigned* genCounter, cudaStream_t st) {
     const size_t smem = useSmem ? smemBytes : 0;
-    cudaError_t e = bnb_attr(exact, 1, useSmem);
+    cudaError_t e = bnb_attr(exact, 1, useSmem, ct);
     if (e != cudaSuccess) return e;
-    bnb_kernel(exact, 1, useSmem)<<<ctas, threads, smem, st>>>(pairs, nullptr, nullptr, 0, nullptr, heaps, heapCap, gscratch, gstride, NdP, NdQ, useSmem, q, (uint4*)memo, memoCap, genCounter, gridOff, S3p);
+    bnb_kernel(exact, 1, useSmem, ct)<<<ctas, threads, smem, st>>>(pairs, nullptr, nullptr, 0, nullptr, heaps, heapCap, gscratch, gstride, NdP, NdQ, useSmem, q, (uint4*)memo, memoCap, genCounter, gridOff, S3p);
     return cudaGetLastError();
 }
 
-int goicp_inner_bnb_persistent_occupancy(size_t smemBytes, int exact, int threads, int useSmem) {
-    if (bnb_attr(exact, 1, useSmem) != cudaSuccess) return 1;
+int goicp_inner_bnb_persistent_occupancy(size_t smemBytes, int exact, int threads, int useSmem, int ct) {
+    if (bnb_attr(exact, 1, useSmem, ct) != cudaSuccess) return 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bnb_kernel(exact, 1, useSmem), threads, useSmem ? smemBytes : 0) != cudaSuccess || n < 1) n = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bnb_kernel(exact, 1, useSmem, ct), threads, useSmem ? smemBytes : 0) != cudaSuccess || n < 1) n = 1;
     return n;
 }
-int goicp_inner_bnb_occupancy(size_t smemBytes, int exact, int threads, int useSmem) {
-    if (bnb_attr(exact, 0, useSmem) != cudaSuccess) return 1;
+int goicp_inner_bnb_occupancy(size_t smemBytes, int exact, int threads, int useSmem, int ct) {
+    if (bnb_attr(exact, 0, useSmem, ct) != cudaSuccess) return 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bnb_kernel(exact, 0, useSmem), threads, useSmem ? smemBytes : 0) != cudaSuccess || n < 1) n = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bnb_kernel(exact, 0, useSmem, ct), threads, useSmem ? smemBytes : 0) != cudaSuccess || n < 1) n = 1;
     return n;
 }
 
@@ -912,15 +926,8 @@ cudaError_t goicp_launch_eval_bounds(const PairDev* pairs, int pair, const float
 // would otherwise wait for that kernel (CUDA lazy module loading)
 cudaError_t goicp_preload_bnb() {
     cudaFuncAttributes a; cudaError_t e;
-    if ((e = cudaFuncGetAttributes(&a, inner_bnb_kernel<true, true, true, true>)) != cudaSuccess) return e;
-    if ((e = cudaFuncGetAttributes(&a, inner_bnb_kernel<false, true, true, true>)) != cudaSuccess) return e;
-    if ((e = cudaFuncGetAttributes(&a, inner_bnb_kernel<true, false, true, true>)) != cudaSuccess) return e;
-    if ((e = cudaFuncGetAttributes(&a, inner_bnb_kernel<false, false, true, true>)) != cudaSuccess) return e;
-    if ((e = cudaFuncGetAttributes(&a, inner_bnb_kernel<true, true, true, false>)) != cudaSuccess) return e;
-    if ((e = cudaFuncGetAttributes(&a, inner_bnb_kernel<true, true, false, false>)) != cudaSuccess) return e;
-    if ((e = cudaFuncGetAttributes(&a, inner_bnb_kernel<false, true, true, false>)) != cudaSuccess) return e;
-    if ((e = cudaFuncGetAttributes(&a, inner_bnb_kernel<true, false, true, false>)) != cudaSuccess) return e;
-    if ((e = cudaFuncGetAttributes(&a, inner_bnb_kernel<false, false, true, false>)) != cudaSuccess) return e;
+    for (int exact = 0; exact < 2; exact++) for (int persist = 0; persist < 2; persist++) for (int smem = 0; smem < 3; smem++) for (int ct = 0; ct < 2; ct++)
+        if ((e = cudaFuncGetAttributes(&a, bnb_kernel(exact, persist, smem, ct))) != cudaSuccess) return e;
     if ((e = cudaFuncGetAttributes(&a, eval_bounds_kernel)) != cudaSuccess) return e;
     return cudaSuccess;
 }
