@@ -1175,7 +1175,9 @@ static goicp_status register_all(Eng* h) {
     std::atomic<int> next(0);
     int groups = 1, slots = 1;
     if (np > 1) {
-        groups = h->groups > 0 ? h->groups : (int)std::min<unsigned>(32u, std::max(4u, std::thread::hardware_concurrency()));
+        unsigned cores = std::max(1u, std::thread::hardware_concurrency());
+        { const char* e = getenv("LOCAL_WORLD_SIZE"); const int lws = e ? atoi(e) : 1; if (lws > 1) cores = std::max(2u, cores / (unsigned)lws); }   // one process per GPU (torchrun): share the host cores
+        groups = h->groups > 0 ? h->groups : (int)std::min<unsigned>(32u, std::max(cores >= 4u ? 4u : 2u, cores));
         slots = h->slots > 0 ? h->slots : std::min(128, std::max(8, (np + groups - 1) / groups));
         groups = std::min(groups, (np + slots - 1) / slots);
     }
