@@ -169,6 +169,7 @@ struct Problem {
     std::vector<PendReq> pend;
     std::unordered_set<unsigned long long> inflight;
     bool icpQueued = false;
+    bool dirty = false;       // resident scheduler: queued for the worker's next pass
     int icpSlot[2] = {-1, -1};
     // ICP exchange
     bool icpPending = false;
@@ -243,7 +244,7 @@ struct goicp_handle_s {
     DevBuf arenaIn, arenaWork, dPairs, dTmp, dTmp2, dTmp3, dSepBits, dSepNx, dSepNxy;
     PinBuf hStage, hPairs;
     WaveCtx main;
-    MapBuf qOuts, qOrder, qIcp; DevBuf qClaim, qHeaps, qScratch, qMemo, dGen;   // persistent-queue mode (batches)
+    MapBuf qOuts, qOrder, qIcp, qDone; DevBuf qClaim, qHeaps, qScratch, qMemo, dGen;   // persistent-queue mode (batches)
     int shardRank = 0, shardN = 1; goicp_allgather_fn allgather = nullptr; void* allgatherUser = nullptr;   // frontier sharding
     std::vector<InnerOut> xSend, xRecv;
     std::atomic<int> outstanding{0};   // requests published and not yet harvested (persistent scheduler)
@@ -921,6 +922,7 @@ static goicp_status register_group(Eng* h, WaveCtx& c, const BnbCfg& cfg, std::a
 // side stream.  A deep pair therefore delays nobody else, and the GPU always holds a mix of calls of hundreds of pairs.
 struct PQ {
     QueueCell* cells; InnerOut* outs; unsigned cellMask, cellShift;
+    volatile unsigned* doneRing = nullptr; unsigned doneCap = 0;   // completion hints, one ring per worker (QueueDev)
     std::atomic<unsigned> reserve{0};
     // request words first, the two lap tags last (x86 stores are observed in program order; a 32-byte half of the cell that
     // shows its tag therefore shows its request words too)
@@ -940,8 +942,12 @@ static inline bool out_ready(const InnerOut& o) {
 }
 static inline void out_arm(InnerOut& o) { *reinterpret_cast<volatile unsigned*>(&o.seq0) = 0u; *reinterpret_cast<volatile unsigned*>(&o.seq1) = 0u; }
 
-static goicp_status persistent_worker(Eng* h, WaveCtx& c, PQ& pq, std::atomic<int>& next, int slots, int slotLo, int slotHi, const BnbCfg& cfg) {
+static goicp_status persistent_worker(Eng* h, WaveCtx& c, PQ& pq, std::atomic<int>& next, int slots, int slotLo, int slotHi, const BnbCfg& cfg, int worker) {
     const int np = (int)h->probs.size();
+    std::vector<int> slotPair(slotHi - slotLo, -1);   // pair that published the request in each of this worker's result slots
+    std::vector<int> dirtyList, todo;                 // pairs with news: a completed request, just admitted, or waiting for a free slot
+    volatile unsigned* ring = pq.doneRing + (size_t)worker * pq.doneCap; unsigned ringHead = 0;
+    auto mark = [&](int i) { Problem& Q = h->probs[i]; if (!Q.dirty) { Q.dirty = true; dirtyList.push_back(i); } };
     std::vector<int> freeSlots; freeSlots.reserve(slotHi - slotLo);
     for (int sidx = slotHi - 1; sidx >= slotLo; --sidx) freeSlots.push_back(sidx);
     std::vector<int> active;
@@ -990,7 +996,7 @@ static goicp_status persistent_worker(Eng* h, WaveCtx& c, PQ& pq, std::atomic<in
             const unsigned lo = (unsigned)(ptr & 0xFFFFFFFFull), hi = (unsigned)(ptr >> 32);
             memcpy(&ip.R[0], &lo, 4); memcpy(&ip.R[1], &hi, 4);
             out_arm(pq.outs[slot]);
-            P.icpSlot[k] = slot;
+            P.icpSlot[k] = slot; slotPair[slot - slotLo] = i;
             pq.publish((unsigned)slot, &ip);
         }
         P.icpQueued = true;
@@ -998,15 +1004,27 @@ static goicp_status persistent_worker(Eng* h, WaveCtx& c, PQ& pq, std::atomic<in
         return true;
     };
     for (;;) {
-        while ((int)active.size() < slots) { const int i = next.fetch_add(1); if (i >= np) break; reset_search(h->probs[i]); active.push_back(i); h->activePairs.fetch_add(1); }
+        while ((int)active.size() < slots) { const int i = next.fetch_add(1); if (i >= np) break; reset_search(h->probs[i]); h->probs[i].dirty = false; active.push_back(i); h->activePairs.fetch_add(1); mark(i); }
         if (active.empty() && zombies.empty()) break;
         bool progressed = false;
         c.callsUsed++;   // loop iterations
         if (slotLo == 0 && dbgTimeline) { const double tnow = secs_since(tStart); if (tnow >= nextSample) { fprintf(stderr, "[timeline] t=%.3f active_pairs=%d outstanding=%d\n", tnow, h->activePairs.load(), h->outstanding.load()); nextSample += 0.05; } }
         auto tIter = clk::now();
-        // ---- every active pair: harvest finished calls, advance, publish what it needs next ----
-        for (int i : active) {
+        // ---- completion hints of the resident kernel: which pairs have news ----
+        for (unsigned v; (v = ring[ringHead & (pq.doneCap - 1u)]) != 0u; ringHead++) {
+            ring[ringHead & (pq.doneCap - 1u)] = 0u;
+            // the hint may overtake its record on the bus (two stores, no fence): wait for the record's own flags
+            for (long spin = 0; !out_ready(pq.outs[v - 1u]) && spin < 100000000L; spin++) __builtin_ia32_pause();
+            const int owner = slotPair[(int)(v - 1u) - slotLo];
+            if (owner >= 0 && h->probs[owner].phase != PH_DONE) mark(owner);
+            progressed = true;
+        }
+        // ---- every pair with news: harvest finished calls, advance, publish what it needs next ----
+        todo.swap(dirtyList); dirtyList.clear();
+        for (int i : todo) h->probs[i].dirty = false;
+        for (int i : todo) {
             Problem& P = h->probs[i];
+            if (P.phase == PH_DONE) continue;
             if (harvest(P, P.pend, true)) progressed = true;
             if (P.status == GOICP_ERR_OVERFLOW) {   // abandon the pair here; register_persistent re-runs it with growing queues
                 for (auto& r : P.pend) zombies.push_back(r);
@@ -1017,7 +1035,7 @@ static goicp_status persistent_worker(Eng* h, WaveCtx& c, PQ& pq, std::atomic<in
             }
             if (P.phase == PH_START) { P.phase = PH_WAIT_INIT; P.icpQueued = false; }
             if (P.phase == PH_WAIT_INIT || P.phase == PH_WAIT_ICP) {
-                if (!P.icpQueued) { if (send_icp(i)) progressed = true; continue; }
+                if (!P.icpQueued) { if (send_icp(i)) progressed = true; else mark(i); continue; }
                 const bool d0 = out_ready(pq.outs[P.icpSlot[0]]), d1 = out_ready(pq.outs[P.icpSlot[1]]);
                 if (!(d0 && d1)) continue;
                 std::atomic_thread_fence(std::memory_order_acquire);
@@ -1032,7 +1050,7 @@ static goicp_status persistent_worker(Eng* h, WaveCtx& c, PQ& pq, std::atomic<in
             advance(h, i);
             if (P.phase != before || P.j != jb || P.par.id != idb) progressed = true;
             if (P.phase == PH_DONE) { for (auto& r : P.pend) zombies.push_back(r); P.pend.clear(); P.inflight.clear(); h->activePairs.fetch_sub(1); continue; }
-            if (P.phase == PH_WAIT_ICP) { P.icpQueued = false; if (send_icp(i)) progressed = true; continue; }
+            if (P.phase == PH_WAIT_ICP) { P.icpQueued = false; if (send_icp(i)) progressed = true; else mark(i); continue; }
             // blocked on an InnerBnB result: is it already on its way?
             const unsigned long long need = call_key(P.par.id, P.j, P.phase == PH_CHILD_LB ? 1 : 0);
             if (P.inflight.count(need)) continue;
@@ -1043,7 +1061,7 @@ static goicp_status persistent_worker(Eng* h, WaveCtx& c, PQ& pq, std::atomic<in
             for (size_t k = 0; k < reqs.size(); k++) {
                 if (freeSlots.empty() || h->outstanding.load(std::memory_order_relaxed) > (int)(pq.cellMask >> 1)) break;   // out of slots / ring half full: the rest is regathered later
                 const int slot = freeSlots.back(); freeSlots.pop_back();
-                out_arm(pq.outs[slot]);
+                out_arm(pq.outs[slot]); slotPair[slot - slotLo] = i;
                 P.pend.push_back(Problem::PendReq{slot, tags[k].key, tags[k].entryOpt, tags[k].both});
                 P.inflight.insert(tags[k].key);
                 if (tags[k].both) { P.inflight.insert(tags[k].key | 1ull); c.callsLaunched++; }
@@ -1053,6 +1071,7 @@ static goicp_status persistent_worker(Eng* h, WaveCtx& c, PQ& pq, std::atomic<in
             }
             c.tInnerEnq += secs_since(tg);
             if (!reqs.empty()) { progressed = true; c.waves++; }
+            if (!P.inflight.count(need)) mark(i);   // out of slots: the blocking call itself is still unpublished
         }
         active.erase(std::remove_if(active.begin(), active.end(), [&](int i) { return h->probs[i].phase == PH_DONE; }), active.end());
         // ---- results of calls whose pair has already finished (speculation): just recycle the slots ----
@@ -1069,7 +1088,9 @@ static goicp_status persistent_worker(Eng* h, WaveCtx& c, PQ& pq, std::atomic<in
                 return fail(h, GOICP_ERR_CUDA, "persistent scheduler: debug stop");
             }
             if (secs_since(lastProgress) > 45.0) return fail(h, GOICP_ERR_CUDA, "persistent scheduler: no progress for 45 s (device stalled?)");
-            struct timespec ts = {0, 20000}; nanosleep(&ts, nullptr);
+            bool news = false;   // spin briefly on the completion ring before giving the core away
+            for (int spin = 0; spin < 200 && !news; spin++) { news = ring[ringHead & (pq.doneCap - 1u)] != 0u; if (!news) __builtin_ia32_pause(); }
+            if (!news) { struct timespec ts = {0, 5000}; nanosleep(&ts, nullptr); }
             c.tInnerWait += secs_since(ts0);
         }
     }
@@ -1083,8 +1104,9 @@ static goicp_status register_persistent(Eng* h, const BnbCfg& cfg, int groups, i
     // everything is allocated BEFORE the resident kernel starts (cudaMalloc / cudaFree would wait for it forever)
     CU(h->qOuts.ensure(sizeof(InnerOut) * (size_t)NSLOT));
     CU(h->qOrder.ensure(sizeof(QueueCell) * (size_t)ORDER));
-    CU(h->qClaim.ensure(sizeof(unsigned)));
+    CU(h->qClaim.ensure(sizeof(unsigned) * 64));   // [0] ring claim counter, [1 + w] completion-ring tail of worker w
     CU(h->qIcp.ensure(sizeof(IcpState) * 2 * (size_t)np));
+    CU(h->qDone.ensure(sizeof(unsigned) * (size_t)2 * NSLOT));   // per-worker completion rings: groups x (power of two >= NSLOT / groups)
     int perSM = goicp_inner_bnb_persistent_occupancy(cfg.smemBytes, h->exact_sums, cfg.threads, cfg.useSmem, cfg.ct);
     { const char* e = getenv("GOICP_CTAS_PER_SM"); if (e && atoi(e) >= 1) perSM = std::min(perSM, atoi(e)); }
     const int ctas = h->numSM * perSM;   // the resident kernel owns the GPU for the batch: InnerBnB and ICP requests both run on its CTAs
@@ -1106,11 +1128,16 @@ static goicp_status register_persistent(Eng* h, const BnbCfg& cfg, int groups, i
     }
     h->main.callsUsed = 0;
     memset(h->qOrder.h, 0, sizeof(QueueCell) * (size_t)ORDER);
-    CU(cudaMemsetAsync(h->qClaim.p, 0, sizeof(unsigned), h->stream));
-    PQ pq; pq.cells = reinterpret_cast<QueueCell*>(h->qOrder.h); pq.outs = reinterpret_cast<InnerOut*>(h->qOuts.h);
+    CU(cudaMemsetAsync(h->qClaim.p, 0, sizeof(unsigned) * 64, h->stream));
+    const int per = NSLOT / groups;
+    unsigned doneCap = 1; while ((int)doneCap < per) doneCap <<= 1;
+    memset(h->qDone.h, 0, sizeof(unsigned) * (size_t)doneCap * groups);
+    PQ pq; pq.doneRing = reinterpret_cast<volatile unsigned*>(h->qDone.h); pq.doneCap = doneCap;
+    pq.cells = reinterpret_cast<QueueCell*>(h->qOrder.h); pq.outs = reinterpret_cast<InnerOut*>(h->qOuts.h);
     pq.cellMask = ORDER - 1; pq.cellShift = 18;
     QueueDev qd; qd.cells = reinterpret_cast<const QueueCell*>(h->qOrder.d); qd.outs = reinterpret_cast<InnerOut*>(h->qOuts.d);
     qd.cellMask = ORDER - 1; qd.cellShift = 18; qd.claim = h->qClaim.as<unsigned>();
+    qd.doneTail = h->qClaim.as<unsigned>() + 1; qd.doneRing = reinterpret_cast<unsigned*>(h->qDone.d); qd.doneCap = doneCap; qd.slotsPerWorker = (unsigned)per;
     cudaEventRecord(h->main.ev0, h->stream);
     CU(goicp_launch_inner_bnb_persistent(h->dPairs.as<PairDev>(), qd, h->qHeaps.as<HeapEnt>(), heapCap, ctas, h->qScratch.as<float>(), cfg.smemFloats,
                                          cfg.NdP, cfg.NdQ, cfg.smemBytes, cfg.useSmem, cfg.gridOff, cfg.S3p, h->exact_sums, cfg.ct, cfg.threads, h->qMemo.p, memoCap, h->dGen.as<unsigned>(), h->stream));
@@ -1120,10 +1147,9 @@ static goicp_status register_persistent(Eng* h, const BnbCfg& cfg, int groups, i
     h->activePairs.store(0); h->outstanding.store(0); h->stats[14] = 0;
     std::vector<goicp_status> st(groups, GOICP_OK);
     std::vector<std::thread> th;
-    const int per = NSLOT / groups;
     for (int g = 0; g < groups; g++) {
         WaveCtx* w = h->workers[g].get();
-        th.emplace_back([h, w, &pq, &next, &st, g, slots, per, &cfg]() { cudaSetDevice(h->device); st[g] = persistent_worker(h, *w, pq, next, slots, g * per, (g + 1) * per, cfg); });
+        th.emplace_back([h, w, &pq, &next, &st, g, slots, per, &cfg]() { cudaSetDevice(h->device); st[g] = persistent_worker(h, *w, pq, next, slots, g * per, (g + 1) * per, cfg, g); });
     }
     for (auto& t : th) t.join();
     for (int k = 0; k < ctas; k++) pq.publish(0xFFFFFFFFu, nullptr);   // one shut-down marker per CTA
@@ -1303,7 +1329,7 @@ void goicp_destroy(goicp_handle h) {
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->arenaIn, &h->arenaWork, &h->dPairs, &h->dTmp, &h->dTmp2, &h->dTmp3, &h->dSepBits, &h->dSepNx, &h->dSepNxy};
     for (DevBuf* b : bufs) b->release();
-    h->hStage.release(); h->hPairs.release(); h->qOuts.release(); h->qOrder.release(); h->qIcp.release(); h->qClaim.release(); h->qHeaps.release(); h->qScratch.release(); h->qMemo.release(); h->dGen.release();
+    h->hStage.release(); h->hPairs.release(); h->qOuts.release(); h->qOrder.release(); h->qIcp.release(); h->qDone.release(); h->qClaim.release(); h->qHeaps.release(); h->qScratch.release(); h->qMemo.release(); h->dGen.release();
     h->main.release();
     for (auto& w : h->workers) w->release();
     if (h->ownStream) cudaStreamDestroy(h->stream);

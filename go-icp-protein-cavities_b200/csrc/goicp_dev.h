@@ -114,6 +114,12 @@ struct QueueDev {
     unsigned cellMask;        // ring capacity - 1 (power of two)
     unsigned cellShift;       // log2(capacity)
     unsigned* claim;          // device counter
+    // completion hints: after its result record a CTA appends slot+1 to the ring of the host worker that owns the slot
+    // (slot / slotsPerWorker); the worker then looks only at pairs with news (the record's own flags stay authoritative)
+    unsigned* doneTail;       // device counters, one per worker
+    unsigned* doneRing;       // mapped host memory, workers x doneCap
+    unsigned doneCap;         // power of two >= slotsPerWorker
+    unsigned slotsPerWorker;
 };
 
 struct alignas(16) HeapEnt { float lb, w, x, y, z, pad0, pad1, pad2; };   // TRANSNODE without ub (never read, jly_goicp.h:75-87)

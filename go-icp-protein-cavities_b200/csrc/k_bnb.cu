@@ -286,6 +286,7 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
             __syncthreads();
             if (warp == 0) {
                 if (lane < 16) reinterpret_cast<unsigned*>(q.outs + p)[lane] = (lane == 0 || lane == 15) ? 1u : 0u;
+                if (lane == 0) { const unsigned w = (unsigned)p / q.slotsPerWorker; const unsigned k = atomicAdd(q.doneTail + w, 1u); q.doneRing[(size_t)w * q.doneCap + (k & (q.doneCap - 1u))] = (unsigned)p + 1u; }
             }
             continue;
         }
@@ -767,6 +768,7 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
             __syncwarp();
             InnerOut* dst = PERSIST ? q.outs + p : outs + p;
             if (lane < 16) reinterpret_cast<unsigned*>(dst)[lane] = reinterpret_cast<const unsigned*>(&s_out)[lane];
+            if (PERSIST && lane == 0) { const unsigned w = (unsigned)p / q.slotsPerWorker; const unsigned k = atomicAdd(q.doneTail + w, 1u); q.doneRing[(size_t)w * q.doneCap + (k & (q.doneCap - 1u))] = (unsigned)p + 1u; }
         }
     }
 }
