@@ -237,6 +237,7 @@ struct goicp_handle_s {
     goicp_params params; bool haveParams = false;
     int exact_sums = 1, spec_width = 32, use_dt_replay = 1;
     int groups = 0, slots = 0;   // 0 = auto
+    int residentCtas = 0; bool tail_spec = true;   // CTAs of the running resident kernel (0: none)
     int batch_spec_width = 4;    // speculation width inside a batch (pairs already fill the GPU)
     bool merge_calls = true;   // resident scheduler: one request per rotation cube carries its upper- and lower-bound InnerBnB calls
     int bnb_threads = 256;   // threads per InnerBnB CTA (64..512): more threads = shorter pops, fewer resident calls   // batch: worker streams (0 = auto) and pairs advanced in lock-step per stream
@@ -810,7 +811,10 @@ static void gather_requests(Eng* h, int pi, std::vector<InnerProb>& reqs, std::v
         want(P.par, j, 1, ch, R);
     }
     // the next queue nodes in pop order; width grows while the incumbent stays unchanged
-    const int specw = h->probs.size() > 1 ? std::min(h->spec_width, h->batch_spec_width) : h->spec_width;   // inside a batch the pairs themselves fill the GPU
+    // inside a batch the pairs themselves fill the GPU; in its tail (fewer requests in flight than the resident kernel has
+    // CTAs) the remaining deep pairs speculate as widely as a single registration does
+    const bool tail = h->tail_spec && h->residentCtas > 0 && h->outstanding.load(std::memory_order_relaxed) < h->residentCtas;
+    const int specw = (h->probs.size() > 1 && !tail) ? std::min(h->spec_width, h->batch_spec_width) : h->spec_width;
     int width = std::min(specw, P.quiet < 30 ? (1 << std::min(P.quiet, 20)) - 1 : specw);
     if (width > 0 && !P.q.empty()) {
         std::vector<RNode> top(P.q);
@@ -1110,6 +1114,7 @@ static goicp_status register_persistent(Eng* h, const BnbCfg& cfg, int groups, i
     int perSM = goicp_inner_bnb_persistent_occupancy(cfg.smemBytes, h->exact_sums, cfg.threads, cfg.useSmem, cfg.ct);
     { const char* e = getenv("GOICP_CTAS_PER_SM"); if (e && atoi(e) >= 1) perSM = std::min(perSM, atoi(e)); }
     const int ctas = h->numSM * perSM;   // the resident kernel owns the GPU for the batch: InnerBnB and ICP requests both run on its CTAs
+    h->residentCtas = ctas; { const char* e = getenv("GOICP_TAIL_SPEC"); if (e) h->tail_spec = atoi(e) != 0; }
     int heapCap = 1 << 15;
     { const char* e = getenv("GOICP_HEAPCAP"); if (e && atoi(e) >= 129) heapCap = atoi(e); }   // test hook: force the overflow pool
     CU(h->qHeaps.ensure(sizeof(HeapEnt) * (size_t)ctas * heapCap));
@@ -1154,7 +1159,7 @@ static goicp_status register_persistent(Eng* h, const BnbCfg& cfg, int groups, i
     for (auto& t : th) t.join();
     for (int k = 0; k < ctas; k++) pq.publish(0xFFFFFFFFu, nullptr);   // one shut-down marker per CTA
     cudaError_t e = cudaStreamSynchronize(h->stream);
-    g_no_device_alloc.store(false);
+    g_no_device_alloc.store(false); h->residentCtas = 0;
     if (e != cudaSuccess) return fail(h, GOICP_ERR_CUDA, "resident inner_bnb kernel: %s", cudaGetErrorString(e));
     float ms = 0; cudaEventElapsedTime(&ms, h->main.ev0, h->main.ev1); h->main.ms[2] += ms; h->main.launches[2] += 1;
     for (int g = 0; g < groups; g++) if (st[g]) return st[g];
