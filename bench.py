@@ -239,11 +239,13 @@ def main():
             "traffic": None, "peak_source": peak_src, "achieved_aggregate": agg, "frac_aggregate": agg / peaks["hbm_gbs"],
             "algorithmic_bytes_per_eval": bytes_per_eval, "achieved_dt_gather_only": kern_evals_per_gpu * 4 / (kern_ms * 1e-3) / 1e9,
             "note": "algorithmic bytes per eval per SURVEY 8(d): 4 B DT voxel + 20.25 B corner-term gathers when regularization>0. `achieved` = evals x bytes / CUDA-event time of the resident inner_bnb kernel (one launch per step serves every InnerBnB and "
-                    "ICP request of the batch), `achieved_aggregate` = evals x bytes / step time per GPU, `achieved_dt_gather_only` counts the 4 B DT voxel alone. S=20 grids are L1-resident (98 % L1 hit): the binding limit is SM "
-                    "issue + the serial phases of each queue pop, not HBM -- see DESIGN.md section 4. `traffic` = DRAM bytes of one classic-mode launch of the same kernel "
-                    "(ncu cannot replay the resident kernel; profiles/README.md)"}
-    prof = os.path.join(ROOT, "profiles", "r01_inner_bnb_traffic.json")
-    if os.path.exists(prof):
+                    "ICP request of the batch), `achieved_aggregate` = evals x bytes / step time per GPU, `achieved_dt_gather_only` counts the 4 B DT voxel alone. Only evals of calls the reference order consumes are counted (speculative "
+                    "calls and corner evals are not). The 20^3 volumes are staged per call into shared memory by TMA (cp.async.bulk), so the gathers are LDS and DRAM sees only the staging traffic: the binding limit is SM issue + the serial "
+                    "phases of each queue pop, not HBM -- see DESIGN.md section 4. `traffic` = DRAM bytes of one classic-mode launch of the same kernel (ncu cannot replay the resident kernel; profiles/README.md)"}
+    import glob
+    profs = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_inner_bnb_traffic.json")))
+    prof = profs[-1] if profs else ""
+    if prof and os.path.exists(prof):
         try:
             roof["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
         except Exception:
