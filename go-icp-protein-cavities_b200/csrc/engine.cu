@@ -239,8 +239,9 @@ struct goicp_handle_s {
     int groups = 0, slots = 0;   // 0 = auto
     int residentCtas = 0; bool tail_spec = true;   // CTAs of the running resident kernel (0: none)
     int batch_spec_width = 4;    // speculation width inside a batch (pairs already fill the GPU)
+    bool dtUploaded = false;   // the DT came from goicp_dt_upload (test hook): no 16-bit distance codes
     bool merge_calls = true;   // resident scheduler: one request per rotation cube carries its upper- and lower-bound InnerBnB calls
-    int bnb_threads = 256;   // threads per InnerBnB CTA (64..512): more threads = shorter pops, fewer resident calls   // batch: worker streams (0 = auto) and pairs advanced in lock-step per stream
+    int bnb_threads = goicp_bnb_default_threads(); bool bnb_threads_set = false;   // threads per InnerBnB CTA (64..512): more threads = shorter pops, fewer resident calls   // batch: worker streams (0 = auto) and pairs advanced in lock-step per stream
     std::vector<Problem> probs;
     DevBuf arenaIn, arenaWork, dPairs, dTmp, dTmp2, dTmp3, dSepBits, dSepNx, dSepNxy;
     PinBuf hStage, hPairs;
@@ -365,7 +366,8 @@ static goicp_status upload_problems(Eng* h) {
         in += al256(sizeof(int) * std::max(nc, 1)) + al256(sizeof(uint32_t) * (nc + 1)) + al256(sizeof(int) * (nc + 1)) + al256(sizeof(int) * P.Nm);
         P.inBytes = in; P.inOff = inTot; inTot += in;
         size_t w = 0;
-        w += al256(sizeof(float) * S3) + al256(sizeof(int) * S3) + (wantVcell ? 2 * al256(sizeof(int) * S3) + al256(S3 + 16) : 0) + al256(sizeof(double) * GOICP_OVN);
+        w += al256(sizeof(float) * S3) + al256(sizeof(int) * S3) + (wantVcell ? 2 * al256(sizeof(int) * S3) + al256(S3 + 16) : 0) + al256(sizeof(double) * GOICP_OVN)
+             + (S <= 32 ? al256(2 * (S3 + 16)) + al256(sizeof(float) * (3 * (size_t)(S - 1) * (S - 1) + 6)) : 0);
         w += 2 * al256(sizeof(float) * P.NdAll) + al256(sizeof(float) * GOICP_MAXROTLEVEL * (size_t)P.NdAll);
         if (useF && p.regularizationFPFH > 0) w += al256(sizeof(float) * (size_t)P.NdAll * (nc + 1));
         if (p.regularizationNeighbors > 0) w += al256(sizeof(int) * P.NdAll) + al256(sizeof(int) * P.Nm);
@@ -407,6 +409,11 @@ static goicp_status upload_problems(Eng* h) {
         D.g.vnear = reinterpret_cast<int*>(dWork + w); w += al256(sizeof(int) * S3);
         if (wantVcell) { D.g.vcell = reinterpret_cast<int*>(dWork + w); w += al256(sizeof(int) * S3); D.g.vmask = reinterpret_cast<uint32_t*>(dWork + w); w += al256(sizeof(int) * S3); D.g.vmask8 = reinterpret_cast<uint8_t*>(dWork + w); w += al256(S3 + 16); }
         D.g.ovl = reinterpret_cast<double*>(dWork + w); w += al256(sizeof(double) * GOICP_OVN);
+        if (S <= 32) {
+            D.g.dcode = reinterpret_cast<uint16_t*>(dWork + w); w += al256(2 * (S3 + 16));
+            D.g.dlut = reinterpret_cast<float*>(dWork + w); w += al256(sizeof(float) * (3 * (size_t)(S - 1) * (S - 1) + 6));
+            D.g.nlut = 3 * (S - 1) * (S - 1) + 2;
+        }
         D.normData = reinterpret_cast<float*>(dWork + w); w += al256(sizeof(float) * P.NdAll);
         D.weights = reinterpret_cast<float*>(dWork + w); w += al256(sizeof(float) * P.NdAll);
         D.maxRotDis = reinterpret_cast<float*>(dWork + w); w += al256(sizeof(float) * GOICP_MAXROTLEVEL * (size_t)P.NdAll);
@@ -544,12 +551,15 @@ static BnbCfg bnb_config(Eng* h) {
     // small volumes (cavity grids, 20^3): distances + one colour-mask byte per voxel are staged in shared memory per call
     const int S = h->params.distTransSize; const size_t S3 = (size_t)S * S * S;
     const size_t S3p = (S3 + 15) & ~(size_t)15;
-    if (c.useSmem && maxCol <= 8 && !getenv("GOICP_NO_GRID_SMEM") && ((c.smemFloats + 3) & ~(size_t)3) * 4 + S3p * 5 <= 100 * 1024) {
+    const size_t nlutP = ((size_t)3 * (S - 1) * (S - 1) + 2 + 3) & ~(size_t)3;
+    if (c.useSmem && S <= 32 && maxCol <= 8 && !h->dtUploaded && !getenv("GOICP_NO_GRID_SMEM") && ((c.smemFloats + 3) & ~(size_t)3) * 4 + nlutP * 4 + S3p * 3 <= 100 * 1024) {
         c.gridOff = (int)((c.smemFloats + 3) & ~(size_t)3); c.S3p = (int)S3p;
-        c.smemBytes = (size_t)c.gridOff * 4 + S3p * 5;
+        c.smemBytes = (size_t)c.gridOff * 4 + nlutP * 4 + S3p * 3;   // distance table + 16-bit distance codes + colour-mask bytes
         c.useSmem = 2;
     }
-    c.threads = h->bnb_threads;
+    // batches on shared-memory volumes: 192-thread CTAs, four per SM (measured +5 % over 256 x 3; a single registration keeps
+    // the shorter pops of 256-thread CTAs)
+    c.threads = (h->bnb_threads_set || !(c.useSmem == 2 && h->probs.size() > 1)) ? h->bnb_threads : std::min(192, h->bnb_threads);
     c.perSM = goicp_inner_bnb_occupancy(c.smemBytes, h->exact_sums, c.threads, c.useSmem, c.ct);
     return c;
 }
@@ -1382,6 +1392,7 @@ static goicp_status build_dt_impl(goicp_handle h, goicp_dt_info* out, bool repla
     cudaSetDevice(h->device);
     if ((s = prepare_all(h))) return s;
     if ((s = build_dt_all(h, replay))) return s;
+    h->dtUploaded = false;
     if (out) *out = P.info;
     return GOICP_OK;
 }
@@ -1398,7 +1409,7 @@ goicp_status goicp_dt_upload(goicp_handle h, const float* dist, const int32_t* n
     if (!P.dt_built) return fail(h, GOICP_ERR_ARG, "dt_upload before build_dt");
     cudaSetDevice(h->device);
     const int S = P.info.size; const size_t S3 = (size_t)S * S * S;
-    if (dist) CU(cudaMemcpyAsync(P.dev.g.dist, dist, sizeof(float) * S3, cudaMemcpyHostToDevice, h->stream));
+    if (dist) { CU(cudaMemcpyAsync(P.dev.g.dist, dist, sizeof(float) * S3, cudaMemcpyHostToDevice, h->stream)); h->dtUploaded = true; }
     if (nearest_xyz) {
         std::vector<int> vn(S3);
         for (size_t i = 0; i < S3; i++) vn[i] = (nearest_xyz[3 * i + 2] * S + nearest_xyz[3 * i + 1]) * S + nearest_xyz[3 * i];
@@ -1614,7 +1625,7 @@ goicp_status goicp_set_batch_options(goicp_handle h, int32_t groups, int32_t slo
     if (groups >= 0) h->groups = groups;
     if (slots >= 0) h->slots = slots;
     { const char* e = getenv("GOICP_MERGE_CALLS"); if (e) h->merge_calls = atoi(e) != 0; }
-    { const char* e = getenv("GOICP_BNB_THREADS"); if (e) { int t = atoi(e); if (t >= 64 && t <= 256 && t % 32 == 0) h->bnb_threads = t; } }
+    { const char* e = getenv("GOICP_BNB_THREADS"); if (e) { int t = atoi(e); if (t >= 64 && t <= goicp_bnb_default_threads() && t % 32 == 0) { h->bnb_threads = t; h->bnb_threads_set = true; } } }
     return GOICP_OK;
 }
 goicp_status goicp_get_stats(goicp_handle h, double* out16) {

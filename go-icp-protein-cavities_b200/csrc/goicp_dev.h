@@ -26,6 +26,9 @@ struct GridDev {
     int* cell_vox;           // ncells   voxel of each occupied cell, ascending
     uint32_t* cmask;         // ncells+1   bit k set <=> a source point of colour index k is compatible (checkProperty)
     uint32_t* vmask;         // S^3   cmask of the voxel's closest cell (one gather for the incompatibility term)
+    uint16_t* dcode;         // S^3 (padded to 16) squared voxel distance q of each voxel (nlut-1: no seed), or NULL (S > 32);
+    float* dlut;             // nlut  dist as a function of q: the 16-bit form of `dist` that is staged in shared memory
+    int nlut;                // 3 (S-1)^2 + 2
     uint8_t* vmask8;         // S^3 (padded to 16)   low byte of vmask: the form staged in shared memory when a pair has <= 8 colours
     double* ovl;             // GOICP_OVN   (double)sqrtf(s) / scale for a squared voxel overshoot s (DT3D::Distance outside the grid)
     // FP32 fast path of ROUND((v-min)*scale) (dev_common.cuh:vox_fast): t = fma(p, vfScale, C) + magic keeps vfShift

@@ -17,7 +17,13 @@
 
 namespace {
 
-constexpr int BNB_MAX_THREADS = 256;
+#ifndef GOICP_BNB_THREADS
+#define GOICP_BNB_THREADS 256
+#endif
+#ifndef GOICP_BNB_MIN_CTAS
+#define GOICP_BNB_MIN_CTAS 3
+#endif
+constexpr int BNB_MAX_THREADS = GOICP_BNB_THREADS;
 
 // ---- 1-D TMA (cp.async.bulk) global -> shared with mbarrier completion: the S<=~26 DT volume of a call is staged in shared
 //      memory by the copy engine while the CTA rotates the cloud ----------------------------------------------------------------
@@ -50,9 +56,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 // widths.  Keys [0, HK_SMEM) and payload slots [0, HP_SMEM) live in shared memory, the rest in the CTA's global slab.
 // Only lane 0 of warp 0 touches the queue; it follows libstdc++'s push_heap / pop_heap step for step, so ties between equal
 // (lb, w) keys pop in the reference's order.
-constexpr int HK_SMEM = 1024;
-constexpr int HP_SMEM = 256;
-constexpr int HF_SMEM = 256;
+constexpr int HK_SMEM = 512;
+constexpr int HP_SMEM = 128;
+constexpr int HF_SMEM = 128;
 constexpr int MAX_TLEVEL = 64;
 __device__ __forceinline__ bool key_less(const uint2 a, const uint2 b) {
     const float la = __uint_as_float(a.x), lb = __uint_as_float(b.x);
@@ -199,10 +205,11 @@ struct BnbShared {
 // PERSIST=false: the calls are probs[0..nprob), claimed through counter[0] (one launch per wave).
 // PERSIST=true : the kernel stays resident for a whole batch and serves the host's request ring `q` (see QueueDev).
 // GS=true (needs SMEM): the call's DT volume (float distances + one colour-mask byte per voxel) is staged in shared memory by
-// TMA, so the per-point gathers are LDS instead of L1/L2 sector gathers (S^3 * 5 bytes at dynamic-smem offset gridOff).
+// TMA as 16-bit squared-distance codes + a distance table + one colour-mask byte per voxel (S^3 * 3 bytes + the table at
+// dynamic-smem offset gridOff), so the per-point gathers are LDS instead of L1/L2 sector gathers.
 // CT=false: no c-FPFH / neighbour-count corner terms in any pair of the launch (their code and registers drop out).
 template <bool EXACT, bool PERSIST, bool SMEM, bool GS, bool CT>
-__global__ void __launch_bounds__(BNB_MAX_THREADS, 3)
+__global__ void __launch_bounds__(BNB_MAX_THREADS, GOICP_BNB_MIN_CTAS)
 inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, InnerOut* outs,
                  int nprob, int* __restrict__ counter, HeapEnt* __restrict__ heaps, int heapCap,
                  float* gscratch, size_t gstride, int NdP, int NdQ, int useSmem, QueueDev q,
@@ -222,7 +229,7 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
     float* tx = base; float* ty = tx + NdP; float* tz = ty + NdP; float* wgt = tz + NdP; float* mrd = wgt + NdP;
     uint8_t* dprop_s = reinterpret_cast<uint8_t*>(mrd + NdP);   // [NdP] colour index of each data point
     float* part = mrd + NdP + (NdP >> 2);                       // [8][nchunks][2] + [27][nchunks] per-chunk partial sums (tree-sum mode)
-    float* md = part + ((43 * (NdP >> 5) + 3) & ~3);            // [8][NdQ] clamped residuals d of the 8 child cubes (EXACT / trimmed); rows 16-byte aligned
+    float* md = part + (EXACT ? 0 : ((43 * (NdP >> 5) + 3) & ~3));   // [8][NdQ] clamped residuals d of the 8 child cubes (EXACT / trimmed); rows 16-byte aligned
     float* fp = md + 8 * NdQ;                                   // [27][NdQ]  (EXACT with the c-FPFH term)
     Heap heap;
     {
@@ -232,8 +239,8 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
     }
     uint4* memo = memoAll + 2 * (size_t)blockIdx.x * memoCap;
     const int memoShift = 32 - (31 - __clz(memoCap));   // this CTA's corner memo: direct-mapped, 32 B entries, tagged with the call's generation
-    float* sdist = reinterpret_cast<float*>(dyn_smem4) + gridOff;                     // GS: [S3p] DT distances
-    uint8_t* svm = reinterpret_cast<uint8_t*>(sdist + S3p);                          // GS: [S3p] colour mask of the voxel's closest cell
+    // GS: the pair's volume in shared memory as [nlutP] distance table, [S3p] 16-bit squared-distance codes, [S3p] colour-mask bytes
+    float* slut = reinterpret_cast<float*>(dyn_smem4) + gridOff;
     const int chainWarp = nwarps > 1 ? 1 : 0;
     float* icpTile;   // model tile of an ICP request: aliases the staging arrays (the dynamic region holds >= 3*NN_TILE floats)
     if constexpr (SMEM) icpTile = reinterpret_cast<float*>(dyn_smem4); else { __shared__ float s_tile[3 * NN_TILE]; icpTile = s_tile; }
@@ -293,10 +300,14 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
         const PairDev& P = pairs[pr.pair];
         const GridDev& g = P.g;
         const bool gload = GS && gpair != pr.pair;   // (the __syncthreads at the top of the loop ordered the last reads of the old volume)
+        const int nlutP = (g.nlut + 3) & ~3;
+        const uint16_t* scode = reinterpret_cast<const uint16_t*>(slut + nlutP);
+        const uint8_t* svm = reinterpret_cast<const uint8_t*>(scode + S3p);
         if (gload && tid == 0) {
-            mbar_expect_tx(&s_gbar, (unsigned)S3p * 5u);
-            tma_bulk_g2s(sdist, g.dist, (unsigned)S3p * 4u, &s_gbar);
-            tma_bulk_g2s(svm, g.vmask8, (unsigned)S3p, &s_gbar);
+            mbar_expect_tx(&s_gbar, (unsigned)nlutP * 4u + (unsigned)S3p * 3u);
+            tma_bulk_g2s(slut, g.dlut, (unsigned)nlutP * 4u, &s_gbar);
+            tma_bulk_g2s(const_cast<uint16_t*>(scode), g.dcode, (unsigned)S3p * 2u, &s_gbar);
+            tma_bulk_g2s(const_cast<uint8_t*>(svm), g.vmask8, (unsigned)S3p, &s_gbar);
         }
         // per-problem constants in registers (the PairDev lives in global memory)
         const int Nd = P.Nd;
@@ -398,18 +409,18 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
                 for (int k = 0; k < 4; ++k) vox[k] = vox_fast(vf, S, px, py, pz, sh.DX[k & 1], sh.DX[2 + (k >> 1)], dzc);
                 unsigned flags = 0;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) { dres[k] = GS ? sdist[max(vox[k], 0)] : __ldg(g.dist + max(vox[k], 0)); flags |= (vox[k] < 0 ? 1u : 0u) << k; }
+                for (int k = 0; k < 4; ++k) { dres[k] = GS ? slut[scode[max(vox[k], 0)]] : __ldg(g.dist + max(vox[k], 0)); flags |= (vox[k] < 0 ? 1u : 0u) << k; }
                 unsigned any = __reduce_or_sync(GOICP_FULL, flags);
                 while (any) {   // some lane is outside the grid or on a rounding boundary (rare): overshoot table, else the exact form
                     const int k = __ffs(any) - 1; any &= any - 1;
                     if (flags & (1u << k)) {
                         int idx, s2;
                         if (vox_near(vf, S, px, py, pz, sh.DX[k & 1], sh.DX[2 + ((k >> 1) & 1)], dzc, &idx, &s2)) {
-                            const float d0 = GS ? sdist[idx] : __ldg(g.dist + idx);
+                            const float d0 = __ldg(g.dist + idx);
                             const float dn = (s2 == 0) ? d0 : (float)(__ldg(g.ovl + s2) + (double)d0);
                             if (k == 0) dres[0] = dn; else if (k == 1) dres[1] = dn; else if (k == 2) dres[2] = dn; else dres[3] = dn;
                         } else {
-                            const float dn = dt_distance_v<!GS>(S, g.xMin, g.yMin, g.zMin, g.scale, GS ? sdist : g.dist, px + sh.HX[k & 1], py + sh.HX[2 + ((k >> 1) & 1)], pz + hz);
+                            const float dn = dt_distance_v<true>(S, g.xMin, g.yMin, g.zMin, g.scale, g.dist, px + sh.HX[k & 1], py + sh.HX[2 + ((k >> 1) & 1)], pz + hz);
                             if (k == 0) dres[0] = dn; else if (k == 1) dres[1] = dn; else if (k == 2) dres[2] = dn; else dres[3] = dn;
                         }
                     }
@@ -848,8 +859,9 @@ eval_bounds_kernel(const PairDev* __restrict__ pairs, int pair, const float* __r
 }  // namespace
 
 // ---- launchers ---------------------------------------------------------------------------------------------
+int goicp_bnb_default_threads() { return BNB_MAX_THREADS; }
 size_t goicp_bnb_smem_floats(int NdP, int NdQ, bool exact, bool needMd, bool needFp) {
-    const size_t n = (size_t)5 * NdP + (size_t)(NdP >> 2) + (size_t)((43 * (NdP >> 5) + 3) & ~3) + (needMd ? (size_t)8 * NdQ : 0) + (needFp ? (size_t)27 * NdQ : 0);
+    const size_t n = (size_t)5 * NdP + (size_t)(NdP >> 2) + (exact ? 0 : (size_t)((43 * (NdP >> 5) + 3) & ~3)) + (needMd ? (size_t)8 * NdQ : 0) + (needFp ? (size_t)27 * NdQ : 0);
     return n > 3 * 512 ? n : 3 * 512;   // an ICP request tiles the model cloud through the same region (icp_device.cuh NN_TILE)
 }
 

@@ -157,6 +157,7 @@ dt_replay_kernel(PairDev* __restrict__ pairs, int first) {
         }
         if (dist < 0.f) dist = 0.f;
         g.dist[i] = dist;
+        if (g.dcode) { const int xD = a & 255, yD = (a >> 8) & 255, zD = (a >> 16) & 255; g.dcode[i] = (uint16_t)(a == UNSET ? g.nlut - 1 : xD * xD + yD * yD + zD * zD); }
         const int vn = (cz * S + cy) * S + cx;
         g.vnear[i] = vn;
         if (g.vcell) {   // compact id of that cell: binary search in the ascending occupied-voxel list
@@ -237,6 +238,7 @@ dt_sep_z_kernel(const unsigned* __restrict__ nxy, GridDev g) {
         }
         float dist = (bestq == 0x7FFFFFFF) ? (float)((double)32767.f / g.scale) : (float)((double)sqrtf((float)bestq) / g.scale);
         g.dist[i] = dist;
+        if (g.dcode) g.dcode[i] = (uint16_t)(bestq == 0x7FFFFFFF ? g.nlut - 1 : bestq);
         const int vn = (bz * S + by) * S + bx;
         g.vnear[i] = vn;
         if (g.vcell) {

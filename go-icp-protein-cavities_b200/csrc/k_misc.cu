@@ -18,7 +18,9 @@ initialize_kernel(PairDev* __restrict__ pairs, int first) {
         for (int l = 0; l < GOICP_MAXROTLEVEL; ++l) P.maxRotDis[(size_t)l * Nd + i] = P.s2[l] * nrm;   // :205
         P.weights[i] = 1.f;
     }
-    for (int s = tid; s < GOICP_OVN; s += blockDim.x) P.g.ovl[s] = (double)sqrtf((float)s) / P.g.scale;   // jly_3ddt.cpp:1190 for every near overshoot
+    for (int s = tid; s < GOICP_OVN; s += blockDim.x) P.g.ovl[s] = (double)sqrtf((float)s) / P.g.scale;
+    if (P.g.dlut)   // dist as a function of the squared voxel distance (the expressions of k_dt.cu)
+        for (int q = tid; q < P.g.nlut; q += blockDim.x) P.g.dlut[q] = (q == P.g.nlut - 1) ? (float)((double)32767.f / P.g.scale) : (float)((double)sqrtf((float)q) / P.g.scale);   // jly_3ddt.cpp:1190 for every near overshoot
     if (P.ponderation != 1) return;
     if (tid == 0) { s_max = 0; s_min = 100; }
     __syncthreads();

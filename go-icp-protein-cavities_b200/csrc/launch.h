@@ -5,6 +5,7 @@
 #include "goicp_dev.h"
 
 // k_bnb.cu
+int goicp_bnb_default_threads();   // CTA size the kernel is compiled for (launch bounds)
 size_t goicp_bnb_smem_floats(int NdP, int NdQ, bool exact, bool needMd, bool needFp);
 // useSmem: 0 staging arrays in a global scratch slab, 1 in shared memory, 2 shared memory incl. the DT volume (TMA-staged per call)
 int goicp_inner_bnb_occupancy(size_t smemBytes, int exact, int threads, int useSmem, int ct);
