@@ -6,7 +6,7 @@
 namespace {
 
 // One CTA per pair: normData, maxRotDis[20][Nd], weights (neighborsWeights :1453-1498 when ponderation == 1).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 initialize_kernel(PairDev* __restrict__ pairs, int first) {
     const PairDev& P = pairs[first + blockIdx.x];
     const int Nd = P.Nd, tid = threadIdx.x;
@@ -22,32 +22,89 @@ initialize_kernel(PairDev* __restrict__ pairs, int first) {
     if (P.g.dlut)   // dist as a function of the squared voxel distance (the expressions of k_dt.cu)
         for (int q = tid; q < P.g.nlut; q += blockDim.x) P.g.dlut[q] = (q == P.g.nlut - 1) ? (float)((double)32767.f / P.g.scale) : (float)((double)sqrtf((float)q) / P.g.scale);   // jly_3ddt.cpp:1190 for every near overshoot
     if (P.ponderation != 1) return;
-    if (tid == 0) { s_max = 0; s_min = 100; }
+    // neighborsWeights (:1453-1498): the reference re-counts every point's neighbours for radius^2 = 0.035, 0.036, ... until some
+    // point has >= 19.  Here every pair distance is taken once and binned by the first radius step that makes it a neighbour
+    // (NW_STEPS thresholds, the reference's float recurrence); a second pass counts at the final radius.  Same counts.
+    constexpr int NW_STEPS = 64;
+    __shared__ double s_thr[NW_STEPS];
+    __shared__ int s_stepMax[NW_STEPS];
+    __shared__ unsigned short s_hist[256][NW_STEPS + 1];
+    __shared__ int s_kstar;
+    __shared__ float s_dist;
+    if (tid == 0) {
+        s_max = 0; s_min = 100;
+        float distance = 0.035f;
+        for (int k = 0; k < NW_STEPS; ++k) { s_thr[k] = (double)sqrtf(distance); distance = (float)((double)distance + 0.001); }
+        s_dist = distance;   // radius^2 of step NW_STEPS
+    }
+    if (tid < NW_STEPS) s_stepMax[tid] = 0;
+    __syncthreads();
+    const double thrLast = s_thr[NW_STEPS - 1];
+    const double far2 = thrLast * thrLast * 1.000001;   // beyond this squared distance no step makes the pair neighbours
+    for (int i0 = 0; i0 < Nd; i0 += blockDim.x) {
+        const int i = i0 + tid;
+        if (i < Nd) {
+            unsigned short* hrow = s_hist[tid];
+            for (int k = 0; k < NW_STEPS; ++k) hrow[k] = 0;
+            const float xi = P.dx[i], yi = P.dy[i], zi = P.dz[i];
+            for (int j = 0; j < Nd; ++j) {
+                if (j == i) continue;
+                const double a = (double)(P.dx[j] - xi), b = (double)(P.dy[j] - yi), c = (double)(P.dz[j] - zi);   // isNeighbor :1097
+                const double d2 = a * a + b * b + c * c;
+                if (d2 > far2) continue;
+                const double d = sqrt(d2);
+                int k = 0;
+                while (k < NW_STEPS && !(d < s_thr[k])) ++k;
+                if (k < NW_STEPS) hrow[k]++;
+            }
+            int c = 0;
+            for (int k = 0; k < NW_STEPS; ++k) { c += hrow[k]; atomicMax(&s_stepMax[k], c); if (k == 0) atomicMin(&s_min, c); }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) { int k = 0; while (k < NW_STEPS && s_stepMax[k] < 19) ++k; s_kstar = k; if (k < NW_STEPS) s_max = s_stepMax[k]; else s_max = s_stepMax[NW_STEPS - 1]; }
     __syncthreads();
     int* nb = reinterpret_cast<int*>(P.scratch);
-    float distance = 0.035f;
-    for (;;) {   // :1461-1480; maxN / minN run over every radius tried, nb[] keeps the last radius' counts
-        const double thr = (double)sqrtf(distance);
-        int lmax = 0, lmin = 0x7FFFFFFF;
+    if (s_kstar < NW_STEPS) {   // counts at the final radius
+        const double thr = s_thr[s_kstar], lo2 = thr * thr * 0.999999, hi2 = thr * thr * 1.000001;
         for (int i = tid; i < Nd; i += blockDim.x) {
             const float xi = P.dx[i], yi = P.dy[i], zi = P.dz[i];
             int count = 0;
             for (int j = 0; j < Nd; ++j) {
                 if (j == i) continue;
-                const double a = (double)(P.dx[j] - xi), b = (double)(P.dy[j] - yi), c = (double)(P.dz[j] - zi);   // isNeighbor :1097
-                const double d = sqrt(a * a + b * b + c * c);
-                if (d < thr) count++;
+                const double a = (double)(P.dx[j] - xi), b = (double)(P.dy[j] - yi), c = (double)(P.dz[j] - zi);
+                const double d2 = a * a + b * b + c * c;
+                if (d2 < lo2) count++;
+                else if (d2 <= hi2 && sqrt(d2) < thr) count++;
             }
             nb[i] = count;
-            lmax = max(lmax, count); lmin = min(lmin, count);
         }
-        atomicMax(&s_max, lmax); atomicMin(&s_min, lmin);
-        __syncthreads();
-        const int maxN = s_max;
-        __syncthreads();
-        if (maxN >= 19) break;
-        distance = (float)((double)distance + 0.001);
+    } else {   // no point reaches 19 neighbours within NW_STEPS radius steps: go on as the reference does, one radius at a time
+        float distance = s_dist;
+        for (;;) {   // :1461-1480; maxN / minN run over every radius tried, nb[] keeps the last radius' counts
+            const double thr = (double)sqrtf(distance);
+            int lmax = 0, lmin = 0x7FFFFFFF;
+            for (int i = tid; i < Nd; i += blockDim.x) {
+                const float xi = P.dx[i], yi = P.dy[i], zi = P.dz[i];
+                int count = 0;
+                for (int j = 0; j < Nd; ++j) {
+                    if (j == i) continue;
+                    const double a = (double)(P.dx[j] - xi), b = (double)(P.dy[j] - yi), c = (double)(P.dz[j] - zi);   // isNeighbor :1097
+                    const double d = sqrt(a * a + b * b + c * c);
+                    if (d < thr) count++;
+                }
+                nb[i] = count;
+                lmax = max(lmax, count); lmin = min(lmin, count);
+            }
+            atomicMax(&s_max, lmax); atomicMin(&s_min, lmin);
+            __syncthreads();
+            const int maxN = s_max;
+            __syncthreads();
+            if (maxN >= 19) break;
+            distance = (float)((double)distance + 0.001);
+        }
     }
+    __syncthreads();
     int minN = s_min;
     if (minN == 0) minN = 1;
     for (int i = tid; i < Nd; i += blockDim.x) {
