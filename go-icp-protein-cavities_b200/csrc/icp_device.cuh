@@ -259,7 +259,10 @@ __device__ __forceinline__ void icp_fused_body(const PairDev* __restrict__ pairs
     __shared__ IcpState st;
     const int tid = threadIdx.x, nthr = blockDim.x;
     __syncthreads();
-    if (tid == 0) st = *gstate;
+    // the request lives in mapped host memory and the same address is reused by every ICP request of the pair: read it with
+    // volatile loads, a plain load may be served from an L1 line this SM kept from the pair's previous request
+    { const volatile unsigned* src = reinterpret_cast<const volatile unsigned*>(gstate); unsigned* dst = reinterpret_cast<unsigned*>(&st);
+      for (int k = tid; k < (int)(sizeof(IcpState) / 4); k += nthr) dst[k] = src[k]; }
     __syncthreads();
     const PairDev& P = pairs[st.pair];
     const int Nd = P.Nd, Nm = P.Nm;

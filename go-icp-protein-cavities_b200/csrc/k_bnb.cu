@@ -12,6 +12,7 @@
 //
 // The translation priority queue lives in global memory (one slab per CTA) and follows libstdc++'s
 // push_heap/pop_heap step for step so that ties between equal (lb, w) keys pop in the reference's order.
+#include <cstdlib>
 #include "icp_device.cuh"
 #include "launch.h"
 
@@ -299,7 +300,7 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
         }
         const PairDev& P = pairs[pr.pair];
         const GridDev& g = P.g;
-        const bool gload = GS && gpair != pr.pair;   // (the __syncthreads at the top of the loop ordered the last reads of the old volume)
+        const bool gload = GS && (gpair != pr.pair || (useSmem & 16));   // bit 4 of useSmem: debugging switch, restage for every request   // (the __syncthreads at the top of the loop ordered the last reads of the old volume)
         const int nlutP = (g.nlut + 3) & ~3;
         const uint16_t* scode = reinterpret_cast<const uint16_t*>(slut + nlutP);
         const uint8_t* svm = reinterpret_cast<const uint8_t*>(scode + S3p);
@@ -910,7 +911,8 @@ cudaError_t goicp_launch_inner_bnb_persistent(const PairDev* pairs, const QueueD
     const size_t smem = useSmem ? smemBytes : 0;
     cudaError_t e = bnb_attr(exact, 1, useSmem, ct);
     if (e != cudaSuccess) return e;
-    bnb_kernel(exact, 1, useSmem, ct)<<<ctas, threads, smem, st>>>(pairs, nullptr, nullptr, 0, nullptr, heaps, heapCap, gscratch, gstride, NdP, NdQ, useSmem, q, (uint4*)memo, memoCap, genCounter, gridOff, S3p);
+    static const int restage = getenv("GOICP_NO_GPAIR") ? 16 : 0;
+    bnb_kernel(exact, 1, useSmem, ct)<<<ctas, threads, smem, st>>>(pairs, nullptr, nullptr, 0, nullptr, heaps, heapCap, gscratch, gstride, NdP, NdQ, useSmem | restage, q, (uint4*)memo, memoCap, genCounter, gridOff, S3p);
     return cudaGetLastError();
 }
 

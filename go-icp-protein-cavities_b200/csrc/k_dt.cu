@@ -24,8 +24,8 @@ namespace {
 // ------------------------------------------------------------------------------------------------------------------
 // mask tables (jly_3ddt.cpp:57-712), in the reference's evaluation order
 enum { ZM = 1, ZP = 2, YM = 4, YP = 8, XM = 16, XP = 32 };
-struct MaskE { int cond; int dz, dy, dx; unsigned inc; };   // inc = iv | ih<<8 | id<<16  (v = x-offset, h = y, d = z)
-#define INC(v, h, d) ((unsigned)(v) | ((unsigned)(h) << 8) | ((unsigned)(d) << 16))
+struct MaskE { int cond; int dz, dy, dx; unsigned inc; };   // inc = iv | ih<<5 | id<<10  (v = x-offset, h = y, d = z; S <= 32: 5 bits each,
+#define INC(v, h, d) ((unsigned)(v) | ((unsigned)(h) << 5) | ((unsigned)(d) << 10))   // so a voxel is 16 bits in shared memory)
 __constant__ MaskE M_FWD1[14] = {   // MINforwardDE1 :508-712
     {ZM | YM | XM, -1, -1, -1, INC(1, 1, 1)}, {YM | XM, 0, -1, -1, INC(1, 1, 0)}, {ZP | YM | XM, 1, -1, -1, INC(1, 1, 1)},
     {ZM | XM, -1, 0, -1, INC(1, 0, 1)},       {XM, 0, 0, -1, INC(1, 0, 0)},       {XM | ZP, 1, 0, -1, INC(1, 0, 1)},
@@ -46,14 +46,15 @@ __constant__ MaskE M_BWD3[5] = {   // MINbackwardDE3 :177-258
     {ZM | YM, -1, -1, 0, INC(0, 1, 1)}, {YM, 0, -1, 0, INC(0, 1, 0)}, {ZP | YM, 1, -1, 0, INC(0, 1, 1)}, {0, 0, 0, 0, INC(0, 0, 0)}, {ZM, -1, 0, 0, INC(0, 0, 1)}};
 
 constexpr unsigned UNSET = 0xFFFFFFFFu;   // DEucl3D {infty,infty,infty,infty}
-__device__ __forceinline__ int qof(unsigned a) { int v = a & 255, h = (a >> 8) & 255, d = (a >> 16) & 255; return v * v + h * h + d * d; }
+__device__ __forceinline__ int qof(unsigned a) { int v = a & 31, h = (a >> 5) & 31, d = (a >> 10) & 31; return v * v + h * h + d * d; }
+__device__ __forceinline__ unsigned ldA(const unsigned short* A, int i) { const unsigned u = A[i]; return u == 0xFFFFu ? UNSET : u; }
 // `if (mask[k].distance < min.distance) min = mask[k]` with NaN (unset source) never selected
 __device__ __forceinline__ void take_if_less(unsigned& best, unsigned cand) {
     if (cand != UNSET && (best == UNSET || qof(cand) < qof(best))) best = cand;
 }
 
 // one z-sweep of column (y, x): table T[0..n), in-column entries [ic0, ic1), zdir = +1 ascending / -1 descending
-__device__ __forceinline__ void sweep_column(unsigned* A, int S, int x, int y, const MaskE* T, int n, int ic0, int ic1, int zdir, int lane) {
+__device__ __forceinline__ void sweep_column(unsigned short* A, int S, int x, int y, const MaskE* T, int n, int ic0, int ic1, int zdir, int lane) {
     const int z = lane;
     const bool act = z < S;
     const int have = (z > 0 ? ZM : 0) | (z < S - 1 ? ZP : 0) | (y > 0 ? YM : 0) | (y < S - 1 ? YP : 0) | (x > 0 ? XM : 0) | (x < S - 1 ? XP : 0);
@@ -62,13 +63,13 @@ __device__ __forceinline__ void sweep_column(unsigned* A, int S, int x, int y, c
         for (int k = 0; k < ic0; ++k) {
             const MaskE m = T[k];
             if ((m.cond & have) != m.cond) continue;
-            const unsigned s = A[((x + m.dx) * S + (y + m.dy)) * S + (z + m.dz)];
+            const unsigned s = ldA(A, ((x + m.dx) * S + (y + m.dy)) * S + (z + m.dz));
             take_if_less(pre, s == UNSET ? UNSET : s + m.inc);
         }
         for (int k = ic1; k < n; ++k) {
             const MaskE m = T[k];
             if ((m.cond & have) != m.cond) continue;
-            const unsigned s = A[((x + m.dx) * S + (y + m.dy)) * S + (z + m.dz)];
+            const unsigned s = ldA(A, ((x + m.dx) * S + (y + m.dy)) * S + (z + m.dz));
             take_if_less(post, s == UNSET ? UNSET : s + m.inc);
         }
     }
@@ -88,22 +89,22 @@ __device__ __forceinline__ void sweep_column(unsigned* A, int S, int x, int y, c
         }
     }
     __syncwarp();
-    if (act) A[(x * S + y) * S + z] = res;
+    if (act) A[(x * S + y) * S + z] = (unsigned short)res;   // UNSET -> 0xFFFF
     __syncwarp();
 }
 
 __global__ void __launch_bounds__(32)
 dt_replay_kernel(PairDev* __restrict__ pairs, int first) {
-    extern __shared__ unsigned A[];   // [x][y][z]
+    extern __shared__ unsigned short A[];   // [x][y][z]
     const GridDev g = pairs[first + blockIdx.x].g;
     const int S = g.S, lane = threadIdx.x;
     const int S3 = S * S * S;
-    for (int i = lane; i < S3; i += 32) A[i] = UNSET;
+    for (int i = lane; i < S3; i += 32) A[i] = 0xFFFFu;
     __syncwarp();
     for (int c = lane; c < g.ncells; c += 32) {   // seeds :991-994
         const int v = g.cell_vox[c];
         const int x = v % S, y = (v / S) % S, z = v / (S * S);
-        A[(x * S + y) * S + z] = 0u;
+        A[(x * S + y) * S + z] = 0;
     }
     __syncwarp();
     // DEuclidean :716-750
@@ -130,12 +131,12 @@ dt_replay_kernel(PairDev* __restrict__ pairs, int first) {
     // distances and emptyCells :999-1136
     for (int i = lane; i < S3; i += 32) {
         const int x = i % S, y = (i / S) % S, z = i / (S * S);
-        const unsigned a = A[(x * S + y) * S + z];
+        const unsigned a = ldA(A, (x * S + y) * S + z);
         float dist;
         int cx = x, cy = y, cz = z;
         if (a == UNSET) dist = (float)((double)32767.f / g.scale);
         else {
-            const int xD = a & 255, yD = (a >> 8) & 255, zD = (a >> 16) & 255;
+            const int xD = a & 31, yD = (a >> 5) & 31, zD = (a >> 10) & 31;
             dist = (float)((double)sqrtf((float)(xD * xD + yD * yD + zD * zD)) / g.scale);
             if (dist != 0.f) {
                 // sign combinations in the reference's order (+ before -); a zero offset collapses the list
@@ -157,7 +158,7 @@ dt_replay_kernel(PairDev* __restrict__ pairs, int first) {
         }
         if (dist < 0.f) dist = 0.f;
         g.dist[i] = dist;
-        if (g.dcode) { const int xD = a & 255, yD = (a >> 8) & 255, zD = (a >> 16) & 255; g.dcode[i] = (uint16_t)(a == UNSET ? g.nlut - 1 : xD * xD + yD * yD + zD * zD); }
+        if (g.dcode) { const int xD = a & 31, yD = (a >> 5) & 31, zD = (a >> 10) & 31; g.dcode[i] = (uint16_t)(a == UNSET ? g.nlut - 1 : xD * xD + yD * yD + zD * zD); }
         const int vn = (cz * S + cy) * S + cx;
         g.vnear[i] = vn;
         if (g.vcell) {   // compact id of that cell: binary search in the ascending occupied-voxel list
@@ -275,9 +276,9 @@ __global__ void dt_distance_kernel(const PairDev* __restrict__ pairs, int pair, 
 
 cudaError_t goicp_launch_dt_replay(PairDev* pairs, int first, int count, int S, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
-    const size_t smem = (size_t)S * S * S * sizeof(unsigned);
+    const size_t smem = (size_t)S * S * S * sizeof(unsigned short);
     static bool attr = false;
-    if (!attr) { cudaError_t e = cudaFuncSetAttribute(dt_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 32 * 32 * 4); if (e != cudaSuccess) return e; attr = true; }
+    if (!attr) { cudaError_t e = cudaFuncSetAttribute(dt_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 32 * 32 * 2); if (e != cudaSuccess) return e; attr = true; }
     dt_replay_kernel<<<count, 32, smem, st>>>(pairs, first);
     return cudaGetLastError();
 }
