@@ -79,11 +79,11 @@ def test_initialize_bit_exact(g, po, name):
     assert reg.thresholds() == (o.ssethresh(), o.inliernum())
 
 
-@pytest.mark.parametrize("fp", [False, True, "nb"])
+@pytest.mark.parametrize("fp", [False, True, "nb", "l1"])
 def test_leaf_bounds(g, po, fp):
     """every rotation cube x translation sub-cube x point bound in one launch: (ub, lb) within 1e-5, corner
     incompatibility counts and truncated c-FPFH means (point-inclusion counts) bit-exact"""
-    kw = dict(regularizationNeighbors=0.00001) if fp == "nb" else dict(cfpfh=1, regularizationFPFH=0.000005) if fp else {}
+    kw = dict(regularizationNeighbors=0.00001) if fp == "nb" else dict(norm=1) if fp == "l1" else dict(cfpfh=1, regularizationFPFH=0.000005) if fp else {}
     z, reg, o = _pair(g, po, "pair1", **kw)
     reg.BuildDT(); o.build_dt(); reg.set_nd(int(z["nd"])); o.set_nd(int(z["nd"])); reg.Initialize(); o.initialize()
     rng = np.random.default_rng(2)
@@ -113,11 +113,11 @@ def test_leaf_bounds_multi_rotation_wave(g, po):
         assert np.array_equal(inc[sel], oinc)
 
 
-@pytest.mark.parametrize("name,fp", [("pair1", False), ("pair1", True), ("pair2", False), ("pair1", "nb")])
+@pytest.mark.parametrize("name,fp", [("pair1", False), ("pair1", True), ("pair2", False), ("pair1", "nb"), ("pair1", "l1")])
 def test_inner_bnb(g, po, name, fp):
     """GoICP::InnerBnB calls as OuterBnB makes them: exact-sum mode is bit-identical (value, best node, pop count);
     tree-sum mode within 1e-5"""
-    kw = dict(regularizationNeighbors=0.00001) if fp == "nb" else dict(cfpfh=1, regularizationFPFH=0.000005) if fp else {}
+    kw = dict(regularizationNeighbors=0.00001) if fp == "nb" else dict(norm=1) if fp == "l1" else dict(cfpfh=1, regularizationFPFH=0.000005) if fp else {}
     z, reg, o = _pair(g, po, name, **kw)
     reg.BuildDT(); o.build_dt(); reg.set_nd(int(z["nd"])); o.set_nd(int(z["nd"])); reg.Initialize(); o.initialize()
     rng = np.random.default_rng(4)
@@ -194,6 +194,20 @@ def test_resident_icp_requests_fresh(g):
             reg.set_options(exact_sums=exact)
             r = reg.Register()
             assert abs(r["optError"] - float(z["exp_optError"])) <= REL * float(z["exp_optError"]), (rep, exact, r["optError"], r["trace"])
+
+
+def test_register_l1_norm(g, po):
+    """norm=1 (jly_goicp.cpp:129-130,398-399,411-412,620-621): full Register against the CPU restatement on pair 1 -- optimum,
+    compatibilities, node counters and improvement trace identical in exact-sum mode"""
+    z = golden("pair1")
+    reg = g.GoICP(z["model_xyz"], z["data_xyz"], g.shipped_config(norm=1), **pair_clouds(z))
+    o = po.Oracle("port", z["model_xyz"], z["data_xyz"], po.shipped_config(norm=1), **pair_clouds(z))
+    reg.BuildDT(); o.build_dt(); reg.set_nd(int(z["nd"]))
+    r = reg.Register(); ro = o.register(int(z["nd"]))
+    assert r["optError"] == ro["optError"] and r["optComp"] == ro["optComp"]
+    assert np.abs(r["R"] - ro["R"]).max() < 1e-9 and np.abs(r["t"] - ro["t"]).max() < 1e-9
+    assert r["counters"][:6] == ro["counters"][:6]
+    assert g.error_trace(r["trace"]) == po.error_trace(ro["trace"])
 
 
 def test_register_rand_trim(g):
