@@ -813,11 +813,19 @@ static void gather_requests(Eng* h, int pi, std::vector<InnerProb>& reqs, std::v
         memcpy(ip.R, R, sizeof ip.R);
         reqs.push_back(ip); tags.push_back(ReqTag{pi, key, P.optError, false});
     };
+    // a call that is cached under the current incumbent or already in flight needs no request (and no rotation matrix)
+    auto known = [&](const RNode& par, int j, int kind) {
+        const unsigned long long key = call_key(par.id, j, kind);
+        auto it = P.cache.find(key);
+        return (it != P.cache.end() && it->second.entryOpt == P.optError) || P.inflight.count(key) != 0;
+    };
     // current parent, from the blocking call on
     for (int j = P.j; j < 8; j++) {
+        const bool skipUb = j == P.j && P.phase == PH_CHILD_LB;
+        if ((skipUb || known(P.par, j, 0)) && known(P.par, j, 1)) continue;
         RNode ch = child_of(P.par, j); float R[9];
         if (!child_rotation(ch, R)) continue;
-        if (!(j == P.j && P.phase == PH_CHILD_LB)) want(P.par, j, 0, ch, R);
+        if (!skipUb) want(P.par, j, 0, ch, R);
         want(P.par, j, 1, ch, R);
     }
     // the next queue nodes in pop order; width grows while the incumbent stays unchanged
@@ -827,15 +835,23 @@ static void gather_requests(Eng* h, int pi, std::vector<InnerProb>& reqs, std::v
     const int specw = (h->probs.size() > 1 && !tail) ? std::min(h->spec_width, h->batch_spec_width) : h->spec_width;
     int width = std::min(specw, P.quiet < 30 ? (1 << std::min(P.quiet, 20)) - 1 : specw);
     if (width > 0 && !P.q.empty()) {
-        std::vector<RNode> top(P.q);
-        const int k = std::min<int>(width, (int)top.size());
-        std::partial_sort(top.begin(), top.begin() + k, top.end(), [](const RNode& a, const RNode& b) { return rnode_less(b, a); });
-        for (int i = 0; i < k; i++) {
-            if ((P.optError - top[i].lb) <= SSE) break;
+        // the `width` best nodes of the rotation queue: P.q is a binary heap, so they are reached from the root through a
+        // frontier of candidate positions (no copy, no sort of the whole queue)
+        const int n = (int)P.q.size(), k = std::min(width, n);
+        int cand[80]; int nc = 0; cand[nc++] = 0;
+        for (int i = 0; i < k && nc > 0; i++) {
+            int b = 0;
+            for (int c = 1; c < nc; c++) if (rnode_less(P.q[cand[b]], P.q[cand[c]])) b = c;
+            const int pos = cand[b]; cand[b] = cand[--nc];
+            if (2 * pos + 1 < n && nc < 78) cand[nc++] = 2 * pos + 1;
+            if (2 * pos + 2 < n && nc < 78) cand[nc++] = 2 * pos + 2;
+            const RNode& nd = P.q[pos];
+            if ((P.optError - nd.lb) <= SSE) break;
             for (int j = 0; j < 8; j++) {
-                RNode ch = child_of(top[i], j); float R[9];
+                if (known(nd, j, 0) && known(nd, j, 1)) continue;
+                RNode ch = child_of(nd, j); float R[9];
                 if (!child_rotation(ch, R)) continue;
-                want(top[i], j, 0, ch, R); want(top[i], j, 1, ch, R);
+                want(nd, j, 0, ch, R); want(nd, j, 1, ch, R);
             }
         }
     }
@@ -1624,6 +1640,7 @@ goicp_status goicp_set_batch_options(goicp_handle h, int32_t groups, int32_t slo
     if (!h) return GOICP_ERR_ARG;
     if (groups >= 0) h->groups = groups;
     if (slots >= 0) h->slots = slots;
+    { const char* e = getenv("GOICP_BATCH_SPEC"); if (e && atoi(e) >= 0) h->batch_spec_width = atoi(e); }
     { const char* e = getenv("GOICP_MERGE_CALLS"); if (e) h->merge_calls = atoi(e) != 0; }
     { const char* e = getenv("GOICP_BNB_THREADS"); if (e) { int t = atoi(e); if (t >= 64 && t <= goicp_bnb_default_threads() && t % 32 == 0) { h->bnb_threads = t; h->bnb_threads_set = true; } } }
     return GOICP_OK;
