@@ -551,28 +551,30 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
                     const float px = valid ? tx[i] : 0.f, py = valid ? ty[i] : 0.f, pz = valid ? tz[i] : 0.f;
                     const unsigned dp = valid ? dprop_s[i] : 0u;
                     for (int gq = g0; gq < g1; ++gq) {
-                        if (!use_fpfh && !use_nb) {   // incompatibility counts only: four independent chains, one packed warp reduction
-                            int vox[4];
-                            unsigned flags = 0;
+                        // four missed corners per step as independent chains: voxel of the point at each corner ...
+                        int vox[4];
+                        unsigned flags = 0;
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
+                        for (int k = 0; k < 4; ++k) {
+                            const int m = min(gq * 4 + k, nmiss - 1);
+                            vox[k] = vox_fast(vf, S, px, py, pz, sh.mC[m], sh.mC[27 + m], sh.mC[54 + m]);
+                            flags |= (vox[k] < 0 ? 1u : 0u) << k;
+                        }
+                        unsigned any = __reduce_or_sync(GOICP_FULL, flags);
+                        while (any) {   // clamped INTO the grid (checkCompatibility :976-984): near table, else the exact form
+                            const int k = __ffs(any) - 1; any &= any - 1;
+                            if (flags & (1u << k)) {
                                 const int m = min(gq * 4 + k, nmiss - 1);
-                                vox[k] = vox_fast(vf, S, px, py, pz, sh.mC[m], sh.mC[27 + m], sh.mC[54 + m]);
-                                flags |= (vox[k] < 0 ? 1u : 0u) << k;
+                                const int c = sh.missList[m];
+                                const int cz_ = c / 9, cy_ = (c - 9 * cz_) / 3, cx_ = c - 9 * cz_ - 3 * cy_;
+                                int idx, s2;
+                                if (!vox_near(vf, S, px, py, pz, sh.mC[m], sh.mC[27 + m], sh.mC[54 + m], &idx, &s2))
+                                    idx = clamp_vox_v(S, g.xMin, g.yMin, g.zMin, g.scale, px + sh.X[cx_], py + sh.X[3 + cy_], pz + sh.X[6 + cz_]);
+                                if (k == 0) vox[0] = idx; else if (k == 1) vox[1] = idx; else if (k == 2) vox[2] = idx; else vox[3] = idx;
                             }
-                            unsigned any = __reduce_or_sync(GOICP_FULL, flags);
-                            while (any) {   // clamped INTO the grid (checkCompatibility :976-984): near table, else the exact form
-                                const int k = __ffs(any) - 1; any &= any - 1;
-                                if (flags & (1u << k)) {
-                                    const int m = min(gq * 4 + k, nmiss - 1);
-                                    const int c = sh.missList[m];
-                                    const int cz_ = c / 9, cy_ = (c - 9 * cz_) / 3, cx_ = c - 9 * cz_ - 3 * cy_;
-                                    int idx, s2;
-                                    if (!vox_near(vf, S, px, py, pz, sh.mC[m], sh.mC[27 + m], sh.mC[54 + m], &idx, &s2))
-                                        idx = clamp_vox_v(S, g.xMin, g.yMin, g.zMin, g.scale, px + sh.X[cx_], py + sh.X[3 + cy_], pz + sh.X[6 + cz_]);
-                                    if (k == 0) vox[0] = idx; else if (k == 1) vox[1] = idx; else if (k == 2) vox[2] = idx; else vox[3] = idx;
-                                }
-                            }
+                        }
+                        // ... incompatibility counts (:919-928): one packed warp reduction for the four corners
+                        if (use_reg) {
                             unsigned packed = 0;
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
@@ -584,29 +586,34 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
                                 const unsigned bad = (packed >> (8 * lane)) & 0xFFu;
                                 if (bad) smem_red_add(&sh.cntM[gq * 4 + lane], (int)bad);
                             }
-                        } else {
-                            for (int k = 0; k < 4; ++k) {
-                                const int m = gq * 4 + k;
-                                if (m >= nmiss) break;
-                                const int c = sh.missList[m];
-                                const int cz_ = c / 9, cy_ = (c - 9 * cz_) / 3, cx_ = c - 9 * cz_ - 3 * cy_;
-                                int vox = vox_fast(vf, S, px, py, pz, sh.mC[m], sh.mC[27 + m], sh.mC[54 + m]);
-                                if (vox < 0) vox = clamp_vox_v(S, g.xMin, g.yMin, g.zMin, g.scale, px + sh.X[cx_], py + sh.X[3 + cy_], pz + sh.X[6 + cz_]);
-                                const int cell = __ldg(g.vcell + vox);
-                                if (use_fpfh) {
-                                    const float fv = valid ? __ldg(P.fpfhD + (size_t)i * ncp1 + cell) : 0.f;
-                                    if (EXACT) { if (valid) fp[m * NdQ + i] = fv; }
-                                    else { const float fs = warp_sum(fv); if (lane == 0) part[16 * nchunks + m * nchunks + ch] = fs; }
+                        }
+                        if (use_fpfh || use_nb) {   // (CT) terms that need the closest cell itself
+                            int cell[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) cell[k] = __ldg(g.vcell + vox[k]);
+                            if (use_fpfh) {   // sumFPFH :1689: per point the min descriptor distance to the cell, tabulated per pair
+                                float fv[4];
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) fv[k] = valid ? __ldg(P.fpfhD + (size_t)i * ncp1 + cell[k]) : 0.f;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const int m = gq * 4 + k;
+                                    if (m < nmiss) {
+                                        if (EXACT) { if (valid) fp[m * NdQ + i] = fv[k]; }
+                                        else { const float fs = warp_sum(fv[k]); if (lane == 0) part[16 * nchunks + m * nchunks + ch] = fs; }
+                                    }
                                 }
-                                if (use_nb) {   // nearestNeighbor inside the closest cell + compareNeighbors (:1200-1211, :1250-1288)
-                                    int dn = valid ? nb_diff(P, cell, i, px + sh.X[cx_], py + sh.X[3 + cy_], pz + sh.X[6 + cz_]) : 0;
+                            }
+                            if (use_nb) {   // nearestNeighbor inside the closest cell + compareNeighbors (:1200-1211, :1250-1288)
+                                for (int k = 0; k < 4; ++k) {
+                                    const int m = gq * 4 + k;
+                                    if (m >= nmiss) break;
+                                    const int c = sh.missList[m];
+                                    const int cz_ = c / 9, cy_ = (c - 9 * cz_) / 3, cx_ = c - 9 * cz_ - 3 * cy_;
+                                    const int cl = k == 0 ? cell[0] : k == 1 ? cell[1] : k == 2 ? cell[2] : cell[3];
+                                    int dn = valid ? nb_diff(P, cl, i, px + sh.X[cx_], py + sh.X[3 + cy_], pz + sh.X[6 + cz_]) : 0;
                                     dn = warp_sum_i(dn);
                                     if (lane == 0 && dn) smem_red_add(&sh.cntNM[m], dn);
-                                }
-                                if (use_reg) {
-                                    int bad = ((__ldg(g.cmask + cell) >> dp) & 1u) ? 0 : 1;
-                                    bad = warp_sum_i(valid ? bad : 0);
-                                    if (lane == 0 && bad) smem_red_add(&sh.cntM[m], bad);
                                 }
                             }
                         }
@@ -620,7 +627,13 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
             if (warp == 1 && use_fpfh) {   // c-FPFH sums of the missed corners, one chain per lane
                 if (lane < sh.nmiss) {
                     float s_ = 0.f;
-                    if (EXACT) { const float* f = fp + lane * NdQ; for (int i = 0; i < Nd; ++i) s_ = s_ + f[i]; }   // sumFPFH :1692-1695
+                    if (EXACT) {   // sumFPFH :1692-1695, sequential in index order
+                        const float* f = fp + lane * NdQ; const float4* f4 = reinterpret_cast<const float4*>(f);
+                        const int n4 = Nd >> 2;
+                        float4 cur = f4[0];
+                        for (int k = 0; k < n4; ++k) { const float4 nxt = f4[k + 1]; s_ = s_ + cur.x; s_ = s_ + cur.y; s_ = s_ + cur.z; s_ = s_ + cur.w; cur = nxt; }
+                        for (int i = n4 * 4; i < Nd; ++i) s_ = s_ + f[i];
+                    }
                     else { const float* f = part + 16 * nchunks + lane * nchunks; for (int k = 0; k < nchunks; ++k) s_ = s_ + f[k]; }
                     sh.cf[sh.missList[lane]] = (float)(int)(s_ / (float)Nd);          // :1696, int truncation :468,:495 (H7)
                 }
