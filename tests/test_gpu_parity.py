@@ -210,6 +210,20 @@ def test_register_l1_norm(g, po):
     assert g.error_trace(r["trace"]) == po.error_trace(ro["trace"])
 
 
+@pytest.mark.parametrize("env", ["GOICP_NO_GRID_SMEM", "GOICP_NO_VOXFAST", "GOICP_MERGE_CALLS=0", "GOICP_PERSISTENT=0"])
+def test_alternative_paths_same_result(g, monkeypatch, env):
+    """the fall-back paths (volume gathered from global memory: > 8 colours or large grids; exact FP64 voxel index only; one
+    request per InnerBnB call; wave scheduler) give the reference's optimum, counters and trace too"""
+    k, _, v = env.partition("=")
+    monkeypatch.setenv(k, v or "1")
+    z = golden("pair1")
+    reg = g.GoICP(z["model_xyz"], z["data_xyz"], g.shipped_config(), **pair_clouds(z))
+    reg.BuildDT(); reg.set_nd(int(z["nd"]))
+    r = reg.Register()
+    assert r["optError"] == float(z["exp_optError"]) and r["counters"][:6] == z["exp_counters"][:6].tolist()
+    assert g.error_trace(r["trace"]) == list(z["exp_trace"])
+
+
 def test_register_rand_trim(g):
     """trimFraction 0.1: the radix select replaces intro_select; same certified optimum (tolerance: sum order)"""
     z = golden("rand")
