@@ -378,6 +378,12 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
                                   sh.HX[2 * a + k] = t; sh.DX[2 * a + k] = vox_fast_c(g.vfMagic, t, a == 0 ? g.xMin : a == 1 ? g.yMin : g.zMin, g.scale); }
         }
         uint4 me0 = make_uint4(0u, 0u, 0u, 0u), me1 = make_uint4(0u, 0u, 0u, 0u);   // warp 0, lanes 0..26: this pop's memo look-ups (gen 0 never matches)
+        if (cpart == 1 && corners && warp == 0 && lane < 27 && sh.running) {   // the root lattice was evaluated by the upper-bound call
+            const int cz_ = lane / 9, cy_ = (lane - 9 * cz_) / 3, cx_ = lane - 9 * cz_ - 3 * cy_;
+            const unsigned hsh = memo_hash(__float_as_uint(sh.X[cx_]), __float_as_uint(sh.X[3 + cy_]), __float_as_uint(sh.X[6 + cz_]));
+            const uint4* e = memo + 2 * (size_t)memo_slot(hsh, memoShift);
+            me0 = e[0]; me1 = e[1];
+        }
         // search state of the call, warp-uniform registers of warp 0 (the only warp that runs phase C)
         float optT = pr.optError;                                                    // :297
         int heapN = 0, freeTop = 0, bump = 0, sh_pops = 1, sh_subcubes = 0;
