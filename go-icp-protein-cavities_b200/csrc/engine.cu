@@ -237,7 +237,7 @@ struct goicp_handle_s {
     goicp_params params; bool haveParams = false;
     int exact_sums = 1, spec_width = 32, use_dt_replay = 1;
     int groups = 0, slots = 0;   // 0 = auto
-    int residentCtas = 0; bool tail_spec = true;   // CTAs of the running resident kernel (0: none)
+    int residentCtas = 0; bool tail_spec = true; int tail_spec_mult = 1, tail_thr = 1;   // CTAs of the running resident kernel (0: none)
     int batch_spec_width = 4;    // speculation width inside a batch (pairs already fill the GPU)
     bool dtUploaded = false;   // the DT came from goicp_dt_upload (test hook): no 16-bit distance codes
     bool merge_calls = true;   // resident scheduler: one request per rotation cube carries its upper- and lower-bound InnerBnB calls
@@ -831,8 +831,8 @@ static void gather_requests(Eng* h, int pi, std::vector<InnerProb>& reqs, std::v
     // the next queue nodes in pop order; width grows while the incumbent stays unchanged
     // inside a batch the pairs themselves fill the GPU; in its tail (fewer requests in flight than the resident kernel has
     // CTAs) the remaining deep pairs speculate as widely as a single registration does
-    const bool tail = h->tail_spec && h->residentCtas > 0 && h->outstanding.load(std::memory_order_relaxed) < h->residentCtas;
-    const int specw = (h->probs.size() > 1 && !tail) ? std::min(h->spec_width, h->batch_spec_width) : h->spec_width;
+    const bool tail = h->tail_spec && h->residentCtas > 0 && h->outstanding.load(std::memory_order_relaxed) < h->tail_thr * h->residentCtas;
+    const int specw = (h->probs.size() > 1 && !tail) ? std::min(h->spec_width, h->batch_spec_width) : (tail ? h->tail_spec_mult * h->spec_width : h->spec_width);
     int width = std::min(specw, P.quiet < 30 ? (1 << std::min(P.quiet, 20)) - 1 : specw);
     if (width > 0 && !P.q.empty()) {
         // the `width` best nodes of the rotation queue: P.q is a binary heap, so they are reached from the root through a
@@ -1640,6 +1640,8 @@ goicp_status goicp_set_batch_options(goicp_handle h, int32_t groups, int32_t slo
     if (!h) return GOICP_ERR_ARG;
     if (groups >= 0) h->groups = groups;
     if (slots >= 0) h->slots = slots;
+    { const char* e = getenv("GOICP_TAIL_MULT"); if (e && atoi(e) >= 1) h->tail_spec_mult = std::min(2, atoi(e)); }
+    { const char* e = getenv("GOICP_TAIL_THR"); if (e && atoi(e) >= 1) h->tail_thr = atoi(e); }
     { const char* e = getenv("GOICP_BATCH_SPEC"); if (e && atoi(e) >= 0) h->batch_spec_width = atoi(e); }
     { const char* e = getenv("GOICP_MERGE_CALLS"); if (e) h->merge_calls = atoi(e) != 0; }
     { const char* e = getenv("GOICP_BNB_THREADS"); if (e) { int t = atoi(e); if (t >= 64 && t <= goicp_bnb_default_threads() && t % 32 == 0) { h->bnb_threads = t; h->bnb_threads_set = true; } } }
