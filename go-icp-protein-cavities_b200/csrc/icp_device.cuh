@@ -269,7 +269,9 @@ __device__ __forceinline__ void icp_fused_body(const PairDev* __restrict__ pairs
     float* sx = tile; float* sy = tile + NN_TILE; float* sz = tile + 2 * NN_TILE;
     icp_begin_part(P, st);
     __syncthreads();
-    if (st.mode == 2) { if (tid == 0) *gstate = st; return; }
+    // the state goes back to (possibly mapped host) memory; the system fence orders it before the completion record that thread 0
+    // writes afterwards -- a host that sees the record must see the results
+    if (st.mode == 2) { if (tid == 0) { *gstate = st; __threadfence_system(); } return; }
     if (st.mode == 0) {
         for (;;) {
             const float r00 = (float)st.R[0], r01 = (float)st.R[1], r02 = (float)st.R[2], r10 = (float)st.R[3], r11 = (float)st.R[4],
@@ -304,11 +306,11 @@ __device__ __forceinline__ void icp_fused_body(const PairDev* __restrict__ pairs
             __syncthreads();
             if (done) break;
         }
-        if (st.status != 0) { if (tid == 0) *gstate = st; return; }
+        if (st.status != 0) { if (tid == 0) { *gstate = st; __threadfence_system(); } return; }
     }
     icp_score_part(P, st);
     __syncthreads();
-    if (tid == 0) *gstate = st;
+    if (tid == 0) { *gstate = st; __threadfence_system(); }
 }
 
 

@@ -182,6 +182,25 @@ def test_register_neighbours_term(g):
     assert g.error_trace(r["trace"]) == list(z["expn_trace"])
 
 
+def test_batch_deterministic(g):
+    """regression: results of ICP requests travel through a state block in mapped host memory; without a system fence between
+    that block and the completion record the host could read the block before it had landed (about 0.15 % of pairs then ended
+    at once with optError 0).  The same sweep registered three times must give identical results for every pair."""
+    from conftest import ROOT
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("synth", os.path.join(ROOT, "go-icp-protein-cavities_b200", "synth.py"))
+    synth = importlib.util.module_from_spec(spec); spec.loader.exec_module(synth)
+    pairs = synth.bo1_pairs(768, seed=4096)
+    eng = g.Engine(0)
+    eng.batch_upload(g.shipped_config(), pairs)
+    runs = []
+    for _ in range(3):
+        res = eng.batch_run()
+        runs.append([(x["optError"], tuple(x["counters"][:6]), tuple(np.asarray(x["R"]).ravel())) for x in res])
+    assert all(e[0] > 0 for e in runs[0])
+    assert runs[1] == runs[0] and runs[2] == runs[0]
+
+
 def test_resident_icp_requests_fresh(g):
     """regression: ICP requests of the resident kernel live in mapped host memory at one address per pair; a plain device load
     could be served from a stale L1 line of the pair's previous request (about 2 % of registrations then ended in a worse
