@@ -1,17 +1,20 @@
 // Branch-and-bound bound evaluation kernels (north_star (b)).
 //
-//  inner_bnb_kernel   one CTA runs one whole GoICP::InnerBnB call (jly_goicp.cpp:286-579): the rotated cloud, weights
-//                     and rotation-uncertainty radii are staged in shared memory once, then each pop of the
-//                     translation queue evaluates its 8 child cubes x Nd points (warp = child cube, lane = point:
-//                     translate, voxel index in FP64, DT gather, x weight, - radius, clamp) plus the 27 lattice corners
-//                     of the fork's incompatibility / c-FPFH terms.  Persistent CTAs pull calls from an atomic counter,
-//                     so one launch evaluates every (rotation cube, level) request of every pair of a wave.
-//                     EXACT=true reproduces the reference's sequential float sums bit for bit (16 independent
-//                     FADD chains on 16 lanes), EXACT=false uses warp-shuffle tree sums.
+//  inner_bnb_kernel   one CTA serves one request: a whole GoICP::InnerBnB call (jly_goicp.cpp:286-579) or the upper- and the
+//                     lower-bound call of one rotation cube.  The rotated cloud, weights and rotation-uncertainty radii are
+//                     staged in shared memory once; for cavity-sized grids the DT volume is staged too (TMA: 16-bit
+//                     squared-distance codes + distance table + colour-mask bytes).  Each pop of the translation queue
+//                     evaluates 8 child cubes x Nd points (work item = 32-point chunk x 4 cubes: FP32 magic-number voxel
+//                     index with exact FP64 fallback, gather, x weight, - radius, clamp) plus the lattice corners of the
+//                     fork's incompatibility / c-FPFH / neighbour-count terms the per-call memo does not hold.
+//                     EXACT=true reproduces the reference's sequential float sums bit for bit (16 independent FADD
+//                     chains on 16 lanes of one warp), EXACT=false uses warp-shuffle tree sums.
+//                     PERSIST: resident for a whole batch, serving the host's request ring; else one launch per wave.
 //  eval_bounds_kernel flat wave: one warp per (rotation cube, translation sub-cube), leaf-level (ub, lb) only.
 //
-// The translation priority queue lives in global memory (one slab per CTA) and follows libstdc++'s
-// push_heap/pop_heap step for step so that ties between equal (lb, w) keys pop in the reference's order.
+// The translation priority queue (8-byte keys + payload slots, top in shared memory, rest in a per-CTA global slab) follows
+// libstdc++'s push_heap/pop_heap step for step so that ties between equal (lb, w) keys pop in the reference's order.
+// The structure of one pop and what was measured on the way is in DESIGN.md section 4 and profiles/README.md.
 #include <cstdlib>
 #include "icp_device.cuh"
 #include "launch.h"

@@ -12,7 +12,8 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 pairs = synth.bo1_pairs(n, seed=4096)
 eng = g.Engine(0)
-params = g.shipped_config()
+fp = len(sys.argv) > 3 and sys.argv[3] == "fpfh"
+params = g.shipped_config(**(dict(cfpfh=1, regularizationFPFH=0.000005) if fp else {}))
 eng.batch_upload(params, pairs)
 runs = []
 for r in range(reps):
