@@ -243,7 +243,6 @@ def test_alternative_paths_same_result(g, monkeypatch, env):
     assert g.error_trace(r["trace"]) == list(z["exp_trace"])
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("GOICP_TEST_LARGE_ND"), reason="not yet confirmed on a GPU box (set GOICP_TEST_LARGE_ND=1)")
 def test_inner_bnb_large_source_cloud(g, po):
     """Nd = 4000: the staging arrays no longer fit in shared memory, so the kernel variant that keeps them in a global scratch
     slab runs (SMEM=false); InnerBnB results equal the CPU restatement bit for bit in exact-sum mode"""
