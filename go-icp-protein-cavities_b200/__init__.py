@@ -64,7 +64,7 @@ ABI_SYMBOLS = [
     "goicp_version", "goicp_last_error", "goicp_params_default", "goicp_create", "goicp_destroy",
     "goicp_set_model", "goicp_set_data", "goicp_set_params", "goicp_build_dt", "goicp_build_dt_replay", "goicp_dt_upload",
     "goicp_dt_download", "goicp_dt_distance", "goicp_set_nd", "goicp_initialize", "goicp_get_weights", "goicp_get_maxrotdis",
-    "goicp_get_thresholds", "goicp_eval_bounds", "goicp_inner_bnb", "goicp_icp", "goicp_register", "goicp_last_trace",
+    "goicp_get_thresholds", "goicp_eval_bounds", "goicp_eval_inclusion", "goicp_inner_bnb", "goicp_icp", "goicp_register", "goicp_last_trace",
     "goicp_set_options", "goicp_register_batch", "goicp_batch_upload", "goicp_batch_run", "goicp_get_timings",
     "goicp_set_batch_options", "goicp_get_stats", "goicp_set_frontier_sharding", "goicp_test_exchange",
     "goicp_normalize_cloud", "goicp_scale_cloud", "goicp_rescale_translation", "goicp_apply_rigid", "goicp_rmsd",
@@ -107,6 +107,7 @@ def lib():
     L.goicp_get_maxrotdis.argtypes = [vp, fp]
     L.goicp_get_thresholds.argtypes = [vp, fp, ip]
     L.goicp_eval_bounds.argtypes = [vp, fp, ip, C.c_int32, fp, ip, C.c_int32, fp, fp, ip, ip]
+    L.goicp_eval_inclusion.argtypes = [vp, fp, C.c_int32, fp, C.c_int32, C.POINTER(C.c_uint8), fp]
     L.goicp_inner_bnb.argtypes = [vp, fp, ip, fp, C.c_int32, fp, fp, C.POINTER(C.c_int64)]
     L.goicp_icp.argtypes = [vp, dp, dp, fp, ip]
     L.goicp_register.argtypes = [vp, C.POINTER(Result)]
@@ -399,6 +400,15 @@ class GoICP:
         self.eng.check(self.L.goicp_eval_bounds(self.h, _p(R, C.c_float), _p(level, C.c_int32), len(R), _p(tc, C.c_float), _p(ro, C.c_int32), n,
                                                 _p(ub, C.c_float), _p(lb, C.c_float), _p(inc, C.c_int32), _p(fp, C.c_int32)))
         return ub, lb, inc, fp
+
+    def eval_inclusion(self, R, level, tcubes):
+        """per-cube point-inclusion masks of the trimmed error (intro_select's contract) + the residual rows: (mask[n,Nd] uint8, resid[n,Nd])"""
+        R = _f32(R).reshape(9)
+        tc = _f32(tcubes).reshape(-1, 4)
+        n = len(tc)
+        mask, resid = np.zeros((n, self.Nd), np.uint8), np.zeros((n, self.Nd), np.float32)
+        self.eng.check(self.L.goicp_eval_inclusion(self.h, _p(R, C.c_float), int(level), _p(tc, C.c_float), n, mask.ctypes.data_as(C.POINTER(C.c_uint8)), _p(resid, C.c_float)))
+        return mask, resid
 
     def InnerBnB(self, R, level, opt_error):
         """GoICP::InnerBnB (jly_goicp.cpp:286) for n calls: R (n,9), level (n,), opt_error (n,) -> err, tnode, (pops, subcubes)"""

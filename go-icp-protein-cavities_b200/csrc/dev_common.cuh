@@ -106,8 +106,11 @@ __device__ __forceinline__ int nb_diff(const PairDev& P, int cell, int i, float 
 // further out (the caller then runs the exact FP64 form).  GridDev.ovl[s] = (double)sqrtf(s) / scale.
 __device__ __forceinline__ bool vox_near(const VoxFast& vf, int S, float px, float py, float pz, float Cx, float Cy, float Cz, int* idx, int* s2) {
     const unsigned kx = __float_as_uint(__fmaf_rn(px, vf.sc, Cx)), ky = __float_as_uint(__fmaf_rn(py, vf.sc, Cy)), kz = __float_as_uint(__fmaf_rn(pz, vf.sc, Cz));
-    const int xi = (int)(kx >> vf.sh) - (int)vf.bias, yi = (int)(ky >> vf.sh) - (int)vf.bias, zi = (int)(kz >> vf.sh) - (int)vf.bias;
+    int xi = (int)(kx >> vf.sh) - (int)vf.bias, yi = (int)(ky >> vf.sh) - (int)vf.bias, zi = (int)(kz >> vf.sh) - (int)vf.bias;
     const unsigned fr = min(min(kx & vf.mask, ky & vf.mask), kz & vf.mask);
+    // the mantissa holds floor(t + 0.5); ROUND (jly_3ddt.cpp:30) truncates toward zero, so below the grid's low edge the
+    // reference's voxel is one higher (outside the ambiguity zone t + 0.5 is never an integer): (-1, 0) -> 0, (-2, -1) -> -1 ...
+    xi += (xi < 0); yi += (yi < 0); zi += (zi < 0);
     const int cx = min(max(xi, 0), S - 1), cy = min(max(yi, 0), S - 1), cz = min(max(zi, 0), S - 1);
     const int ax = xi - cx, ay = yi - cy, az = zi - cz;
     *s2 = ax * ax + ay * ay + az * az;
@@ -144,7 +147,8 @@ __device__ __forceinline__ unsigned warp_select_kth(const float* v, int n, int k
 // Sum over the k smallest of v[0..n) (set chosen by warp_select_kth) of f(v) for the two bound sums of
 // InnerBnB (jly_goicp.cpp:393-415).  Tree order: trimmed sums are compared at tolerance (the reference adds them in
 // intro_select's permutation order, which is not reproducible in closed form).
-__device__ __forceinline__ void warp_trimmed_sums(const float* v, int n, int k, int lane, int norm, float mtd, float* ub, float* lb) {
+// mask (optional): mask[i] = 1 when point i is in the k-smallest set -- the per-cube point-inclusion mask (goicp_eval_inclusion).
+__device__ __forceinline__ void warp_trimmed_sums(const float* v, int n, int k, int lane, int norm, float mtd, float* ub, float* lb, uint8_t* mask = nullptr) {
     int need_eq;
     const unsigned T = warp_select_kth(v, n, k, lane, &need_eq);
     float su = 0.f, sl = 0.f;
@@ -158,6 +162,7 @@ __device__ __forceinline__ void warp_trimmed_sums(const float* v, int n, int k, 
         const int rank = eq_seen + __popc(eqm & ((1u << lane) - 1u));
         const bool inc = valid && (u < T || (u == T && rank < need_eq));
         eq_seen += __popc(eqm);
+        if (mask && valid) mask[i] = inc ? 1 : 0;
         if (inc) {
             su += (norm == 2) ? m * m : m;
             const float d = m - mtd;

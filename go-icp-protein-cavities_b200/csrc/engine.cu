@@ -1387,7 +1387,8 @@ goicp_status goicp_set_params(goicp_handle h, const goicp_params* p) {
     if (!h || !p) return GOICP_ERR_ARG;
     const bool gridChanged = !h->haveParams || p->distTransSize != h->params.distTransSize || p->distTransExpandFactor != h->params.distTransExpandFactor ||
                              (p->trimFraction < 0.001) != (h->params.trimFraction < 0.001) ||
-                             p->cfpfh != h->params.cfpfh || p->regularizationFPFH != h->params.regularizationFPFH;
+                             p->cfpfh != h->params.cfpfh || p->regularizationFPFH != h->params.regularizationFPFH ||
+                             (p->regularizationNeighbors > 0) != (h->params.regularizationNeighbors > 0);   // every key the arena layout (upload_problems) depends on
     h->params = *p; h->haveParams = true;
     for (auto& P : h->probs) { P.initialized = false; if (gridChanged) P.prepared = P.dt_built = false; }
     return GOICP_OK;
@@ -1532,6 +1533,28 @@ goicp_status goicp_eval_bounds(goicp_handle h, const float* R, const int32_t* le
     CU(cudaMemcpyAsync(lb, dLb, sizeof(float) * nt, cudaMemcpyDeviceToHost, h->stream));
     if (incomp_minmax) CU(cudaMemcpyAsync(incomp_minmax, dI, sizeof(int) * 2 * nt, cudaMemcpyDeviceToHost, h->stream));
     if (fpfh_minmax) CU(cudaMemcpyAsync(fpfh_minmax, dFm, sizeof(int) * 2 * nt, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return GOICP_OK;
+}
+
+goicp_status goicp_eval_inclusion(goicp_handle h, const float* R, int32_t level, const float* tcube, int32_t nt, uint8_t* mask, float* resid) {
+    if (!h || !R || !tcube || !mask || nt < 0) return GOICP_ERR_ARG;
+    goicp_status s; if ((s = ensure_single(h))) return s;
+    Problem& P = h->probs[0]; if (!P.initialized) return fail(h, GOICP_ERR_ARG, "eval_inclusion before initialize");
+    if (level >= GOICP_MAXROTLEVEL) return fail(h, GOICP_ERR_ARG, "level %d >= MAXROTLEVEL", level);
+    if (nt == 0) return GOICP_OK;
+    cudaSetDevice(h->device);
+    std::vector<WaveCube> cubes(nt);
+    for (int k = 0; k < nt; k++) { cubes[k].x = tcube[4 * k]; cubes[k].y = tcube[4 * k + 1]; cubes[k].z = tcube[4 * k + 2]; cubes[k].w = tcube[4 * k + 3]; cubes[k].rot = 0; }
+    const size_t bR = al256(sizeof(float) * 9), bC = al256(sizeof(WaveCube) * nt), bF = al256(sizeof(float) * (size_t)nt * P.Nd), bM = al256((size_t)nt * P.Nd);
+    CU(h->dTmp.ensure(bR + bC + bF + bM));
+    char* d = h->dTmp.as<char>();
+    float* dR = (float*)d; WaveCube* dC = (WaveCube*)(d + bR); float* dF = (float*)(d + bR + bC); uint8_t* dM = (uint8_t*)(d + bR + bC + bF);
+    CU(cudaMemcpyAsync(dR, R, sizeof(float) * 9, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(dC, cubes.data(), sizeof(WaveCube) * nt, cudaMemcpyHostToDevice, h->stream));
+    CU(goicp_launch_eval_inclusion(h->dPairs.as<PairDev>(), 0, dR, level, dC, nt, dF, dM, std::min(nt, h->numSM * 64), h->stream)); h->main.launches[2]++;
+    CU(cudaMemcpyAsync(mask, dM, (size_t)nt * P.Nd, cudaMemcpyDeviceToHost, h->stream));
+    if (resid) CU(cudaMemcpyAsync(resid, dF, sizeof(float) * (size_t)nt * P.Nd, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return GOICP_OK;
 }

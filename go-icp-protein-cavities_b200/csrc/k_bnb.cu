@@ -879,6 +879,40 @@ eval_bounds_kernel(const PairDev* __restrict__ pairs, int pair, const float* __r
     }
 }
 
+// Per-cube point-inclusion masks of the trimmed error (north_star: "per-cube point-inclusion masks bit-exact"): one warp per
+// child translation cube computes the residual row exactly as the search kernels do (jly_goicp.cpp:343-382) and runs the same
+// radix select + membership rule as their trimmed sums (warp_trimmed_sums).  resid / mask: nt x Nd.
+__global__ void __launch_bounds__(256)
+eval_inclusion_kernel(const PairDev* __restrict__ pairs, int pair, const float* __restrict__ R, int level, const WaveCube* __restrict__ cubes, int nt,
+                      float* __restrict__ resid, uint8_t* __restrict__ mask) {
+    const int lane = threadIdx.x & 31;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    const PairDev& P = pairs[pair];
+    const GridDev& g = P.g;
+    const int Nd = P.Nd;
+    const float r0 = R[0], r1 = R[1], r2 = R[2], r3 = R[3], r4 = R[4], r5 = R[5], r6 = R[6], r7 = R[7], r8 = R[8];
+    for (int k = wid; k < nt; k += nw) {
+        const WaveCube cb = cubes[k];
+        const float half = cb.w / 2;
+        const float transX = cb.x + half, transY = cb.y + half, transZ = cb.z + half;
+        float* md = resid + (size_t)k * Nd;
+        uint8_t* mk = mask + (size_t)k * Nd;
+        for (int i = lane; i < Nd; i += 32) {
+            const float x = P.dx[i], y = P.dy[i], z = P.dz[i];
+            const float px = r0 * x + r1 * y + r2 * z, py = r3 * x + r4 * y + r5 * z, pz = r6 * x + r7 * y + r8 * z;
+            float d = P.weights[i] * dt_distance(g, g.dist, px + transX, py + transY, pz + transZ);
+            if (level >= 0) d = d - P.maxRotDis[(size_t)level * Nd + i];
+            if (d < 0.f) d = 0.f;
+            md[i] = d;
+            if (!P.doTrim) mk[i] = 1;
+        }
+        __syncwarp();
+        if (P.doTrim) { float su, sl; warp_trimmed_sums(md, Nd, P.inlierNum, lane, P.norm, 0.f, &su, &sl, mk); }
+        __syncwarp();
+    }
+}
+
 }  // namespace
 
 // ---- launchers ---------------------------------------------------------------------------------------------
@@ -960,6 +994,12 @@ cudaError_t goicp_launch_eval_bounds(const PairDev* pairs, int pair, const float
     return cudaGetLastError();
 }
 
+cudaError_t goicp_launch_eval_inclusion(const PairDev* pairs, int pair, const float* R, int level, const WaveCube* cubes, int nt, float* resid, uint8_t* mask, int nwarps, cudaStream_t st) {
+    if (nt <= 0) return cudaSuccess;
+    eval_inclusion_kernel<<<(nwarps + 7) / 8, 256, 0, st>>>(pairs, pair, R, level, cubes, nt, resid, mask);
+    return cudaGetLastError();
+}
+
 // forces the (lazily loaded) kernels of this file into the context: a first launch while a resident kernel is spinning
 // would otherwise wait for that kernel (CUDA lazy module loading)
 cudaError_t goicp_preload_bnb() {
@@ -967,5 +1007,6 @@ cudaError_t goicp_preload_bnb() {
     for (int exact = 0; exact < 2; exact++) for (int persist = 0; persist < 2; persist++) for (int smem = 0; smem < 3; smem++) for (int ct = 0; ct < 2; ct++)
         if ((e = cudaFuncGetAttributes(&a, bnb_kernel(exact, persist, smem, ct))) != cudaSuccess) return e;
     if ((e = cudaFuncGetAttributes(&a, eval_bounds_kernel)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, eval_inclusion_kernel)) != cudaSuccess) return e;
     return cudaSuccess;
 }

@@ -119,6 +119,13 @@ goicp_status goicp_get_thresholds(goicp_handle h, float* sse_thresh, int32_t* in
 goicp_status goicp_eval_bounds(goicp_handle h, const float* R, const int32_t* level, int32_t nr,
                                const float* tcube, const int32_t* rot_of, int32_t nt,
                                float* ub, float* lb, int32_t* incomp_minmax, int32_t* fpfh_minmax);
+/* The trimmed-error selection of InnerBnB (intro_select, jly_sorting.hpp:229-313, called at jly_goicp.cpp:384-390) for nt
+ * CHILD translation cubes under one rotation R (9 floats) at `level` (-1: upper-bound mode): mask[nt x Nd] = 1 for the points
+ * whose residual is among the inlierNum smallest (the per-cube point-inclusion mask; points tied with the inlierNum-th
+ * smallest value are taken in ascending index order), resid[nt x Nd] (may be NULL) = the residual rows themselves
+ * (jly_goicp.cpp:343-382).  Without trimming every point is included. */
+goicp_status goicp_eval_inclusion(goicp_handle h, const float* R, int32_t level, const float* tcube, int32_t nt,
+                                  uint8_t* mask, float* resid_or_null);
 /* GoICP::InnerBnB (jly_goicp.cpp:286) for n independent calls made as OuterBnB makes them (:750-768,:861):
  * call k rotates the data by R[k] (9 floats), searches translations best-first on the device and returns
  * err[k] (= optErrorT) and, when tnode != NULL, the best translation node (x,y,z,w). level[k] = -1 for the

@@ -605,6 +605,41 @@ void orc_eval_leaf(orc_ctx* c, const float* R, int level, const float* tcube, in
     }
 }
 
+/* Per-cube point-inclusion set of the trimmed error (jly_goicp.cpp:384-390: intro_select leaves the inlierNum smallest
+ * residuals first).  resid[k*Nd+i] = the clamped residual of point i under cube k (:343-382); mask[k*Nd+i] = 1 when point
+ * i is among the inlierNum smallest.  The set is unique up to ties AT the inlierNum-th smallest value (the reference's
+ * choice among equal values depends on intro_select's permutation and does not change the sum); the canonical form here
+ * takes tied points in ascending index order.  Without trimming every point is included. */
+void orc_eval_inclusion(orc_ctx* c, const float* R, int level, const float* tcube, int n, unsigned char* mask, float* resid) {
+    rotate_data(c, R);
+    const int Nd = c->Nd, k = c->inlierNum;
+    const float* maxRotDisL = level >= 0 ? c->maxRotDis + (size_t)level * Nd : NULL;
+    float* tmp = malloc(sizeof(float) * Nd);
+    for (int q = 0; q < n; q++) {
+        float nw = tcube[4 * q + 3];
+        float transX = tcube[4 * q] + nw / 2, transY = tcube[4 * q + 1] + nw / 2, transZ = tcube[4 * q + 2] + nw / 2;
+        for (int i = 0; i < Nd; i++) {
+            float d = c->weights[i] * dt_distance(c, (double)(c->tx[i] + transX), (double)(c->ty[i] + transY), (double)(c->tz[i] + transZ), 0, 0, 0);
+            if (maxRotDisL) d -= maxRotDisL[i];
+            if (d < 0) d = 0;
+            tmp[i] = d;
+            if (resid) resid[(size_t)q * Nd + i] = d;
+        }
+        if (!c->doTrim || k >= Nd) { memset(mask + (size_t)q * Nd, 1, Nd); continue; }
+        float* srt = c->minDis; memcpy(srt, tmp, sizeof(float) * Nd);
+        qsort(srt, Nd, sizeof(float), cmp_float);
+        const float T = srt[k - 1];
+        int below = 0; for (int i = 0; i < Nd; i++) below += tmp[i] < T;
+        int need_eq = k - below;
+        for (int i = 0; i < Nd; i++) {
+            unsigned char in = 0;
+            if (tmp[i] < T) in = 1; else if (tmp[i] == T && need_eq > 0) { in = 1; need_eq--; }
+            mask[(size_t)q * Nd + i] = in;
+        }
+    }
+    free(tmp);
+}
+
 /* ================================================================================================
  * ICP: ICP3D<float>::Run jly_icp3d.hpp:197-311 (exact NN by exhaustive search instead of nanoflann; same
  * float distance expression as L2_Simple_Adaptor nanoflann.hpp, first-found wins ties), then the DT re-score

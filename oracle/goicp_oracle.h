@@ -67,6 +67,9 @@ float orc_inner_bnb(orc_ctx*, const float* R, int level, float optError, float* 
  * ub/lb INCLUDING the corner terms; incomp[2n]/fpfh[2n] = (min,max) over the 8 corners (0 when disabled). */
 void orc_eval_leaf(orc_ctx*, const float* R, int level, const float* tcube, int n,
                    float* ub, float* lb, int* incomp, int* fpfh);
+/* trimmed-error inclusion set per cube (intro_select's contract, jly_goicp.cpp:384-390): mask[n x Nd] (1 = among the inlierNum
+ * smallest residuals, ties at the threshold value in ascending index order), resid[n x Nd] (may be NULL) */
+void orc_eval_inclusion(orc_ctx*, const float* R, int level, const float* tcube, int n, unsigned char* mask, float* resid);
 /* GoICP::ICP (jly_goicp.cpp:102) -> ICP3D::Run (jly_icp3d.hpp:197) */
 float orc_icp(orc_ctx*, double* R, double* t, int* corr);
 /* GoICP::Register (jly_goicp.cpp:878) incl. BuildDT when not built. trace = the reference's "Error*:" lines. */

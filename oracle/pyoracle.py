@@ -106,12 +106,14 @@ def _lib(kind):
     if kind == "port":
         lib.orc_eval_leaf.argtypes = [vp, fp, C.c_int, fp, C.c_int, fp, fp, ip, ip]
         lib.orc_dt_upload.argtypes = [vp, fp, ip]
+        lib.orc_eval_inclusion.argtypes = [vp, fp, C.c_int, fp, C.c_int, C.POINTER(C.c_ubyte), fp]
         lib.orc_round6.argtypes = [dp, C.c_int, fp]
         lib.orc_rescale_translation.argtypes = [C.c_double, dp, dp, dp, dp, dp]
         lib.orc_apply_rigid.argtypes = [dp, C.c_int, dp, dp, dp]
         lib.orc_rmsd.restype = C.c_float
         lib.orc_rmsd.argtypes = [dp, dp, C.c_int]
     else:
+        lib.ref_eval_inclusion.argtypes = [vp, fp, C.c_int, fp, C.c_int, fp, fp]
         lib.ref_read_mol2.restype = C.c_int
         lib.ref_read_mol2.argtypes = [C.c_char_p, dp, ip, C.c_int]
         lib.ref_write_xyz.restype = C.c_int
@@ -234,6 +236,21 @@ class Oracle:
         self.lib.orc_eval_leaf(self.h, _ptr(Rp, C.c_float), level, _ptr(tc, C.c_float), n, _ptr(ub, C.c_float), _ptr(lb, C.c_float),
                                _ptr(inc, C.c_int), _ptr(fp, C.c_int))
         return ub, lb, inc, fp
+
+    def eval_inclusion(self, R, level, tcubes):
+        """trimmed-error inclusion per cube.  port: (mask[n,Nd] uint8, resid[n,Nd]); ref: (first-k values after the reference's own
+        intro_select [n,inlierNum], resid[n,Nd])"""
+        Rp = _f32(R).reshape(9)
+        tc = _f32(tcubes).reshape(-1, 4)
+        n = len(tc)
+        resid = np.zeros((n, self.Nd), np.float32)
+        if self.kind == "port":
+            mask = np.zeros((n, self.Nd), np.uint8)
+            self.lib.orc_eval_inclusion(self.h, _ptr(Rp, C.c_float), level, _ptr(tc, C.c_float), n, mask.ctypes.data_as(C.POINTER(C.c_ubyte)), _ptr(resid, C.c_float))
+            return mask, resid
+        firstk = np.zeros((n, self.inliernum()), np.float32)
+        self.lib.ref_eval_inclusion(self.h, _ptr(Rp, C.c_float), level, _ptr(tc, C.c_float), n, _ptr(firstk, C.c_float), _ptr(resid, C.c_float))
+        return firstk, resid
 
     def icp(self, R, t):
         R = np.ascontiguousarray(R, dtype=np.float64).reshape(9).copy()

@@ -36,6 +36,7 @@
 #define private public
 #include "jly_goicp.h"
 #undef private
+#include "jly_sorting.hpp"   // intro_select (template header; jly_goicp.cpp:41 includes it the same way)
 #include "ref_counters.h"
 
 long long goicp_ref_cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -207,6 +208,34 @@ float ref_inner_bnb(void* hv, const float* R, int level, float optError, float* 
     float e = g->InnerBnB(level >= 0 ? g->maxRotDis[level] : NULL, tnode ? &tn : NULL);
     if (tnode) { tnode[0] = tn.x; tnode[1] = tn.y; tnode[2] = tn.z; tnode[3] = tn.w; }
     return e;
+}
+
+// The residual row of one child translation cube as InnerBnB's loop fills minDis (jly_goicp.cpp:331-382), then the REFERENCE's
+// own intro_select (jly_sorting.hpp:229, called as at jly_goicp.cpp:389).  firstk[n x inlierNum] receives the values the
+// reference's trimmed sums run over (the first inlierNum entries after the partial partition), resid[n x Nd] the row before it.
+void ref_eval_inclusion(void* hv, const float* R, int level, const float* tcube, int n, float* firstk, float* resid) {
+    ref_handle* h = (ref_handle*)hv; GoICP* g = h->g; CoutCapture cap;
+    const int Nd = g->Nd;
+    for (int i = 0; i < Nd; i++) {
+        POINT3D& p = g->pData[i];
+        g->pDataTemp[i].x = R[0] * p.x + R[1] * p.y + R[2] * p.z;
+        g->pDataTemp[i].y = R[3] * p.x + R[4] * p.y + R[5] * p.z;
+        g->pDataTemp[i].z = R[6] * p.x + R[7] * p.y + R[8] * p.z;
+    }
+    float* maxRotDisL = level >= 0 ? g->maxRotDis[level] : NULL;
+    for (int q = 0; q < n; q++) {
+        const float w = tcube[4 * q + 3];
+        float transX = tcube[4 * q] + w / 2, transY = tcube[4 * q + 1] + w / 2, transZ = tcube[4 * q + 2] + w / 2;
+        int cx, cy, cz;
+        for (int i = 0; i < Nd; i++) {
+            g->minDis[i] = g->weights[i] * g->dt.Distance(g->pDataTemp[i].x + transX, g->pDataTemp[i].y + transY, g->pDataTemp[i].z + transZ, cx, cy, cz);
+            if (maxRotDisL) g->minDis[i] -= maxRotDisL[i];
+            if (g->minDis[i] < 0) g->minDis[i] = 0;
+            if (resid) resid[(size_t)q * Nd + i] = g->minDis[i];
+        }
+        if (g->doTrim) intro_select(g->minDis, 0, Nd - 1, g->inlierNum - 1);
+        memcpy(firstk + (size_t)q * g->inlierNum, g->minDis, sizeof(float) * g->inlierNum);
+    }
 }
 
 // GoICP::ICP from a given pose; R,t in/out (row-major doubles), corr[Nd] = id_model per data point.

@@ -128,9 +128,32 @@ def make_demo(name, model_f, data_f, nd, trim, sizes):
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **fx)
 
 
+def make_inclusion():
+    """trimmed-error inclusion sets: the reference's own intro_select (jly_sorting.hpp:229) on residual rows of the rand demo
+    clouds (trimFraction 0.1, DT 64^3) for random rotations / child translation cubes -> the values its trimmed sums run over."""
+    print("inclusion")
+    z = np.load(os.path.join(OUT, "rand.npz"))
+    rng = np.random.default_rng(31)
+    o = po.Oracle("ref", z["model_xyz"], z["data_xyz"], po.upstream_config(trimFraction=0.1, distTransSize=64))
+    o.build_dt(); o.set_nd(int(z["nd"])); o.initialize()
+    fx = {}
+    for q, level in enumerate((-1, 0, 3)):
+        v = rng.normal(size=3); v *= rng.uniform(0, np.pi) / np.linalg.norm(v)
+        t = np.linalg.norm(v); k = v / t
+        K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+        R = (np.eye(3) + np.sin(t) * K + (1 - np.cos(t)) * K @ K).astype(np.float32)
+        w = np.float32(0.25)
+        tc = np.concatenate([rng.uniform(-0.5, 0.25, (40, 3)), np.full((40, 1), w)], 1).astype(np.float32)
+        tc[:4, :3] += 3.0   # far outside the grid: many tied residuals
+        firstk, resid = o.eval_inclusion(R, level, tc)
+        fx.update({f"R{q}": R, f"level{q}": level, f"tc{q}": tc, f"firstk_sorted{q}": np.sort(firstk, 1), f"resid{q}": resid})
+    o.close()
+    np.savez_compressed(os.path.join(OUT, "rand_inclusion.npz"), **fx)
+
+
 if __name__ == "__main__":
     po.build("ref")
-    which = sys.argv[1:] or ["pair1", "pair2", "rand", "bunny"]
+    which = sys.argv[1:] or ["pair1", "pair2", "rand", "bunny", "inclusion"]
     with tempfile.TemporaryDirectory() as tmp:
         if "pair1" in which:
             make_pair("pair1", "1eq2_6", "2x86_3", 238, tmp, fpfh_variant=True)
@@ -140,3 +163,5 @@ if __name__ == "__main__":
             make_demo("rand", "model_rand.txt", "data_rand.txt", 100, 0.1, [64, 300])
         if "bunny" in which:
             make_demo("bunny", "model_bunny.txt", "data_bunny.txt", 1000, 0.0, [100, 300])
+        if "inclusion" in which:
+            make_inclusion()

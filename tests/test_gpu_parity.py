@@ -276,6 +276,106 @@ def test_register_rand_trim(g):
     assert np.abs(r["R"] - z["exp64_R"]).max() < 1e-5 and np.abs(r["t"] - z["exp64_t"]).max() < 1e-5
 
 
+def test_register_bunny300(g):
+    """BASELINE config 1 at its full size (bunny, Nd = 1000, DT 300^3, upstream config) with the GPU's own separable DT: the
+    optimum, R, t and the node counters of the frozen reference run (demo/output.txt; 375 / 2540 / 5080 / 46 024 / 331 744 / 3)"""
+    z = golden("bunny")
+    reg = g.GoICP(z["model_xyz"], z["data_xyz"], g.upstream_config(distTransSize=300))
+    reg.BuildDT(); reg.set_nd(int(z["nd"]))
+    r = reg.Register()
+    assert abs(r["optError"] - float(z["exp300_optError"])) <= REL * float(z["exp300_optError"]) and abs(r["optError"] - 0.145875812) < 1e-6
+    assert np.abs(r["R"] - z["exp300_R"]).max() < 1e-5 and np.abs(r["t"] - z["exp300_t"]).max() < 1e-5
+    assert r["counters"][:6] == z["exp300_counters"][:6].tolist()
+    assert g.error_trace(r["trace"]) == list(z["exp300_trace"])
+
+
+def test_register_rand_trim300(g):
+    """BASELINE config 3 at its full size (rand clouds, trimFraction 0.1, DT 300^3) against the frozen reference run
+    (optError 0.0506506786); trimmed sums are tree sums here, so 1e-5"""
+    z = golden("rand")
+    reg = g.GoICP(z["model_xyz"], z["data_xyz"], g.upstream_config(trimFraction=0.1, distTransSize=300))
+    reg.BuildDT(); reg.set_nd(int(z["nd"]))
+    r = reg.Register()
+    assert abs(float(z["exp300_optError"]) - 0.0506506786) < 1e-8
+    assert abs(r["optError"] - float(z["exp300_optError"])) <= REL * float(z["exp300_optError"])
+    assert np.abs(r["R"] - z["exp300_R"]).max() < 1e-5 and np.abs(r["t"] - z["exp300_t"]).max() < 1e-5
+
+
+@pytest.mark.parametrize("S,trim", [(64, 0.1), (64, 0.35), (32, 0.1)])
+def test_trimmed_inclusion_masks_bit_exact(g, po, S, trim):
+    """north_star: "per-cube point-inclusion masks bit-exact".  The radix select that replaces intro_select (jly_sorting.hpp:229)
+    marks, per child translation cube, exactly the points of the reference's k-smallest residual set (oracle: the residual row of
+    jly_goicp.cpp:343-382 sorted; ties at the k-th value in index order); the residual rows themselves are bit-identical.
+    Includes cubes pushed outside the grid, where many residuals tie."""
+    z = golden("rand")
+    kw = dict(trimFraction=trim, distTransSize=S)
+    reg = g.GoICP(z["model_xyz"], z["data_xyz"], g.upstream_config(**kw))
+    o = po.Oracle("port", z["model_xyz"], z["data_xyz"], po.upstream_config(**kw))
+    reg.BuildDT(); o.build_dt()
+    if S > 32:
+        d, near, _ = reg.dt_download(); o.dt_upload(d, near)          # same volume on both sides (separable DT vs 8SED)
+    reg.set_nd(int(z["nd"])); o.set_nd(int(z["nd"])); reg.Initialize(); o.initialize()
+    rng = np.random.default_rng(9)
+    k = o.inliernum()
+    for level in (-1, 0, 2, 6):
+        R = rand_rot(rng)
+        w = np.float32(2.0 ** -rng.integers(0, 5))
+        tc = np.concatenate([rng.uniform(-0.5, 0.5 - w, (300, 3)), np.full((300, 1), w)], 1).astype(np.float32)
+        tc[:20, :3] += 3.0                                            # far outside the grid: overshoot path
+        m, resid = reg.eval_inclusion(R, level, tc)
+        om, oresid = o.eval_inclusion(R, level, tc)
+        assert np.array_equal(resid, oresid)
+        assert (m.sum(1) == k).all()
+        assert np.array_equal(m, om)
+
+
+def test_batch_cfpfh_vs_oracle(g, po):
+    """the c-FPFH term inside a BATCH (the resident scheduler's CT=true instantiation): every pair's optimum, compatibilities and
+    node counters equal the CPU restatement's single registration of the same pair"""
+    from conftest import ROOT
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("synth", os.path.join(ROOT, "go-icp-protein-cavities_b200", "synth.py"))
+    synth = importlib.util.module_from_spec(spec); spec.loader.exec_module(synth)
+    pairs = synth.bo1_pairs(64, seed=77)
+    kw = dict(cfpfh=1, regularizationFPFH=0.000005)
+    eng = g.Engine(0)
+    res = eng.register_batch(g.shipped_config(**kw), pairs)
+    order = np.argsort([r["counters"][2] for r in res])              # the CPU check runs the 24 shallowest + 2 mid-depth pairs
+    for i in list(order[:24]) + [order[40], order[48]]:
+        p = pairs[i]
+        o = po.Oracle("port", p["model_xyz"], p["data_xyz"], po.shipped_config(**kw), model_c=p["model_c"], data_c=p["data_c"], model_fpfh=p["model_fpfh"], data_fpfh=p["data_fpfh"])
+        ro = o.register(p["nd"]); o.close()
+        r = res[i]
+        assert r["optError"] == ro["optError"] and r["optComp"] == ro["optComp"], (i, r["optError"], ro["optError"])
+        assert r["counters"][:6] == ro["counters"][:6], (i, r["counters"], ro["counters"])
+        assert np.abs(r["R"] - ro["R"]).max() < 1e-9 and np.abs(r["t"] - ro["t"]).max() < 1e-9
+
+
+def test_inner_bnb_points_below_grid(g, po):
+    """source points that fall BELOW the grid's low edge (target smaller than the source, large translation domain): ROUND
+    truncates toward zero (jly_3ddt.cpp:30), so (-1, 0) maps to voxel 0 with no overshoot -- the FP32 overshoot tier must agree
+    with the exact FP64 form.  InnerBnB results equal the CPU restatement bit for bit."""
+    rng = np.random.default_rng(21)
+    model = rng.uniform(-0.25, 0.25, (300, 3)).astype(np.float32)
+    data = rng.uniform(-0.6, 0.6, (200, 3)).astype(np.float32)
+    kw = dict(distTransSize=20, distTransExpandFactor=1.1, transMinX=-1.0, transMinY=-1.0, transMinZ=-1.0, transWidth=2.0, regularization=0.0, ponderation=0)
+    reg = g.GoICP(model, data, g.shipped_config(**kw))
+    o = po.Oracle("port", model, data, po.shipped_config(**kw))
+    reg.BuildDT(); o.build_dt(); reg.Initialize(); o.initialize()
+    n = 12
+    Rs = np.stack([rand_rot(rng) for _ in range(n)]); lv = np.array([-1, 0, -1, 2] * 3, np.int32)
+    e0 = 200.0
+    ref = [o.inner_bnb(Rs[k], int(lv[k]), e0) for k in range(n)]
+    reg.set_options(exact_sums=1)
+    err, tn, ps = reg.InnerBnB(Rs, lv, np.full(n, e0, np.float32))
+    for k in range(n):
+        assert err[k] == np.float32(ref[k][0]), (k, err[k], ref[k][0])
+    tc = np.concatenate([rng.uniform(-1.0, 0.5, (400, 3)), np.full((400, 1), 0.5)], 1).astype(np.float32)
+    _, resid = reg.eval_inclusion(Rs[0], -1, tc)                      # exact FP64 path
+    _, oresid = o.eval_inclusion(Rs[0], -1, tc)
+    assert np.array_equal(resid, oresid)
+
+
 def test_register_bunny100(g, po):
     """bunny, DT 100^3, with the GPU's own separable DT: same optimum, trace and node counters as the reference run"""
     z = golden("bunny")

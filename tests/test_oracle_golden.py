@@ -146,3 +146,20 @@ def test_pair1_neighbours_term(po):
     assert r["optError"] == float(z["expn_optError"]) and r["optComp"] == int(z["expn_optComp"])
     assert r["counters"][:6] == z["expn_counters"][:6].tolist() and po.error_trace(r["trace"]) == list(z["expn_trace"])
     assert np.abs(r["R"] - z["expn_R"]).max() < 1e-12
+
+
+def test_trimmed_inclusion_vs_reference_intro_select(po):
+    """intro_select's contract (jly_sorting.hpp:229-313, called at jly_goicp.cpp:389): the values the reference's trimmed sums run
+    over (frozen from the reference's own intro_select, tests/golden/rand_inclusion.npz) are exactly the residuals the oracle's
+    inclusion mask selects; the residual rows are bit-identical"""
+    z, fx = golden("rand"), golden("rand_inclusion")
+    o = po.Oracle("port", z["model_xyz"], z["data_xyz"], po.upstream_config(trimFraction=0.1, distTransSize=64))
+    o.build_dt(); o.set_nd(int(z["nd"])); o.initialize()
+    k = o.inliernum()
+    assert k == 90
+    for q in range(3):
+        mask, resid = o.eval_inclusion(fx[f"R{q}"], int(fx[f"level{q}"]), fx[f"tc{q}"])
+        assert np.array_equal(resid, fx[f"resid{q}"])
+        assert (mask.sum(1) == k).all()
+        sel = np.sort(np.where(mask.astype(bool), resid, np.inf), 1)[:, :k]
+        assert np.array_equal(sel, fx[f"firstk_sorted{q}"])
