@@ -33,6 +33,7 @@
 #include "../../include/goicp_b200.h"
 #include "goicp_dev.h"
 #include "launch.h"
+#include "search_dev.h"
 
 namespace {
 
@@ -247,6 +248,9 @@ struct goicp_handle_s {
     PinBuf hStage, hPairs;
     WaveCtx main;
     MapBuf qOuts, qOrder, qIcp, qDone; DevBuf qClaim, qHeaps, qScratch, qMemo, dGen;   // persistent-queue mode (batches)
+    DevBuf sCtl, sHdrs, sSlots, sRq, sIcp, sOuts; PinBuf hOuts;   // device-resident search (k_search.cu)
+    int resident_search = 1;     // 1: OuterBnB runs on the device (k_search.cu); 0: host state machine + request ring (the round-1 scheduler)
+    int spec_groups = SR_NGROUP - 4;   // device-resident search: most rotation-queue nodes with speculative calls per owner CTA (0: never speculate)
     int shardRank = 0, shardN = 1; goicp_allgather_fn allgather = nullptr; void* allgatherUser = nullptr;   // frontier sharding
     std::vector<InnerOut> xSend, xRecv;
     std::atomic<int> outstanding{0};   // requests published and not yet harvested (persistent scheduler)
@@ -1221,6 +1225,98 @@ static goicp_status register_persistent(Eng* h, const BnbCfg& cfg, int groups, i
     return GOICP_OK;
 }
 
+// ---- device-resident search (k_search.cu): the whole batch in one launch, results read back once --------------------------------
+static bool host_libm_uses_fma() {   // glibc's ifunc rule for sinf / cosf on x86-64 (sysdeps/x86_64/fpu/multiarch/ifunc-fma.h)
+#if defined(__x86_64__)
+    __builtin_cpu_init();
+    return __builtin_cpu_supports("fma") && __builtin_cpu_supports("avx2");
+#else
+    return true;
+#endif
+}
+static goicp_status register_resident(Eng* h, const BnbCfg& cfg) {
+    const goicp_params& p = h->params;
+    const int np = (int)h->probs.size();
+    int perSM = goicp_search_occupancy(cfg.smemBytes, h->exact_sums, cfg.threads, cfg.useSmem, cfg.ct);
+    { const char* e = getenv("GOICP_CTAS_PER_SM"); if (e && atoi(e) >= 1) perSM = std::min(perSM, atoi(e)); }
+    int ctas = h->numSM * perSM;
+    { const char* e = getenv("GOICP_CTAS"); if (e && atoi(e) >= 1) ctas = std::min(ctas, atoi(e)); }
+    int heapCap = 1 << 15;
+    { const char* e = getenv("GOICP_HEAPCAP"); if (e && atoi(e) >= 129) heapCap = atoi(e); }   // test hook: force the overflow re-run
+    const int rqCap = 1 << 13;
+    const int memoCap = 8192;
+    CU(h->sCtl.ensure(sizeof(SearchCtl)));
+    CU(h->sHdrs.ensure(goicp_search_hdr_bytes() * (size_t)ctas));
+    CU(h->sSlots.ensure(goicp_search_slot_bytes() * (size_t)ctas * SR_NSLOT));
+    CU(h->sRq.ensure(goicp_search_rnode_bytes() * (size_t)ctas * 2 * rqCap));
+    CU(h->sIcp.ensure(sizeof(IcpState) * 2 * (size_t)ctas));
+    CU(h->sOuts.ensure(sizeof(PairOut) * (size_t)np));
+    CU(h->hOuts.ensure(sizeof(PairOut) * (size_t)np));
+    CU(h->qHeaps.ensure(sizeof(HeapEnt) * (size_t)ctas * heapCap));
+    if (!cfg.useSmem) CU(h->qScratch.ensure(sizeof(float) * cfg.smemFloats * (size_t)ctas));
+    if (h->qMemo.cap < (size_t)32 * memoCap * ctas) { CU(h->qMemo.ensure((size_t)32 * memoCap * ctas)); CU(cudaMemsetAsync(h->qMemo.p, 0, h->qMemo.cap, h->stream)); }
+    CU(cudaMemsetAsync(h->sCtl.p, 0, sizeof(SearchCtl), h->stream));
+    CU(cudaMemsetAsync(h->sHdrs.p, 0, goicp_search_hdr_bytes() * (size_t)ctas, h->stream));
+    CU(cudaMemsetAsync(h->sSlots.p, 0, goicp_search_slot_bytes() * (size_t)ctas * SR_NSLOT, h->stream));
+    SearchArgs A{};
+    A.pairs = h->dPairs.as<PairDev>(); A.npairs = np; A.nCtas = ctas;
+    A.rotMinX = p.rotMinX; A.rotMinY = p.rotMinY; A.rotMinZ = p.rotMinZ; A.rotWidth = p.rotWidth;
+    A.fma = host_libm_uses_fma() ? 1 : 0;
+    { const char* e = getenv("GOICP_LIBM_FMA"); if (e) A.fma = atoi(e) != 0; }
+    A.specMax = std::max(0, std::min(h->spec_groups, SR_NGROUP - 4));
+    { const char* e = getenv("GOICP_SPEC_GROUPS"); if (e) A.specMax = std::max(0, std::min(atoi(e), SR_NGROUP - 4)); }
+    A.ctl = h->sCtl.as<SearchCtl>(); A.hdrs = h->sHdrs.as<OwnerHdr>(); A.slots = h->sSlots.as<SearchSlot>(); A.rq = h->sRq.p; A.rqCap = rqCap;
+    A.icp = h->sIcp.as<IcpState>(); A.outs = h->sOuts.as<PairOut>();
+    A.heaps = h->qHeaps.as<HeapEnt>(); A.heapCap = heapCap; A.gscratch = h->qScratch.as<float>(); A.gstride = cfg.smemFloats; A.NdP = cfg.NdP; A.NdQ = cfg.NdQ; A.useSmem = cfg.useSmem;
+    A.memo = reinterpret_cast<uint4*>(h->qMemo.p); A.memoCap = memoCap; A.genCounter = h->dGen.as<unsigned>(); A.gridOff = cfg.gridOff; A.S3p = cfg.S3p;
+    cudaEventRecord(h->main.ev0, h->stream);
+    CU(goicp_launch_search(A, ctas, cfg.threads, cfg.smemBytes, h->exact_sums, cfg.ct, h->stream));
+    cudaEventRecord(h->main.ev1, h->stream);
+    CU(cudaMemcpyAsync(h->hOuts.p, h->sOuts.p, sizeof(PairOut) * (size_t)np, cudaMemcpyDeviceToHost, h->stream));
+    {
+        cudaError_t e = h->main.sync();
+        if (e != cudaSuccess) return fail(h, GOICP_ERR_CUDA, "device-resident search kernel: %s", cudaGetErrorString(e));
+    }
+    float ms = 0; cudaEventElapsedTime(&ms, h->main.ev0, h->main.ev1); h->main.ms[2] += ms; h->main.launches[2] += 1;
+    const PairOut* outs = h->hOuts.as<PairOut>();
+    std::vector<int> redo;
+    long long icpCalls = 0;
+    for (int i = 0; i < np; i++) {
+        Problem& P = h->probs[i]; const PairOut& o = outs[i];
+        reset_search(P);
+        if (o.status == GOICP_SR_UNSUPPORTED) return fail(h, GOICP_ERR_UNSUPPORTED, "ICP with trimming supports Nd <= 2048");
+        if (o.status != 0) { redo.push_back(i); continue; }
+        memcpy(P.optR, o.R, sizeof P.optR); memcpy(P.optT, o.t, sizeof P.optT);
+        P.optError = o.optError; P.optComp = o.optComp;
+        for (int k = 0; k < 6; k++) P.cnt[k] = o.cnt[k];
+        icpCalls += o.cnt[5];
+        static const char* kinds[3] = {"Init", "ICP", "BNB"};
+        for (int k = 0; k < o.nEvents; k++) tracef(P.trace, "Error*: %g (%s)\n", o.ev[k].v, kinds[o.ev[k].kind % 3]);
+        if (o.endKind == 1) tracef(P.trace, "Rotation Queue Empty\nError*: %g, LB: %g\n", P.optError, o.endLb);
+        else tracef(P.trace, "Threshold reached\nError*: %g, LB: %g, epsilon: %g\n", P.optError, o.endLb, P.dev.SSEThresh);
+        P.phase = PH_DONE;
+    }
+    h->stats[14] = (double)redo.size();
+    if (!redo.empty()) {   // a queue outgrew its per-CTA slab: re-run those pairs with the wave scheduler, which grows the slabs on demand
+        std::atomic<int> nx(0);
+        h->main.ctaCap = 0;
+        goicp_status s2 = register_group(h, h->main, cfg, nx, std::min<int>(64, (int)redo.size()), &redo);
+        if (s2) return s2;
+    }
+    { unsigned long long st8[20]; cudaMemcpy(st8, h->dGen.as<char>() + 8, sizeof st8, cudaMemcpyDeviceToHost); cudaMemset(h->dGen.as<char>() + 8, 0, 160);
+      h->stats[8] = (double)st8[3]; h->stats[9] = (double)st8[1]; h->stats[10] = (double)st8[0]; h->stats[11] = (double)st8[2]; h->stats[12] = (double)st8[4]; h->stats[13] = ctas;
+      h->stats[15] = (double)st8[7];
+      h->stats[5] = h->stats[6] = h->stats[7] = 0;
+      h->main.callsLaunched += (long long)st8[3];
+      if (getenv("GOICP_DEBUG")) {
+          fprintf(stderr, "[search] ctas %d calls %llu pops %llu busy-cycles/pop %.0f corner-misses/pop %.2f; CTA cycles: total %.4g in calls %.4g scheduling+idle %.4g; icp requests %llu\n", ctas, st8[3], st8[1],
+                  (double)st8[0] / std::max<double>(1, st8[1]), (double)st8[2] / std::max<double>(1, st8[1]), (double)st8[7], (double)st8[0], (double)st8[4], st8[6]);
+          if (st8[8]) fprintf(stderr, "[phases] cycles per pop: stage(per call) %.0f  A1 %.0f  A2 %.0f (chain on warp 0: %.0f)  C %.0f\n", (double)st8[8] / std::max<double>(1, st8[3]), (double)st8[9] / std::max<double>(1, st8[1]), (double)st8[10] / std::max<double>(1, st8[1]), (double)st8[12] / std::max<double>(1, st8[1]), (double)st8[11] / std::max<double>(1, st8[1]));
+      } }
+    (void)icpCalls;
+    return GOICP_OK;
+}
+
 // GoICP::Register (jly_goicp.cpp:878) for every problem of the handle.  One problem: waves on the handle's stream.
 // A batch: `groups` worker threads, each with its own stream, pull pairs from a shared counter.
 static goicp_status register_all(Eng* h) {
@@ -1241,7 +1337,11 @@ static goicp_status register_all(Eng* h) {
     { const char* e = getenv("GOICP_PERSISTENT"); if (e) { h->persistent = atoi(e) != 0; h->persistent_single = atoi(e) == 1; } }   // 0 off, 1 on, 2 batches only
     bool allSmall = true;
     for (auto& P : h->probs) if ((size_t)P.Nd * P.Nm > ((size_t)1 << 21) || (P.dev.doTrim && P.Nd > 2048)) allSmall = false;
-    if (h->persistent && allSmall && h->shardN <= 1 && (np > 1 || h->persistent_single)) {
+    { const char* e = getenv("GOICP_RESIDENT_SEARCH"); if (e) h->resident_search = atoi(e) != 0; }
+    if (h->persistent && allSmall && h->shardN <= 1 && (np > 1 || h->persistent_single) && h->resident_search) {
+        groups = 0;
+        if ((s = register_resident(h, cfg))) return s;
+    } else if (h->persistent && allSmall && h->shardN <= 1 && (np > 1 || h->persistent_single)) {
         if (h->slots <= 0) slots = std::min(512, std::max(8, (np + groups - 1) / groups));
         if ((s = register_persistent(h, cfg, groups, slots))) return s;
     } else if (groups <= 1) {
@@ -1344,7 +1444,7 @@ goicp_status goicp_create(goicp_handle* out, int device, void* stream_or_null) {
     h->device = device; h->numSM = prop.multiProcessorCount;
     if (stream_or_null) { h->stream = (cudaStream_t)stream_or_null; h->ownStream = false; }
     else { if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete h; return fail(nullptr, GOICP_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); } h->ownStream = true; }
-    if ((e = goicp_preload_bnb()) != cudaSuccess || (e = goicp_preload_dt()) != cudaSuccess || (e = goicp_preload_icp()) != cudaSuccess || (e = goicp_preload_misc()) != cudaSuccess) {
+    if ((e = goicp_preload_bnb()) != cudaSuccess || (e = goicp_preload_dt()) != cudaSuccess || (e = goicp_preload_icp()) != cudaSuccess || (e = goicp_preload_misc()) != cudaSuccess || (e = goicp_preload_search()) != cudaSuccess) {
         delete h; return fail(nullptr, GOICP_ERR_CUDA, "kernel preload failed: %s (library built for sm_100a only)", cudaGetErrorString(e));
     }
     if (h->dGen.ensure(256) != cudaSuccess || cudaMemset(h->dGen.p, 0, 256) != cudaSuccess) { delete h; return fail(nullptr, GOICP_ERR_CUDA, "device allocation failed"); }
@@ -1358,9 +1458,9 @@ void goicp_destroy(goicp_handle h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf* bufs[] = {&h->arenaIn, &h->arenaWork, &h->dPairs, &h->dTmp, &h->dTmp2, &h->dTmp3, &h->dSepBits, &h->dSepNx, &h->dSepNxy};
+    DevBuf* bufs[] = {&h->arenaIn, &h->arenaWork, &h->dPairs, &h->dTmp, &h->dTmp2, &h->dTmp3, &h->dSepBits, &h->dSepNx, &h->dSepNxy, &h->sCtl, &h->sHdrs, &h->sSlots, &h->sRq, &h->sIcp, &h->sOuts};
     for (DevBuf* b : bufs) b->release();
-    h->hStage.release(); h->hPairs.release(); h->qOuts.release(); h->qOrder.release(); h->qIcp.release(); h->qDone.release(); h->qClaim.release(); h->qHeaps.release(); h->qScratch.release(); h->qMemo.release(); h->dGen.release();
+    h->hStage.release(); h->hPairs.release(); h->hOuts.release(); h->qOuts.release(); h->qOrder.release(); h->qIcp.release(); h->qDone.release(); h->qClaim.release(); h->qHeaps.release(); h->qScratch.release(); h->qMemo.release(); h->dGen.release();
     h->main.release();
     for (auto& w : h->workers) w->release();
     if (h->ownStream) cudaStreamDestroy(h->stream);
