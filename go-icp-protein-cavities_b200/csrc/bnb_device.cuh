@@ -202,16 +202,17 @@ struct BnbShared {
 struct CallCtx {
     unsigned gphase = 0;                       // parity of the DT-staging mbarrier
     int gpair = -1;                            // pair whose DT volume sits in shared memory
-    const volatile unsigned* cancelWord = nullptr;   // CANCEL: the call is abandoned (status 7) once *cancelWord != cancelGen
-    unsigned cancelGen = 0;
 };
+// CANCEL (speculative calls of the device-resident search): lives in shared memory; the call is abandoned (status 7) once
+// *word != gen.  One lane of the last warp polls the word while the corners are evaluated; warp 0 only reads the flag.
+struct CancelSh { const volatile unsigned* word; unsigned gen; int flag; };
 
 // One request = one InnerBnB call, or (level >= GOICP_REQ_BOTH) the upper- and the lower-bound call of one rotation cube.
 // Called by every thread of the CTA; `pr` and `s_out` live in shared memory; the result is left in `s_out` (thread 0 wrote it;
 // a __syncthreads / __syncwarp of warp 0 is needed before other threads read it).  `s_gbar` is an mbarrier initialised once by the
 // kernel (GS only).  dstat: device counters [0] busy cycles [1] pops [2] corner misses [3] calls.
 template <bool EXACT, bool SMEM, bool GS, bool CT, bool CANCEL>
-__device__ __forceinline__ void inner_call(const PairDev* __restrict__ pairs, const InnerProb& pr, InnerOut& s_out, unsigned long long& s_gbar, CallCtx& cx,
+__device__ __forceinline__ void inner_call(const PairDev* __restrict__ pairs, const InnerProb& pr, InnerOut& s_out, unsigned long long& s_gbar, CallCtx& cx, CancelSh& cs,
                                            HeapEnt* __restrict__ heaps, int heapCap, float* gscratch, size_t gstride, int NdP, int NdQ, int useSmem,
                                            uint4* memoAll, int memoCap, unsigned* genCounter, int gridOff, int S3p) {
     unsigned long long* dstat = reinterpret_cast<unsigned long long*>(genCounter) + 1;
@@ -451,6 +452,7 @@ __device__ __forceinline__ void inner_call(const PairDev* __restrict__ pairs, co
                 if (tid == 0) sh.tp[10] += clock64() - sh.tmark;
 #endif
             }
+            if (CANCEL && warp == nwarps - 1 && lane == 0 && cs.word != nullptr && *cs.word != cs.gen) cs.flag = 1;
             // ---- phase A2: warp 0 sums the residuals while the other warps evaluate the corners the memo missed -----------
             if (doTrim) {   // radix select replaces intro_select (:384-390); one warp per child
                 for (int c = warp; c < 8; c += nwarps) {
@@ -717,7 +719,7 @@ __device__ __forceinline__ void inner_call(const PairDev* __restrict__ pairs, co
                     }
                 }
             }
-            if (CANCEL && running && cx.cancelWord != nullptr && *cx.cancelWord != cx.cancelGen) { running = 0; status = 7; }   // the owner of this (speculative) call has moved on
+            if (CANCEL && running && *reinterpret_cast<volatile int*>(&cs.flag)) { running = 0; status = 7; }   // the owner of this (speculative) call has moved on
             if (lane == 0) { sh.running = running; sh.status = status; }
         }
         if (tid == 0) {

@@ -248,7 +248,7 @@ struct goicp_handle_s {
     PinBuf hStage, hPairs;
     WaveCtx main;
     MapBuf qOuts, qOrder, qIcp, qDone; DevBuf qClaim, qHeaps, qScratch, qMemo, dGen;   // persistent-queue mode (batches)
-    DevBuf sCtl, sHdrs, sSlots, sRq, sIcp, sOuts; PinBuf hOuts;   // device-resident search (k_search.cu)
+    DevBuf sCtl, sHdrs, sSlots, sStates, sRq, sIcp, sOuts; PinBuf hOuts;   // device-resident search (k_search.cu)
     int resident_search = 1;     // 1: OuterBnB runs on the device (k_search.cu); 0: host state machine + request ring (the round-1 scheduler)
     int spec_groups = SR_NGROUP - 4;   // device-resident search: most rotation-queue nodes with speculative calls per owner CTA (0: never speculate)
     int shardRank = 0, shardN = 1; goicp_allgather_fn allgather = nullptr; void* allgatherUser = nullptr;   // frontier sharding
@@ -1248,6 +1248,7 @@ static goicp_status register_resident(Eng* h, const BnbCfg& cfg) {
     CU(h->sCtl.ensure(sizeof(SearchCtl)));
     CU(h->sHdrs.ensure(goicp_search_hdr_bytes() * (size_t)ctas));
     CU(h->sSlots.ensure(goicp_search_slot_bytes() * (size_t)ctas * SR_NSLOT));
+    CU(h->sStates.ensure(sizeof(unsigned) * (size_t)ctas * SR_NSLOT));
     CU(h->sRq.ensure(goicp_search_rnode_bytes() * (size_t)ctas * 2 * rqCap));
     CU(h->sIcp.ensure(sizeof(IcpState) * 2 * (size_t)ctas));
     CU(h->sOuts.ensure(sizeof(PairOut) * (size_t)np));
@@ -1257,7 +1258,7 @@ static goicp_status register_resident(Eng* h, const BnbCfg& cfg) {
     if (h->qMemo.cap < (size_t)32 * memoCap * ctas) { CU(h->qMemo.ensure((size_t)32 * memoCap * ctas)); CU(cudaMemsetAsync(h->qMemo.p, 0, h->qMemo.cap, h->stream)); }
     CU(cudaMemsetAsync(h->sCtl.p, 0, sizeof(SearchCtl), h->stream));
     CU(cudaMemsetAsync(h->sHdrs.p, 0, goicp_search_hdr_bytes() * (size_t)ctas, h->stream));
-    CU(cudaMemsetAsync(h->sSlots.p, 0, goicp_search_slot_bytes() * (size_t)ctas * SR_NSLOT, h->stream));
+    CU(cudaMemsetAsync(h->sStates.p, 0, sizeof(unsigned) * (size_t)ctas * SR_NSLOT, h->stream));
     SearchArgs A{};
     A.pairs = h->dPairs.as<PairDev>(); A.npairs = np; A.nCtas = ctas;
     A.rotMinX = p.rotMinX; A.rotMinY = p.rotMinY; A.rotMinZ = p.rotMinZ; A.rotWidth = p.rotWidth;
@@ -1265,7 +1266,13 @@ static goicp_status register_resident(Eng* h, const BnbCfg& cfg) {
     { const char* e = getenv("GOICP_LIBM_FMA"); if (e) A.fma = atoi(e) != 0; }
     A.specMax = std::max(0, std::min(h->spec_groups, SR_NGROUP - 4));
     { const char* e = getenv("GOICP_SPEC_GROUPS"); if (e) A.specMax = std::max(0, std::min(atoi(e), SR_NGROUP - 4)); }
-    A.ctl = h->sCtl.as<SearchCtl>(); A.hdrs = h->sHdrs.as<OwnerHdr>(); A.slots = h->sSlots.as<SearchSlot>(); A.rq = h->sRq.p; A.rqCap = rqCap;
+    A.quietRamp = 1;
+    { const char* e = getenv("GOICP_QUIET_RAMP"); if (e) A.quietRamp = atoi(e) != 0; }
+    A.managerRatio = 8;
+    { const char* e = getenv("GOICP_MANAGER_RATIO"); if (e && atoi(e) >= 0) A.managerRatio = atoi(e); }
+    A.deepCalls = 2048;
+    { const char* e = getenv("GOICP_DEEP_CALLS"); if (e && atoi(e) >= 1) A.deepCalls = atoi(e); }
+    A.ctl = h->sCtl.as<SearchCtl>(); A.hdrs = h->sHdrs.as<OwnerHdr>(); A.slots = h->sSlots.as<SearchSlot>(); A.states = h->sStates.as<unsigned>(); A.rq = h->sRq.p; A.rqCap = rqCap;
     A.icp = h->sIcp.as<IcpState>(); A.outs = h->sOuts.as<PairOut>();
     A.heaps = h->qHeaps.as<HeapEnt>(); A.heapCap = heapCap; A.gscratch = h->qScratch.as<float>(); A.gstride = cfg.smemFloats; A.NdP = cfg.NdP; A.NdQ = cfg.NdQ; A.useSmem = cfg.useSmem;
     A.memo = reinterpret_cast<uint4*>(h->qMemo.p); A.memoCap = memoCap; A.genCounter = h->dGen.as<unsigned>(); A.gridOff = cfg.gridOff; A.S3p = cfg.S3p;
@@ -1309,6 +1316,18 @@ static goicp_status register_resident(Eng* h, const BnbCfg& cfg) {
       h->stats[5] = h->stats[6] = h->stats[7] = 0;
       h->main.callsLaunched += (long long)st8[3];
       if (getenv("GOICP_DEBUG")) {
+          SearchCtl ctl; cudaMemcpy(&ctl, h->sCtl.p, sizeof ctl, cudaMemcpyDeviceToHost);
+          fprintf(stderr, "[search] CTA cycles: OuterBnB state machine %.3g, publishing %.3g, help scan %.3g, idle (no pair) %.3g, owner waiting %.3g, ICP(2nd) %.3g; helper calls %llu (abandoned %llu); pair counter ran out at %.1f..%.1f ms\n",
+                  (double)ctl.dbg[0], (double)ctl.dbg[1], (double)ctl.dbg[2], (double)ctl.dbg[3], (double)ctl.dbg[4], (double)ctl.dbg[7], ctl.dbg[5], ctl.dbg[6], ctl.dbg[9] * 1e-6, ctl.dbg[8] * 1e-6);
+          fprintf(stderr, "[search] CTA cycles: queue pruning after improvements %.3g, rotation-queue pops %.3g\n", (double)ctl.dbg[10], (double)ctl.dbg[11]);
+          { std::vector<int> idx(np); for (int i = 0; i < np; i++) idx[i] = i; std::sort(idx.begin(), idx.end(), [&](int x, int y) { return outs[x].tEndMs > outs[y].tEndMs; });
+            for (int k = 0; k < std::min(np, 12); k++) { const PairOut& o = outs[idx[k]]; fprintf(stderr, "[search] late pair %d: claimed %.1f ms, finished %.1f ms, %lld calls, %lld rotation pops, %d events\n", idx[k], o.tStartMs, o.tEndMs, o.cnt[0], o.cnt[3], o.nEvents); }
+            std::sort(idx.begin(), idx.end(), [&](int x, int y) { return outs[x].cnt[0] > outs[y].cnt[0]; });
+            for (int k = 0; k < std::min(np, 12); k++) { const PairOut& o = outs[idx[k]]; fprintf(stderr, "[search] deep pair %d: claimed %.1f ms, finished %.1f ms, %lld calls, %lld rotation pops, %d events\n", idx[k], o.tStartMs, o.tEndMs, o.cnt[0], o.cnt[3], o.nEvents); } }
+          std::string a = "[search] pairs finished per 4 ms:", b = "[search] helper calls per 4 ms:  ";
+          int last = 0; for (int k = 0; k < 256; k++) if (ctl.finishHist[k] || ctl.helpHist[k]) last = k;
+          for (int k = 0; k <= last; k++) { char t[32]; snprintf(t, sizeof t, " %d", ctl.finishHist[k]); a += t; snprintf(t, sizeof t, " %d", ctl.helpHist[k]); b += t; }
+          fprintf(stderr, "%s\n%s\n", a.c_str(), b.c_str());
           fprintf(stderr, "[search] ctas %d calls %llu pops %llu busy-cycles/pop %.0f corner-misses/pop %.2f; CTA cycles: total %.4g in calls %.4g scheduling+idle %.4g; icp requests %llu\n", ctas, st8[3], st8[1],
                   (double)st8[0] / std::max<double>(1, st8[1]), (double)st8[2] / std::max<double>(1, st8[1]), (double)st8[7], (double)st8[0], (double)st8[4], st8[6]);
           if (st8[8]) fprintf(stderr, "[phases] cycles per pop: stage(per call) %.0f  A1 %.0f  A2 %.0f (chain on warp 0: %.0f)  C %.0f\n", (double)st8[8] / std::max<double>(1, st8[3]), (double)st8[9] / std::max<double>(1, st8[1]), (double)st8[10] / std::max<double>(1, st8[1]), (double)st8[12] / std::max<double>(1, st8[1]), (double)st8[11] / std::max<double>(1, st8[1]));
@@ -1458,7 +1477,7 @@ void goicp_destroy(goicp_handle h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf* bufs[] = {&h->arenaIn, &h->arenaWork, &h->dPairs, &h->dTmp, &h->dTmp2, &h->dTmp3, &h->dSepBits, &h->dSepNx, &h->dSepNxy, &h->sCtl, &h->sHdrs, &h->sSlots, &h->sRq, &h->sIcp, &h->sOuts};
+    DevBuf* bufs[] = {&h->arenaIn, &h->arenaWork, &h->dPairs, &h->dTmp, &h->dTmp2, &h->dTmp3, &h->dSepBits, &h->dSepNx, &h->dSepNxy, &h->sCtl, &h->sHdrs, &h->sSlots, &h->sStates, &h->sRq, &h->sIcp, &h->sOuts};
     for (DevBuf* b : bufs) b->release();
     h->hStage.release(); h->hPairs.release(); h->hOuts.release(); h->qOuts.release(); h->qOrder.release(); h->qIcp.release(); h->qDone.release(); h->qClaim.release(); h->qHeaps.release(); h->qScratch.release(); h->qMemo.release(); h->dGen.release();
     h->main.release();

@@ -51,6 +51,7 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
     float* icpTile;   // model tile of an ICP request: aliases the staging arrays (the dynamic region holds >= 3*NN_TILE floats)
     if constexpr (SMEM) icpTile = reinterpret_cast<float*>(dyn_smem4); else { __shared__ float s_tile[3 * NN_TILE]; icpTile = s_tile; }
     CallCtx cx;
+    __shared__ CancelSh s_cancel;   // unused here (CANCEL = false)
     if (GS) { if (tid == 0) mbar_init(&s_gbar, 1); __syncthreads(); }
 
     for (;;) {
@@ -103,7 +104,7 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
             }
             continue;
         }
-        inner_call<EXACT, SMEM, GS, CT, false>(pairs, pr, s_out, s_gbar, cx, heaps, heapCap, gscratch, gstride, NdP, NdQ, useSmem, memoAll, memoCap, genCounter, gridOff, S3p);
+        inner_call<EXACT, SMEM, GS, CT, false>(pairs, pr, s_out, s_gbar, cx, s_cancel, heaps, heapCap, gscratch, gstride, NdP, NdQ, useSmem, memoAll, memoCap, genCounter, gridOff, S3p);
         if (warp == 0) {   // the record leaves the SM as ONE coalesced 64-byte store (it may live in mapped host memory)
             __syncwarp();
             InnerOut* dst = PERSIST ? q.outs + p : outs + p;

@@ -26,7 +26,7 @@ namespace {
 enum { SL_FREE = 0, SL_QUEUED = 1, SL_RUNNING = 2, SL_DONE = 3, SL_SKIP = 4 };
 enum { OW_NONE = 0, OW_START, OW_AFTER_INIT, OW_POP, OW_CHILD, OW_AFTER_IMPROVE };
 enum { ACT_NONE = 0, ACT_CALL, ACT_ICP, ACT_EXIT };
-enum { RQ_ACTION = 0, RQ_SPAWN, RQ_FINDWORK };
+enum { RQ_ACTION = 0, RQ_SPAWN, RQ_FINDWORK, RQ_AGAIN, RQ_WAIT };
 
 struct alignas(16) RNodeD { float lb; int l; int group; float ub; float a, b, c, w; };   // ROTNODE (jly_goicp.h:59-73) + the slot group that holds its children's calls
 
@@ -38,11 +38,17 @@ struct OwnerSh {
     long long cnt[6];
     RNodeD par; int j, needLbOnly; float ubChild, lastLb;
     int heapN, nEvents, status;
-    int grpUse[SR_NGROUP];       // 0 free, 1 current node / queue node, 2 draining (calls of an abandoned incumbent may still run)
-    int specGroups;              // groups attached to queue nodes
+    int grpUse[SR_NGROUP];       // 0 free, 1 holds the calls of a node (the current one or a queue node), 2 draining (abandoned calls may still run)
+    alignas(16) unsigned grpKey[SR_NGROUP][4];   // the node a group belongs to: level and the bits of (a, b, c)
+    unsigned grpStamp[SR_NGROUP];                // last look-ahead walk that found the node among the next ones to pop
+    unsigned walkStamp;
+    int specGroups;              // (diagnostic) groups attached during the last walk
     int action, actOwner, actSlot, actCancel;
-    int noMorePairs, lastSpawnJ;
-    int cand[64]; int ncand;
+    int noMorePairs, lastSpawnJ, manager;
+    int quiet;                   // rotation nodes popped since the incumbent last improved: look-ahead grows 1, 3, 7, ... with it (calls made under an incumbent that is about to improve are wasted)
+    // results of the current node's children as last fetched by the warp (a slot that was done then stays done until the owner frees it)
+    unsigned pfState[8]; float pfOpt[8]; alignas(64) unsigned pfOut[8][16];   // (rows are read as InnerOut records)
+    int cand[64]; unsigned long long candKey[64]; int ncand;
 };
 
 __device__ __forceinline__ unsigned ld_vol(const unsigned* p) { return *reinterpret_cast<const volatile unsigned*>(p); }
@@ -116,12 +122,15 @@ __device__ bool child_rotation(bool fma, const RNodeD& nr, float* R) {
 struct Cta {   // what every routine of this file needs about the CTA's place in the world
     const SearchArgs& A;
     OwnerSh& os;
-    SearchSlot* slots;       // this CTA's own slots
+    SearchSlot* slots;       // this CTA's own slots ...
+    unsigned* st;            // ... and their state words: SL_* in the low byte, queued calls carry their priority above it
     OwnerHdr* hdr;           // this CTA's header
     RNodeD* rq;              // this CTA's rotation queue
     IcpState* icp;           // this CTA's two ICP states
     int me, lane;
 };
+__device__ __forceinline__ unsigned st_of(unsigned w) { return w & 0xFFu; }
+__device__ __forceinline__ unsigned queued_word(unsigned prio) { return SL_QUEUED | (prio & 0xFFFFFF00u); }   // prio: float bits of the node's lb (>= 0: bit order = value order)
 
 __device__ __forceinline__ void add_event(Cta& c, int kind, float v) {
     OwnerSh& os = c.os;
@@ -130,13 +139,18 @@ __device__ __forceinline__ void add_event(Cta& c, int kind, float v) {
     os.nEvents++;
 }
 
-// a request for child `ch` (rotation R) of the current incumbent into slot s; state is set by the caller
-__device__ __forceinline__ void fill_request(Cta& c, SearchSlot* s, const RNodeD& ch, const float* R, bool lbOnly, unsigned prio) {
+// a request for child `ch` (rotation R) of the current incumbent into slot s; the state word is set by the caller
+__device__ __forceinline__ void fill_request(Cta& c, SearchSlot* s, const RNodeD& ch, const float* R, bool lbOnly) {
     const int lbLevel = min(ch.l, GOICP_MAXROTLEVEL - 1);   // Q2: the reference indexes maxRotDis[level] without a bound check; clamped
     s->pr.pair = c.os.pair; s->pr.level = lbOnly ? lbLevel : GOICP_REQ_BOTH + lbLevel; s->pr.optError = c.os.optError;
 #pragma unroll
     for (int k = 0; k < 9; k++) s->pr.R[k] = R[k];
-    s->prio = prio; s->gen = ld_vol(&c.hdr->gen);
+    s->gen = ld_vol(&c.hdr->gen);
+}
+// withdraws a queued call; false if a helper has just claimed it
+__device__ __forceinline__ bool withdraw(Cta& c, int s, unsigned w) {
+    if (atomicCAS(c.st + s, w, (unsigned)SL_FREE) == w) { atomicSub(&c.hdr->nQueued, 1u); return true; }
+    return false;
 }
 
 // the incumbent changed (or the pair ended): every speculative call is void.  Unclaimed ones are withdrawn, running ones are left to
@@ -147,31 +161,67 @@ __device__ void invalidate_spec(Cta& c) {
     __syncwarp();
     for (int s = c.lane; s < SR_NSLOT; s += 32) {
         if (os.grpUse[s >> 3] == 0) continue;
-        SearchSlot* sl = c.slots + s;
-        const unsigned st = ld_vol(&sl->state);
-        if (st == SL_QUEUED) { if (atomicCAS(&sl->state, (unsigned)SL_QUEUED, (unsigned)SL_FREE) == SL_QUEUED) atomicSub(&c.hdr->nQueued, 1u); }
-        else if (st == SL_DONE || st == SL_SKIP) st_vol(&sl->state, SL_FREE);
+        const unsigned w = ld_vol(c.st + s);
+        if (st_of(w) == SL_QUEUED) withdraw(c, s, w);
+        else if (st_of(w) == SL_DONE || st_of(w) == SL_SKIP) st_vol(c.st + s, SL_FREE);
     }
     __syncwarp();
     if (c.lane == 0) { for (int g = 0; g < SR_NGROUP; g++) if (os.grpUse[g] != 0) os.grpUse[g] = 2; os.specGroups = 0; }
+    if (c.lane < 8) os.pfState[c.lane] = SL_FREE;
     __syncwarp();
 }
-// a free slot group (all 8 slots FREE), or -1.  Draining groups whose calls have all finished are recycled.  Lane 0.
-__device__ int alloc_group(Cta& c, int reserve) {
+__device__ __forceinline__ uint4 node_key(const RNodeD& n) { return make_uint4((unsigned)n.l, __float_as_uint(n.a), __float_as_uint(n.b), __float_as_uint(n.c)); }
+// the group that holds the calls of node `key`, or -1.  Lane 0 (serial form, used at a pop).
+__device__ int lookup_group(Cta& c, const uint4 key) {
     OwnerSh& os = c.os;
-    if (reserve > 0) { int used = 0; for (int g = 0; g < SR_NGROUP; g++) used += os.grpUse[g] != 0; if (used + reserve >= SR_NGROUP) return -1; }   // speculation leaves groups for the node being expanded
     for (int g = 0; g < SR_NGROUP; g++) {
-        if (os.grpUse[g] == 2) {
-            bool busy = false;
-            for (int k = 0; k < 8; k++) {
-                SearchSlot* sl = c.slots + 8 * g + k;
-                unsigned st = ld_vol(&sl->state);
-                if (st == SL_QUEUED) { if (atomicCAS(&sl->state, (unsigned)SL_QUEUED, (unsigned)SL_FREE) == SL_QUEUED) { atomicSub(&c.hdr->nQueued, 1u); st = SL_FREE; } else st = SL_RUNNING; }
-                if (st == SL_RUNNING) busy = true; else if (st != SL_FREE) st_vol(&sl->state, SL_FREE);
-            }
-            if (!busy) os.grpUse[g] = 0;
-        }
+        if (os.grpUse[g] != 1) continue;
+        const uint4 k = *reinterpret_cast<const uint4*>(os.grpKey[g]);
+        if (k.x == key.x && k.y == key.y && k.z == key.z && k.w == key.w) return g;
+    }
+    return -1;
+}
+// the same by all lanes
+__device__ __forceinline__ int lookup_group_w(Cta& c, const uint4 key) {
+    OwnerSh& os = c.os;
+    int f = -1;
+    for (int g = c.lane; g < SR_NGROUP; g += 32) {
+        if (os.grpUse[g] != 1) continue;
+        const uint4 k = *reinterpret_cast<const uint4*>(os.grpKey[g]);
+        if (k.x == key.x && k.y == key.y && k.z == key.z && k.w == key.w) f = g;
+    }
+    return __reduce_max_sync(GOICP_FULL, f);
+}
+// empties group g: unclaimed calls are withdrawn, finished ones dropped; false if a call is still running somewhere (the group
+// then drains: grpUse = 2)
+__device__ bool clear_group(Cta& c, int g) {
+    bool busy = false;
+    for (int k = 0; k < 8; k++) {
+        const unsigned w = ld_vol(c.st + 8 * g + k);
+        unsigned st = st_of(w);
+        if (st == SL_QUEUED) st = withdraw(c, 8 * g + k, w) ? SL_FREE : SL_RUNNING;
+        if (st == SL_RUNNING) busy = true; else if (st != SL_FREE) st_vol(c.st + 8 * g + k, SL_FREE);
+    }
+    c.os.grpUse[g] = busy ? 2 : 0;
+    return !busy;
+}
+// A group for a node: a free one, a drained one, or -- when every group is taken -- the one whose node has been longest out of
+// the look-ahead window (its node sank in the queue; speculation follows the front).  -1: nothing available right now.  Lane 0.
+__device__ int alloc_group(Cta& c, int keep) {
+    OwnerSh& os = c.os;
+    for (int g = 0; g < SR_NGROUP; g++) {
+        if (os.grpUse[g] == 2) clear_group(c, g);
         if (os.grpUse[g] == 0) { os.grpUse[g] = 1; return g; }
+    }
+    for (int tries = 0; tries < 4; tries++) {
+        int victim = -1; unsigned oldest = 0;
+        for (int g = 0; g < SR_NGROUP; g++) {
+            if (os.grpUse[g] != 1 || g == keep || os.grpStamp[g] == os.walkStamp) continue;
+            const unsigned age = os.walkStamp - os.grpStamp[g];
+            if (victim < 0 || age > oldest) { victim = g; oldest = age; }
+        }
+        if (victim < 0) return -1;
+        if (clear_group(c, victim)) { os.grpUse[victim] = 1; return victim; }
     }
     return -1;
 }
@@ -183,17 +233,41 @@ __device__ void finish_pair(Cta& c, int endKind) {   // lane 0
     for (int k = 0; k < 3; k++) o.t[k] = os.optT[k];
     o.optError = os.optError; o.optComp = os.optComp;
     for (int k = 0; k < 6; k++) o.cnt[k] = os.cnt[k];
+    { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); o.tEndMs = (float)((now - c.A.ctl->t0ns) * 1e-6); }
     o.status = os.status; o.endKind = endKind; o.endLb = endKind == 2 ? os.par.lb : os.lastLb; o.nEvents = min(os.nEvents, SR_MAXEV);
 }
 
+// The state words of the current node's 8 children in one load, then the result records of the finished ones (two round trips to
+// L2 for the whole node instead of a dozen dependent ones per child).  All lanes of warp 0.
+__device__ __forceinline__ void prefetch_group(Cta& c) {
+    OwnerSh& os = c.os;
+    const int g = os.par.group, lane = c.lane;
+    unsigned w = SL_FREE;
+    if (lane < 8) w = ld_vol(c.st + 8 * g + lane);
+    const unsigned doneMask = __ballot_sync(GOICP_FULL, lane < 8 && st_of(w) == SL_DONE && os.pfState[lane & 7] != SL_DONE);
+    __threadfence();
+    if (doneMask) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int k = (lane + 32 * q) >> 4, word = (lane + 32 * q) & 15;
+            if ((doneMask >> k) & 1u) os.pfOut[k][word] = reinterpret_cast<const volatile unsigned*>(&c.slots[8 * g + k].out)[word];
+        }
+        if (lane < 8 && ((doneMask >> lane) & 1u)) os.pfOpt[lane] = *reinterpret_cast<const volatile float*>(&c.slots[8 * g + lane].pr.optError);
+    }
+    if (lane < 8 && os.pfState[lane] != SL_DONE) os.pfState[lane] = st_of(w);
+    __syncwarp();
+}
+
 // ---- the OuterBnB state machine, lane 0 of the owner's warp 0.  Returns what it needs next. --------------------------------------
-__device__ __noinline__ int owner_serial(Cta& c) {
+__device__ __forceinline__ int owner_serial(Cta& c) {
     OwnerSh& os = c.os;
     const SearchArgs& A = c.A;
     for (;;) {
         switch (os.phase) {
         case OW_START: {   // initial error (:601-627) and ICP from the identity (:634)
             const PairDev& P = A.pairs[os.pair];
+            { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); A.outs[os.pair].tStartMs = (float)((now - A.ctl->t0ns) * 1e-6); }
+            os.quiet = 0;
             os.SSE = P.SSEThresh; os.optComp = 0; os.status = 0; os.nEvents = 0; os.heapN = 0; os.lastLb = 0.f; os.needLbOnly = 0;
             for (int k = 0; k < 6; k++) os.cnt[k] = 0;
             for (int k = 0; k < 9; k++) os.optR[k] = (k % 4 == 0) ? 1.0 : 0.0;
@@ -236,60 +310,75 @@ __device__ __noinline__ int owner_serial(Cta& c) {
         case OW_POP: {
             if (os.status != 0) { finish_pair(c, 0); os.phase = OW_NONE; break; }
             if (os.heapN == 0) { finish_pair(c, 1); os.phase = OW_NONE; break; }                   // :670-677
-            os.par = rq_pop(c.rq, os.heapN); os.cnt[3]++;
-            if (os.par.group >= 0) os.specGroups--;
+            os.quiet++;
+            { const long long tp0 = clock64(); os.par = rq_pop(c.rq, os.heapN); atomicAdd(&A.ctl->dbg[11], (unsigned long long)(clock64() - tp0)); } os.cnt[3]++;
             if ((os.optError - os.par.lb) <= os.SSE) { finish_pair(c, 2); os.phase = OW_NONE; break; }   // :685
-            if (os.par.group < 0) {
-                int g;
-                while ((g = alloc_group(c, 0)) < 0) __nanosleep(200);   // every group still drains calls of an abandoned incumbent (they stop at their next pop)
+            {
+                const uint4 key = node_key(os.par);
+                int g = lookup_group(c, key);   // calls made ahead of time for this node?
+                if (g < 0) {
+                    while ((g = alloc_group(c, -1)) < 0) __nanosleep(200);   // every group has calls running (they stop at their next pop if abandoned)
+                    *reinterpret_cast<uint4*>(os.grpKey[g]) = key;
+                }
+                os.grpStamp[g] = os.walkStamp + 1u;   // the walk that follows must not take it away
                 os.par.group = g;
             }
+            for (int k = 0; k < 8; k++) os.pfState[k] = SL_FREE;
             os.j = 0; os.needLbOnly = 0; os.phase = OW_CHILD; os.lastSpawnJ = 0;
             return RQ_SPAWN;
         }
         case OW_CHILD: {
             if (os.j >= 8) {
-                for (int k = 0; k < 8; k++) st_vol(&c.slots[8 * os.par.group + k].state, SL_FREE);
+                for (int k = 0; k < 8; k++) st_vol(c.st + 8 * os.par.group + k, SL_FREE);
                 os.grpUse[os.par.group] = 0;
                 os.phase = OW_POP; break;
             }
-            SearchSlot* sl = c.slots + 8 * os.par.group + os.j;
-            unsigned st = ld_vol(&sl->state);
-            if (st == SL_SKIP) { os.j++; break; }
-            if (st == SL_FREE) {
-                if (A.specMax > 0 && os.lastSpawnJ != os.j && ld_voli(&A.ctl->nextPair) >= A.npairs) { os.lastSpawnJ = os.j; return RQ_SPAWN; }   // helpers may have appeared since the last pop
-                const RNodeD ch = child_of(os.par, os.j);
-                float R[9];
-                if (!child_rotation(A.fma != 0, ch, R)) { os.j++; break; }
-                fill_request(c, sl, ch, R, os.needLbOnly != 0, 0u);
-                st_vol(&sl->state, SL_RUNNING);
-                os.action = ACT_CALL; os.actOwner = c.me; os.actSlot = 8 * os.par.group + os.j; os.actCancel = 0;
-                return RQ_ACTION;
-            }
-            if (st == SL_QUEUED) {
-                if (atomicCAS(&sl->state, (unsigned)SL_QUEUED, (unsigned)SL_RUNNING) == SL_QUEUED) {
-                    atomicSub(&c.hdr->nQueued, 1u);
-                    __threadfence();
-                    os.action = ACT_CALL; os.actOwner = c.me; os.actSlot = 8 * os.par.group + os.j; os.actCancel = 0;
+            const int sidx = 8 * os.par.group + os.j;
+            SearchSlot* sl = c.slots + sidx;
+            if (os.pfState[os.j] != SL_DONE) {   // not finished when the warp last looked: what is it doing now?
+                const unsigned w = ld_vol(c.st + sidx);
+                const unsigned st = st_of(w);
+                if (st == SL_DONE) return RQ_AGAIN;   // finished meanwhile: fetch its record
+                if (st == SL_SKIP) { os.j++; break; }
+                if (st == SL_FREE) {
+                    if (A.specMax > 0 && os.lastSpawnJ != os.j && os.cnt[0] >= 16) { os.lastSpawnJ = os.j; return RQ_SPAWN; }   // helpers may have appeared since the last pop
+                    const RNodeD ch = child_of(os.par, os.j);
+                    float R[9];
+                    if (!child_rotation(A.fma != 0, ch, R)) { os.j++; break; }
+                    fill_request(c, sl, ch, R, os.needLbOnly != 0);
+                    if (os.manager) {   // plenty of helpers: the owner only manages; a helper runs the call
+                        __threadfence(); st_vol(c.st + sidx, queued_word(0u)); atomicAdd(&c.hdr->nQueued, 1u); atomicOr(&A.ctl->wantHelp[c.me >> 5], 1u << (c.me & 31));
+                        return RQ_WAIT;
+                    }
+                    st_vol(c.st + sidx, SL_RUNNING);
+                    os.action = ACT_CALL; os.actOwner = c.me; os.actSlot = sidx; os.actCancel = 0;
                     return RQ_ACTION;
                 }
-                break;   // a helper took it this instant
+                if (st == SL_QUEUED) {
+                    if (os.manager) { atomicOr(&A.ctl->wantHelp[c.me >> 5], 1u << (c.me & 31)); return RQ_WAIT; }   // (a helper that found nothing a moment ago may have cleared the hint)
+                    if (atomicCAS(c.st + sidx, w, (unsigned)SL_RUNNING) == w) {
+                        atomicSub(&c.hdr->nQueued, 1u);
+                        __threadfence();
+                        os.action = ACT_CALL; os.actOwner = c.me; os.actSlot = sidx; os.actCancel = 0;
+                        return RQ_ACTION;
+                    }
+                    break;   // a helper took it this instant
+                }
+                return os.manager ? RQ_WAIT : RQ_FINDWORK;   // running on a helper: do something useful meanwhile
             }
-            if (st == SL_RUNNING) return RQ_FINDWORK;   // a helper is on it: do something useful meanwhile
-            // SL_DONE: consume in the reference's order
-            __threadfence();
-            const volatile InnerOut* o = &sl->out;
-            const int ost = o->status;
-            if (ost == 7) { st_vol(&sl->state, SL_FREE); break; }   // abandoned under an older generation (cannot be the call we wait for, but harmless): redo
-            if (ost != 0) { os.status = GOICP_SR_OVERFLOW; finish_pair(c, 0); os.phase = OW_NONE; break; }
-            if (*reinterpret_cast<const volatile float*>(&sl->pr.optError) != os.optError) { st_vol(&sl->state, SL_FREE); break; }     // made under another incumbent: redo (defensive; invalidation withdraws these)
+            // done: consume in the reference's order (the record was fetched by prefetch_group)
+            const InnerOut& o = *reinterpret_cast<const InnerOut*>(os.pfOut[os.j]);
+            os.pfState[os.j] = SL_FREE;
+            if (o.status == 7) { st_vol(c.st + sidx, SL_FREE); break; }   // abandoned under an older generation (cannot be the call we wait for, but harmless): redo
+            if (o.status != 0) { os.status = GOICP_SR_OVERFLOW; finish_pair(c, 0); os.phase = OW_NONE; break; }
+            if (os.pfOpt[os.j] != os.optError) { st_vol(c.st + sidx, SL_FREE); break; }     // made under another incumbent: redo (defensive; invalidation withdraws these)
             if (!os.needLbOnly) {
-                os.cnt[4]++; os.cnt[0]++; os.cnt[1] += o->pops; os.cnt[2] += o->subcubes;   // :768
-                os.ubChild = o->err;
-                if (o->err < os.optError) {                                                  // :771-790
-                    os.optError = o->err;
+                os.cnt[4]++; os.cnt[0]++; os.cnt[1] += o.pops; os.cnt[2] += o.subcubes;     // :768
+                os.ubChild = o.err;
+                if (o.err < os.optError) {                                                  // :771-790
+                    os.optError = o.err;
                     for (int k = 0; k < 9; k++) os.optR[k] = (double)*reinterpret_cast<const volatile float*>(&sl->pr.R[k]);
-                    const float n0 = o->node[0], n1 = o->node[1], n2 = o->node[2], nw = o->node[3];
+                    const float n0 = o.node[0], n1 = o.node[1], n2 = o.node[2], nw = o.node[3];
                     os.optT[0] = (double)(n0 + nw / 2); os.optT[1] = (double)(n1 + nw / 2); os.optT[2] = (double)(n2 + nw / 2);
                     for (int q = 0; q < 2; q++) {   // updateCompatibilities (:791) + ICP(R, t) (:810) at the new incumbent
                         IcpState& s = c.icp[q];
@@ -299,29 +388,30 @@ __device__ __noinline__ int owner_serial(Cta& c) {
                         s.err = -1.f; s.iter = 0; s.done = 0; s.status = 0; s.error = 0.f; s.incomp = 0; s.fpfh = 0.f; s.compat_pose = 0;
                     }
                     __threadfence();
-                    st_vol(&sl->state, SL_FREE);
+                    st_vol(c.st + sidx, SL_FREE);
+                    os.quiet = 0;
                     os.needLbOnly = 1; os.phase = OW_AFTER_IMPROVE; os.action = ACT_ICP;
                     return RQ_ACTION;
                 }
-                if (!o->ran2) { st_vol(&sl->state, SL_FREE); os.needLbOnly = 1; break; }     // (cannot happen: the second call is skipped only on improvement)
-                os.cnt[0]++; os.cnt[1] += o->pops2; os.cnt[2] += o->subcubes2;                // :861
-                os.lastLb = o->err2;
-                if (!(o->err2 >= os.optError)) {                                             // :863-871
-                    RNodeD nr = child_of(os.par, os.j); nr.ub = os.ubChild; nr.lb = o->err2;
+                if (!o.ran2) { st_vol(c.st + sidx, SL_FREE); os.needLbOnly = 1; break; }     // (cannot happen: the second call is skipped only on improvement)
+                os.cnt[0]++; os.cnt[1] += o.pops2; os.cnt[2] += o.subcubes2;                 // :861
+                os.lastLb = o.err2;
+                if (!(o.err2 >= os.optError)) {                                             // :863-871
+                    RNodeD nr = child_of(os.par, os.j); nr.ub = os.ubChild; nr.lb = o.err2;
                     if (os.heapN >= A.rqCap) { os.status = GOICP_SR_OVERFLOW; finish_pair(c, 0); os.phase = OW_NONE; break; }
                     rq_push(c.rq, os.heapN, nr);
                 }
             } else {
-                os.cnt[0]++; os.cnt[1] += o->pops; os.cnt[2] += o->subcubes;
-                os.lastLb = o->err;
-                if (!(o->err >= os.optError)) {
-                    RNodeD nr = child_of(os.par, os.j); nr.ub = os.ubChild; nr.lb = o->err;
+                os.cnt[0]++; os.cnt[1] += o.pops; os.cnt[2] += o.subcubes;
+                os.lastLb = o.err;
+                if (!(o.err >= os.optError)) {
+                    RNodeD nr = child_of(os.par, os.j); nr.ub = os.ubChild; nr.lb = o.err;
                     if (os.heapN >= A.rqCap) { os.status = GOICP_SR_OVERFLOW; finish_pair(c, 0); os.phase = OW_NONE; break; }
                     rq_push(c.rq, os.heapN, nr);
                 }
                 os.needLbOnly = 0;
             }
-            st_vol(&sl->state, SL_FREE);
+            st_vol(c.st + sidx, SL_FREE);
             os.j++;
             break;
         }
@@ -342,13 +432,16 @@ __device__ __noinline__ int owner_serial(Cta& c) {
             // :843-853: pop in order into a new queue until the first node with lb >= optError.  Pushing in pop order never sifts
             // (no parent is "less" than a later key), so the new heap array is the popped prefix itself.
             {
+                const long long tp0 = clock64();
                 RNodeD* tmp = c.rq + A.rqCap;   // second half of the slab
                 int n = os.heapN, m = 0;
-                while (n > 0) { RNodeD nd = rq_pop(c.rq, n); if (nd.lb < os.optError) { nd.group = -1; st_node(tmp + m, nd); m++; } else break; }
+                while (n > 0) { RNodeD nd = rq_pop(c.rq, n); if (nd.lb < os.optError) { st_node(tmp + m, nd); m++; } else break; }
                 for (int k = 0; k < m; k++) st_node(c.rq + k, ld_node(tmp + k));
                 os.heapN = m;
+                atomicAdd(&A.ctl->dbg[10], (unsigned long long)(clock64() - tp0));
             }
-            { int g; while ((g = alloc_group(c, 0)) < 0) __nanosleep(200); os.par.group = g; }   // the old group drains (calls of the previous incumbent)
+            { int g; while ((g = alloc_group(c, -1)) < 0) __nanosleep(200); os.par.group = g; *reinterpret_cast<uint4*>(os.grpKey[g]) = node_key(os.par); os.grpStamp[g] = os.walkStamp + 1u; }   // the old group drains (calls of the previous incumbent)
+            for (int k = 0; k < 8; k++) os.pfState[k] = SL_FREE;
             os.lastSpawnJ = os.j;
             os.phase = OW_CHILD;
             return RQ_SPAWN;
@@ -359,23 +452,37 @@ __device__ __noinline__ int owner_serial(Cta& c) {
     }
 }
 
-// How many slot groups the owner should keep attached to queue nodes: none while unclaimed pairs remain (idle CTAs take pairs),
-// afterwards the helpers are shared among the owners.  All lanes (warp-uniform result).
+// How many slot groups the owner should keep attached to queue nodes: none while unclaimed pairs remain (idle CTAs take pairs) unless
+// the pair is already deep; afterwards the helpers are shared among the owners.  All lanes (warp-uniform result).
 __device__ __forceinline__ int spec_target(Cta& c) {
     const SearchArgs& A = c.A;
     int t = 0;
-    if (c.lane == 0 && A.specMax > 0 && ld_voli(&A.ctl->nextPair) >= A.npairs) {
-        const int owners = max(1, ld_voli(&A.ctl->owners));
-        const int helpers = max(0, A.nCtas - owners);
-        const int tasks = (helpers + owners - 1) / owners;     // calls in flight per owner that keep every helper busy
-        t = min(A.specMax, (tasks + 7) / 8 + (tasks > 0 ? 1 : 0));
+    if (c.lane == 0 && A.specMax > 0) {
+        // a pair that has already consumed many calls is likely one of the few deep ones that decide when the batch ends: it
+        // asks for help early (CTAs look for such calls before they claim their next pair), the more the deeper it gets
+        const long long calls = c.os.cnt[0];
+        int manager = 0;
+        // (the bar sinks as the pair list runs out: a deep pair that is claimed late has little time left to show its depth)
+        const int next = ld_voli(&A.ctl->nextPair);
+        const long long bar = max(16ll, (long long)A.deepCalls * max(0, A.npairs - next) / max(1, A.npairs));
+        if (calls >= bar) t = (int)min((long long)A.specMax, calls / bar);
+        if (next >= A.npairs) {
+            const int owners = max(1, ld_voli(&A.ctl->owners));
+            const int helpers = max(0, A.nCtas - owners);
+            const int tasks = (helpers + owners - 1) / owners;     // calls in flight per owner that keep every helper busy
+            if (tasks > 0) t = A.specMax;   // helpers outnumber what one node can feed: look as far ahead as the slots allow (a node that is popped without
+                                            // results costs a whole call of latency, so the hit rate matters more than the abandoned work)
+            manager = A.managerRatio > 0 && helpers >= A.managerRatio * owners;
+        }
+        c.os.manager = manager;
+        if (A.quietRamp && next < A.npairs && c.os.quiet < 6) t = min(t, (1 << c.os.quiet) - 1);   // (helpers are scarce only while pairs are still being claimed)
     }
     return __shfl_sync(GOICP_FULL, t, 0);
 }
 
 // Publish speculative calls: the remaining children of the current node, then the children of the next queue nodes in pop order.
 // All lanes of warp 0.
-__device__ __noinline__ void spawn_spec(Cta& c) {
+__device__ __forceinline__ void spawn_spec(Cta& c) {
     OwnerSh& os = c.os;
     const SearchArgs& A = c.A;
     const int target = spec_target(c);
@@ -384,111 +491,168 @@ __device__ __noinline__ void spawn_spec(Cta& c) {
     int published = 0;
     // children after the current one (the current one is the owner's own next call)
     if (lane < 8 && lane > os.j) {
-        SearchSlot* sl = c.slots + 8 * os.par.group + lane;
-        if (ld_vol(&sl->state) == SL_FREE) {
+        const int sidx = 8 * os.par.group + lane;
+        if (st_of(ld_vol(c.st + sidx)) == SL_FREE) {
             const RNodeD ch = child_of(os.par, lane);
             float R[9];
-            if (!child_rotation(A.fma != 0, ch, R)) st_vol(&sl->state, SL_SKIP);
-            else { fill_request(c, sl, ch, R, false, 0u); __threadfence(); st_vol(&sl->state, SL_QUEUED); published++; }
+            if (!child_rotation(A.fma != 0, ch, R)) st_vol(c.st + sidx, SL_SKIP);
+            else { fill_request(c, c.slots + sidx, ch, R, false); __threadfence(); st_vol(c.st + sidx, queued_word(0u)); published++; }
         }
     }
-    // the next nodes in pop order: the queue is a binary heap, so they are reached from the root through a frontier of candidate
-    // positions; candidate keys are compared by all lanes at once
-    if (lane == 0) { os.ncand = 0; if (os.heapN > 0) { os.cand[0] = 0; os.ncand = 1; } }
+    // The next nodes in pop order: the queue is a binary heap, so they are reached from the root through a frontier of candidate
+    // positions whose keys sit in shared memory and are compared by all lanes at once.  The walk is only made when several groups
+    // are missing (one walk then attaches them all).
+    if (lane == 0) { os.walkStamp++; os.grpStamp[os.par.group] = os.walkStamp; os.specGroups = 0; os.ncand = 0; if (os.heapN > 0) { os.cand[0] = 0; const RNodeD nd = ld_node(c.rq); os.candKey[0] = ((unsigned long long)__float_as_uint(nd.lb) << 32) | ((unsigned long long)(unsigned)nd.l << 8); os.ncand = 1; } }
     __syncwarp();
-    int withGroup = 0;
-    for (int it = 0; it < A.specMax + 8 && withGroup < target; it++) {
+    for (int it = 0; it < target; it++) {
         const int nc = os.ncand;
         if (nc == 0) break;
         unsigned long long best = ~0ull;
-        for (int k = lane; k < nc; k += 32) {
-            const RNodeD nd = ld_node(c.rq + os.cand[k]);
-            const unsigned long long key = ((unsigned long long)__float_as_uint(nd.lb) << 32) | ((unsigned long long)(unsigned)nd.l << 8) | (unsigned)k;
-            best = key < best ? key : best;
-        }
+        for (int k = lane; k < nc; k += 32) { const unsigned long long key = os.candKey[k] | (unsigned)k; best = key < best ? key : best; }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(GOICP_FULL, best, o); best = v < best ? v : best; }
         const int k = (int)(best & 0xFFu);
         const int pos = os.cand[k];
         __syncwarp();
-        if (lane == 0) {
-            os.cand[k] = os.cand[nc - 1]; int n2 = nc - 1;
-            if (2 * pos + 1 < os.heapN && n2 < 62) os.cand[n2++] = 2 * pos + 1;
-            if (2 * pos + 2 < os.heapN && n2 < 62) os.cand[n2++] = 2 * pos + 2;
-            os.ncand = n2;
+        if (lane < 2) {   // the node leaves the frontier, its two heap children enter
+            const int cp = 2 * pos + 1 + lane;
+            unsigned long long key = 0; const bool have = cp < os.heapN;
+            if (have) { const RNodeD nd = ld_node(c.rq + cp); key = ((unsigned long long)__float_as_uint(nd.lb) << 32) | ((unsigned long long)(unsigned)nd.l << 8); }
+            const unsigned hm = __ballot_sync(0x3u, have);
+            int n2 = nc - 1;
+            if (lane == 0) { os.cand[k] = os.cand[n2]; os.candKey[k] = os.candKey[n2]; }
+            __syncwarp(0x3u);
+            const int slot = n2 + __popc(hm & ((1u << lane) - 1u));
+            if (have && slot < 62) { os.cand[slot] = cp; os.candKey[slot] = key; }
+            if (lane == 0) os.ncand = min(62, n2 + __popc(hm));
         }
         __syncwarp();
-        RNodeD nd = ld_node(c.rq + pos);
+        const RNodeD nd = ld_node(c.rq + pos);
         if ((os.optError - nd.lb) <= os.SSE) break;   // the search ends when this node is popped (:685)
-        if (nd.group < 0) {
-            int g = -1;
-            if (lane == 0) g = alloc_group(c, 2);
-            g = __shfl_sync(GOICP_FULL, g, 0);
-            if (g < 0) break;
-            nd.group = g;
-            if (lane == 0) { st_node(c.rq + pos, nd); os.specGroups++; }
-            if (lane < 8) {
-                SearchSlot* sl = c.slots + 8 * g + lane;
-                const RNodeD ch = child_of(nd, lane);
-                float R[9];
-                if (!child_rotation(A.fma != 0, ch, R)) st_vol(&sl->state, SL_SKIP);
-                else { fill_request(c, sl, ch, R, false, __float_as_uint(nd.lb) | 1u); __threadfence(); st_vol(&sl->state, SL_QUEUED); published++; }
-            }
+        const uint4 key = node_key(nd);
+        int g = lookup_group_w(c, key);
+        if (g >= 0) { if (lane == 0) os.grpStamp[g] = os.walkStamp; __syncwarp(); continue; }   // its calls are already out
+        if (lane == 0) g = alloc_group(c, os.par.group);
+        g = __shfl_sync(GOICP_FULL, g, 0);
+        if (g < 0) break;
+        if (lane == 0) { *reinterpret_cast<uint4*>(os.grpKey[g]) = key; os.grpStamp[g] = os.walkStamp; os.specGroups++; }
+        if (lane < 8) {
+            const int sidx = 8 * g + lane;
+            const RNodeD ch = child_of(nd, lane);
+            float R[9];
+            if (!child_rotation(A.fma != 0, ch, R)) st_vol(c.st + sidx, SL_SKIP);
+            else { fill_request(c, c.slots + sidx, ch, R, false); __threadfence(); st_vol(c.st + sidx, queued_word(__float_as_uint(nd.lb) | 0x100u)); published++; }
         }
-        withGroup++;
+        __syncwarp();
     }
     published = __reduce_add_sync(GOICP_FULL, published);
-    if (lane == 0 && published) atomicAdd(&c.hdr->nQueued, (unsigned)published);
+    if (lane == 0 && published) { atomicAdd(&c.hdr->nQueued, (unsigned)published); atomicOr(&A.ctl->wantHelp[c.me >> 5], 1u << (c.me & 31)); }
     __syncwarp();
 }
 
-// the unclaimed call with the smallest priority in owner `o`'s slots; claims it.  All lanes; returns the slot or -1.
-__device__ int claim_from(Cta& c, int o) {
-    SearchSlot* sl = c.A.slots + (size_t)o * SR_NSLOT;
-    for (int tries = 0; tries < 4; tries++) {
-        unsigned long long best = ~0ull;
-        for (int s = c.lane; s < SR_NSLOT; s += 32) {
-            if (ld_vol(&sl[s].state) == SL_QUEUED) { const unsigned long long key = ((unsigned long long)ld_vol(&sl[s].prio) << 16) | (unsigned)s; best = key < best ? key : best; }
-        }
+// Claims an unclaimed call of owner `o`.  While pairs are still being claimed helpers are scarce and take the most urgent call (the
+// smallest priority); afterwards hundreds of helpers look at the same owner at once, so each takes a different one (the r-th in slot
+// order, r derived from the CTA index).  All lanes; returns the slot, -1 if nothing is queued, -2 if other helpers were faster.
+__device__ int claim_from(Cta& c, int o, bool urgent) {
+    unsigned* st = c.A.states + (size_t)o * SR_NSLOT;
+    for (int tries = 0; tries < 3; tries++) {
+        unsigned w[SR_NSLOT / 32];
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) { const unsigned long long v = __shfl_xor_sync(GOICP_FULL, best, off); best = v < best ? v : best; }
-        if (best == ~0ull) return -1;
-        const int s = (int)(best & 0xFFFFu);
+        for (int q = 0; q < SR_NSLOT / 32; q++) w[q] = ld_vol(st + 32 * q + c.lane);   // one round trip: the state words are contiguous
+        int s = -1; unsigned word = 0;
+        if (urgent) {
+            unsigned long long best = ~0ull;
+#pragma unroll
+            for (int q = 0; q < SR_NSLOT / 32; q++) if (st_of(w[q]) == SL_QUEUED) { const unsigned long long key = ((unsigned long long)w[q] << 16) | (unsigned)(32 * q + c.lane); best = key < best ? key : best; }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) { const unsigned long long v = __shfl_xor_sync(GOICP_FULL, best, off); best = v < best ? v : best; }
+            if (best == ~0ull) return -1;
+            s = (int)(best & 0xFFFFu); word = (unsigned)(best >> 16);
+        } else {
+            unsigned masks[SR_NSLOT / 32]; int total = 0;
+#pragma unroll
+            for (int q = 0; q < SR_NSLOT / 32; q++) { masks[q] = __ballot_sync(GOICP_FULL, st_of(w[q]) == SL_QUEUED); total += __popc(masks[q]); }
+            if (total == 0) return -1;
+            int r = (int)(((unsigned)c.me * 2654435761u + (unsigned)tries * 40503u) >> 8) % total;
+#pragma unroll
+            for (int q = 0; q < SR_NSLOT / 32; q++) {
+                const int n = __popc(masks[q]);
+                if (s < 0) { if (r < n) { unsigned m = masks[q]; for (int k = 0; k < r; k++) m &= m - 1; const int ln = __ffs(m) - 1; s = 32 * q + ln; word = __shfl_sync(GOICP_FULL, w[q], ln); } else r -= n; }
+            }
+        }
         int ok = 0;
-        if (c.lane == 0) { ok = atomicCAS(&sl[s].state, (unsigned)SL_QUEUED, (unsigned)SL_RUNNING) == SL_QUEUED; if (ok) { atomicSub(&c.A.hdrs[o].nQueued, 1u); __threadfence(); } }
+        if (c.lane == 0) { ok = atomicCAS(st + s, word, (unsigned)SL_RUNNING) == word; if (ok) { atomicSub(&c.A.hdrs[o].nQueued, 1u); __threadfence(); } }
         ok = __shfl_sync(GOICP_FULL, ok, 0);
         if (ok) return s;
+    }
+    return -2;
+}
+// an owner that has published calls nobody has claimed yet (a hint bitmap: owners set their bit when they publish, a helper that
+// finds nothing queued there clears it); claims one of its calls.  All lanes; returns the owner (slot in *slot) or -1.
+__device__ int find_help(Cta& c, int* slot) {
+    const SearchArgs& A = c.A;
+    const int nw = (A.nCtas + 31) >> 5;
+    bool urgent = false;
+    if (c.lane == 0) urgent = ld_voli(&A.ctl->nextPair) < A.npairs;
+    urgent = __shfl_sync(GOICP_FULL, urgent ? 1 : 0, 0) != 0;
+    for (int tries = 0; tries < 3; tries++) {
+        unsigned m = 0;
+        if (c.lane < nw) m = ld_vol(&A.ctl->wantHelp[c.lane]);
+        if (c.lane == (c.me >> 5)) m &= ~(1u << (c.me & 31));
+        const unsigned any = __ballot_sync(GOICP_FULL, m != 0u);
+        if (!any) return -1;
+        // start from a word / bit that depends on the CTA so that helpers spread over the owners
+        const int rot = (c.me * 5 + tries * 3) % nw;
+        const unsigned anyRot = (rot == 0) ? any : ((any >> rot) | (any << (32 - rot)));
+        const int wsel = (__ffs(anyRot) - 1 + rot) % 32;
+        const unsigned word = __shfl_sync(GOICP_FULL, m, wsel);
+        const int brot = (c.me + 7 * tries) & 31;
+        const unsigned wr = (brot == 0) ? word : ((word >> brot) | (word << (32 - brot)));
+        const int o = 32 * wsel + (__ffs(wr) - 1 + brot) % 32;
+        const int s = claim_from(c, o, urgent);
+        if (s >= 0) { *slot = s; return o; }
+        if (s == -1 && c.lane == 0) atomicAnd(&A.ctl->wantHelp[o >> 5], ~(1u << (o & 31)));   // (the owner sets it again with its next call)
+        __syncwarp();
     }
     return -1;
 }
 
 // warp 0: decide what the CTA does next
-__device__ __noinline__ void schedule(Cta& c) {
+__device__ __forceinline__ void schedule(Cta& c) {
     OwnerSh& os = c.os;
     const SearchArgs& A = c.A;
     const int lane = c.lane;
     for (;;) {
-        // ---- no pair: claim the next one ----
+        // ---- no pair: first see whether a deep pair asks for help, then claim the next pair ----
         if (os.pair < 0 && !os.noMorePairs) {
+            if (A.specMax > 0) {
+                int s = -1;
+                const int o = find_help(c, &s);
+                if (o >= 0) { if (lane == 0) { os.action = ACT_CALL; os.actOwner = o; os.actSlot = s; os.actCancel = 1; atomicAdd(&A.ctl->dbg[5], 1ull); } __syncwarp(); return; }
+            }
             int i = 0;
             if (lane == 0) i = atomicAdd(&A.ctl->nextPair, 1);
             i = __shfl_sync(GOICP_FULL, i, 0);
             if (lane == 0) {
-                if (i < A.npairs) { os.pair = i; os.phase = OW_START; st_vol(reinterpret_cast<unsigned*>(&c.hdr->pair), (unsigned)i); atomicAdd(&A.ctl->owners, 1); }
-                else os.noMorePairs = 1;
+                if (i < A.npairs) { os.pair = i; os.phase = OW_START; os.manager = 0; st_vol(reinterpret_cast<unsigned*>(&c.hdr->pair), (unsigned)i); atomicAdd(&A.ctl->owners, 1); }
+                else { os.noMorePairs = 1; unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); atomicMax(&A.ctl->dbg[8], now - A.ctl->t0ns); atomicCAS(&A.ctl->dbg[9], 0ull, now - A.ctl->t0ns); }
             }
             __syncwarp();
         }
         // ---- own pair: advance the search ----
         if (os.pair >= 0) {
             int rq = 0;
-            if (lane == 0) rq = owner_serial(c);
+            const long long tq0 = clock64();
+            if (os.phase == OW_CHILD && os.j < 8) prefetch_group(c);
+            if (lane == 0) { rq = owner_serial(c); atomicAdd(&A.ctl->dbg[0], (unsigned long long)(clock64() - tq0)); }
             rq = __shfl_sync(GOICP_FULL, rq, 0);
             __syncwarp();
-            if (rq == RQ_SPAWN) { spawn_spec(c); continue; }
+            if (rq == RQ_AGAIN) continue;
+            if (rq == RQ_SPAWN) { const long long ts0 = clock64(); spawn_spec(c); if (lane == 0) atomicAdd(&A.ctl->dbg[1], (unsigned long long)(clock64() - ts0)); continue; }
             if (rq == RQ_ACTION) {
                 if (os.phase == OW_AFTER_IMPROVE && os.action == ACT_ICP) invalidate_spec(c);   // the incumbent just improved
                 if (os.phase == OW_NONE) {   // the pair is finished
+                    if (lane == 0) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); atomicAdd(&A.ctl->finishHist[min(255ull, (now - A.ctl->t0ns) / 4000000ull)], 1); }
                     invalidate_spec(c);
                     if (lane == 0) { os.pair = -1; st_vol(reinterpret_cast<unsigned*>(&c.hdr->pair), 0xFFFFFFFFu); atomicSub(&A.ctl->owners, 1); __threadfence(); atomicAdd(&A.ctl->pairsDone, 1); }
                     __syncwarp();
@@ -497,28 +661,26 @@ __device__ __noinline__ void schedule(Cta& c) {
                 if (os.action != ACT_NONE) return;
                 continue;
             }
+            if (rq == RQ_WAIT) {   // manager: a helper runs the call the search waits for
+                const long long tw0 = clock64();
+                __nanosleep(100);
+                if (lane == 0) atomicAdd(&A.ctl->dbg[4], (unsigned long long)(clock64() - tw0));
+                continue;
+            }
             // RQ_FINDWORK: the call the search waits for runs on a helper; take the next unclaimed call of this pair instead
-            const int s = claim_from(c, c.me);
+            const int s = claim_from(c, c.me, true);
             if (s >= 0) { if (lane == 0) { os.action = ACT_CALL; os.actOwner = c.me; os.actSlot = s; os.actCancel = 1; } __syncwarp(); return; }
         }
         // ---- nothing of its own to run: help another owner ----
+        const long long th0 = clock64();
         {
-            int found = -1;
-            const int start = (c.me * 7 + 1) % A.nCtas;
-            for (int base = 0; base < A.nCtas && found < 0; base += 32) {
-                const int o = (start + base + lane) % A.nCtas;
-                const bool has = (base + lane) < A.nCtas && o != c.me && (int)ld_vol(&A.hdrs[o].nQueued) > 0;
-                const unsigned m = __ballot_sync(GOICP_FULL, has);
-                if (m) found = __shfl_sync(GOICP_FULL, o, __ffs(m) - 1);
-            }
-            if (found >= 0) {
-                const int s = claim_from(c, found);
-                if (s >= 0) {
-                    if (lane == 0) { os.action = ACT_CALL; os.actOwner = found; os.actSlot = s; os.actCancel = 1; }
-                    __syncwarp();
-                    return;
-                }
-                continue;
+            int s = -1;
+            const int o = find_help(c, &s);
+            if (o >= 0) {
+                if (lane == 0) { os.action = ACT_CALL; os.actOwner = o; os.actSlot = s; os.actCancel = 1; atomicAdd(&A.ctl->dbg[2], (unsigned long long)(clock64() - th0)); atomicAdd(&A.ctl->dbg[5], 1ull);
+                                 unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); atomicAdd(&A.ctl->helpHist[min(255ull, (now - A.ctl->t0ns) / 4000000ull)], 1); }
+                __syncwarp();
+                return;
             }
         }
         // ---- idle ----
@@ -528,7 +690,8 @@ __device__ __noinline__ void schedule(Cta& c) {
             done = __shfl_sync(GOICP_FULL, done, 0);
             if (done) { if (lane == 0) os.action = ACT_EXIT; __syncwarp(); return; }
         }
-        __nanosleep(os.pair >= 0 ? 200 : 1000);
+        __nanosleep(os.pair >= 0 ? 200 : 500);
+        if (lane == 0) atomicAdd(&A.ctl->dbg[os.pair >= 0 ? 4 : 3], (unsigned long long)(clock64() - th0));
         __syncwarp();
     }
 }
@@ -545,45 +708,52 @@ search_kernel(const SearchArgs A) {
     float* icpTile;
     if constexpr (SMEM) icpTile = reinterpret_cast<float*>(dyn_smem4); else { __shared__ float s_tile[3 * NN_TILE]; icpTile = s_tile; }
     CallCtx cx;
-    unsigned long long* dstat = reinterpret_cast<unsigned long long*>(A.genCounter) + 1;
+    __shared__ CancelSh s_cancel;
+    __shared__ long long s_tStart, s_tIdle;
     if (tid == 0) {
-        os.pair = -1; os.phase = OW_NONE; os.noMorePairs = 0; os.lastSpawnJ = -1; os.specGroups = 0; os.action = ACT_NONE;
+        os.pair = -1; os.phase = OW_NONE; os.noMorePairs = 0; os.lastSpawnJ = -1; os.manager = 0; os.walkStamp = 1u; for (int k = 0; k < 8; k++) os.pfState[k] = SL_FREE; os.specGroups = 0; os.action = ACT_NONE;
         for (int g = 0; g < SR_NGROUP; g++) os.grpUse[g] = 0;
         if (GS) mbar_init(&s_gbar, 1);
+        unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); atomicCAS(&A.ctl->t0ns, 0ull, now);
     }
     __syncthreads();
-    Cta c{A, os, A.slots + (size_t)blockIdx.x * SR_NSLOT, A.hdrs + blockIdx.x, reinterpret_cast<RNodeD*>(A.rq) + (size_t)blockIdx.x * 2 * A.rqCap, A.icp + 2 * (size_t)blockIdx.x, (int)blockIdx.x, lane};
-    const long long tStart = clock64();
-    long long tIdle = 0;
+    if (tid == 0) { s_tStart = clock64(); s_tIdle = 0; }
 
     for (;;) {
         __syncthreads();
-        if (warp == 0) { const long long t0 = clock64(); schedule(c); if (lane == 0) tIdle += clock64() - t0; }
+        if (warp == 0) {
+            Cta c{A, os, A.slots + (size_t)blockIdx.x * SR_NSLOT, A.states + (size_t)blockIdx.x * SR_NSLOT, A.hdrs + blockIdx.x, reinterpret_cast<RNodeD*>(A.rq) + (size_t)blockIdx.x * 2 * A.rqCap, A.icp + 2 * (size_t)blockIdx.x, (int)blockIdx.x, lane};
+            const long long t0 = clock64(); schedule(c); if (lane == 0) s_tIdle += clock64() - t0;
+        }
         __syncthreads();
         const int act = os.action;
         if (act == ACT_EXIT) break;
         if (act == ACT_ICP) {
-            icp_fused_body(A.pairs, c.icp, icpTile);
+            IcpState* icp = A.icp + 2 * (size_t)blockIdx.x;
+            const long long ti0 = clock64();
+            icp_fused_body(A.pairs, icp, icpTile);
             __syncthreads();
-            icp_fused_body(A.pairs, c.icp + 1, icpTile);
-            if (tid == 0) atomicAdd(dstat + 6, 2ull);
+            icp_fused_body(A.pairs, icp + 1, icpTile);
+            if (tid == 0) { atomicAdd(reinterpret_cast<unsigned long long*>(A.genCounter) + 1 + 6, 2ull); atomicAdd(&A.ctl->dbg[7], (unsigned long long)(clock64() - ti0)); }
             continue;
         }
         // ACT_CALL: one request out of slot (actOwner, actSlot)
-        SearchSlot* sl = A.slots + (size_t)os.actOwner * SR_NSLOT + os.actSlot;
-        if (tid < (int)(sizeof(InnerProb) / 4)) reinterpret_cast<unsigned*>(&s_pr)[tid] = reinterpret_cast<const volatile unsigned*>(&sl->pr)[tid];
-        cx.cancelWord = os.actCancel ? &A.hdrs[os.actOwner].gen : nullptr;
-        cx.cancelGen = os.actCancel ? ld_vol(&sl->gen) : 0u;
-        inner_call<EXACT, SMEM, GS, CT, true>(A.pairs, s_pr, s_out, s_gbar, cx, A.heaps, A.heapCap, A.gscratch, A.gstride, A.NdP, A.NdQ, A.useSmem, A.memo, A.memoCap, A.genCounter, A.gridOff, A.S3p);
+        {
+            SearchSlot* sl = A.slots + (size_t)os.actOwner * SR_NSLOT + os.actSlot;
+            if (tid < (int)(sizeof(InnerProb) / 4)) reinterpret_cast<unsigned*>(&s_pr)[tid] = reinterpret_cast<const volatile unsigned*>(&sl->pr)[tid];
+            if (tid == 32) { s_cancel.word = os.actCancel ? &A.hdrs[os.actOwner].gen : nullptr; s_cancel.gen = os.actCancel ? ld_vol(&sl->gen) : 0u; s_cancel.flag = 0; }
+        }
+        inner_call<EXACT, SMEM, GS, CT, true>(A.pairs, s_pr, s_out, s_gbar, cx, s_cancel, A.heaps, A.heapCap, A.gscratch, A.gstride, A.NdP, A.NdQ, A.useSmem, A.memo, A.memoCap, A.genCounter, A.gridOff, A.S3p);
         if (warp == 0) {
+            SearchSlot* sl = A.slots + (size_t)os.actOwner * SR_NSLOT + os.actSlot;
             __syncwarp();
             if (lane < 16) reinterpret_cast<volatile unsigned*>(&sl->out)[lane] = reinterpret_cast<const unsigned*>(&s_out)[lane];
             __threadfence();
             __syncwarp();
-            if (lane == 0) st_vol(&sl->state, SL_DONE);
+            if (lane == 0) { st_vol(A.states + (size_t)os.actOwner * SR_NSLOT + os.actSlot, SL_DONE); if (os.actCancel && s_out.status == 7) atomicAdd(&A.ctl->dbg[6], 1ull); }
         }
     }
-    if (tid == 0) { atomicAdd(dstat + 4, (unsigned long long)tIdle); atomicAdd(dstat + 7, (unsigned long long)(clock64() - tStart)); }
+    if (tid == 0) { unsigned long long* dstat = reinterpret_cast<unsigned long long*>(A.genCounter) + 1; atomicAdd(dstat + 4, (unsigned long long)s_tIdle); atomicAdd(dstat + 7, (unsigned long long)(clock64() - s_tStart)); }
 }
 
 typedef void (*search_kernel_t)(const SearchArgs);

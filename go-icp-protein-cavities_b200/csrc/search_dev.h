@@ -10,14 +10,13 @@
 #define GOICP_SR_UNSUPPORTED 3       // = GOICP_ERR_UNSUPPORTED
 #define GOICP_SR_OVERFLOW 4          // = GOICP_ERR_OVERFLOW: a queue / event list outgrew its slab; the host re-runs the pair with growing slabs
 
-// One InnerBnB request + its result.  state: 0 free, 1 queued (any CTA may claim it), 2 running, 3 done, 4 skip (child cube outside
+// One InnerBnB request + its result; its state word lives in SearchArgs.states (contiguous per owner, so that a helper reads all
+// of an owner's states in one round trip).  state: 0 free, 1 queued (any CTA may claim it), 2 running, 3 done, 4 skip (child cube outside
 // the pi-ball).  Only the owner moves a slot to free / queued / skip; a claim is a compare-and-swap queued -> running; the CTA that
 // ran the call stores the result, fences and sets done.
 struct alignas(128) SearchSlot {
-    unsigned state;
-    unsigned prio;       // smaller = needed sooner
     unsigned gen;        // the owner's generation when the request was made
-    int pad0;
+    int pad0[3];
     InnerProb pr;        // 48 bytes
     InnerOut out;        // 64 bytes
 };
@@ -27,7 +26,15 @@ struct alignas(128) OwnerHdr {
     unsigned nQueued;    // slots in state queued (a hint for helpers; may be transiently off by the calls being claimed)
     unsigned pad;
 };
-struct SearchCtl { int nextPair, pairsDone, owners, pad; };
+struct SearchCtl {
+    int nextPair, pairsDone, owners, pad;
+    // diagnostics (GOICP_DEBUG): CTA cycles by activity and 4 ms histograms over the kernel's run time
+    unsigned long long dbg[16];      // [0] OuterBnB state machine [1] publishing speculative calls [2] looking for calls to help with [3] idle, no pair
+                                     // [4] owner waiting for a helper's result [5] calls run for another owner [6] of which abandoned [7] ICP [8] ns when the pair counter ran out
+    unsigned long long t0ns;
+    int finishHist[256], helpHist[256];
+    unsigned wantHelp[32];           // bit per CTA: it has published calls nobody has claimed yet (a hint)
+};
 
 struct PairOut {         // GoICP::Register's outputs for one pair
     double R[9], t[3];
@@ -37,6 +44,7 @@ struct PairOut {         // GoICP::Register's outputs for one pair
     int endKind;         // 1 "Rotation Queue Empty", 2 "Threshold reached"
     float endLb;
     int nEvents;
+    float tStartMs, tEndMs;   // diagnostics: when the pair was claimed / finished, relative to the kernel's start
     struct { int kind; float v; } ev[SR_MAXEV];   // the "Error*:" trace: kind 0 Init, 1 ICP, 2 BNB
 };
 
@@ -45,7 +53,10 @@ struct SearchArgs {
     float rotMinX, rotMinY, rotMinZ, rotWidth;   // initNodeRot (jly_main.cpp:241-244)
     int fma;             // which build of sinf / cosf the host libm runs (libm_exact.h)
     int specMax;         // most slot groups attached to rotation-queue nodes (0: never speculate)
-    SearchCtl* ctl; OwnerHdr* hdrs; SearchSlot* slots; void* rq; int rqCap; IcpState* icp; PairOut* outs;
+    int quietRamp;       // 1: after an improvement the look-ahead restarts at 1 node and doubles per rotation pop
+    int managerRatio;    // an owner stops running calls itself (and only manages) once helpers >= managerRatio x owners (0: never)
+    int deepCalls;       // a pair asks for help while unclaimed pairs remain once it has consumed this many InnerBnB calls (one more group per multiple)
+    SearchCtl* ctl; OwnerHdr* hdrs; SearchSlot* slots; unsigned* states; void* rq; int rqCap; IcpState* icp; PairOut* outs;
     // inner_call
     HeapEnt* heaps; int heapCap; float* gscratch; size_t gstride; int NdP, NdQ, useSmem; uint4* memo; int memoCap; unsigned* genCounter; int gridOff, S3p;
 };
