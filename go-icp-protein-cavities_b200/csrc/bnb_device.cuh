@@ -192,8 +192,7 @@ struct BnbShared {
 //   phase C (warp 0)      c-FPFH corner sums, memo update, per-child corner min/max on 8 lanes, the eight decisions as a warp
 //                         prefix-min, then lane 0: pushes and the next pop; lanes 0..14 derive the next node's voxel constants
 //                         and lanes 0..26 issue its memo look-ups.
-// PERSIST=false: the calls are probs[0..nprob), claimed through counter[0] (one launch per wave).
-// PERSIST=true : the kernel stays resident for a whole batch and serves the host's request ring `q` (see QueueDev).
+// (k_bnb.cu: the calls of a wave are claimed through a counter; k_search.cu: the device-resident search hands them out itself.)
 // GS=true (needs SMEM): the call's DT volume (float distances + one colour-mask byte per voxel) is staged in shared memory by
 // TMA as 16-bit squared-distance codes + a distance table + one colour-mask byte per voxel (S^3 * 3 bytes + the table at
 // dynamic-smem offset gridOff), so the per-point gathers are LDS instead of L1/L2 sector gathers.

@@ -13,7 +13,6 @@
 #define GOICP_OVLIM 24                      // voxels outside the grid served by the overshoot table GridDev.ovl
 #define GOICP_OVN (3 * GOICP_OVLIM * GOICP_OVLIM + 1)
 #define GOICP_REQ_BOTH 0x100               // InnerProb.level = GOICP_REQ_BOTH + level: upper-bound call, then the lower-bound call at `level`
-#define GOICP_REQ_ICP (-100)               // InnerProb.level of an ICP request in the resident batch kernel
 
 // DT3D (jly_3ddt.h:123-139) as laid out in HBM: structure-of-arrays, voxel index (z*S+y)*S+x.
 struct GridDev {
@@ -86,9 +85,9 @@ struct InnerProb {          // one GoICP::InnerBnB call (jly_goicp.cpp:286)
     float R[9];
 };
 struct alignas(64) InnerOut {   // one 64-byte record: it leaves the SM as a single coalesced warp store
-    unsigned seq0;          // resident-queue mode: both flags equal the request's tag once the record is complete (each 32-byte
-    float err;              // optErrorT                                   half of the record carries one flag, so a reader that
-    float node[4];          // best translation node x,y,z,w               sees both has seen every word -- no system fence needed)
+    unsigned seq0;          // (unused)
+    float err;              // optErrorT
+    float node[4];          // best translation node x,y,z,w
     int improved;
     int pops;
     int subcubes;
@@ -98,31 +97,6 @@ struct alignas(64) InnerOut {   // one 64-byte record: it leaves the SM as a sin
     int ran2;
     int pad;
     unsigned seq1;
-};
-
-// Resident-queue mode (batches): the host publishes requests into a ring of 64-byte cells in mapped host memory; CTAs claim
-// ring indices from a device counter, wait until BOTH flags of their cell carry the tag of that lap (the request words in
-// between are then complete), run the call and write outs[slot].  Cells are never handed back: the host keeps fewer requests
-// in flight than the ring has cells, and claims are sequential, so a cell is consumed before its index comes round again.
-struct alignas(64) QueueCell {
-    unsigned seqA;          // lap tag (ring index / capacity + 1)
-    unsigned slot;          // result slot; 0xFFFFFFFF = shut down
-    InnerProb pr;           // 48 bytes
-    unsigned pad;
-    unsigned seqB;
-};
-struct QueueDev {
-    const QueueCell* cells;   // mapped host memory ring
-    InnerOut* outs;           // mapped host memory, one per slot
-    unsigned cellMask;        // ring capacity - 1 (power of two)
-    unsigned cellShift;       // log2(capacity)
-    unsigned* claim;          // device counter
-    // completion hints: after its result record a CTA appends slot+1 to the ring of the host worker that owns the slot
-    // (slot / slotsPerWorker); the worker then looks only at pairs with news (the record's own flags stay authoritative)
-    unsigned* doneTail;       // device counters, one per worker
-    unsigned* doneRing;       // mapped host memory, workers x doneCap
-    unsigned doneCap;         // power of two >= slotsPerWorker
-    unsigned slotsPerWorker;
 };
 
 struct alignas(16) HeapEnt { float lb, w, x, y, z, pad0, pad1, pad2; };   // TRANSNODE without ub (never read, jly_goicp.h:75-87)

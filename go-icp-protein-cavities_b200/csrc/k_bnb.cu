@@ -9,7 +9,8 @@
 //                     fork's incompatibility / c-FPFH / neighbour-count terms the per-call memo does not hold.
 //                     EXACT=true reproduces the reference's sequential float sums bit for bit (16 independent FADD
 //                     chains on 16 lanes of one warp), EXACT=false uses warp-shuffle tree sums.
-//                     PERSIST: resident for a whole batch, serving the host's request ring; else one launch per wave.
+//                     One launch per wave of calls (the wave scheduler of engine.cu); the device-resident search (k_search.cu)
+//                     runs the same call code (bnb_device.cuh) inside its own kernel.
 //  eval_bounds_kernel flat wave: one warp per (rotation cube, translation sub-cube), leaf-level (ub, lb) only.
 //
 // The translation priority queue (8-byte keys + payload slots, top in shared memory, rest in a per-CTA global slab) follows
@@ -29,17 +30,16 @@ namespace {
 //   phase C (warp 0)      c-FPFH corner sums, memo update, per-child corner min/max on 8 lanes, the eight decisions as a warp
 //                         prefix-min, then lane 0: pushes and the next pop; lanes 0..14 derive the next node's voxel constants
 //                         and lanes 0..26 issue its memo look-ups.
-// PERSIST=false: the calls are probs[0..nprob), claimed through counter[0] (one launch per wave).
-// PERSIST=true : the kernel stays resident for a whole batch and serves the host's request ring `q` (see QueueDev).
+// The calls are probs[0..nprob), claimed through counter[0] (one launch per wave).
 // GS=true (needs SMEM): the call's DT volume (float distances + one colour-mask byte per voxel) is staged in shared memory by
 // TMA as 16-bit squared-distance codes + a distance table + one colour-mask byte per voxel (S^3 * 3 bytes + the table at
 // dynamic-smem offset gridOff), so the per-point gathers are LDS instead of L1/L2 sector gathers.
 // CT=false: no c-FPFH / neighbour-count corner terms in any pair of the launch (their code and registers drop out).
-template <bool EXACT, bool PERSIST, bool SMEM, bool GS, bool CT>
+template <bool EXACT, bool SMEM, bool GS, bool CT>
 __global__ void __launch_bounds__(BNB_MAX_THREADS, GOICP_BNB_MIN_CTAS)
 inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, InnerOut* outs,
                  int nprob, int* __restrict__ counter, HeapEnt* __restrict__ heaps, int heapCap,
-                 float* gscratch, size_t gstride, int NdP, int NdQ, int useSmem, QueueDev q,
+                 float* gscratch, size_t gstride, int NdP, int NdQ, int useSmem,
                  uint4* memoAll, int memoCap, unsigned* genCounter, int gridOff, int S3p) {
     unsigned long long* dstat = reinterpret_cast<unsigned long long*>(genCounter) + 1;   // [0] busy cycles [1] pops [2] corner misses [3] calls [4] poll cycles
     extern __shared__ float4 dyn_smem4[];
@@ -56,7 +56,7 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
 
     for (;;) {
         __syncthreads();
-        if (!PERSIST) {
+        {
             if (tid == 0) shk.prob = atomicAdd(counter, 1);
             __syncthreads();
             if (shk.prob >= nprob) {   // the last CTA to leave re-arms the counters, so the host never has to memset them
@@ -64,52 +64,15 @@ inner_bnb_kernel(const PairDev* __restrict__ pairs, const InnerProb* probs, Inne
                 return;
             }
             if (tid < (int)(sizeof(InnerProb) / 4)) reinterpret_cast<int*>(&s_pr)[tid] = reinterpret_cast<const volatile int*>(probs + shk.prob)[tid];
-        } else if (warp == 0) {
-            // claim the next ring index; the 16 lanes read the 64-byte cell with one load until both lap tags are there
-            unsigned i = 0;
-            const long long tp0 = clock64();
-            if (lane == 0) i = atomicAdd(q.claim, 1u);
-            i = __shfl_sync(GOICP_FULL, i, 0);
-            const unsigned want = (i >> q.cellShift) + 1u;
-            const volatile unsigned* cell = reinterpret_cast<const volatile unsigned*>(q.cells + (i & q.cellMask));
-            unsigned w = 0, backoff = 64; unsigned long long t0 = 0, now; int notReady = 0; bool dead = false;
-            for (;;) {
-                if (lane < 16) w = cell[lane];
-                const unsigned a = __shfl_sync(GOICP_FULL, w, 0), b = __shfl_sync(GOICP_FULL, w, 15);
-                if (a == want && b == want) break;
-                notReady = 1;
-                __nanosleep(backoff); if (backoff < 16384) backoff <<= 1;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-                if (t0 == 0) t0 = now;
-                else if (now - t0 > 60000000000ull) { dead = true; break; }   // safety net: 60 s without work -> leave
-            }
-            const unsigned slot = __shfl_sync(GOICP_FULL, w, 1);
-            if (lane >= 2 && lane < 14) reinterpret_cast<unsigned*>(&s_pr)[lane - 2] = w;
-            if (lane == 0) {
-                shk.prob = (dead || slot == 0xFFFFFFFFu) ? -1 : (int)slot;
-                atomicAdd(dstat + 4, (unsigned long long)(clock64() - tp0)); atomicAdd(dstat + 5, (unsigned long long)notReady);
-            }
         }
         __syncthreads();
         const int p = shk.prob;
-        if (PERSIST && p < 0) return;
         const InnerProb& pr = s_pr;   // (stays in shared memory: R is only read while staging)
-        if (PERSIST && pr.level == GOICP_REQ_ICP) {   // an ICP / scoring request (GoICP::ICP): state pointer packed into R[0..1]
-            IcpState* gst = reinterpret_cast<IcpState*>(((unsigned long long)__float_as_uint(pr.R[1]) << 32) | (unsigned long long)__float_as_uint(pr.R[0]));
-            icp_fused_body(pairs, gst, icpTile);
-            __syncthreads();
-            if (warp == 0) {
-                if (lane < 16) reinterpret_cast<unsigned*>(q.outs + p)[lane] = (lane == 0 || lane == 15) ? 1u : 0u;
-                if (lane == 0) { const unsigned w = (unsigned)p / q.slotsPerWorker; const unsigned k = atomicAdd(q.doneTail + w, 1u); q.doneRing[(size_t)w * q.doneCap + (k & (q.doneCap - 1u))] = (unsigned)p + 1u; }
-            }
-            continue;
-        }
         inner_call<EXACT, SMEM, GS, CT, false>(pairs, pr, s_out, s_gbar, cx, s_cancel, heaps, heapCap, gscratch, gstride, NdP, NdQ, useSmem, memoAll, memoCap, genCounter, gridOff, S3p);
         if (warp == 0) {   // the record leaves the SM as ONE coalesced 64-byte store (it may live in mapped host memory)
             __syncwarp();
-            InnerOut* dst = PERSIST ? q.outs + p : outs + p;
+            InnerOut* dst = outs + p;
             if (lane < 16) reinterpret_cast<unsigned*>(dst)[lane] = reinterpret_cast<const unsigned*>(&s_out)[lane];
-            if (PERSIST && lane == 0) { const unsigned w = (unsigned)p / q.slotsPerWorker; const unsigned k = atomicAdd(q.doneTail + w, 1u); q.doneRing[(size_t)w * q.doneCap + (k & (q.doneCap - 1u))] = (unsigned)p + 1u; }
         }
     }
 }
@@ -229,27 +192,24 @@ size_t goicp_bnb_smem_floats(int NdP, int NdQ, bool exact, bool needMd, bool nee
     return n > 3 * 512 ? n : 3 * 512;   // an ICP request tiles the model cloud through the same region (icp_device.cuh NN_TILE)
 }
 
-typedef void (*bnb_kernel_t)(const PairDev*, const InnerProb*, InnerOut*, int, int*, HeapEnt*, int, float*, size_t, int, int, int, QueueDev, uint4*, int, unsigned*, int, int);
+typedef void (*bnb_kernel_t)(const PairDev*, const InnerProb*, InnerOut*, int, int*, HeapEnt*, int, float*, size_t, int, int, int, uint4*, int, unsigned*, int, int);
 template <bool SMEM, bool GS, bool CT>
-static bnb_kernel_t bnb_kernel_sel(int exact, int persist) {
-    if (persist) return exact ? inner_bnb_kernel<true, true, SMEM, GS, CT> : inner_bnb_kernel<false, true, SMEM, GS, CT>;
-    return exact ? inner_bnb_kernel<true, false, SMEM, GS, CT> : inner_bnb_kernel<false, false, SMEM, GS, CT>;
-}
+static bnb_kernel_t bnb_kernel_sel(int exact) { return exact ? inner_bnb_kernel<true, SMEM, GS, CT> : inner_bnb_kernel<false, SMEM, GS, CT>; }
 // smem: 0 staging arrays in a global slab, 1 in shared memory, 2 shared memory incl. the DT volume; ct: generic corner terms
-static bnb_kernel_t bnb_kernel(int exact, int persist, int smem, int ct) {
-    if (smem == 2) return ct ? bnb_kernel_sel<true, true, true>(exact, persist) : bnb_kernel_sel<true, true, false>(exact, persist);
-    if (smem == 1) return ct ? bnb_kernel_sel<true, false, true>(exact, persist) : bnb_kernel_sel<true, false, false>(exact, persist);
-    return ct ? bnb_kernel_sel<false, false, true>(exact, persist) : bnb_kernel_sel<false, false, false>(exact, persist);
+static bnb_kernel_t bnb_kernel(int exact, int smem, int ct) {
+    if (smem == 2) return ct ? bnb_kernel_sel<true, true, true>(exact) : bnb_kernel_sel<true, true, false>(exact);
+    if (smem == 1) return ct ? bnb_kernel_sel<true, false, true>(exact) : bnb_kernel_sel<true, false, false>(exact);
+    return ct ? bnb_kernel_sel<false, false, true>(exact) : bnb_kernel_sel<false, false, false>(exact);
 }
-static int g_bnb_attr_set[32] = {0};
-static cudaError_t bnb_attr(int exact, int persist, int smem, int ct) {
-    const int k = (exact ? 1 : 0) + (persist ? 2 : 0) + 4 * smem + 16 * (ct ? 1 : 0);
+static int g_bnb_attr_set[16] = {0};
+static cudaError_t bnb_attr(int exact, int smem, int ct) {
+    const int k = (exact ? 1 : 0) + 2 * smem + 8 * (ct ? 1 : 0);
     if (g_bnb_attr_set[k]) return cudaSuccess;
     cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, bnb_kernel(exact, persist, smem, ct));
+    cudaError_t e = cudaFuncGetAttributes(&fa, bnb_kernel(exact, smem, ct));
     if (e != cudaSuccess) return e;
     const int maxDyn = 227 * 1024 - (int)fa.sharedSizeBytes - 1024;   // static (queue top, ICP tiles) + dynamic <= 227 KB per CTA
-    e = cudaFuncSetAttribute(bnb_kernel(exact, persist, smem, ct), cudaFuncAttributeMaxDynamicSharedMemorySize, maxDyn);
+    e = cudaFuncSetAttribute(bnb_kernel(exact, smem, ct), cudaFuncAttributeMaxDynamicSharedMemorySize, maxDyn);
     if (e == cudaSuccess) g_bnb_attr_set[k] = 1;
     return e;
 }
@@ -259,36 +219,18 @@ cudaError_t goicp_launch_inner_bnb(const PairDev* pairs, const InnerProb* probs,
                                    int NdP, int NdQ, size_t smemBytes, int useSmem, int gridOff, int S3p, int exact, int ct, int threads, void* memo, int memoCap, unsigned* genCounter, cudaStream_t st, int* ctasLaunched) {
     if (nprob <= 0) { if (ctasLaunched) *ctasLaunched = 0; return cudaSuccess; }
     const size_t smem = useSmem ? smemBytes : 0;
-    cudaError_t e = bnb_attr(exact, 0, useSmem, ct);
+    cudaError_t e = bnb_attr(exact, useSmem, ct);
     if (e != cudaSuccess) return e;
     int grid = nprob < maxCtas ? nprob : maxCtas;
     if (ctasLaunched) *ctasLaunched = grid;
-    QueueDev q{};
-    bnb_kernel(exact, 0, useSmem, ct)<<<grid, threads, smem, st>>>(pairs, probs, outs, nprob, counter, heaps, heapCap, gscratch, gstride, NdP, NdQ, useSmem, q, (uint4*)memo, memoCap, genCounter, gridOff, S3p);
+    bnb_kernel(exact, useSmem, ct)<<<grid, threads, smem, st>>>(pairs, probs, outs, nprob, counter, heaps, heapCap, gscratch, gstride, NdP, NdQ, useSmem, (uint4*)memo, memoCap, genCounter, gridOff, S3p);
     return cudaGetLastError();
 }
 
-// the resident kernel of a batch: `ctas` CTAs serve the request ring until each has seen a shut-down marker
-cudaError_t goicp_launch_inner_bnb_persistent(const PairDev* pairs, const QueueDev& q, HeapEnt* heaps, int heapCap, int ctas, float* gscratch, size_t gstride,
-                                              int NdP, int NdQ, size_t smemBytes, int useSmem, int gridOff, int S3p, int exact, int ct, int threads, void* memo, int memoCap, unsigned* genCounter, cudaStream_t st) {
-    const size_t smem = useSmem ? smemBytes : 0;
-    cudaError_t e = bnb_attr(exact, 1, useSmem, ct);
-    if (e != cudaSuccess) return e;
-    static const int restage = getenv("GOICP_NO_GPAIR") ? 16 : 0;
-    bnb_kernel(exact, 1, useSmem, ct)<<<ctas, threads, smem, st>>>(pairs, nullptr, nullptr, 0, nullptr, heaps, heapCap, gscratch, gstride, NdP, NdQ, useSmem | restage, q, (uint4*)memo, memoCap, genCounter, gridOff, S3p);
-    return cudaGetLastError();
-}
-
-int goicp_inner_bnb_persistent_occupancy(size_t smemBytes, int exact, int threads, int useSmem, int ct) {
-    if (bnb_attr(exact, 1, useSmem, ct) != cudaSuccess) return 1;
-    int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bnb_kernel(exact, 1, useSmem, ct), threads, useSmem ? smemBytes : 0) != cudaSuccess || n < 1) n = 1;
-    return n;
-}
 int goicp_inner_bnb_occupancy(size_t smemBytes, int exact, int threads, int useSmem, int ct) {
-    if (bnb_attr(exact, 0, useSmem, ct) != cudaSuccess) return 1;
+    if (bnb_attr(exact, useSmem, ct) != cudaSuccess) return 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bnb_kernel(exact, 0, useSmem, ct), threads, useSmem ? smemBytes : 0) != cudaSuccess || n < 1) n = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bnb_kernel(exact, useSmem, ct), threads, useSmem ? smemBytes : 0) != cudaSuccess || n < 1) n = 1;
     return n;
 }
 
@@ -311,8 +253,8 @@ cudaError_t goicp_launch_eval_inclusion(const PairDev* pairs, int pair, const fl
 // would otherwise wait for that kernel (CUDA lazy module loading)
 cudaError_t goicp_preload_bnb() {
     cudaFuncAttributes a; cudaError_t e;
-    for (int exact = 0; exact < 2; exact++) for (int persist = 0; persist < 2; persist++) for (int smem = 0; smem < 3; smem++) for (int ct = 0; ct < 2; ct++)
-        if ((e = cudaFuncGetAttributes(&a, bnb_kernel(exact, persist, smem, ct))) != cudaSuccess) return e;
+    for (int exact = 0; exact < 2; exact++) for (int smem = 0; smem < 3; smem++) for (int ct = 0; ct < 2; ct++)
+        if ((e = cudaFuncGetAttributes(&a, bnb_kernel(exact, smem, ct))) != cudaSuccess) return e;
     if ((e = cudaFuncGetAttributes(&a, eval_bounds_kernel)) != cudaSuccess) return e;
     if ((e = cudaFuncGetAttributes(&a, eval_inclusion_kernel)) != cudaSuccess) return e;
     return cudaSuccess;

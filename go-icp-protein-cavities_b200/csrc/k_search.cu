@@ -45,6 +45,7 @@ struct OwnerSh {
     int specGroups;              // (diagnostic) groups attached during the last walk
     int action, actOwner, actSlot, actCancel;
     int noMorePairs, lastSpawnJ, manager;
+    int waitPolls;               // manager mode: polls spent waiting for a helper to take the call the search needs next
     int quiet;                   // rotation nodes popped since the incumbent last improved: look-ahead grows 1, 3, 7, ... with it (calls made under an incumbent that is about to improve are wasted)
     // results of the current node's children as last fetched by the warp (a slot that was done then stays done until the owner frees it)
     unsigned pfState[8]; float pfOpt[8]; alignas(64) unsigned pfOut[8][16];   // (rows are read as InnerOut records)
@@ -335,6 +336,7 @@ __device__ __forceinline__ int owner_serial(Cta& c) {
             }
             const int sidx = 8 * os.par.group + os.j;
             SearchSlot* sl = c.slots + sidx;
+            if (os.pfState[os.j] == SL_DONE) os.waitPolls = 0;
             if (os.pfState[os.j] != SL_DONE) {   // not finished when the warp last looked: what is it doing now?
                 const unsigned w = ld_vol(c.st + sidx);
                 const unsigned st = st_of(w);
@@ -355,7 +357,7 @@ __device__ __forceinline__ int owner_serial(Cta& c) {
                     return RQ_ACTION;
                 }
                 if (st == SL_QUEUED) {
-                    if (os.manager) { atomicOr(&A.ctl->wantHelp[c.me >> 5], 1u << (c.me & 31)); return RQ_WAIT; }   // (a helper that found nothing a moment ago may have cleared the hint)
+                    if (os.manager && ++os.waitPolls < 400) { atomicOr(&A.ctl->wantHelp[c.me >> 5], 1u << (c.me & 31)); return RQ_WAIT; }   // (a helper that found nothing a moment ago may have cleared the hint; after ~50 us without a taker the owner runs the call itself)
                     if (atomicCAS(c.st + sidx, w, (unsigned)SL_RUNNING) == w) {
                         atomicSub(&c.hdr->nQueued, 1u);
                         __threadfence();
@@ -711,7 +713,7 @@ search_kernel(const SearchArgs A) {
     __shared__ CancelSh s_cancel;
     __shared__ long long s_tStart, s_tIdle;
     if (tid == 0) {
-        os.pair = -1; os.phase = OW_NONE; os.noMorePairs = 0; os.lastSpawnJ = -1; os.manager = 0; os.walkStamp = 1u; for (int k = 0; k < 8; k++) os.pfState[k] = SL_FREE; os.specGroups = 0; os.action = ACT_NONE;
+        os.pair = -1; os.phase = OW_NONE; os.noMorePairs = 0; os.lastSpawnJ = -1; os.manager = 0; os.waitPolls = 0; os.walkStamp = 1u; for (int k = 0; k < 8; k++) os.pfState[k] = SL_FREE; os.specGroups = 0; os.action = ACT_NONE;
         for (int g = 0; g < SR_NGROUP; g++) os.grpUse[g] = 0;
         if (GS) mbar_init(&s_gbar, 1);
         unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); atomicCAS(&A.ctl->t0ns, 0ull, now);
@@ -795,7 +797,11 @@ int goicp_search_occupancy(size_t smemBytes, int exact, int threads, int useSmem
 cudaError_t goicp_launch_search(const SearchArgs& A, int ctas, int threads, size_t smemBytes, int exact, int ct, cudaStream_t st) {
     cudaError_t e = search_attr(exact, A.useSmem & 3, ct);
     if (e != cudaSuccess) return e;
-    search_fn(exact, A.useSmem & 3, ct)<<<ctas, threads, (A.useSmem & 3) ? smemBytes : 0, st>>>(A);
+    // CTAs wait for one another (an owner for its helpers' results), so all of them must be resident at once: a cooperative launch
+    // guarantees that or fails (the grid is sized from the occupancy query)
+    void* args[] = {const_cast<SearchArgs*>(&A)};
+    e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(search_fn(exact, A.useSmem & 3, ct)), dim3(ctas), dim3(threads), args, (A.useSmem & 3) ? smemBytes : 0, st);
+    if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
 cudaError_t goicp_preload_search() {

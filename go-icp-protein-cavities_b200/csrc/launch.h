@@ -9,12 +9,9 @@ int goicp_bnb_default_threads();   // CTA size the kernel is compiled for (launc
 size_t goicp_bnb_smem_floats(int NdP, int NdQ, bool exact, bool needMd, bool needFp);
 // useSmem: 0 staging arrays in a global scratch slab, 1 in shared memory, 2 shared memory incl. the DT volume (TMA-staged per call)
 int goicp_inner_bnb_occupancy(size_t smemBytes, int exact, int threads, int useSmem, int ct);
-int goicp_inner_bnb_persistent_occupancy(size_t smemBytes, int exact, int threads, int useSmem, int ct);
 cudaError_t goicp_launch_inner_bnb(const PairDev* pairs, const InnerProb* probs, InnerOut* outs, int nprob, int* counter,
                                    HeapEnt* heaps, int heapCap, int maxCtas, float* gscratch, size_t gstride,
                                    int NdP, int NdQ, size_t smemBytes, int useSmem, int gridOff, int S3p, int exact, int ct, int threads, void* memo, int memoCap, unsigned* genCounter, cudaStream_t st, int* ctasLaunched);
-cudaError_t goicp_launch_inner_bnb_persistent(const PairDev* pairs, const QueueDev& q, HeapEnt* heaps, int heapCap, int ctas, float* gscratch, size_t gstride,
-                                              int NdP, int NdQ, size_t smemBytes, int useSmem, int gridOff, int S3p, int exact, int ct, int threads, void* memo, int memoCap, unsigned* genCounter, cudaStream_t st);
 cudaError_t goicp_launch_eval_bounds(const PairDev* pairs, int pair, const float* Rs, const int* levels, const WaveCube* cubes,
                                      int nt, float* ub, float* lb, int* incomp_mm, int* fpfh_mm, float* scratch, int nwarps,
                                      cudaStream_t st);

@@ -183,9 +183,8 @@ def test_register_neighbours_term(g):
 
 
 def test_batch_deterministic(g):
-    """regression: results of ICP requests travel through a state block in mapped host memory; without a system fence between
-    that block and the completion record the host could read the block before it had landed (about 0.15 % of pairs then ended
-    at once with optError 0).  The same sweep registered three times must give identical results for every pair."""
+    """the device-resident search hands calls between CTAs through global memory (slot records, state words, generation counters): the
+    same sweep registered three times must give identical results for every pair, whatever the interleaving of owners and helpers"""
     from conftest import ROOT
     import importlib.util, os
     spec = importlib.util.spec_from_file_location("synth", os.path.join(ROOT, "go-icp-protein-cavities_b200", "synth.py"))
@@ -202,9 +201,9 @@ def test_batch_deterministic(g):
 
 
 def test_resident_icp_requests_fresh(g):
-    """regression: ICP requests of the resident kernel live in mapped host memory at one address per pair; a plain device load
-    could be served from a stale L1 line of the pair's previous request (about 2 % of registrations then ended in a worse
-    optimum, 9.81876 instead of 8.45388).  Repeated registrations must all reach the certified optimum."""
+    """regression (round 1: an ICP request block re-used at one address was once read through a stale L1 line, and about 2 % of
+    registrations ended in a worse optimum, 9.81876 instead of 8.45388): the ICP state blocks of the device-resident search are re-used by
+    every ICP call of a CTA too.  Repeated registrations must all reach the certified optimum."""
     z = golden("pair1")
     for rep in range(25):
         reg = g.GoICP(z["model_xyz"], z["data_xyz"], g.shipped_config(), **pair_clouds(z))
@@ -229,10 +228,11 @@ def test_register_l1_norm(g, po):
     assert g.error_trace(r["trace"]) == po.error_trace(ro["trace"])
 
 
-@pytest.mark.parametrize("env", ["GOICP_NO_GRID_SMEM", "GOICP_NO_VOXFAST", "GOICP_MERGE_CALLS=0", "GOICP_PERSISTENT=0"])
+@pytest.mark.parametrize("env", ["GOICP_NO_GRID_SMEM", "GOICP_NO_VOXFAST", "GOICP_SPEC_GROUPS=0", "GOICP_MANAGER_RATIO=0", "GOICP_PERSISTENT=0"])
 def test_alternative_paths_same_result(g, monkeypatch, env):
-    """the fall-back paths (volume gathered from global memory: > 8 colours or large grids; exact FP64 voxel index only; one
-    request per InnerBnB call; wave scheduler) give the reference's optimum, counters and trace too"""
+    """the alternative paths (volume gathered from global memory: > 8 colours or large grids; exact FP64 voxel index only; device-resident
+    search without look-ahead calls / with the owner always computing; wave scheduler with the host-side OuterBnB) give the reference's
+    optimum, counters and trace too"""
     k, _, v = env.partition("=")
     monkeypatch.setenv(k, v or "1")
     z = golden("pair1")
@@ -520,7 +520,7 @@ def test_cli_sweep_batch(tmp_path):
 
 
 def test_deep_queue_overflow_rerun(g, monkeypatch):
-    """a translation queue that outgrows the resident kernel's per-CTA slab: the pair is re-run by the wave scheduler
+    """a translation queue that outgrows the search kernel's per-CTA slab: the pair is re-run by the wave scheduler
     (growing slabs); forcing a tiny slab (160 entries) must not change anything about pair 2's search (2.6 M sub-cubes)"""
     monkeypatch.setenv("GOICP_HEAPCAP", "160")
     z = golden("pair2")
