@@ -219,11 +219,12 @@ class Engine:
     def stats(self):
         o = (C.c_double * 16)()
         self.check(self.L.goicp_get_stats(self.h, o))
-        d = dict(rounds=int(o[0]), calls_launched=int(o[1]), calls_used=int(o[2]), host_threads=int(o[3]), host_seconds=o[4],
-                 host_thread_seconds=dict(build_requests=o[5], publish=o[6], wait=o[7]))
-        if o[13] > 0:
-            d["resident_kernel"] = dict(ctas=int(o[13]), calls=int(o[8]), pops=int(o[9]), busy_cycles_per_pop=o[10] / max(o[9], 1.0),
-                                        corner_misses_per_pop=o[11] / max(o[9], 1.0), busy_cycles=o[10], poll_cycles=o[12])
+        d = dict(waves=int(o[0]), calls_executed=int(o[1]), calls_used=int(o[2]), host_worker_threads=int(o[3]), host_seconds=o[4])
+        if o[13] > 0:   # device-resident search (k_search.cu)
+            d["search_kernel"] = dict(ctas=int(o[13]), calls=int(o[8]), pops=int(o[9]), cycles_per_pop_in_calls=o[10] / max(o[9], 1.0), corner_misses_per_pop=o[11] / max(o[9], 1.0),
+                                      cta_cycles_total=o[15], cta_cycles_in_calls=o[10], cta_cycles_scheduling_and_idle=o[12], pairs_rerun_by_wave_scheduler=int(o[14]))
+        else:           # wave scheduler
+            d["host_thread_seconds"] = dict(build_requests=o[5], enqueue=o[6], wait=o[7])
         return d
 
     def set_options(self, exact_sums=-1, spec_width=-1, use_dt_replay=-1):

@@ -156,7 +156,8 @@ goicp_status goicp_set_frontier_sharding(goicp_handle h, int32_t rank, int32_t n
 goicp_status goicp_test_exchange(goicp_handle h, const void* send, void* recv, int64_t bytes_per_rank);
 
 /* ---- batch of independent pairs (the dataset sweep of bo1_GoICP.py, one GPU) ------------------------- */
-/* BuildDT + Register for npairs pairs with shared params; pairs advance in lock-step waves on one device. */
+/* BuildDT + Register for npairs pairs with shared params: one DT-build launch, one Initialize launch and ONE search launch for
+ * the whole batch (the rotation BnB of every pair runs on the device; CTAs claim pairs from a counter). */
 goicp_status goicp_register_batch(goicp_handle h, const goicp_params* p, int32_t npairs,
                                   const goicp_pair_desc* pairs, goicp_result* results);
 /* Same, split so that inputs can be made resident first (bench.py "value" leg): upload copies host->device,
@@ -166,15 +167,16 @@ goicp_status goicp_batch_run(goicp_handle h, goicp_result* results);
 /* device-event timings (ms) and launch counts of the last batch_run / register:
  * out[0] dt build, [1] initialize, [2] inner-BnB kernels, [3] ICP kernels, [4] other; launches[0..4] likewise */
 goicp_status goicp_get_timings(goicp_handle h, float* ms5, int64_t* launches5);
-/* batch scheduling: `groups` worker streams (0 = auto: one per host core, 4..32), each advancing `slots` pairs
- * (0 = auto: npairs / groups, 8..128) in lock-step waves and pulling the next pair from a shared counter when one finishes (bo1_GoICP.py:40-54 is serial). */
+/* wave scheduler only (large clouds, frontier sharding, GOICP_PERSISTENT=0): `groups` worker streams (0 = auto), each advancing
+ * `slots` pairs (0 = auto) in lock-step waves and pulling the next pair from a shared counter when one finishes.  The default
+ * device-resident search needs no host threads (bo1_GoICP.py:40-54 is one serial process per pair). */
 goicp_status goicp_set_batch_options(goicp_handle h, int32_t groups, int32_t slots);
-/* search statistics of the last register / batch_run (16 doubles): [0] request rounds, [1] InnerBnB calls launched (incl.
- * speculative), [2] InnerBnB calls the reference order consumed, [3] host worker threads, [4] host seconds of the search,
- * [5..7] host seconds summed over workers: building requests, publishing / enqueueing, waiting;
- * resident-kernel mode only: [8] calls served, [9] translation-queue pops, [10] CTA busy cycles, [11] corner evaluations the
- * memo missed, [12] CTA cycles spent polling the request ring, [13] resident CTAs, [14] pairs re-run by the wave scheduler
- * because a translation queue outgrew the resident kernel's slab; [15] reserved */
+/* search statistics of the last register / batch_run (16 doubles): [0] waves (wave scheduler), [1] InnerBnB calls executed (incl.
+ * look-ahead calls that were abandoned), [2] InnerBnB calls the reference order consumed, [3] host worker threads (0: device-resident
+ * search), [4] host seconds of the search, [5..7] wave scheduler: host seconds building requests, enqueueing, waiting;
+ * device-resident search: [8] calls, [9] translation-queue pops, [10] CTA cycles inside calls, [11] corner evaluations the memo
+ * missed, [12] CTA cycles scheduling / waiting / idle, [13] CTAs, [14] pairs re-run by the wave scheduler because a queue outgrew
+ * its slab, [15] CTA cycles in total */
 goicp_status goicp_get_stats(goicp_handle h, double* out16);
 
 /* ---- Transformation (transformation.cpp), per-pair pre/post-processing -------------------------------- */

@@ -151,6 +151,21 @@ def make_inclusion():
     np.savez_compressed(os.path.join(OUT, "rand_inclusion.npz"), **fx)
 
 
+def make_deep_small():
+    """BASELINE config 4 (synthetic deep search) at a size the reference finishes in minutes: target 20 000 points on the bumpy
+    sphere, source 2 000 of them moved by a random rigid motion + noise (go-icp-protein-cavities_b200/synth.py:deep_pair, seed 1241),
+    DT 128^3, MSEThresh 1e-4, no trimming.  The initial ICP does not reach the optimum: 2 146 rotation nodes are expanded."""
+    print("deep_small")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("synth", os.path.join(ROOT, "go-icp-protein-cavities_b200", "synth.py"))
+    synth = importlib.util.module_from_spec(spec); spec.loader.exec_module(synth)
+    p = synth.deep_pair(1241, nm=20000, nd=2000)
+    fx = dict(model_xyz=p["model_xyz"], data_xyz=p["data_xyz"], nd=2000, trim=np.float32(0.0), R_true=p["R_true"], t_true=p["t_true"])
+    exp = run_ref(p["model_xyz"], p["data_xyz"], po.upstream_config(distTransSize=128, MSEThresh=1e-4), 2000)
+    fx.update({"exp128_" + k: v for k, v in exp.items()})
+    np.savez_compressed(os.path.join(OUT, "deep_small.npz"), **fx)
+
+
 if __name__ == "__main__":
     po.build("ref")
     which = sys.argv[1:] or ["pair1", "pair2", "rand", "bunny", "inclusion"]
@@ -165,3 +180,5 @@ if __name__ == "__main__":
             make_demo("bunny", "model_bunny.txt", "data_bunny.txt", 1000, 0.0, [100, 300])
         if "inclusion" in which:
             make_inclusion()
+        if "deep_small" in which:
+            make_deep_small()

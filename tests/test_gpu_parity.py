@@ -376,6 +376,22 @@ def test_inner_bnb_points_below_grid(g, po):
     assert np.array_equal(resid, oresid)
 
 
+def test_register_deep_small(g):
+    """BASELINE config 4 (synthetic deep search: bumpy-sphere target, moved + noisy subset as source) at a size the reference could
+    freeze (20 000 x 2 000 points, DT 128^3; tests/golden/deep_small.npz): the first ICP does NOT reach the optimum and ~2 100 rotation
+    nodes are expanded.  Same certified optimum and pose as the reference; the node counters differ by < 1 % because the DT comes
+    from the separable builder here (8SED is inexact on a few voxels at this size)."""
+    z = golden("deep_small")
+    reg = g.GoICP(z["model_xyz"], z["data_xyz"], g.upstream_config(distTransSize=128, MSEThresh=1e-4))
+    reg.BuildDT(); reg.set_nd(int(z["nd"]))
+    r = reg.Register()
+    assert abs(r["optError"] - float(z["exp128_optError"])) <= REL * float(z["exp128_optError"])
+    assert np.abs(r["R"] - z["exp128_R"]).max() < 1e-5 and np.abs(r["t"] - z["exp128_t"]).max() < 1e-5
+    assert np.abs(r["R"] - z["R_true"]).max() < 2e-3 and np.abs(r["t"] - z["t_true"]).max() < 2e-3      # and it is the generating motion
+    assert int(z["exp128_counters"][3]) > 1000 and abs(r["counters"][3] - int(z["exp128_counters"][3])) <= 0.01 * int(z["exp128_counters"][3])
+    assert g.error_trace(r["trace"])[:len(z["exp128_trace"])] == list(z["exp128_trace"])
+
+
 def test_register_bunny100(g, po):
     """bunny, DT 100^3, with the GPU's own separable DT: same optimum, trace and node counters as the reference run"""
     z = golden("bunny")
