@@ -5,9 +5,10 @@
 //  dt_replay_kernel   S <= 32 (the cavity grids, distTransSize = 20): a bit-exact replay of the reference's sequential
 //                     8SED vector propagation (DEuclidean :716-750 and its six mask functions :57-712, including the two
 //                     copy-paste slips) and of the emptyCells sign-resolution order (:999-1136).  One warp per grid,
-//                     lane = z, the whole S^3 offset volume in shared memory ([x][y][z], conflict-free); the 13 mask
-//                     entries that read other columns are evaluated by all lanes at once, only the in-column z
-//                     dependency is walked sequentially with shuffles.  A batch of pairs runs one warp each.
+//                     lane = z, the whole S^3 offset volume in shared memory ([x][y][z], conflict-free); the mask entries
+//                     that read other columns are reduced by all lanes at once (keys whose unsigned minimum is the
+//                     reference's first-smallest rule), the in-column recurrences are walked by one lane with four dependent
+//                     integer operations per voxel.  A batch of pairs runs one warp each.
 //  dt_sep_*           any S: an exact separable Euclidean DT (x, then y, then z pass; every pass one thread per voxel
 //                     searching outwards along its axis with early exit) that also emits the nearest occupied voxel.
 //                     Where 8SED is exact (it is not an exact EDT) values are identical; ties between equidistant
@@ -22,80 +23,134 @@
 namespace {
 
 // ------------------------------------------------------------------------------------------------------------------
-// mask tables (jly_3ddt.cpp:57-712), in the reference's evaluation order
+// mask tables (jly_3ddt.cpp:57-712), in the reference's evaluation order.  constexpr functions: after unrolling every entry folds
+// into immediate offsets and increments.
 enum { ZM = 1, ZP = 2, YM = 4, YP = 8, XM = 16, XP = 32 };
-struct MaskE { int cond; int dz, dy, dx; unsigned inc; };   // inc = iv | ih<<5 | id<<10  (v = x-offset, h = y, d = z; S <= 32: 5 bits each,
-#define INC(v, h, d) ((unsigned)(v) | ((unsigned)(h) << 5) | ((unsigned)(d) << 10))   // so a voxel is 16 bits in shared memory)
-__constant__ MaskE M_FWD1[14] = {   // MINforwardDE1 :508-712
-    {ZM | YM | XM, -1, -1, -1, INC(1, 1, 1)}, {YM | XM, 0, -1, -1, INC(1, 1, 0)}, {ZP | YM | XM, 1, -1, -1, INC(1, 1, 1)},
-    {ZM | XM, -1, 0, -1, INC(1, 0, 1)},       {XM, 0, 0, -1, INC(1, 0, 0)},       {XM | ZP, 1, 0, -1, INC(1, 0, 1)},
-    {XM | ZM | YP, -1, 1, -1, INC(1, 1, 1)},  {XM | YP, 0, 1, -1, INC(1, 1, 0)},  {XM | YP | ZP, 1, 1, -1, INC(1, 1, 1)},
-    {ZM | YM, -1, -1, 0, INC(0, 1, 1)},       {YM, 0, -1, 0, INC(0, 1, 0)},       {ZP | YM, 1, -1, 0, INC(0, 1, 1)},
-    {0, 0, 0, 0, INC(0, 0, 0)},               {ZM, -1, 0, 0, INC(0, 0, 1)}};
-__constant__ MaskE M_BWD1[14] = {   // MINbackwardDE1 :301-506 (entry 10 reads [z+1][y][x], sic :459-464)
-    {ZM | YM | XP, -1, -1, 1, INC(1, 1, 1)},  {YM | XP, 0, -1, 1, INC(1, 1, 0)},  {ZP | YM | XP, 1, -1, 1, INC(1, 1, 1)},
-    {ZM | XP, -1, 0, 1, INC(1, 0, 1)},        {XP, 0, 0, 1, INC(1, 0, 0)},        {XP | ZP, 1, 0, 1, INC(1, 0, 1)},
-    {XP | ZM | YP, -1, 1, 1, INC(1, 1, 1)},   {XP | YP, 0, 1, 1, INC(1, 1, 0)},   {XP | YP | ZP, 1, 1, 1, INC(1, 1, 1)},
-    {ZP, 1, 0, 0, INC(0, 0, 1)},              {YP | ZP, 1, 0, 0, INC(0, 1, 1)},
-    {YP, 0, 1, 0, INC(0, 1, 0)},              {0, 0, 0, 0, INC(0, 0, 0)},         {ZM | YP, -1, 1, 0, INC(0, 1, 1)}};
-__constant__ MaskE M_FWD2[2] = {{ZP, 1, 0, 0, INC(0, 0, 1)}, {0, 0, 0, 0, INC(0, 0, 0)}};    // MINforwardDE2 :260-299
-__constant__ MaskE M_FWD4[2] = {{ZM, -1, 0, 0, INC(0, 0, 1)}, {0, 0, 0, 0, INC(0, 0, 0)}};   // MINforwardDE4 :139-175
-__constant__ MaskE M_FWD3[5] = {   // MINforwardDE3 :57-136 (entry 1 reads [z+1][y][x], sic :88-93)
-    {ZP, 1, 0, 0, INC(0, 0, 1)}, {YP | ZP, 1, 0, 0, INC(0, 1, 1)}, {YP, 0, 1, 0, INC(0, 1, 0)}, {0, 0, 0, 0, INC(0, 0, 0)}, {ZM | YP, -1, 1, 0, INC(0, 1, 1)}};
-__constant__ MaskE M_BWD3[5] = {   // MINbackwardDE3 :177-258
-    {ZM | YM, -1, -1, 0, INC(0, 1, 1)}, {YM, 0, -1, 0, INC(0, 1, 0)}, {ZP | YM, 1, -1, 0, INC(0, 1, 1)}, {0, 0, 0, 0, INC(0, 0, 0)}, {ZM, -1, 0, 0, INC(0, 0, 1)}};
+struct MaskE { int cond; int dz, dy, dx; int iv, ih, id; };   // reads A[x+dx][y+dy][z+dz] where it exists (cond) and adds (iv, ih, id) to its |x|,|y|,|z| offsets
+enum { T_FWD1, T_BWD1, T_FWD3, T_BWD3 };
+__host__ __device__ constexpr MaskE mask_entry(int tbl, int k) {
+    switch (tbl) {
+    case T_FWD1:   // MINforwardDE1 :508-712
+        switch (k) {
+        case 0: return {ZM | YM | XM, -1, -1, -1, 1, 1, 1}; case 1: return {YM | XM, 0, -1, -1, 1, 1, 0}; case 2: return {ZP | YM | XM, 1, -1, -1, 1, 1, 1};
+        case 3: return {ZM | XM, -1, 0, -1, 1, 0, 1};       case 4: return {XM, 0, 0, -1, 1, 0, 0};       case 5: return {XM | ZP, 1, 0, -1, 1, 0, 1};
+        case 6: return {XM | ZM | YP, -1, 1, -1, 1, 1, 1};  case 7: return {XM | YP, 0, 1, -1, 1, 1, 0};  case 8: return {XM | YP | ZP, 1, 1, -1, 1, 1, 1};
+        case 9: return {ZM | YM, -1, -1, 0, 0, 1, 1};       case 10: return {YM, 0, -1, 0, 0, 1, 0};      case 11: return {ZP | YM, 1, -1, 0, 0, 1, 1};
+        case 12: return {0, 0, 0, 0, 0, 0, 0};              default: return {ZM, -1, 0, 0, 0, 0, 1};
+        }
+    case T_BWD1:   // MINbackwardDE1 :301-506 (entry 10 reads [z+1][y][x], sic :459-464)
+        switch (k) {
+        case 0: return {ZM | YM | XP, -1, -1, 1, 1, 1, 1};  case 1: return {YM | XP, 0, -1, 1, 1, 1, 0};  case 2: return {ZP | YM | XP, 1, -1, 1, 1, 1, 1};
+        case 3: return {ZM | XP, -1, 0, 1, 1, 0, 1};        case 4: return {XP, 0, 0, 1, 1, 0, 0};        case 5: return {XP | ZP, 1, 0, 1, 1, 0, 1};
+        case 6: return {XP | ZM | YP, -1, 1, 1, 1, 1, 1};   case 7: return {XP | YP, 0, 1, 1, 1, 1, 0};   case 8: return {XP | YP | ZP, 1, 1, 1, 1, 1, 1};
+        case 9: return {ZP, 1, 0, 0, 0, 0, 1};              case 10: return {YP | ZP, 1, 0, 0, 0, 1, 1};
+        case 11: return {YP, 0, 1, 0, 0, 1, 0};             case 12: return {0, 0, 0, 0, 0, 0, 0};        default: return {ZM | YP, -1, 1, 0, 0, 1, 1};
+        }
+    case T_FWD3:   // MINforwardDE3 :57-136 (entry 1 reads [z+1][y][x], sic :88-93)
+        switch (k) {
+        case 0: return {ZP, 1, 0, 0, 0, 0, 1}; case 1: return {YP | ZP, 1, 0, 0, 0, 1, 1}; case 2: return {YP, 0, 1, 0, 0, 1, 0}; case 3: return {0, 0, 0, 0, 0, 0, 0};
+        default: return {ZM | YP, -1, 1, 0, 0, 1, 1};
+        }
+    default:       // T_BWD3: MINbackwardDE3 :177-258
+        switch (k) {
+        case 0: return {ZM | YM, -1, -1, 0, 0, 1, 1}; case 1: return {YM, 0, -1, 0, 0, 1, 0}; case 2: return {ZP | YM, 1, -1, 0, 0, 1, 1}; case 3: return {0, 0, 0, 0, 0, 0, 0};
+        default: return {ZM, -1, 0, 0, 0, 0, 1};
+        }
+    }
+}
+// MINforwardDE2 :260-299 = {z+1 (+1 in z), self}, MINforwardDE4 :139-175 = {z-1 (+1 in z), self}: the pure in-column sweeps that follow every
+// full one
 
 constexpr unsigned UNSET = 0xFFFFFFFFu;   // DEucl3D {infty,infty,infty,infty}
-__device__ __forceinline__ int qof(unsigned a) { int v = a & 31, h = (a >> 5) & 31, d = (a >> 10) & 31; return v * v + h * h + d * d; }
 __device__ __forceinline__ unsigned ldA(const unsigned short* A, int i) { const unsigned u = A[i]; return u == 0xFFFFu ? UNSET : u; }
-// `if (mask[k].distance < min.distance) min = mask[k]` with NaN (unset source) never selected
-__device__ __forceinline__ void take_if_less(unsigned& best, unsigned cand) {
-    if (cand != UNSET && (best == UNSET || qof(cand) < qof(best))) best = cand;
+
+// A voxel in shared memory is its 16-bit code v | h << 5 | d << 10 (the |x|,|y|,|z| offsets to the nearest seed found so far;
+// S <= 32: 5 bits each), 0xFFFF = no seed yet.  While a mask is evaluated a candidate is the KEY (q << 20) | (entry index << 15) | code
+// with q = v^2 + h^2 + d^2: the unsigned minimum of the keys is "smallest squared distance, the EARLIEST entry among equals" = the
+// reference's chain of `if (mask[k].distance < min.distance) min = mask[k]` (strict <, jly_3ddt.cpp:131-133 etc.).  "No seed" is
+// q = 3000 (above every real q <= 3 * 31^2): a candidate derived from it stays above every real one without a special case in the
+// dependent chain, and is written back as 0xFFFF.
+constexpr unsigned KMASK = 0xFu << 15, UNSETQ = 3000u;
+__device__ __forceinline__ unsigned key_of_code(unsigned code16) {
+    const unsigned v = code16 & 31u, h = (code16 >> 5) & 31u, d = (code16 >> 10) & 31u;
+    return code16 == 0xFFFFu ? (UNSETQ << 20) : (((v * v + h * h + d * d) << 20) | code16);
+}
+__device__ __forceinline__ unsigned code_of_key(unsigned key) { return (key >> 20) >= UNSETQ ? 0xFFFFu : (key & 0x7FFFu); }
+// the key of (cell + (IV, IH, ID)) as entry K; `key` has its entry bits clear:  (v+1)^2 = v^2 + 2v + 1
+template <int IV, int IH, int ID>
+__device__ __forceinline__ unsigned key_add(unsigned key, unsigned k) {
+    unsigned lin = 0;
+    if (IV) lin += key & 31u;
+    if (IH) lin += (key >> 5) & 31u;
+    if (ID) lin += (key >> 10) & 31u;
+    return key + ((2u * lin + (unsigned)(IV + IH + ID)) << 20) + (unsigned)(IV | (IH << 5) | (ID << 10)) + (k << 15);
 }
 
-// one z-sweep of column (y, x): table T[0..n), in-column entries [ic0, ic1), zdir = +1 ascending / -1 descending
-__device__ __forceinline__ void sweep_column(unsigned short* A, int S, int x, int y, const MaskE* T, int n, int ic0, int ic1, int zdir, int lane) {
+// One row step = a full mask sweep of column (y, x) followed by the pure in-column sweep in the opposite z direction
+// (DEuclidean :716-750: FWD1 then FWD2, FWD3 then FWD4, BWD1 then FWD4, BWD3 then FWD2).  The entries that read OTHER columns are
+// reduced by the lanes (lane = z) into sOther[z]; the in-column recurrences (each z needs the value its neighbour just got) are then
+// walked by lane 0 alone, from shared memory, with four dependent integer operations per z instead of a shuffle round trip.
+// IC0..IC1: the in-column entries of the table (one, or two reading the same neighbour: the reference's copy-paste slips);
+// ZDIR: direction of the full sweep (+1 ascending).
+template <int TBL, int N, int IC0, int IC1, int ZDIR>
+__device__ __forceinline__ void row_step(unsigned short* A, unsigned* sOther, unsigned* sRes, int S, int x, int y, int lane) {
     const int z = lane;
     const bool act = z < S;
     const int have = (z > 0 ? ZM : 0) | (z < S - 1 ? ZP : 0) | (y > 0 ? YM : 0) | (y < S - 1 ? YP : 0) | (x > 0 ? XM : 0) | (x < S - 1 ? XP : 0);
-    unsigned pre = UNSET, post = UNSET;
+    unsigned other = UNSETQ << 20;
     if (act) {
-        for (int k = 0; k < ic0; ++k) {
-            const MaskE m = T[k];
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            if (k >= IC0 && k < IC1) continue;
+            constexpr MaskE dummy = {0, 0, 0, 0, 0, 0, 0}; (void)dummy;
+            const MaskE m = mask_entry(TBL, k);
             if ((m.cond & have) != m.cond) continue;
-            const unsigned s = ldA(A, ((x + m.dx) * S + (y + m.dy)) * S + (z + m.dz));
-            take_if_less(pre, s == UNSET ? UNSET : s + m.inc);
+            const unsigned key = key_of_code(A[((x + m.dx) * S + (y + m.dy)) * S + (z + m.dz)]);
+            unsigned c;
+            if (m.iv && m.ih && m.id) c = key_add<1, 1, 1>(key, (unsigned)k);
+            else if (m.iv && m.ih) c = key_add<1, 1, 0>(key, (unsigned)k);
+            else if (m.iv && m.id) c = key_add<1, 0, 1>(key, (unsigned)k);
+            else if (m.ih && m.id) c = key_add<0, 1, 1>(key, (unsigned)k);
+            else if (m.iv) c = key_add<1, 0, 0>(key, (unsigned)k);
+            else if (m.ih) c = key_add<0, 1, 0>(key, (unsigned)k);
+            else if (m.id) c = key_add<0, 0, 1>(key, (unsigned)k);
+            else c = key_add<0, 0, 0>(key, (unsigned)k);
+            other = min(other, c);
         }
-        for (int k = ic1; k < n; ++k) {
-            const MaskE m = T[k];
-            if ((m.cond & have) != m.cond) continue;
-            const unsigned s = ldA(A, ((x + m.dx) * S + (y + m.dy)) * S + (z + m.dz));
-            take_if_less(post, s == UNSET ? UNSET : s + m.inc);
-        }
-    }
-    unsigned res = UNSET;
-    for (int step = 0; step < S; ++step) {
-        const int zc = zdir > 0 ? step : S - 1 - step;
-        const unsigned src = __shfl_sync(GOICP_FULL, res, (zc - zdir) & 31);   // new value of the in-column neighbour
-        if (lane == zc) {
-            unsigned best = pre;
-            for (int k = ic0; k < ic1; ++k) {
-                const MaskE m = T[k];
-                if ((m.cond & have) != m.cond) continue;
-                take_if_less(best, src == UNSET ? UNSET : src + m.inc);
-            }
-            take_if_less(best, post);
-            res = best;
-        }
+        sOther[z] = other;
     }
     __syncwarp();
-    if (act) A[(x * S + y) * S + z] = (unsigned short)res;   // UNSET -> 0xFFFF
+    if (lane == 0) {
+        // in-column entries of the full sweep: entry IC0 adds (0, 0, 1); a second one (IC0 + 1, the slips) adds (0, 1, 1) and needs y < S - 1
+        const bool two = (IC1 - IC0 == 2) && (y < S - 1);
+        unsigned prev = 0;
+        for (int step = 0; step < S; ++step) {
+            const int zc = ZDIR > 0 ? step : S - 1 - step;
+            unsigned best = sOther[zc];
+            if (step > 0) {
+                best = min(best, key_add<0, 0, 1>(prev, (unsigned)IC0));
+                if (two) best = min(best, key_add<0, 1, 1>(prev, (unsigned)(IC0 + 1)));
+            }
+            prev = best & ~KMASK;
+            sRes[zc] = prev;
+        }
+        // the pure in-column sweep, opposite direction: entry 0 = the neighbour just updated + (0, 0, 1), entry 1 = the voxel itself
+        prev = 0;
+        for (int step = 0; step < S; ++step) {
+            const int zc = ZDIR > 0 ? S - 1 - step : step;
+            unsigned best = sRes[zc] | (1u << 15);
+            if (step > 0) best = min(best, key_add<0, 0, 1>(prev, 0u));
+            prev = best & ~KMASK;
+            A[(x * S + y) * S + zc] = (unsigned short)code_of_key(prev);
+        }
+    }
     __syncwarp();
 }
 
 __global__ void __launch_bounds__(32)
 dt_replay_kernel(PairDev* __restrict__ pairs, int first) {
     extern __shared__ unsigned short A[];   // [x][y][z]
+    __shared__ unsigned sOther[32], sRes[32];
     const GridDev g = pairs[first + blockIdx.x].g;
     const int S = g.S, lane = threadIdx.x;
     const int S3 = S * S * S;
@@ -109,24 +164,12 @@ dt_replay_kernel(PairDev* __restrict__ pairs, int first) {
     __syncwarp();
     // DEuclidean :716-750
     for (int x = 0; x < S; ++x) {
-        for (int y = 0; y < S; ++y) {
-            sweep_column(A, S, x, y, M_FWD1, 14, 13, 14, +1, lane);
-            sweep_column(A, S, x, y, M_FWD2, 2, 0, 1, -1, lane);
-        }
-        for (int y = S - 1; y > -1; --y) {
-            sweep_column(A, S, x, y, M_FWD3, 5, 0, 2, -1, lane);
-            sweep_column(A, S, x, y, M_FWD4, 2, 0, 1, +1, lane);
-        }
+        for (int y = 0; y < S; ++y) row_step<T_FWD1, 14, 13, 14, +1>(A, sOther, sRes, S, x, y, lane);
+        for (int y = S - 1; y > -1; --y) row_step<T_FWD3, 5, 0, 2, -1>(A, sOther, sRes, S, x, y, lane);
     }
     for (int x = S - 1; x > -1; --x) {
-        for (int y = S - 1; y > -1; --y) {
-            sweep_column(A, S, x, y, M_BWD1, 14, 9, 11, -1, lane);
-            sweep_column(A, S, x, y, M_FWD4, 2, 0, 1, +1, lane);
-        }
-        for (int y = 0; y < S; ++y) {
-            sweep_column(A, S, x, y, M_BWD3, 5, 4, 5, +1, lane);
-            sweep_column(A, S, x, y, M_FWD2, 2, 0, 1, -1, lane);
-        }
+        for (int y = S - 1; y > -1; --y) row_step<T_BWD1, 14, 9, 11, -1>(A, sOther, sRes, S, x, y, lane);
+        for (int y = 0; y < S; ++y) row_step<T_BWD3, 5, 4, 5, +1>(A, sOther, sRes, S, x, y, lane);
     }
     // distances and emptyCells :999-1136
     for (int i = lane; i < S3; i += 32) {
