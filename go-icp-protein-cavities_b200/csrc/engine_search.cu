@@ -400,9 +400,11 @@ static goicp_status register_resident(Eng* h, const BnbCfg& cfg) {
     { const char* e = getenv("GOICP_CTAS_PER_SM"); if (e && atoi(e) >= 1) perSM = std::min(perSM, atoi(e)); }
     int ctas = h->numSM * perSM;
     { const char* e = getenv("GOICP_CTAS"); if (e && atoi(e) >= 1) ctas = std::min(ctas, atoi(e)); }
-    int heapCap = 1 << 15;
+    // per-CTA slabs: translation queue (32 B per entry) and rotation queue (2 x 32 B per node); a pair that outgrows either is re-run by
+    // the wave scheduler with growing slabs -- slow, so the slabs are generous (4 MB + 1 MB per CTA)
+    int heapCap = 1 << 17;
     { const char* e = getenv("GOICP_HEAPCAP"); if (e && atoi(e) >= 129) heapCap = atoi(e); }   // test hook: force the overflow re-run
-    const int rqCap = 1 << 13;
+    const int rqCap = 1 << 14;
     const int memoCap = 8192;
     CU(h->sCtl.ensure(sizeof(SearchCtl)));
     CU(h->sHdrs.ensure(goicp_search_hdr_bytes() * (size_t)ctas));
