@@ -45,6 +45,7 @@ struct OwnerSh {
     int specGroups;              // (diagnostic) groups attached during the last walk
     int action, actOwner, actSlot, actCancel;
     int noMorePairs, lastSpawnJ, manager;
+    int waited;
     int waitPolls;               // manager mode: polls spent waiting for a helper to take the call the search needs next
     int quiet;                   // rotation nodes popped since the incumbent last improved: look-ahead grows 1, 3, 7, ... with it (calls made under an incumbent that is about to improve are wasted)
     // results of the current node's children as last fetched by the warp (a slot that was done then stays done until the owner frees it)
@@ -317,6 +318,7 @@ __device__ __forceinline__ int owner_serial(Cta& c) {
             {
                 const uint4 key = node_key(os.par);
                 int g = lookup_group(c, key);   // calls made ahead of time for this node?
+                atomicAdd(&A.ctl->dbg[g >= 0 ? 12 : 13], 1ull);
                 if (g < 0) {
                     while ((g = alloc_group(c, -1)) < 0) __nanosleep(200);   // every group has calls running (they stop at their next pop if abandoned)
                     *reinterpret_cast<uint4*>(os.grpKey[g]) = key;
@@ -336,7 +338,7 @@ __device__ __forceinline__ int owner_serial(Cta& c) {
             }
             const int sidx = 8 * os.par.group + os.j;
             SearchSlot* sl = c.slots + sidx;
-            if (os.pfState[os.j] == SL_DONE) os.waitPolls = 0;
+            if (os.pfState[os.j] == SL_DONE) { atomicAdd(&A.ctl->dbg[os.waited ? 15 : 14], 1ull); os.waited = 0; os.waitPolls = 0; } else os.waited = 1;
             if (os.pfState[os.j] != SL_DONE) {   // not finished when the warp last looked: what is it doing now?
                 const unsigned w = ld_vol(c.st + sidx);
                 const unsigned st = st_of(w);
