@@ -65,17 +65,19 @@ int main(int argc, char** argv) {
     const double time = std::chrono::duration<double>(std::chrono::steady_clock::now() - c0).count();
     std::cout << goicp.Trace();
 
-    std::cout << "Optimal Rotation Matrix:" << std::endl << matrix_rows(goicp.optR, 3, 3) << std::endl;
-    std::cout << "Optimal Translation Vector:" << std::endl << matrix_rows(goicp.optT, 3, 1) << std::endl;
+    std::cout << "Optimal Rotation Matrix:" << std::endl << goicp.optR << std::endl;
+    std::cout << "Optimal Translation Vector:" << std::endl << goicp.optT << std::endl;
     std::cout << "Finished in " << time << std::endl << std::endl;
 
-    write_output_file(outputF, time, goicp.optR, goicp.optT, goicp.optError, goicp.Nd - goicp.optComp);
+    double Ropt[9], topt[3];
+    goicp.optR.getData(Ropt); goicp.optT.getData(topt);
+    write_output_file(outputF, time, Ropt, topt, goicp.optError, goicp.Nd - goicp.optComp);
 
     // rescaleCloud (transformation.cpp:403-417)
     const double meanT[3] = {xMeanT, yMeanT, zMeanT}, meanS[3] = {xMean, yMean, zMean};
     double tr[3];
-    t.rescaleTranslation(scale, meanT, meanS, goicp.optR, goicp.optT, tr);
-    write_rescaled_file(outputF, time, goicp.optR, tr, goicp.optError);
+    t.rescaleTranslation(scale, meanT, meanS, Ropt, topt, tr);
+    write_rescaled_file(outputF, time, Ropt, tr, goicp.optError);
 
     delete[] goicp.pModel; delete[] goicp.pData;
     return 0;

@@ -64,7 +64,7 @@ ABI_SYMBOLS = [
     "goicp_version", "goicp_last_error", "goicp_params_default", "goicp_create", "goicp_destroy",
     "goicp_set_model", "goicp_set_data", "goicp_set_params", "goicp_build_dt", "goicp_build_dt_replay", "goicp_dt_upload",
     "goicp_dt_download", "goicp_dt_distance", "goicp_set_nd", "goicp_initialize", "goicp_get_weights", "goicp_get_maxrotdis",
-    "goicp_get_thresholds", "goicp_eval_bounds", "goicp_eval_inclusion", "goicp_inner_bnb", "goicp_icp", "goicp_register", "goicp_last_trace",
+    "goicp_get_thresholds", "goicp_eval_bounds", "goicp_eval_inclusion", "goicp_inner_bnb", "goicp_icp", "goicp_register", "goicp_outer_bnb", "goicp_last_trace",
     "goicp_set_options", "goicp_register_batch", "goicp_batch_upload", "goicp_batch_run", "goicp_get_timings",
     "goicp_set_batch_options", "goicp_get_stats", "goicp_set_frontier_sharding", "goicp_test_exchange",
     "goicp_normalize_cloud", "goicp_scale_cloud", "goicp_rescale_translation", "goicp_apply_rigid", "goicp_rmsd",
@@ -111,6 +111,7 @@ def lib():
     L.goicp_inner_bnb.argtypes = [vp, fp, ip, fp, C.c_int32, fp, fp, C.POINTER(C.c_int64)]
     L.goicp_icp.argtypes = [vp, dp, dp, fp, ip]
     L.goicp_register.argtypes = [vp, C.POINTER(Result)]
+    L.goicp_outer_bnb.argtypes = [vp, C.POINTER(Result)]
     L.goicp_set_options.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
     L.goicp_register_batch.argtypes = [vp, C.POINTER(Params), C.c_int32, C.POINTER(PairDesc), C.POINTER(Result)]
     L.goicp_batch_upload.argtypes = [vp, C.POINTER(Params), C.c_int32, C.POINTER(PairDesc)]

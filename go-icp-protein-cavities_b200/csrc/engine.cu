@@ -316,6 +316,13 @@ goicp_status goicp_register(goicp_handle h, goicp_result* out) {
     fill_result(h, P, out);
     return GOICP_OK;
 }
+goicp_status goicp_outer_bnb(goicp_handle h, goicp_result* out) {
+    if (!h || !out) return GOICP_ERR_ARG;
+    goicp_status s; if ((s = ensure_single(h))) return s;
+    Problem& P = h->probs[0];
+    if (!P.initialized) return fail(h, GOICP_ERR_ARG, "outer_bnb before initialize");
+    return goicp_register(h, out);   // (Initialize is idempotent: the search starts from the same prepared state)
+}
 const char* goicp_last_trace(goicp_handle h) { return h ? h->trace.c_str() : ""; }
 
 // ---- batch -----------------------------------------------------------------------------------------------------------

@@ -137,6 +137,9 @@ goicp_status goicp_inner_bnb(goicp_handle h, const float* R, const int32_t* leve
 goicp_status goicp_icp(goicp_handle h, double* R /*9*/, double* t /*3*/, float* err, int32_t* corr_or_null /*Nd*/);
 /* GoICP::Register (jly_goicp.cpp:878) = Initialize + OuterBnB + Clear; builds the DT if needed. */
 goicp_status goicp_register(goicp_handle h, goicp_result* out);
+/* GoICP::OuterBnB (jly_goicp.cpp:582-876) alone: the search on a problem that goicp_initialize has prepared (Register = Initialize +
+ * OuterBnB + Clear, :878-885). */
+goicp_status goicp_outer_bnb(goicp_handle h, goicp_result* out);
 /* the "Error*:" improvement trace of the last goicp_register (what OuterBnB prints, jly_goicp.cpp:627-839) */
 const char* goicp_last_trace(goicp_handle h);
 /* search options: exact_sums=1 (default) reproduces the reference's sequential float sums bit for bit;

@@ -507,6 +507,70 @@ def test_cli_pair1_golden(tmp_path):
         assert got[0].startswith("Time: ") and got[1:] == want[1:], (f, got, want)
 
 
+def test_unmodified_reference_main(tmp_path):
+    """the reference's UNMODIFIED jly_main.cpp, compiled in the build container against include/compat + include/goicp_dropin.hpp and
+    linked against libgoicp_b200.so alone (examples/Makefile: GoICP_ref_main; the binary travels to the GPU box), run as bo1_GoICP.py:51
+    runs the reference: the files the reference ships for pair 1 come out byte for byte (except the Time: line)"""
+    import os
+    import shutil
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "examples", "GoICP_ref_main")
+    if not os.path.exists(exe):
+        pytest.skip("examples/GoICP_ref_main is built only where the reference checkout exists")
+    src = os.path.join(ROOT, "tests", "golden", "cli")
+    for d in ("cavities", "cfpfh"):
+        shutil.copytree(os.path.join(src, d), tmp_path / d)
+    shutil.copy(os.path.join(src, "config.txt"), tmp_path / "config.txt")
+    os.makedirs(tmp_path / "cavitiesN"); os.makedirs(tmp_path / "output")
+    out = subprocess.run([exe, "cavities/1eq2_6_cavity6.mol2", "cavities/2x86_3_cavity6.mol2", "238", "config.txt", "output/similar1.txt", "1"],
+                         cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    exp = os.path.join(src, "expected")
+    for f in ("1eq2_6_cavity6_sim1N.xyz", "2x86_3_cavity6_sim1N.xyz"):
+        assert open(tmp_path / "cavitiesN" / f, "rb").read() == open(os.path.join(exp, f), "rb").read(), f
+    for f in ("similar1.txt", "similar1_rescaled.txt"):
+        got = open(tmp_path / "output" / f).read().split("\n")
+        want = open(os.path.join(exp, f)).read().split("\n")
+        assert got[0].startswith("Time: ") and got[1:] == want[1:], (f, got, want)
+
+
+def test_dropin_named_methods(g, tmp_path):
+    """the five methods north_star names on the drop-in class (Initialize / OuterBnB / InnerBnB / ICP / Clear), DT3D::emptyCells /
+    cellPoints and Matrix: a C++ caller (examples/dropin_methods.cpp) runs pair 1 through them and prints what the python binding
+    returns for the same calls"""
+    import os
+    import subprocess
+    from conftest import ROOT
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "examples"), "dropin_methods"])
+    z = golden("pair1")
+
+    def dump(path, xyz, c, fp):
+        with open(path, "w") as f:
+            f.write("%d\n" % len(xyz))
+            for p, cc, row in zip(xyz, c, fp):
+                f.write("%.9g %.9g %.9g %d " % (p[0], p[1], p[2], cc) + " ".join("%.9g" % v for v in row) + "\n")
+    dump(tmp_path / "model.txt", z["model_xyz"], z["model_c"], z["model_fpfh"]); dump(tmp_path / "data.txt", z["data_xyz"], z["data_c"], z["data_fpfh"])
+    out = subprocess.run([os.path.join(ROOT, "examples", "dropin_methods"), str(tmp_path / "model.txt"), str(tmp_path / "data.txt"), str(int(z["nd"]))], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    kv = dict(line.split("=", 1) for line in out.stdout.strip().split("\n") if "=" in line)
+    assert float(kv["register_optError"]) == pytest.approx(float(z["exp_optError"]), rel=1e-7) and int(kv["register_optComp"]) == int(z["exp_optComp"])
+    assert float(kv["outer_optError"]) == pytest.approx(float(z["exp_optError"]), rel=1e-7)
+    reg = g.GoICP(z["model_xyz"], z["data_xyz"], g.shipped_config(), **pair_clouds(z))
+    reg.BuildDT(); reg.set_nd(int(z["nd"])); reg.Initialize()
+    sse, inl = reg.thresholds()
+    assert float(kv["SSEThresh"]) == pytest.approx(sse, rel=1e-7) and int(kv["inlierNum"]) == inl
+    assert float(kv["maxRotDis_3_5"]) == pytest.approx(float(reg.maxRotDis()[3, 5]), rel=1e-7) and float(kv["weight_7"]) == pytest.approx(float(reg.weights()[7]), rel=1e-7)
+    err, tn, _ = reg.InnerBnB(np.eye(3, dtype=np.float32).reshape(1, 9), np.array([-1], np.int32), np.array([30.0], np.float32))
+    assert float(kv["inner_ub"]) == pytest.approx(float(err[0]), rel=1e-7)
+    e, R, t, _ = reg.ICP(np.eye(3), np.zeros(3))
+    assert float(kv["icp_err"]) == pytest.approx(e, rel=1e-7) and float(kv["icp_R00"]) == pytest.approx(R[0, 0], abs=1e-7)
+    d, near, cc = reg.dt_download()
+    S = 20; v = (3 * S + 4) * S + 5
+    assert [int(kv["empty_x"]), int(kv["empty_y"]), int(kv["empty_z"])] == near[v].tolist() and int(kv["cell_c"]) == int(cc[(near[v][2] * S + near[v][1]) * S + near[v][0]])
+    assert int(kv["cell_npoints"]) >= 1 and kv["matrix_row0"].split() == ["%.7f" % x for x in np.asarray(z["exp_R"])[0]]
+
+
 def test_cli_sweep_batch(tmp_path):
     """examples/GoICP_b200_sweep = bo1_GoICP.py's loop as one in-process batch: a pair list (TSV, columns 3/4) in, the
     per-pair files of the reference out -- byte-identical to the shipped pair-1 files (except the Time: line) for every row"""
