@@ -92,6 +92,28 @@ int main(int argc, char** argv) {
         t.rescaleTranslation(pf.scale, pf.meanT, pf.meanS, r.R, r.t, tr);
         write_rescaled_file(pf.outputF, time, r.R, tr, r.optError);
         std::cout << prefix << pf.pair << ": " << pf.target << " <- " << pf.source << "  Error: " << r.optError << "  Compatibilities: " << pf.Nd - r.optComp << std::endl;
+        // protein-level post-processing (the block of jly_main.cpp:159-172, README.md:25): when chains/<source>_protein.mol2 is there, the
+        // rescaled transform is applied to the whole protein (rot/rot_<protein>) and its backbone RMSD against
+        // ref_proteins/<source>.<target>/aligned_<protein> is appended to resultsRMSD.txt.  Like the reference, the directories
+        // cavitiesR/ and rot/ must exist.
+        const string src6 = stem_between(pf.source).substr(0, 6), tgt6 = stem_between(pf.target).substr(0, 6);
+        const string protein = src6 + "_protein.mol2";
+        if (std::ifstream("chains/" + protein).good()) {
+            {   // applyTransformationProtein reads cavitiesR/similar<pair>.txt = the rescaled result (transformation.cpp:470)
+                std::ifstream a(pf.outputF.substr(0, pf.outputF.find(".")) + "_rescaled.txt", std::ios::binary);
+                std::ofstream b("cavitiesR/similar" + std::to_string(pf.pair) + ".txt", std::ios::binary);
+                b << a.rdbuf();
+            }
+            std::ofstream rotOut("rot/rot_" + protein);
+            t.applyTransformationProtein(rotOut, "chains/" + protein, pf.pair);
+            std::ifstream aligned("ref_proteins/" + src6 + "." + tgt6 + "/aligned_" + protein), rot("rot/rot_" + protein);
+            if (aligned.is_open() && rot.is_open()) {
+                const float rmsd = t.computeRMSD(aligned, rot);
+                std::ofstream rf("resultsRMSD.txt", std::ios::app);
+                if (rf.is_open()) rf << pf.pair << "\t" << src6 << "\t" << tgt6 << "\t" << std::to_string(rmsd) << std::endl;
+                std::cout << "---> RMSD: " << rmsd << std::endl;
+            }
+        }
     }
     std::cout << "Finished " << pairs.size() << " pairs in " << total << " s (" << pairs.size() / total << " pairs/s)" << std::endl;
     goicp_destroy(h);

@@ -599,6 +599,38 @@ def test_cli_sweep_batch(tmp_path):
     assert not os.path.exists(tmp_path / "output" / "similar4.txt")
 
 
+def test_cli_sweep_protein_rmsd(tmp_path):
+    """the sweep CLI's protein-level post-processing (README.md:25, the block of jly_main.cpp:159-172): the rescaled transform of pair 1
+    applied to the whole 2x86_3 protein reproduces the reference's shipped rot/rot_2x86_3_protein.mol2 line for line (except the last
+    atom, which the reference reads out of range: SURVEY Q6) and resultsRMSD.txt holds the RMSD 1.736753"""
+    import os
+    import shutil
+    import subprocess
+    import tarfile
+    from conftest import ROOT
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "examples")])
+    exe = os.path.join(ROOT, "examples", "GoICP_b200_sweep")
+    src = os.path.join(ROOT, "tests", "golden", "cli")
+    for d in ("cavities", "cfpfh"):
+        shutil.copytree(os.path.join(src, d), tmp_path / d)
+    shutil.copy(os.path.join(src, "config.txt"), tmp_path / "config.txt")
+    with tarfile.open(os.path.join(src, "proteins.tar.gz")) as tf:
+        tf.extractall(tmp_path / "prot")
+    shutil.copytree(tmp_path / "prot" / "chains", tmp_path / "chains"); shutil.copytree(tmp_path / "prot" / "ref_proteins", tmp_path / "ref_proteins")
+    for d in ("cavitiesN", "output", "cavitiesR", "rot"):
+        os.makedirs(tmp_path / d)
+    (tmp_path / "pairs.tsv").write_text("P67911\tP67910\t2x86_3\t1eq2_6\t0.8638\tIsomerase\tcluster_2\n")
+    out = subprocess.run([exe, "pairs.tsv", "config.txt"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    got = open(tmp_path / "rot" / "rot_2x86_3_protein.mol2").read().split("\n")
+    want = open(tmp_path / "prot" / "rot" / "rot_2x86_3_protein.mol2").read().split("\n")
+    assert len(got) == len(want)
+    diff = [k for k, (a, b) in enumerate(zip(got, want)) if a != b]
+    assert len(diff) <= 1, (len(diff), diff[:5], [got[k] for k in diff[:2]], [want[k] for k in diff[:2]])
+    row = open(tmp_path / "resultsRMSD.txt").read().split()
+    assert row[:3] == ["1", "2x86_3", "1eq2_6"] and abs(float(row[3]) - 1.736753) < 2e-6
+
+
 def test_deep_queue_overflow_rerun(g, monkeypatch):
     """a translation queue that outgrows the search kernel's per-CTA slab: the pair is re-run by the wave scheduler
     (growing slabs); forcing a tiny slab (160 entries) must not change anything about pair 2's search (2.6 M sub-cubes)"""
