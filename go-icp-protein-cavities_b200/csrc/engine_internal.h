@@ -219,7 +219,7 @@ struct goicp_handle_s {
     bool dtUploaded = false;   // the DT came from goicp_dt_upload (test hook): no 16-bit distance codes
     int bnb_threads = goicp_bnb_default_threads(); bool bnb_threads_set = false;   // threads per InnerBnB CTA (64..512): more threads = shorter pops, fewer resident calls   // batch: worker streams (0 = auto) and pairs advanced in lock-step per stream
     std::vector<Problem> probs;
-    DevBuf arenaIn, arenaWork, dPairs, dTmp, dTmp2, dTmp3, dSepBits, dSepNx, dSepNxy;
+    DevBuf arenaIn, arenaWork, dPairs, dTmp, dTmp2, dTmp3, dSepBits, dSepNx, dSepNxy, dSepCid;
     PinBuf hStage, hPairs;
     WaveCtx main;
     DevBuf qHeaps, qScratch, qMemo, dGen;   // per-CTA slabs of the device-resident search: translation queues, staging arrays (large Nd), corner memo; counters

@@ -226,7 +226,8 @@ goicp_status build_dt_all(Eng* h, bool replay) {
         CU(h->dSepBits.ensure((size_t)S * S * SW * sizeof(unsigned)));
         CU(h->dSepNx.ensure(S3 * sizeof(unsigned short)));
         CU(h->dSepNxy.ensure(S3 * sizeof(unsigned)));
-        for (auto& P : h->probs) { CU(goicp_launch_dt_separable(P.dev.g, h->dSepBits.as<unsigned>(), h->dSepNx.as<unsigned short>(), h->dSepNxy.as<unsigned>(), h->numSM, h->stream)); nl += 4; }
+        CU(h->dSepCid.ensure(S3 * sizeof(int)));
+        for (auto& P : h->probs) { CU(goicp_launch_dt_separable(P.dev.g, h->dSepBits.as<unsigned>(), h->dSepNx.as<unsigned short>(), h->dSepNxy.as<unsigned>(), h->dSepCid.as<int>(), h->numSM, h->stream)); nl += 4; }
     }
     tm.stop(nl);
     CU(cudaGetLastError());

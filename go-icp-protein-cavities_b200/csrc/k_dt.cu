@@ -9,11 +9,11 @@
 //                     that read other columns are reduced by all lanes at once (keys whose unsigned minimum is the
 //                     reference's first-smallest rule), the in-column recurrences are walked by one lane with four dependent
 //                     integer operations per voxel.  A batch of pairs runs one warp each.
-//  dt_sep_*           any S: an exact separable Euclidean DT (x, then y, then z pass; every pass one thread per voxel
-//                     searching outwards along its axis with early exit) that also emits the nearest occupied voxel.
-//                     Where 8SED is exact (it is not an exact EDT) values are identical; ties between equidistant
-//                     occupied voxels are resolved by the documented rule "smaller |offset| along the later axis
-//                     first, negative side before positive", which differs from 8SED's scan-order choice.
+//  dt_sep_*           any S: an exact separable Euclidean DT that also emits the nearest occupied voxel: pass X from a bit
+//                     mask of the seeds (one thread per voxel), passes Y and Z as lower-envelope scans of the parabolas along
+//                     each grid line (Meijster et al., one thread per line, integer arithmetic).  Where 8SED is exact (it is
+//                     not an exact EDT) values are identical; ties between equidistant occupied voxels go to the smaller
+//                     coordinate along x, then y, then z (per pass), which differs from 8SED's scan-order choice.
 //
 // Distances: an integer squared voxel offset q -> (float)((double)(float)sqrt(q) / scale), as :1004 computes it
 // (sqrt in double rounded to float equals the correctly rounded float sqrt for q < 2^24).
@@ -244,52 +244,82 @@ dt_sep_x_kernel(const unsigned* __restrict__ bits, int S, int SW, unsigned short
         nx[i] = (unsigned short)best;
     }
 }
-// pass Y: nearest (x', y') in the z-slice; outward search along y with early exit
-__global__ void __launch_bounds__(256)
-dt_sep_y_kernel(const unsigned short* __restrict__ nx, int S, unsigned* __restrict__ nxy) {
-    const size_t total = (size_t)S * S * S;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int x = (int)(i % S), y = (int)((i / S) % S);
-        const size_t zbase = (i / ((size_t)S * S)) * S * S;
-        int bestq = 0x7FFFFFFF; unsigned best = UNSET;
-        for (int r = 0; r < S; ++r) {
-            if (r * r >= bestq) break;
-            bool any = false;
-            const int y0 = y - r, y1 = y + r;
-            if (y0 >= 0) { any = true; const int c = __ldg(nx + zbase + (size_t)y0 * S + x); if (c != 0xFFFF) { const int q = r * r + (c - x) * (c - x); if (q < bestq) { bestq = q; best = (unsigned)c | ((unsigned)y0 << 16); } } }
-            if (r > 0 && y1 < S) { any = true; const int c = __ldg(nx + zbase + (size_t)y1 * S + x); if (c != 0xFFFF) { const int q = r * r + (c - x) * (c - x); if (q < bestq) { bestq = q; best = (unsigned)c | ((unsigned)y1 << 16); } } }
-            if (!any) break;
+// Passes Y and Z: the lower envelope of the parabolas (u - i)^2 + g2(i) along one grid line (Meijster, Roerdink & Hesselink's exact
+// linear-time EDT scan, in integers), one thread per line: a first sweep keeps the stack of sites whose parabola is lowest somewhere
+// (s = site, t = first position it owns), a second sweep reads the owner of every position.  Consecutive threads handle consecutive
+// x, so every load / store of a sweep step is coalesced; the stacks live in local memory (interleaved per thread, L1-resident).
+// Ties between equidistant sites go to the site with the smaller coordinate along the pass (a parabola replaces an older one only
+// where it is STRICTLY lower).
+constexpr long long EDT_INF = 1ll << 40;
+__device__ __forceinline__ long long edt_floordiv(long long a, long long b) { long long q = a / b; if ((a % b != 0) && ((a < 0) != (b < 0))) --q; return q; }   // b > 0 here
+template <int MAXS, class G2>
+__device__ __forceinline__ int edt_envelope(int S, short* s, short* t, int* gs, G2 g2of) {
+    int q = -1;
+    for (int u = 0; u < S; ++u) {
+        const long long gu = g2of(u);
+        if (gu >= EDT_INF) continue;   // no site on this line at u
+        while (q >= 0) {
+            const long long tq = t[q], d0 = tq - s[q], d1 = tq - u;
+            if (d0 * d0 + gs[q] > d1 * d1 + gu) --q; else break;
         }
-        nxy[i] = best;
+        if (q < 0) { q = 0; s[0] = (short)u; t[0] = 0; gs[0] = (int)gu; }
+        else {
+            // Sep(i, u) = floor((u^2 - i^2 + g2(u) - g2(i)) / (2 (u - i))): the last position the older site i still owns
+            const long long i = s[q];
+            const long long w = 1 + edt_floordiv((long long)u * u - i * i + gu - gs[q], 2 * (u - i));
+            if (w < S) { ++q; s[q] = (short)u; t[q] = (short)(w < 0 ? 0 : w); gs[q] = (int)gu; }
+        }
+    }
+    return q;   // top of the stack; -1: the line has no site at all
+}
+// pass Y: nearest (x', y') in the z-slice for every voxel; nx from pass X
+template <int MAXS>
+__global__ void __launch_bounds__(128)
+dt_sep_y_kernel(const unsigned short* __restrict__ nx, int S, unsigned* __restrict__ nxy) {
+    short s[MAXS], t[MAXS]; int gs[MAXS];
+    const int lines = S * S;
+    for (int line = blockIdx.x * blockDim.x + threadIdx.x; line < lines; line += gridDim.x * blockDim.x) {
+        const int x = line % S, z = line / S;
+        const unsigned short* col = nx + (size_t)z * S * S + x;
+        int q = edt_envelope<MAXS>(S, s, t, gs, [&](int u) -> long long { const int c = __ldg(col + (size_t)u * S); if (c == 0xFFFF) return EDT_INF; const long long d = c - x; return d * d; });
+        unsigned* out = nxy + (size_t)z * S * S + x;
+        for (int u = S - 1; u >= 0; --u) {
+            unsigned v = UNSET;
+            if (q >= 0) { const int yy = s[q]; v = (unsigned)__ldg(col + (size_t)yy * S) | ((unsigned)yy << 16); if (u == t[q]) --q; }
+            out[(size_t)u * S] = v;
+        }
     }
 }
-// pass Z: nearest occupied voxel; writes the distance and the index map
-__global__ void __launch_bounds__(256)
-dt_sep_z_kernel(const unsigned* __restrict__ nxy, GridDev g) {
+// scatter: compact cell id of every occupied voxel (ncells elsewhere), so that the epilogue of pass Z needs one gather instead of a binary search
+__global__ void dt_sep_cid_kernel(const int* __restrict__ cell_vox, int ncells, int* __restrict__ cid) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < ncells) cid[cell_vox[c]] = c;
+}
+// pass Z: nearest occupied voxel; writes the distance, the index map and the per-voxel copies the search kernels gather
+template <int MAXS>
+__global__ void __launch_bounds__(128)
+dt_sep_z_kernel(const unsigned* __restrict__ nxy, const int* __restrict__ cid, GridDev g) {
+    short s[MAXS], t[MAXS]; int gs[MAXS];
     const int S = g.S;
-    const size_t total = (size_t)S * S * S, plane = (size_t)S * S;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int x = (int)(i % S), y = (int)((i / S) % S), z = (int)(i / plane);
-        const size_t col = (size_t)y * S + x;
-        int bestq = 0x7FFFFFFF, bx = x, by = y, bz = z;
-        for (int r = 0; r < S; ++r) {
-            if (r * r >= bestq) break;
-            bool any = false;
-            const int z0 = z - r, z1 = z + r;
-            if (z0 >= 0) { any = true; const unsigned c = __ldg(nxy + (size_t)z0 * plane + col); if (c != UNSET) { const int cx = c & 0xFFFF, cy = c >> 16; const int q = r * r + (cx - x) * (cx - x) + (cy - y) * (cy - y); if (q < bestq) { bestq = q; bx = cx; by = cy; bz = z0; } } }
-            if (r > 0 && z1 < S) { any = true; const unsigned c = __ldg(nxy + (size_t)z1 * plane + col); if (c != UNSET) { const int cx = c & 0xFFFF, cy = c >> 16; const int q = r * r + (cx - x) * (cx - x) + (cy - y) * (cy - y); if (q < bestq) { bestq = q; bx = cx; by = cy; bz = z1; } } }
-            if (!any) break;
-        }
-        float dist = (bestq == 0x7FFFFFFF) ? (float)((double)32767.f / g.scale) : (float)((double)sqrtf((float)bestq) / g.scale);
-        g.dist[i] = dist;
-        if (g.dcode) g.dcode[i] = (uint16_t)(bestq == 0x7FFFFFFF ? g.nlut - 1 : bestq);
-        const int vn = (bz * S + by) * S + bx;
-        g.vnear[i] = vn;
-        if (g.vcell) {
-            int lo = 0, hi = g.ncells - 1, id = g.ncells;
-            while (lo <= hi) { const int mid = (lo + hi) >> 1; const int v = __ldg(g.cell_vox + mid); if (v == vn) { id = mid; break; } if (v < vn) lo = mid + 1; else hi = mid - 1; }
-            g.vcell[i] = id;
-            if (g.vmask) { g.vmask[i] = g.cmask[id]; g.vmask8[i] = (uint8_t)g.cmask[id]; }
+    const size_t plane = (size_t)S * S;
+    for (int line = blockIdx.x * blockDim.x + threadIdx.x; line < (int)plane; line += gridDim.x * blockDim.x) {
+        const int x = line % S, y = line / S;
+        const unsigned* col = nxy + line;
+        int q = edt_envelope<MAXS>(S, s, t, gs, [&](int u) -> long long { const unsigned c = __ldg(col + (size_t)u * plane); if (c == UNSET) return EDT_INF; const long long dx = (int)(c & 0xFFFF) - x, dy = (int)(c >> 16) - y; return dx * dx + dy * dy; });
+        for (int u = S - 1; u >= 0; --u) {
+            const size_t i = (size_t)u * plane + line;
+            int bx = x, by = y, bz = u; long long bestq = -1;
+            if (q >= 0) { bz = s[q]; const unsigned c = __ldg(col + (size_t)bz * plane); bx = c & 0xFFFF; by = c >> 16; const long long dz = u - bz; bestq = dz * dz + gs[q]; if (u == t[q]) --q; }
+            const float dist = (bestq < 0) ? (float)((double)32767.f / g.scale) : (float)((double)sqrtf((float)bestq) / g.scale);
+            g.dist[i] = dist;
+            if (g.dcode) g.dcode[i] = (uint16_t)(bestq < 0 ? g.nlut - 1 : bestq);
+            const int vn = (bz * S + by) * S + bx;
+            g.vnear[i] = vn;
+            if (g.vcell) {
+                const int id = bestq < 0 ? g.ncells : __ldg(cid + vn);
+                g.vcell[i] = id;
+                if (g.vmask) { const unsigned m = __ldg(g.cmask + id); g.vmask[i] = m; g.vmask8[i] = (uint8_t)m; }
+            }
         }
     }
 }
@@ -326,18 +356,31 @@ cudaError_t goicp_launch_dt_replay(PairDev* pairs, int first, int count, int S, 
     return cudaGetLastError();
 }
 
-cudaError_t goicp_launch_dt_separable(const GridDev& g, unsigned* bits, unsigned short* nx, unsigned* nxy, int numSM, cudaStream_t st) {
+template <int MAXS>
+static void launch_sep_yz(const GridDev& g, const unsigned short* nx, unsigned* nxy, const int* cid, int numSM, cudaStream_t st) {
+    const int S = g.S, lines = S * S;
+    int blocks = (lines + 127) / 128;
+    if (blocks > numSM * 16) blocks = numSM * 16;
+    dt_sep_y_kernel<MAXS><<<blocks, 128, 0, st>>>(nx, S, nxy);
+    dt_sep_z_kernel<MAXS><<<blocks, 128, 0, st>>>(nxy, cid, g);
+}
+cudaError_t goicp_launch_dt_separable(const GridDev& g, unsigned* bits, unsigned short* nx, unsigned* nxy, int* cid, int numSM, cudaStream_t st) {
     const int S = g.S, SW = (S + 31) / 32;
+    const size_t total = (size_t)S * S * S;
     cudaError_t e = cudaMemsetAsync(bits, 0, (size_t)S * S * SW * sizeof(unsigned), st);
     if (e != cudaSuccess) return e;
-    if (g.ncells > 0) dt_sep_seed_kernel<<<(g.ncells + 255) / 256, 256, 0, st>>>(g.cell_vox, g.ncells, S, SW, bits);
-    const size_t total = (size_t)S * S * S;
+    if (g.ncells > 0) {
+        dt_sep_seed_kernel<<<(g.ncells + 255) / 256, 256, 0, st>>>(g.cell_vox, g.ncells, S, SW, bits);
+        dt_sep_cid_kernel<<<(g.ncells + 255) / 256, 256, 0, st>>>(g.cell_vox, g.ncells, cid);   // (entries of unoccupied voxels are never read)
+    }
     int blocks = (int)((total + 255) / 256);
     const int cap = numSM * 8 * 16;
     if (blocks > cap) blocks = cap;
     dt_sep_x_kernel<<<blocks, 256, 0, st>>>(bits, S, SW, nx);
-    dt_sep_y_kernel<<<blocks, 256, 0, st>>>(nx, S, nxy);
-    dt_sep_z_kernel<<<blocks, 256, 0, st>>>(nxy, g);
+    if (S <= 128) launch_sep_yz<128>(g, nx, nxy, cid, numSM, st);
+    else if (S <= 320) launch_sep_yz<320>(g, nx, nxy, cid, numSM, st);
+    else if (S <= 512) launch_sep_yz<512>(g, nx, nxy, cid, numSM, st);
+    else launch_sep_yz<1024>(g, nx, nxy, cid, numSM, st);
     return cudaGetLastError();
 }
 
@@ -359,8 +402,15 @@ cudaError_t goicp_preload_dt() {
     if ((e = cudaFuncGetAttributes(&a, dt_replay_kernel)) != cudaSuccess) return e;
     if ((e = cudaFuncGetAttributes(&a, dt_sep_seed_kernel)) != cudaSuccess) return e;
     if ((e = cudaFuncGetAttributes(&a, dt_sep_x_kernel)) != cudaSuccess) return e;
-    if ((e = cudaFuncGetAttributes(&a, dt_sep_y_kernel)) != cudaSuccess) return e;
-    if ((e = cudaFuncGetAttributes(&a, dt_sep_z_kernel)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, dt_sep_y_kernel<128>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, dt_sep_z_kernel<128>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, dt_sep_y_kernel<320>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, dt_sep_z_kernel<320>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, dt_sep_y_kernel<512>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, dt_sep_z_kernel<512>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, dt_sep_y_kernel<1024>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, dt_sep_z_kernel<1024>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, dt_sep_cid_kernel)) != cudaSuccess) return e;
     if ((e = cudaFuncGetAttributes(&a, dt_vcell_kernel)) != cudaSuccess) return e;
     if ((e = cudaFuncGetAttributes(&a, dt_distance_kernel)) != cudaSuccess) return e;
     return cudaSuccess;

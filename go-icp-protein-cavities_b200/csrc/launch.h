@@ -18,7 +18,7 @@ cudaError_t goicp_launch_eval_bounds(const PairDev* pairs, int pair, const float
 cudaError_t goicp_launch_eval_inclusion(const PairDev* pairs, int pair, const float* R, int level, const WaveCube* cubes, int nt, float* resid, uint8_t* mask, int nwarps, cudaStream_t st);
 // k_dt.cu
 cudaError_t goicp_launch_dt_replay(PairDev* pairs, int first, int count, int S, cudaStream_t st);
-cudaError_t goicp_launch_dt_separable(const GridDev& g, unsigned* bits, unsigned short* nx, unsigned* nxy, int numSM, cudaStream_t st);
+cudaError_t goicp_launch_dt_separable(const GridDev& g, unsigned* bits, unsigned short* nx, unsigned* nxy, int* cid, int numSM, cudaStream_t st);
 cudaError_t goicp_launch_dt_vcell(const GridDev& g, int numSM, cudaStream_t st);
 cudaError_t goicp_launch_dt_distance(const PairDev* pairs, int pair, const double* xyz, int n, float* out, int* cell, cudaStream_t st);
 // k_icp.cu
