@@ -65,7 +65,7 @@ ABI_SYMBOLS = [
     "goicp_set_model", "goicp_set_data", "goicp_set_params", "goicp_build_dt", "goicp_build_dt_replay", "goicp_dt_upload",
     "goicp_dt_download", "goicp_dt_distance", "goicp_set_nd", "goicp_initialize", "goicp_get_weights", "goicp_get_maxrotdis",
     "goicp_get_thresholds", "goicp_eval_bounds", "goicp_eval_inclusion", "goicp_inner_bnb", "goicp_icp", "goicp_register", "goicp_outer_bnb", "goicp_last_trace",
-    "goicp_set_options", "goicp_register_batch", "goicp_batch_upload", "goicp_batch_run", "goicp_get_timings",
+    "goicp_set_options", "goicp_set_search_mode", "goicp_register_batch", "goicp_batch_upload", "goicp_batch_run", "goicp_get_timings",
     "goicp_set_batch_options", "goicp_get_stats", "goicp_set_frontier_sharding", "goicp_test_exchange",
     "goicp_normalize_cloud", "goicp_scale_cloud", "goicp_rescale_translation", "goicp_apply_rigid", "goicp_rmsd",
 ]
@@ -113,6 +113,7 @@ def lib():
     L.goicp_register.argtypes = [vp, C.POINTER(Result)]
     L.goicp_outer_bnb.argtypes = [vp, C.POINTER(Result)]
     L.goicp_set_options.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
+    L.goicp_set_search_mode.argtypes = [vp, C.c_int32, C.c_int32]
     L.goicp_register_batch.argtypes = [vp, C.POINTER(Params), C.c_int32, C.POINTER(PairDesc), C.POINTER(Result)]
     L.goicp_batch_upload.argtypes = [vp, C.POINTER(Params), C.c_int32, C.POINTER(PairDesc)]
     L.goicp_batch_run.argtypes = [vp, C.POINTER(Result)]
@@ -231,6 +232,10 @@ class Engine:
     def set_options(self, exact_sums=-1, spec_width=-1, use_dt_replay=-1):
         self.check(self.L.goicp_set_options(self.h, exact_sums, spec_width, use_dt_replay))
 
+    def set_search_mode(self, relaxed_order=-1, wave_nodes=-1):
+        """single registrations: 0 = the reference's visitation order (default), 1 = relaxed-order frontier waves of `wave_nodes` rotation nodes"""
+        self.check(self.L.goicp_set_search_mode(self.h, relaxed_order, wave_nodes))
+
     def set_batch_options(self, groups=-1, slots=-1):
         self.check(self.L.goicp_set_batch_options(self.h, groups, slots))
 
@@ -336,6 +341,9 @@ class GoICP:
     def set_params(self, params):
         self.params = params
         self.eng.check(self.L.goicp_set_params(self.h, C.byref(params)))
+
+    def set_search_mode(self, relaxed_order=-1, wave_nodes=-1):
+        self.eng.set_search_mode(relaxed_order, wave_nodes)
 
     def set_options(self, exact_sums=-1, spec_width=-1, use_dt_replay=-1):
         self.eng.check(self.L.goicp_set_options(self.h, exact_sums, spec_width, use_dt_replay))

@@ -373,6 +373,12 @@ goicp_status goicp_test_exchange(goicp_handle h, const void* send, void* recv, i
     if (!h || !send || !recv || bytes_per_rank < 1 || !h->allgather) return GOICP_ERR_ARG;
     return h->allgather(send, recv, bytes_per_rank, h->allgatherUser) == 0 ? GOICP_OK : fail(h, GOICP_ERR_ARG, "all-gather callback failed");
 }
+goicp_status goicp_set_search_mode(goicp_handle h, int32_t relaxed_order, int32_t wave_nodes) {
+    if (!h) return GOICP_ERR_ARG;
+    if (relaxed_order >= 0) h->relaxed = relaxed_order ? 1 : 0;
+    if (wave_nodes >= 1) h->wave_nodes = wave_nodes;
+    return GOICP_OK;
+}
 goicp_status goicp_set_batch_options(goicp_handle h, int32_t groups, int32_t slots) {
     if (!h) return GOICP_ERR_ARG;
     if (groups >= 0) h->groups = groups;

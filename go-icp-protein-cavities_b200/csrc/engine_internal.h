@@ -227,6 +227,7 @@ struct goicp_handle_s {
     int spec_groups = SR_NGROUP - 4;   // device-resident search: most rotation-queue nodes with speculative calls per owner CTA (0: never speculate)
     int shardRank = 0, shardN = 1; goicp_allgather_fn allgather = nullptr; void* allgatherUser = nullptr;   // frontier sharding
     std::vector<InnerOut> xSend, xRecv;
+    int relaxed = 0, wave_nodes = 64;   // single registrations: 1 = relaxed-order wave search (goicp_set_search_mode), wave_nodes rotation nodes per wave
     int resident = 1;            // 1: device-resident search (k_search.cu) whenever the clouds allow it; 0: wave scheduler (one launch per wave, host-side OuterBnB)
     std::vector<std::unique_ptr<WaveCtx>> workers;
     std::mutex errMutex;

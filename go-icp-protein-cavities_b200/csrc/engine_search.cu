@@ -384,6 +384,104 @@ static goicp_status register_group(Eng* h, WaveCtx& c, const BnbCfg& cfg, std::a
 }
 
 
+// ---- relaxed-order wave search of ONE registration (north_star (b): "the host priority queue expands frontier waves") ----
+// The exact-order schedulers reproduce the reference's visitation order, so a single deep registration advances one rotation node at
+// a time along its dependency chain.  Here every wave pops the `wave_nodes` best rotation nodes at once, evaluates ALL their children
+// (upper- and lower-bound InnerBnB call of each cube as one request) in one launch under the incumbent error of the wave's start,
+// and then applies the results together: the best improving upper bound becomes the incumbent (followed by updateCompatibilities +
+// ICP as in jly_goicp.cpp:791-840 and the queue pruning of :843-853), children whose lower bound stays below it are pushed.  Node
+// visitation order differs from the reference; the certificate is the reference's own: the search ends when the queue is empty or
+// optError - (smallest lower bound in the queue) <= SSEThresh (:685).  With frontier sharding (goicp_set_frontier_sharding) the
+// requests of a wave are dealt to the ranks and their results exchanged once per wave (run_inner), so every rank applies the same
+// results and holds the same queue and incumbent: the minimum over the wave's upper bounds is the per-wave "allreduce(min)".
+static goicp_status register_relaxed(Eng* h, WaveCtx& c, const BnbCfg& cfg, int pi) {
+    const goicp_params& p = h->params;
+    Problem& P = h->probs[pi];
+    reset_search(P);
+    goicp_status s;
+    std::vector<IcpState> icps;
+    icps.push_back(make_icp_state(pi, 1, nullptr, nullptr)); icps.push_back(make_icp_state(pi, 0, P.optR, P.optT));
+    P.phase = PH_WAIT_INIT;
+    if ((s = run_icp(h, c, icps))) return s;
+    absorb_icp(P, icps[0]); absorb_icp(P, icps[1]);
+    after_icp(h, pi);   // initial error, first ICP, root node pushed (:601-664)
+    const float SSE = P.dev.SSEThresh;
+    struct Item { RNode node; float R[9]; bool lbOnly; float ub; };
+    std::vector<Item> items, carry;   // carry: cubes whose upper bound improved the incumbent of their wave: their lower-bound call is still due (:856-861)
+    std::vector<InnerProb> reqs; std::vector<InnerOut> outs;
+    const int W = std::max(1, h->wave_nodes);
+    for (;;) {
+        items.clear(); items.swap(carry);
+        int popped = 0;
+        while (!P.q.empty() && popped < W && (P.optError - P.q.front().lb) > SSE) {
+            const RNode par = rheap_pop(P.q); P.cnt[3]++; popped++;
+            for (int j = 0; j < 8; j++) {
+                Item it; it.node = child_of(par, j); it.lbOnly = false; it.ub = 0.f;
+                if (!child_rotation(it.node, it.R)) continue;
+                items.push_back(it);
+            }
+        }
+        if (items.empty()) {
+            if (P.q.empty()) tracef(P.trace, "Rotation Queue Empty\nError*: %g, LB: %g\n", P.optError, P.lastLb);
+            else { tracef(P.trace, "Threshold reached\nError*: %g, LB: %g, epsilon: %g\n", P.optError, P.q.front().lb, SSE); P.cnt[3]++; }
+            break;
+        }
+        reqs.resize(items.size());
+        for (size_t k = 0; k < items.size(); k++) {
+            const int lbLevel = std::min(items[k].node.l, GOICP_MAXROTLEVEL - 1);
+            reqs[k].pair = pi; reqs[k].level = items[k].lbOnly ? lbLevel : GOICP_REQ_BOTH + lbLevel; reqs[k].optError = P.optError;
+            memcpy(reqs[k].R, items[k].R, sizeof reqs[k].R);
+        }
+        c.waves++;
+        if ((s = run_inner(h, c, cfg, reqs, outs))) return s;
+        int best = -1;
+        for (size_t k = 0; k < items.size(); k++) {
+            const InnerOut& o = outs[k];
+            P.cnt[0]++; P.cnt[1] += o.pops; P.cnt[2] += o.subcubes;
+            if (items[k].lbOnly) continue;
+            P.cnt[4]++;
+            items[k].ub = o.err;
+            if (o.err < P.optError && (best < 0 || o.err < outs[best].err)) best = (int)k;
+        }
+        const float entryOpt = P.optError;
+        if (best >= 0) {   // :771-840 for the wave's best cube
+            const InnerOut& o = outs[best];
+            P.optError = o.err;
+            for (int k = 0; k < 9; k++) P.optR[k] = items[best].R[k];
+            P.optT[0] = o.node[0] + o.node[3] / 2; P.optT[1] = o.node[1] + o.node[3] / 2; P.optT[2] = o.node[2] + o.node[3] / 2;
+            icps.clear();
+            icps.push_back(make_icp_state(pi, 2, P.optR, P.optT)); icps.push_back(make_icp_state(pi, 0, P.optR, P.optT));
+            if ((s = run_icp(h, c, icps))) return s;
+            absorb_icp(P, icps[0]); absorb_icp(P, icps[1]);
+            P.optComp = P.compatPose;
+            tracef(P.trace, "Error*: %g (BNB)\n", P.optError);
+            P.cnt[5]++;
+            if (P.icpErr < P.optError) {
+                P.optError = P.icpErr; memcpy(P.optR, P.icpR, sizeof P.optR); memcpy(P.optT, P.icpT, sizeof P.optT); P.optComp = P.icpIncomp;
+                tracef(P.trace, "Error*: %g (ICP)\n", P.icpErr);
+            }
+        }
+        for (size_t k = 0; k < items.size(); k++) {   // lower bounds (:856-871)
+            const InnerOut& o = outs[k];
+            float lb;
+            if (items[k].lbOnly) lb = o.err;
+            else if (o.ran2) { P.cnt[0]++; P.cnt[1] += o.pops2; P.cnt[2] += o.subcubes2; lb = o.err2; }
+            else { Item it = items[k]; it.lbOnly = true; carry.push_back(it); continue; }   // its upper bound improved on the wave's incumbent: lower bound in the next wave
+            P.lastLb = lb;
+            if (!(lb >= P.optError)) { RNode nr = items[k].node; nr.ub = items[k].ub; nr.lb = lb; nr.id = P.nextId++; rheap_push(P.q, nr); }
+        }
+        if (best >= 0) {   // :843-853 (order-independent form: drop every node whose lower bound reaches the incumbent)
+            std::vector<RNode> qn;
+            for (const RNode& n : P.q) if (n.lb < P.optError) rheap_push(qn, n);
+            P.q.swap(qn);
+        }
+        (void)entryOpt;
+    }
+    P.phase = PH_DONE;
+    (void)p;
+    return GOICP_OK;
+}
+
 // ---- device-resident search (k_search.cu): the whole batch in one launch, results read back once --------------------------------
 static bool host_libm_uses_fma() {   // glibc's ifunc rule for sinf / cosf on x86-64 (sysdeps/x86_64/fpu/multiarch/ifunc-fma.h)
 #if defined(__x86_64__)
@@ -517,8 +615,11 @@ goicp_status register_all(Eng* h) {
     { const char* e = getenv("GOICP_PERSISTENT"); if (e) h->resident = atoi(e) != 0; }   // 0: wave scheduler (one launch per wave, OuterBnB on the host)
     bool allSmall = true;
     for (auto& P : h->probs) if ((size_t)P.Nd * P.Nm > ((size_t)1 << 21) || (P.dev.doTrim && P.Nd > 2048)) allSmall = false;
-    const bool resident = h->resident && allSmall && h->shardN <= 1;
-    if (resident) {
+    const bool resident = h->resident && allSmall && h->shardN <= 1 && !(h->relaxed && np == 1);
+    if (h->relaxed && np == 1) {
+        h->main.ctaCap = 0;
+        if ((s = register_relaxed(h, h->main, cfg, 0))) return s;
+    } else if (resident) {
         groups = 0;
         if ((s = register_resident(h, cfg))) return s;
     } else if (groups <= 1) {

@@ -147,6 +147,12 @@ const char* goicp_last_trace(goicp_handle h);
  * speculatively per device launch (results are used only when the reference's order reaches them). */
 goicp_status goicp_set_options(goicp_handle h, int32_t exact_sums, int32_t spec_width, int32_t use_dt_replay);
 
+/* Search order of SINGLE registrations.  relaxed_order = 0 (default): the reference's visitation order is reproduced exactly (same
+ * node counters and improvement trace).  relaxed_order = 1: frontier waves -- every wave pops the `wave_nodes` (default 64) best
+ * rotation nodes, evaluates all their child cubes in one launch and applies the results together (visitation order may
+ * differ, the certificate optError - min lower bound <= SSEThresh is the reference's, jly_goicp.cpp:685).  -1 leaves a value as is. */
+goicp_status goicp_set_search_mode(goicp_handle h, int32_t relaxed_order, int32_t wave_nodes);
+
 /* ---- one deep registration sharded over several GPUs (second shard) -------------------------------
  * Every rank holds the same clouds / DT and runs the same (deterministic) rotation queue; each wave's InnerBnB calls are
  * dealt round-robin to the ranks and the results are exchanged with ONE all-gather per wave, so every rank sees every

@@ -392,6 +392,50 @@ def test_register_deep_small(g):
     assert g.error_trace(r["trace"])[:len(z["exp128_trace"])] == list(z["exp128_trace"])
 
 
+@pytest.mark.parametrize("case", ["pair2", "deep_small", "bunny"])
+def test_register_relaxed_order(g, case):
+    """relaxed-order search (goicp_set_search_mode: the W best rotation nodes of the frontier are expanded per wave instead of one):
+    another visiting order of the same branch-and-bound, so the SAME certificate holds (the returned optimum is within SSEThresh of
+    the global one, hence within SSEThresh of the exact-order optimum), the counters may differ.  On the fixtures whose optimum is
+    unique at that resolution the very same optimum and pose come back."""
+    z = golden(case)
+    if case == "pair2":
+        params, cl, ref = g.shipped_config(), pair_clouds(z), float(z["exp_optError"])
+    elif case == "deep_small":
+        params, cl, ref = g.upstream_config(distTransSize=128, MSEThresh=1e-4), {}, float(z["exp128_optError"])
+    else:
+        params, cl, ref = g.upstream_config(distTransSize=100), {}, float(z["exp100_optError"])
+    reg = g.GoICP(z["model_xyz"], z["data_xyz"], params, **cl)
+    reg.BuildDT(); reg.set_nd(int(z["nd"]))
+    exact = reg.Register()
+    assert abs(exact["optError"] - ref) <= REL * ref
+    sse = float(params.MSEThresh) * int(z["nd"])
+    for W in (16, 64):
+        reg.set_search_mode(1, W)
+        r = reg.Register()
+        assert abs(r["optError"] - exact["optError"]) <= sse + REL * ref, (W, r["optError"], exact["optError"])
+        assert r["counters"][3] > 0 or exact["counters"][3] == 0
+        if case != "bunny":
+            assert abs(r["optError"] - exact["optError"]) <= REL * ref
+            assert np.abs(r["R"] - exact["R"]).max() < 1e-5 and np.abs(r["t"] - exact["t"]).max() < 1e-5
+    reg.set_search_mode(0, -1)
+    again = reg.Register()
+    assert again["optError"] == exact["optError"] and again["counters"][:6] == exact["counters"][:6]   # and back: exact order is untouched
+
+
+def test_icp_grid_nn_same_result(g, monkeypatch):
+    """GOICP_ICP_NN_GRID=1: the nearest neighbours of the host-driven ICP come from the DT grid's cell lists (one warp per point, far
+    points handed to the exhaustive kernel); bit-identical correspondences, so the same run as test_register_bunny100"""
+    monkeypatch.setenv("GOICP_ICP_NN_GRID", "1")
+    z = golden("bunny")
+    reg = g.GoICP(z["model_xyz"], z["data_xyz"], g.upstream_config(distTransSize=100))
+    reg.BuildDT(); reg.set_nd(int(z["nd"]))
+    r = reg.Register()
+    assert abs(r["optError"] - float(z["exp100_optError"])) <= REL * float(z["exp100_optError"])
+    assert np.abs(r["R"] - z["exp100_R"]).max() < 1e-5 and np.abs(r["t"] - z["exp100_t"]).max() < 1e-5
+    assert r["counters"][:6] == z["exp100_counters"][:6].tolist()
+
+
 def test_register_bunny100(g, po):
     """bunny, DT 100^3, with the GPU's own separable DT: same optimum, trace and node counters as the reference run"""
     z = golden("bunny")
@@ -615,7 +659,7 @@ def test_cli_sweep_protein_rmsd(tmp_path):
         shutil.copytree(os.path.join(src, d), tmp_path / d)
     shutil.copy(os.path.join(src, "config.txt"), tmp_path / "config.txt")
     with tarfile.open(os.path.join(src, "proteins.tar.gz")) as tf:
-        tf.extractall(tmp_path / "prot")
+        tf.extractall(tmp_path / "prot", filter="data")
     shutil.copytree(tmp_path / "prot" / "chains", tmp_path / "chains"); shutil.copytree(tmp_path / "prot" / "ref_proteins", tmp_path / "ref_proteins")
     for d in ("cavitiesN", "output", "cavitiesR", "rot"):
         os.makedirs(tmp_path / d)
