@@ -78,14 +78,16 @@ __device__ void svd3(const double H[9], double U[9], double W[3], double V[9]) {
 // ---- per-iteration update: [trim sort], centroids, err, H, SVD, compose (jly_icp3d.hpp:252-308) ---------------------
 constexpr int SORT_CAP = 2048;
 // returns true (uniformly) when the call has finished (converged / maxIter / error)
-__device__ __forceinline__ bool icp_update_part(const PairDev& P, IcpState& st) {
+// `sT`/`sCap`: optional shared-memory staging for the seven term rows (the sequential sum chains below then run at shared-memory
+// instead of L2 latency); used when 7*Nd floats fit, the pair's global scratch otherwise.  Same arithmetic either way.
+__device__ __forceinline__ bool icp_update_part(const PairDev& P, IcpState& st, float* sT = nullptr, int sCap = 0) {
     const int n = P.Nd, num = P.inlierNum, tid = threadIdx.x;
     const int iter0 = st.iter;   // st.iter is only written by thread 0 after the last barrier below
     __shared__ double s_mu[6];
     __shared__ double s_H[9];
     __shared__ float s_err;
     __shared__ int s_done;
-    float* T = P.scratch;   // [7][n]: p_m xyz, p_d xyz, dis  (positions follow `order`)
+    float* T = (sT != nullptr && (size_t)7 * n <= (size_t)sCap) ? sT : P.scratch;   // [7][n]: p_m xyz, p_d xyz, dis  (positions follow `order`)
 
     if (P.doTrim) {   // qsort of POINTREF by dis (:252-255); ties keep index order.  Bitonic sort in the pair's global scratch
         unsigned long long* keys = P.sortKeys;
@@ -123,17 +125,22 @@ __device__ __forceinline__ bool icp_update_part(const PairDev& P, IcpState& st) 
         T[6 * n + i] = __uint_as_float((unsigned)(k >> 32));
     }
     __syncthreads();
-    if (tid < 7) {   // seven sequential chains: mu_m, mu_d (double, never reset: Q4), err_new (float accumulator)
+    // seven sequential chains: mu_m, mu_d (double, never reset: Q4) on six lanes of warp 0, err_new on warp 1 (its own warp, so the
+    // two loops run side by side instead of as two divergent halves of one warp)
+    if (tid < 6) {
         const float* row = T + (size_t)tid * n;
-        if (tid < 6) {
-            double acc = (tid < 3) ? st.mu_m[tid] : st.mu_d[tid - 3];
-            for (int i = 0; i < num; ++i) acc = acc + (double)row[i];
-            s_mu[tid] = acc;
-        } else {
-            float e = 0.f;
-            for (int i = 0; i < num; ++i) e = (float)((double)e + (double)row[i]);
-            s_err = e;
-        }
+        double acc = (tid < 3) ? st.mu_m[tid] : st.mu_d[tid - 3];
+#pragma unroll 8
+        for (int i = 0; i < num; ++i) acc = acc + (double)row[i];
+        s_mu[tid] = acc;
+    } else if (tid == 32) {
+        // the reference accumulates `float += double(float)`: (float)((double)e + (double)r).  The double sum of two floats rounded to
+        // float equals the float sum (53 >= 2*24+2 bits: double rounding is innocuous for +), so one FADD per element, same bits
+        const float* row = T + (size_t)6 * n;
+        float e = 0.f;
+#pragma unroll 8
+        for (int i = 0; i < num; ++i) e = __fadd_rn(e, row[i]);
+        s_err = e;
     }
     __syncthreads();
     if (tid == 0) {
@@ -156,6 +163,7 @@ __device__ __forceinline__ bool icp_update_part(const PairDev& P, IcpState& st) 
         const float* pd = T + (size_t)(3 + a) * n; const float* pm = T + (size_t)b * n;
         const double mud = s_mu[3 + a], mum = s_mu[b];
         double s = 0;
+#pragma unroll 8
         for (int k = 0; k < num; ++k) s = s + ((double)pd[k] - mud) * ((double)pm[k] - mum);
         s_H[tid] = s;
     }
@@ -255,7 +263,7 @@ __device__ __forceinline__ void icp_score_part(const PairDev& P, IcpState& st) {
 //      request; the model cloud is tiled through shared memory for the exact nearest-neighbour pass ---------------------
 // Runs on one CTA (any multiple of 32 threads).  `gstate` may live in mapped host memory: the request is staged in shared memory and
 // written back once at the end.
-__device__ __forceinline__ void icp_fused_body(const PairDev* __restrict__ pairs, IcpState* gstate, float* tile /* shared, 3*NN_TILE floats */) {
+__device__ __forceinline__ void icp_fused_body(const PairDev* __restrict__ pairs, IcpState* gstate, float* tile /* shared, >= 3*NN_TILE floats */, int tileCap /* floats */) {
     __shared__ IcpState st;
     const int tid = threadIdx.x, nthr = blockDim.x;
     __syncthreads();
@@ -302,7 +310,7 @@ __device__ __forceinline__ void icp_fused_body(const PairDev* __restrict__ pairs
                 if (i < Nd) P.nn[i] = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned)bi;
             }
             __syncthreads();
-            const bool done = icp_update_part(P, st);
+            const bool done = icp_update_part(P, st, tile, tileCap);   // (the model tile is idle during the update)
             __syncthreads();
             if (done) break;
         }

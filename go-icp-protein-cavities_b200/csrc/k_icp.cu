@@ -124,10 +124,11 @@ icp_nn_grid_kernel(const PairDev* __restrict__ pairs, IcpState* __restrict__ sta
 }
 
 __global__ void __launch_bounds__(256)
-icp_update_kernel(const PairDev* __restrict__ pairs, IcpState* __restrict__ states) {
+icp_update_kernel(const PairDev* __restrict__ pairs, IcpState* __restrict__ states, int rowCap) {
     IcpState& st = states[blockIdx.x];
     if (st.done || st.mode != 0) return;
-    icp_update_part(pairs[st.pair], st);
+    extern __shared__ float s_rows[];
+    icp_update_part(pairs[st.pair], st, s_rows, rowCap);
 }
 __global__ void __launch_bounds__(256)
 icp_score_kernel(const PairDev* __restrict__ pairs, IcpState* __restrict__ states) {
@@ -137,7 +138,7 @@ icp_score_kernel(const PairDev* __restrict__ pairs, IcpState* __restrict__ state
 }
 
 __global__ void __launch_bounds__(256, 4)
-icp_fused_kernel(const PairDev* __restrict__ pairs, IcpState* states) { __shared__ float s_tile[3 * NN_TILE]; icp_fused_body(pairs, states + blockIdx.x, s_tile); }
+icp_fused_kernel(const PairDev* __restrict__ pairs, IcpState* states) { __shared__ float s_tile[7 * 1024]; icp_fused_body(pairs, states + blockIdx.x, s_tile, 7 * 1024); }
 
 }  // namespace
 
@@ -162,7 +163,11 @@ cudaError_t goicp_launch_icp_iter(const PairDev* pairs, IcpState* states, int n,
         icp_nn_grid_kernel<<<dim3((maxNd + 3) / 4, n), 128, 0, st>>>(pairs, states);
         icp_nn_kernel<<<dim3(gx, gy, n), NN_THREADS, 0, st>>>(pairs, states, gy, 1);
     }
-    icp_update_kernel<<<n, 256, 0, st>>>(pairs, states);
+    // the seven term rows of the update in shared memory when they fit (<= 200 KB: Nd <= 7314)
+    size_t rowBytes = (size_t)7 * maxNd * sizeof(float);
+    if (rowBytes > 200 * 1024) rowBytes = 0;
+    if (rowBytes > 48 * 1024) { cudaError_t e = cudaFuncSetAttribute(icp_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); if (e != cudaSuccess) return e; }
+    icp_update_kernel<<<n, 256, rowBytes, st>>>(pairs, states, (int)(rowBytes / sizeof(float)));
     return cudaGetLastError();
 }
 cudaError_t goicp_launch_icp_fused(const PairDev* pairs, IcpState* states, int n, cudaStream_t st) {

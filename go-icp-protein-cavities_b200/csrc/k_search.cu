@@ -709,8 +709,8 @@ search_kernel(const SearchArgs A) {
     __shared__ unsigned long long s_gbar;
     __shared__ OwnerSh os;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float* icpTile;
-    if constexpr (SMEM) icpTile = reinterpret_cast<float*>(dyn_smem4); else { __shared__ float s_tile[3 * NN_TILE]; icpTile = s_tile; }
+    float* icpTile; int icpCap = 3 * NN_TILE;   // the call staging region is idle while an ICP request runs
+    if constexpr (SMEM) { icpTile = reinterpret_cast<float*>(dyn_smem4); icpCap = (int)A.gstride; } else { __shared__ float s_tile[3 * NN_TILE]; icpTile = s_tile; }
     CallCtx cx;
     __shared__ CancelSh s_cancel;
     __shared__ long long s_tStart, s_tIdle;
@@ -735,9 +735,9 @@ search_kernel(const SearchArgs A) {
         if (act == ACT_ICP) {
             IcpState* icp = A.icp + 2 * (size_t)blockIdx.x;
             const long long ti0 = clock64();
-            icp_fused_body(A.pairs, icp, icpTile);
+            icp_fused_body(A.pairs, icp, icpTile, icpCap);
             __syncthreads();
-            icp_fused_body(A.pairs, icp + 1, icpTile);
+            icp_fused_body(A.pairs, icp + 1, icpTile, icpCap);
             if (tid == 0) { atomicAdd(reinterpret_cast<unsigned long long*>(A.genCounter) + 1 + 6, 2ull); atomicAdd(&A.ctl->dbg[7], (unsigned long long)(clock64() - ti0)); }
             continue;
         }
