@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-per-pair", action="store_true", help="skip the per-pair wall times of configs 1-4")
     ap.add_argument("--per-pair-cpu-deep", action="store_true", help="also time the reference on config 4 at 512^3 (several minutes of one core)")
+    ap.add_argument("--workload", default="sweep", choices=["sweep", "deep"], help="sweep: the BO1-shaped batch (headline); deep: ONE deep registration (BASELINE config 4) "
+                    "in relaxed-order wave mode, the InnerBnB calls of every wave sharded over the ranks (strong scaling)")
+    ap.add_argument("--wave-nodes", type=int, default=256, help="deep workload: rotation nodes expanded per wave")
     ap.add_argument("--seed", type=int, default=4096)
     ap.add_argument("--groups", type=int, default=-1, help="wave scheduler only: worker streams per GPU (-1: library default)")
     ap.add_argument("--slots", type=int, default=-1, help="wave scheduler only: pairs advanced in lock-step per stream (-1: library default)")
@@ -198,6 +201,76 @@ def reference_arm(args, synth, cores):
                       "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def deep_arm(args, g, synth, rank, world, local):
+    """`--workload deep`: SURVEY 8(e) second shard.  Every rank holds the same pair and its DT; the rotation frontier is advanced in
+    waves of --wave-nodes nodes, each wave's InnerBnB calls are split over the ranks and the result records all-gathered, every rank
+    applies them identically (same optimum, counters and trace on every rank: checked).  A step = one whole registration."""
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    def golden(name):
+        return np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    p = synth.deep_pair(1236)
+    z2, zs = golden("pair2"), golden("deep_small")
+    cases = [("config4 synthetic deep (Nm 100000, Nd 10000, DT 512^3, MSE 1e-4, seed 1236)", p["model_xyz"], p["data_xyz"], 10000, g.upstream_config(distTransSize=512, MSEThresh=1e-4), {}),
+             ("config4 shape at 20000 x 2000, DT 128^3 (tests/golden/deep_small)", zs["model_xyz"], zs["data_xyz"], int(zs["nd"]), g.upstream_config(distTransSize=128, MSEThresh=1e-4), {}),
+             ("cavity pair 2 (2ktd_1 -> 4imo_2, shipped config.txt)", z2["model_xyz"], z2["data_xyz"], int(z2["nd"]), g.shipped_config(),
+              dict(model_c=z2["model_c"], data_c=z2["data_c"], model_fpfh=z2["model_fpfh"], data_fpfh=z2["data_fpfh"]))]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    rows = []
+    for name, m, d, nd, params, cl in cases:
+        reg = g.GoICP(m, d, params, device=local, **cl)
+        reg.BuildDT(); reg.set_nd(nd)
+        exact, t_exact = None, None
+        if rank == 0:    # the reference's visitation order on one GPU, for the comparison (before the sharding is switched on: no collective inside)
+            reg.set_search_mode(0, -1)
+            reg.Register()
+            torch.cuda.synchronize(dev); t0 = time.perf_counter(); exact = reg.Register(); torch.cuda.synchronize(dev); t_exact = 1e3 * (time.perf_counter() - t0)
+        if world > 1:
+            dist.barrier()
+            reg.eng.set_frontier_sharding(rank, world, dev)
+        reg.set_search_mode(1, args.wave_nodes)
+        for _ in range(args.warmup):
+            reg.Register()
+        ts, r = [], None
+        for _ in range(args.steps):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter(); r = reg.Register(); torch.cuda.synchronize(dev); ts.append(1e3 * (time.perf_counter() - t0))
+        sig = torch.tensor([sum(ts), r["optError"]] + [float(v) for v in r["counters"][:6]], dtype=torch.float64, device=dev)
+        same = True
+        if world > 1:
+            ref = sig.clone(); dist.broadcast(ref, 0); same = bool(torch.equal(ref[1:], sig[1:]))
+            mx = sig.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX); total_ms = mx[0].item()
+            ok = torch.tensor([1.0 if same else 0.0], dtype=torch.float64, device=dev); dist.all_reduce(ok, op=dist.ReduceOp.MIN); same = bool(ok.item() > 0)
+        else:
+            total_ms = sum(ts)
+        evals = float(r["counters"][2]) * nd
+        rows.append({"case": name, "ms_per_registration": total_ms / args.steps, "evals_per_registration": evals, "value": evals * args.steps / (total_ms * 1e-3),
+                     "opt_error": r["optError"], "rotation_pops": int(r["counters"][3]), "inner_calls": int(r["counters"][0]), "gpu_ms_bnb": r["gpu_ms_bnb"], "gpu_ms_icp": r["gpu_ms_icp"], "launches_per_registration": int(r["counters"][6]),
+                     "same_result_on_every_rank": same,
+                     "exact_order_1gpu": None if exact is None else {"ms": t_exact, "opt_error": exact["optError"], "rotation_pops": int(exact["counters"][3]), "inner_calls": int(exact["counters"][0])}})
+        del reg
+    sampler.stop_flag = True
+    if rank == 0:
+        h = rows[0]
+        print(json.dumps({"metric": METRIC, "value": h["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": h["ms_per_registration"],
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+                          "config": {"workload": "deep: " + h["case"] + "; relaxed-order waves of %d rotation nodes, calls sharded over %d rank(s), one all-gather of result records per wave; "
+                                     "inputs resident (DT built before the timed region); ICP runs replicated on every rank" % (args.wave_nodes, world)},
+                          "gpu_launches": int(rows[0]["launches_per_registration"]) * args.steps, "cases": rows, "clocks": sampler.summary()}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -212,6 +285,10 @@ def main():
     if args.impl == "reference":
         if rank == 0:
             reference_arm(args, synth, cores)
+        return
+
+    if args.workload == "deep":
+        deep_arm(args, g, synth, rank, world, local)
         return
 
     import torch

@@ -67,11 +67,10 @@ icp_nn_kernel(const PairDev* __restrict__ pairs, IcpState* __restrict__ states, 
 // build emits); the nearest point of that cell bounds the answer, and the occupied voxels of the cube that encloses the bounding
 // sphere are then searched through the CSR cell lists, 32 voxels per step.  Same float distance expression and the same tie rule
 // (lowest model index: the minimum of the packed (distance bits, index) keys) as the exhaustive kernel, so both give bit-identical
-// correspondences.  A point whose cube would exceed NN_CUBE_MAX voxels (far from the model: the first iterations of a badly aligned
+// correspondences.  A point whose cube would exceed `cubeMax` voxels (far from the model: the first iterations of a badly aligned
 // start) is flagged instead and left to the tiled exhaustive kernel, which then only works on flagged points.
-constexpr int NN_CUBE_MAX = 2197;   // 13^3: bounding radius up to 6 voxels
 __global__ void __launch_bounds__(128)
-icp_nn_grid_kernel(const PairDev* __restrict__ pairs, IcpState* __restrict__ states) {
+icp_nn_grid_kernel(const PairDev* __restrict__ pairs, IcpState* __restrict__ states, int cubeMax) {
     const IcpState& st = states[blockIdx.y];
     if (st.done || st.mode != 0) return;
     const PairDev& P = pairs[st.pair];
@@ -108,7 +107,7 @@ icp_nn_grid_kernel(const PairDev* __restrict__ pairs, IcpState* __restrict__ sta
         const int rv = (int)ceilf(sqrtf(__uint_as_float((unsigned)(best >> 32))) * sc) + 2;   // voxels: the sphere through the best point so far, plus rounding slack
         lx = max(ix - rv, 0); ly = max(iy - rv, 0); lz = max(iz - rv, 0);
         nx = min(ix + rv, S - 1) - lx + 1; ny = min(iy + rv, S - 1) - ly + 1; nz = min(iz + rv, S - 1) - lz + 1;
-        if (nx <= 0 || ny <= 0 || nz <= 0 || (long long)nx * ny * nz > NN_CUBE_MAX) isFar = true;
+        if (nx <= 0 || ny <= 0 || nz <= 0 || (long long)nx * ny * nz > cubeMax) isFar = true;
     }
     if (isFar) { if (lane == 0) far[i] = 1; return; }   // (P.nn[i] stays GOICP_NN_EMPTY)
     const int vol = nx * ny * nz;
@@ -157,10 +156,13 @@ cudaError_t goicp_launch_icp_iter(const PairDev* pairs, IcpState* states, int n,
     if (gy > 65535) gy = 65535;
     // The tiled exhaustive kernel is the default: measured on B200 the grid kernel only pays for clouds far larger than the fork's
     // (bunny 39.5 vs 65.5 ms of ICP per Register, 100k-point model 1247 vs 1195 ms; both bit-identical).  GOICP_ICP_NN_GRID=1 selects it.
-    const bool brute = getenv("GOICP_ICP_NN_GRID") == nullptr;   // (read per call: the tests switch it)
+    const char* genv = getenv("GOICP_ICP_NN_GRID");   // (read per call: the tests switch it); value = largest bounding radius in voxels (default 6)
+    const bool brute = genv == nullptr;
+    int rmax = genv ? atoi(genv) : 0; if (rmax < 2) rmax = 6; if (rmax > 40) rmax = 40;
+    const int cubeMax = (2 * rmax + 1) * (2 * rmax + 1) * (2 * rmax + 1);
     if (brute) icp_nn_kernel<<<dim3(gx, gy, n), NN_THREADS, 0, st>>>(pairs, states, gy, 0);
     else {
-        icp_nn_grid_kernel<<<dim3((maxNd + 3) / 4, n), 128, 0, st>>>(pairs, states);
+        icp_nn_grid_kernel<<<dim3((maxNd + 3) / 4, n), 128, 0, st>>>(pairs, states, cubeMax);
         icp_nn_kernel<<<dim3(gx, gy, n), NN_THREADS, 0, st>>>(pairs, states, gy, 1);
     }
     // the seven term rows of the update in shared memory when they fit (<= 200 KB: Nd <= 7314)

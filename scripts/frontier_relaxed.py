@@ -1,6 +1,8 @@
-"""One deep registration in relaxed-order wave mode with the calls of every wave sharded over the ranks of a torchrun job
-(second shard): torchrun --nproc-per-node N scripts/frontier_relaxed.py [pair2|bunny|deep_small] [wave_nodes]
-Every rank applies the same gathered results, so every rank must end with the same optimum, counters and trace."""
+"""One deep registration with the InnerBnB calls of every wave sharded over the ranks of a torchrun job (second shard):
+torchrun --nproc-per-node N scripts/frontier_relaxed.py [pair2|bunny|deep_small] [wave_nodes]
+wave_nodes > 0: relaxed-order wave mode; 0: the reference's visitation order (wave scheduler with look-ahead calls; for pair2 the
+Error*: trace must then equal the reference's).  Every rank applies the same gathered results, so every rank must end with the same
+optimum, counters and trace."""
 import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -24,7 +26,7 @@ else:
     reg = g.GoICP(z["model_xyz"], z["data_xyz"], g.shipped_config(), model_c=z["model_c"], data_c=z["data_c"], model_fpfh=z["model_fpfh"], data_fpfh=z["data_fpfh"], device=local)
 if world > 1:
     reg.eng.set_frontier_sharding(rank, world, torch.device("cuda", local))
-reg.set_search_mode(1, W)
+reg.set_search_mode(1 if W > 0 else 0, W if W > 0 else -1)
 reg.BuildDT(); reg.set_nd(int(z["nd"]))
 reg.Register()   # warm-up
 ts = []
@@ -37,6 +39,9 @@ same = True
 if world > 1:
     ref = sig.clone(); dist.broadcast(ref, 0); same = bool(torch.equal(ref, sig))
 evals = r["counters"][2] * int(z["nd"])
-print(f"rank {rank}/{world} {case} relaxed W={W}: optError {r['optError']:.9g} counters {r['counters'][:6]} same_on_every_rank {same} register {min(ts)*1e3:.1f} ms ({evals / min(ts):.3g} evals/s)", flush=True)
-assert same
+trace_ok = None
+if W == 0 and case == "pair2":
+    trace_ok = g.error_trace(r["trace"]) == list(z["exp_trace"]) and r["optError"] == float(z["exp_optError"]) and r["counters"][:6] == z["exp_counters"][:6].tolist()
+print(f"rank {rank}/{world} {case} {'relaxed W=%d' % W if W else 'exact order'}: reference_trace_and_counters {trace_ok} optError {r['optError']:.9g} counters {r['counters'][:6]} same_on_every_rank {same} register {min(ts)*1e3:.1f} ms ({evals / min(ts):.3g} evals/s)", flush=True)
+assert same and trace_ok is not False
 if world > 1: dist.destroy_process_group()

@@ -2,6 +2,7 @@
 golden fixtures (the reference's own outputs).  Bars: bit-exact for DT values / index map / voxel indices / inclusion
 counts / node counters and for every float the exact-sum mode produces; 1e-5 relative for tree-sum bounds and trimmed
 sums; 1e-5 on R, t."""
+import os
 import numpy as np
 import pytest
 
@@ -421,6 +422,27 @@ def test_register_relaxed_order(g, case):
     reg.set_search_mode(0, -1)
     again = reg.Register()
     assert again["optError"] == exact["optError"] and again["counters"][:6] == exact["counters"][:6]   # and back: exact order is untouched
+
+
+@pytest.mark.parametrize("wave_nodes", [0, 64])
+def test_frontier_shard_two_gpus(wave_nodes):
+    """SURVEY 8(e), second shard, on real devices (skipped with fewer than 2 GPUs): the InnerBnB calls of every wave of ONE registration
+    (pair 2) dealt to two ranks over NCCL.  Exact order (0): the reference's optimum, counters and Error*: trace on both ranks;
+    relaxed order (64): the same result on both ranks.  scripts/frontier_relaxed.py asserts both and exits non-zero otherwise."""
+    import subprocess, sys, socket
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0)); port = sk.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "frontier_relaxed.py"), "pair2", str(wave_nodes)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("rank ")]
+    assert len(lines) == 2 and all("same_on_every_rank True" in l for l in lines)
+    if wave_nodes == 0:
+        assert all("reference_trace_and_counters True" in l for l in lines)
 
 
 def test_icp_grid_nn_same_result(g, monkeypatch):
