@@ -78,16 +78,18 @@ __device__ void svd3(const double H[9], double U[9], double W[3], double V[9]) {
 // ---- per-iteration update: [trim sort], centroids, err, H, SVD, compose (jly_icp3d.hpp:252-308) ---------------------
 constexpr int SORT_CAP = 2048;
 // returns true (uniformly) when the call has finished (converged / maxIter / error)
-// `sT`/`sCap`: optional shared-memory staging for the seven term rows (the sequential sum chains below then run at shared-memory
-// instead of L2 latency); used when 7*Nd floats fit, the pair's global scratch otherwise.  Same arithmetic either way.
-__device__ __forceinline__ bool icp_update_part(const PairDev& P, IcpState& st, float* sT = nullptr, int sCap = 0) {
+// `sT`/`sCap`: shared-memory staging (16-byte aligned, sCap floats, at least 18*32).  The order-sensitive sums of the reference are
+// sequential chains; everything that is NOT on a chain (gathers, float->double conversions, the centred products of H) is produced by
+// the whole CTA into `sT`, chunk by chunk, so that a chain step is one shared-memory load and one add.
+__device__ __forceinline__ bool icp_update_part(const PairDev& P, IcpState& st, float* sT, int sCap) {
     const int n = P.Nd, num = P.inlierNum, tid = threadIdx.x;
     const int iter0 = st.iter;   // st.iter is only written by thread 0 after the last barrier below
     __shared__ double s_mu[6];
     __shared__ double s_H[9];
     __shared__ float s_err;
     __shared__ int s_done;
-    float* T = (sT != nullptr && (size_t)7 * n <= (size_t)sCap) ? sT : P.scratch;   // [7][n]: p_m xyz, p_d xyz, dis  (positions follow `order`)
+    double* D = reinterpret_cast<double*>(sT);
+    const int C = min(num > 0 ? num : 1, sCap / 18);   // positions of `order` per chunk: 9 double rows (pass 2) = 18 floats per position
 
     if (P.doTrim) {   // qsort of POINTREF by dis (:252-255); ties keep index order.  Bitonic sort in the pair's global scratch
         unsigned long long* keys = P.sortKeys;
@@ -113,34 +115,40 @@ __device__ __forceinline__ bool icp_update_part(const PairDev& P, IcpState& st, 
     const float r00 = (float)st.R[0], r01 = (float)st.R[1], r02 = (float)st.R[2], r10 = (float)st.R[3], r11 = (float)st.R[4],
                 r12 = (float)st.R[5], r20 = (float)st.R[6], r21 = (float)st.R[7], r22 = (float)st.R[8];
     const float t0 = (float)st.t[0], t1 = (float)st.t[1], t2 = (float)st.t[2];
-    for (int i = tid; i < num; i += blockDim.x) {   // :257-271 terms
-        const int id = P.order[i];
-        const unsigned long long k = P.nn[id];
-        const int m = (int)(k & 0xFFFFFFFFu);
-        const float x = P.dx[id], y = P.dy[id], z = P.dz[id];
-        T[i] = P.mx[m]; T[n + i] = P.my[m]; T[2 * n + i] = P.mz[m];
-        T[3 * n + i] = r00 * x + r01 * y + r02 * z + t0;
-        T[4 * n + i] = r10 * x + r11 * y + r12 * z + t1;
-        T[5 * n + i] = r20 * x + r21 * y + r22 * z + t2;
-        T[6 * n + i] = __uint_as_float((unsigned)(k >> 32));
-    }
-    __syncthreads();
-    // seven sequential chains: mu_m, mu_d (double, never reset: Q4) on six lanes of warp 0, err_new on warp 1 (its own warp, so the
-    // two loops run side by side instead of as two divergent halves of one warp)
-    if (tid < 6) {
-        const float* row = T + (size_t)tid * n;
-        double acc = (tid < 3) ? st.mu_m[tid] : st.mu_d[tid - 3];
+    // pass 1 (:257-271): rows 0-2 = p_m xyz, 3-5 = p_d xyz as doubles, then the float row of squared distances.
+    // Seven sequential chains: mu_m, mu_d (double, never reset: Q4) on six lanes of warp 0, err_new on warp 1 (its own warp, so the
+    // two loops run side by side instead of as two divergent halves of one warp).
+    // err_new: the reference accumulates `float += double(float)`, i.e. (float)((double)e + (double)r).  The double sum of two floats
+    // rounded to float equals the float sum (53 >= 2*24+2 bits: double rounding is innocuous for +), so one FADD per element, same bits
+    {
+        float* E = reinterpret_cast<float*>(D + (size_t)6 * C);
+        double acc = 0; float e = 0.f;
+        if (tid < 6) acc = (tid < 3) ? st.mu_m[tid] : st.mu_d[tid - 3];
+        for (int base = 0; base < num; base += C) {
+            const int cnt = min(C, num - base);
+            if (base > 0) __syncthreads();
+            for (int j = tid; j < cnt; j += blockDim.x) {
+                const int id = P.order[base + j];
+                const unsigned long long k = P.nn[id];
+                const int m = (int)(k & 0xFFFFFFFFu);
+                const float x = P.dx[id], y = P.dy[id], z = P.dz[id];
+                D[j] = (double)P.mx[m]; D[C + j] = (double)P.my[m]; D[2 * C + j] = (double)P.mz[m];
+                D[3 * C + j] = (double)(r00 * x + r01 * y + r02 * z + t0);
+                D[4 * C + j] = (double)(r10 * x + r11 * y + r12 * z + t1);
+                D[5 * C + j] = (double)(r20 * x + r21 * y + r22 * z + t2);
+                E[j] = __uint_as_float((unsigned)(k >> 32));
+            }
+            __syncthreads();
+            if (tid < 6) {
+                const double* row = D + (size_t)tid * C;
 #pragma unroll 8
-        for (int i = 0; i < num; ++i) acc = acc + (double)row[i];
-        s_mu[tid] = acc;
-    } else if (tid == 32) {
-        // the reference accumulates `float += double(float)`: (float)((double)e + (double)r).  The double sum of two floats rounded to
-        // float equals the float sum (53 >= 2*24+2 bits: double rounding is innocuous for +), so one FADD per element, same bits
-        const float* row = T + (size_t)6 * n;
-        float e = 0.f;
+                for (int i = 0; i < cnt; ++i) acc = acc + row[i];
+            } else if (tid == 32) {
 #pragma unroll 8
-        for (int i = 0; i < num; ++i) e = __fadd_rn(e, row[i]);
-        s_err = e;
+                for (int i = 0; i < cnt; ++i) e = __fadd_rn(e, E[i]);
+            }
+        }
+        if (tid < 6) s_mu[tid] = acc; else if (tid == 32) s_err = e;
     }
     __syncthreads();
     if (tid == 0) {
@@ -158,14 +166,32 @@ __device__ __forceinline__ bool icp_update_part(const PairDev& P, IcpState& st, 
     }
     __syncthreads();
     if (s_done) return true;
-    if (tid < 9) {   // H = ~q_t * q_m (:284), Matrix operator* accumulates over k in order
-        const int a = tid / 3, b = tid % 3;
-        const float* pd = T + (size_t)(3 + a) * n; const float* pm = T + (size_t)b * n;
-        const double mud = s_mu[3 + a], mum = s_mu[b];
-        double s = 0;
+    {   // H = ~q_t * q_m (:284), Matrix operator* accumulates over k in order: nine chains on nine lanes; the centred products
+        // (p_d[a] - mu_d[a]) * (p_m[b] - mu_m[b]) are not on the chains and come from the whole CTA
+        double s_ = 0;
+        const double mm0 = s_mu[0], mm1 = s_mu[1], mm2 = s_mu[2], md0 = s_mu[3], md1 = s_mu[4], md2 = s_mu[5];
+        for (int base = 0; base < num; base += C) {
+            const int cnt = min(C, num - base);
+            __syncthreads();
+            for (int j = tid; j < cnt; j += blockDim.x) {
+                const int id = P.order[base + j];
+                const int m = (int)(P.nn[id] & 0xFFFFFFFFu);
+                const float x = P.dx[id], y = P.dy[id], z = P.dz[id];
+                const double pm0 = (double)P.mx[m] - mm0, pm1 = (double)P.my[m] - mm1, pm2 = (double)P.mz[m] - mm2;
+                const double pd0 = (double)(r00 * x + r01 * y + r02 * z + t0) - md0, pd1 = (double)(r10 * x + r11 * y + r12 * z + t1) - md1,
+                             pd2 = (double)(r20 * x + r21 * y + r22 * z + t2) - md2;
+                D[j] = pd0 * pm0; D[C + j] = pd0 * pm1; D[2 * C + j] = pd0 * pm2;
+                D[3 * C + j] = pd1 * pm0; D[4 * C + j] = pd1 * pm1; D[5 * C + j] = pd1 * pm2;
+                D[6 * C + j] = pd2 * pm0; D[7 * C + j] = pd2 * pm1; D[8 * C + j] = pd2 * pm2;
+            }
+            __syncthreads();
+            if (tid < 9) {
+                const double* row = D + (size_t)tid * C;
 #pragma unroll 8
-        for (int k = 0; k < num; ++k) s = s + ((double)pd[k] - mud) * ((double)pm[k] - mum);
-        s_H[tid] = s;
+                for (int k = 0; k < cnt; ++k) s_ = s_ + row[k];
+            }
+        }
+        if (tid < 9) s_H[tid] = s_;
     }
     __syncthreads();
     if (tid == 0) {

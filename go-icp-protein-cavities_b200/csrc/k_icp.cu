@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256)
 icp_update_kernel(const PairDev* __restrict__ pairs, IcpState* __restrict__ states, int rowCap) {
     IcpState& st = states[blockIdx.x];
     if (st.done || st.mode != 0) return;
-    extern __shared__ float s_rows[];
+    extern __shared__ __align__(16) float s_rows[];
     icp_update_part(pairs[st.pair], st, s_rows, rowCap);
 }
 __global__ void __launch_bounds__(256)
@@ -137,7 +137,7 @@ icp_score_kernel(const PairDev* __restrict__ pairs, IcpState* __restrict__ state
 }
 
 __global__ void __launch_bounds__(256, 4)
-icp_fused_kernel(const PairDev* __restrict__ pairs, IcpState* states) { __shared__ float s_tile[7 * 1024]; icp_fused_body(pairs, states + blockIdx.x, s_tile, 7 * 1024); }
+icp_fused_kernel(const PairDev* __restrict__ pairs, IcpState* states) { __shared__ __align__(16) float s_tile[18 * 512]; icp_fused_body(pairs, states + blockIdx.x, s_tile, 18 * 512); }
 
 }  // namespace
 
@@ -165,10 +165,9 @@ cudaError_t goicp_launch_icp_iter(const PairDev* pairs, IcpState* states, int n,
         icp_nn_grid_kernel<<<dim3((maxNd + 3) / 4, n), 128, 0, st>>>(pairs, states, cubeMax);
         icp_nn_kernel<<<dim3(gx, gy, n), NN_THREADS, 0, st>>>(pairs, states, gy, 1);
     }
-    // the seven term rows of the update in shared memory when they fit (<= 200 KB: Nd <= 7314)
-    size_t rowBytes = (size_t)7 * maxNd * sizeof(float);
-    if (rowBytes > 200 * 1024) rowBytes = 0;
-    if (rowBytes > 48 * 1024) { cudaError_t e = cudaFuncSetAttribute(icp_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); if (e != cudaSuccess) return e; }
+    // staging for the update's chains: 72 bytes per position, at most 2048 positions (144 KB) at a time
+    const size_t rowBytes = (size_t)72 * (maxNd < 2048 ? (maxNd < 32 ? 32 : maxNd) : 2048);
+    if (rowBytes > 48 * 1024) { cudaError_t e = cudaFuncSetAttribute(icp_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 2048); if (e != cudaSuccess) return e; }
     icp_update_kernel<<<n, 256, rowBytes, st>>>(pairs, states, (int)(rowBytes / sizeof(float)));
     return cudaGetLastError();
 }

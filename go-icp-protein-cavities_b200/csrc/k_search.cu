@@ -710,7 +710,7 @@ search_kernel(const SearchArgs A) {
     __shared__ OwnerSh os;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float* icpTile; int icpCap = 3 * NN_TILE;   // the call staging region is idle while an ICP request runs
-    if constexpr (SMEM) { icpTile = reinterpret_cast<float*>(dyn_smem4); icpCap = (int)A.gstride; } else { __shared__ float s_tile[3 * NN_TILE]; icpTile = s_tile; }
+    if constexpr (SMEM) { icpTile = reinterpret_cast<float*>(dyn_smem4); icpCap = (int)A.gstride; } else { __shared__ __align__(16) float s_tile[3 * NN_TILE]; icpTile = s_tile; }
     CallCtx cx;
     __shared__ CancelSh s_cancel;
     __shared__ long long s_tStart, s_tIdle;
