@@ -254,6 +254,8 @@ struct EvTimer {   // CUDA-event time of a kernel group on a wave context's stre
     void stop(int nlaunch) { cudaEventRecord(c.ev1, c.stream); cudaEventSynchronize(c.ev1); float ms = 0; cudaEventElapsedTime(&ms, c.ev0, c.ev1); c.ms[slot] += ms; c.launches[slot] += nlaunch; }
 };
 
+// keys of the trimmed-ICP bitonic sort (icp_device.cuh): next power of two >= n, at least 32
+inline size_t sort_cap(int n) { size_t c = 32; while (c < (size_t)n) c <<= 1; return c; }
 struct BnbCfg { int NdP, NdQ; size_t smemFloats, smemBytes; int useSmem, perSM, threads, gridOff, S3p, ct; };
 
 // engine_setup.cu

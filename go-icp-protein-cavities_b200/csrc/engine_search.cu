@@ -93,7 +93,7 @@ goicp_status run_icp(Eng* h, WaveCtx& c, std::vector<IcpState>& states) {
         CU(c.sync());
         float ms = 0; cudaEventElapsedTime(&ms, c.ev0, c.ev1); c.ms[3] += ms; c.launches[3] += 1;
         for (int i = 0; i < n; i++) states[i] = ms_[i];
-        for (int i = 0; i < n; i++) if (states[i].status != 0) return fail(h, GOICP_ERR_UNSUPPORTED, "ICP with trimming supports Nd <= 2048");
+        for (int i = 0; i < n; i++) if (states[i].status != 0) return fail(h, GOICP_ERR_ARG, "trimmed ICP without its sort workspace (trimFraction changed after the clouds were set?)");
         return GOICP_OK;
     }
     CU(c.dIcp.ensure(sizeof(IcpState) * n));
@@ -125,7 +125,7 @@ goicp_status run_icp(Eng* h, WaveCtx& c, std::vector<IcpState>& states) {
     CU(c.sync());
     float ms = 0; cudaEventElapsedTime(&ms, c.ev0, c.ev1); c.ms[3] += ms; c.launches[3] += nl;
     for (int i = 0; i < n; i++) states[i] = hs[i];
-    for (int i = 0; i < n; i++) if (states[i].status != 0) return fail(h, GOICP_ERR_UNSUPPORTED, "ICP with trimming supports Nd <= 2048");
+    for (int i = 0; i < n; i++) if (states[i].status != 0) return fail(h, GOICP_ERR_ARG, "trimmed ICP without its sort workspace (trimFraction changed after the clouds were set?)");
     return GOICP_OK;
 }
 
@@ -550,7 +550,7 @@ static goicp_status register_resident(Eng* h, const BnbCfg& cfg) {
     for (int i = 0; i < np; i++) {
         Problem& P = h->probs[i]; const PairOut& o = outs[i];
         reset_search(P);
-        if (o.status == GOICP_SR_UNSUPPORTED) return fail(h, GOICP_ERR_UNSUPPORTED, "ICP with trimming supports Nd <= 2048");
+        if (o.status == GOICP_SR_UNSUPPORTED) return fail(h, GOICP_ERR_ARG, "trimmed ICP without its sort workspace (trimFraction changed after the clouds were set?)");
         if (o.status != 0) { redo.push_back(i); continue; }
         memcpy(P.optR, o.R, sizeof P.optR); memcpy(P.optT, o.t, sizeof P.optT);
         P.optError = o.optError; P.optComp = o.optComp;

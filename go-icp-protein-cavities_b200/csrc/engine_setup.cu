@@ -95,7 +95,7 @@ goicp_status upload_problems(Eng* h) {
         if (useF && p.regularizationFPFH > 0) w += al256(sizeof(float) * (size_t)P.NdAll * (nc + 1));
         if (p.regularizationNeighbors > 0) w += al256(sizeof(int) * P.NdAll) + al256(sizeof(int) * P.Nm);
         w += al256(sizeof(unsigned long long) * P.NdAll) + al256(sizeof(int) * P.NdAll) + al256(sizeof(float) * 8 * (size_t)std::max(P.NdAll, 1));
-        if (!(p.trimFraction < 0.001)) w += al256(sizeof(unsigned long long) * 2048);
+        if (!(p.trimFraction < 0.001)) w += al256(sizeof(unsigned long long) * sort_cap(P.NdAll));
         P.workBytes = w; P.workOff = workTot; workTot += w;
     }
     CU(h->arenaIn.ensure(inTot));
@@ -145,7 +145,7 @@ goicp_status upload_problems(Eng* h) {
         D.nn = reinterpret_cast<unsigned long long*>(dWork + w); w += al256(sizeof(unsigned long long) * P.NdAll);
         D.order = reinterpret_cast<int*>(dWork + w); w += al256(sizeof(int) * P.NdAll);
         D.scratch = reinterpret_cast<float*>(dWork + w); w += al256(sizeof(float) * 8 * (size_t)std::max(P.NdAll, 1));
-        if (!(p.trimFraction < 0.001)) { D.sortKeys = reinterpret_cast<unsigned long long*>(dWork + w); w += al256(sizeof(unsigned long long) * 2048); }
+        if (!(p.trimFraction < 0.001)) { D.sortKeys = reinterpret_cast<unsigned long long*>(dWork + w); w += al256(sizeof(unsigned long long) * sort_cap(P.NdAll)); }
         D.g.S = S; D.g.ncells = nc; D.g.xMin = P.info.xMin; D.g.yMin = P.info.yMin; D.g.zMin = P.info.zMin; D.g.scale = P.info.scale;
         D.Nm = P.Nm; D.Nd = P.Nd; D.NdAll = P.NdAll;
     });

@@ -75,7 +75,7 @@ struct PairDev {
     unsigned long long* nn;              // Nd packed (float bits of squared distance << 32 | model index)
     int* order;                          // Nd: id_data of points[i] (identity unless trimmed, jly_icp3d.hpp:252)
     float* scratch;                      // 8*Nd floats
-    unsigned long long* sortKeys;        // 2048 keys for the trimmed-ICP sort (NULL unless trimming)
+    unsigned long long* sortKeys;        // next power of two >= NdAll (at least 32) keys for the trimmed-ICP sort (NULL unless trimming)
 };
 
 struct InnerProb {          // one GoICP::InnerBnB call (jly_goicp.cpp:286)

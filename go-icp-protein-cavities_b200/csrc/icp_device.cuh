@@ -76,7 +76,6 @@ __device__ void svd3(const double H[9], double U[9], double W[3], double V[9]) {
 }
 
 // ---- per-iteration update: [trim sort], centroids, err, H, SVD, compose (jly_icp3d.hpp:252-308) ---------------------
-constexpr int SORT_CAP = 2048;
 // returns true (uniformly) when the call has finished (converged / maxIter / error)
 // `sT`/`sCap`: shared-memory staging (16-byte aligned, sCap floats, at least 18*32).  The order-sensitive sums of the reference are
 // sequential chains; everything that is NOT on a chain (gathers, float->double conversions, the centred products of H) is produced by
@@ -92,14 +91,15 @@ __device__ __forceinline__ bool icp_update_part(const PairDev& P, IcpState& st, 
     const int C = min(num > 0 ? num : 1, sCap / 18);   // positions of `order` per chunk: 9 double rows (pass 2) = 18 floats per position
 
     if (P.doTrim) {   // qsort of POINTREF by dis (:252-255); ties keep index order.  Bitonic sort in the pair's global scratch
-        unsigned long long* keys = P.sortKeys;
-        if (n > SORT_CAP || keys == nullptr) { if (tid == 0) { st.status = 3; st.done = 1; } return true; }
-        for (int i = tid; i < SORT_CAP; i += blockDim.x)
+        unsigned long long* keys = P.sortKeys;   // next power of two >= Nd keys (engine_setup.cu)
+        if (keys == nullptr) { if (tid == 0) { st.status = 3; st.done = 1; } return true; }
+        int cap = 32; while (cap < n) cap <<= 1;
+        for (int i = tid; i < cap; i += blockDim.x)
             keys[i] = (i < n) ? (((P.nn[i] >> 32) << 32) | (unsigned)i) : GOICP_NN_EMPTY;
         __syncthreads();
-        for (int k = 2; k <= SORT_CAP; k <<= 1)
+        for (int k = 2; k <= cap; k <<= 1)
             for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int i = tid; i < SORT_CAP; i += blockDim.x) {
+                for (int i = tid; i < cap; i += blockDim.x) {
                     const int ixj = i ^ j;
                     if (ixj > i) {
                         const unsigned long long a = keys[i], b = keys[ixj];

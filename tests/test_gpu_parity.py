@@ -149,6 +149,25 @@ def test_icp(g, po):
         assert e == eo and np.abs(R - Ro).max() < 1e-12 and np.abs(t - to).max() < 1e-12 and np.array_equal(corr, co)
 
 
+def test_icp_trimmed_large_source(g, po):
+    """trimmed ICP (jly_icp3d.hpp:252-255: qsort of the point references by distance, the closest 80 % enter the update) with more
+    source points than one 2048-key sort block: Nd = 3000.  Pose and correspondences equal the CPU restatement's."""
+    rng = np.random.default_rng(21)
+    model = rng.normal(size=(500, 3)); model = (0.7 * model / np.abs(model).max()).astype(np.float32)
+    data = rng.normal(size=(3000, 3)); data = (0.6 * data / np.abs(data).max()).astype(np.float32)
+    kw = dict(distTransSize=32, trimFraction=0.2)
+    reg = g.GoICP(model, data, g.upstream_config(**kw))
+    o = po.Oracle("port", model, data, po.upstream_config(**kw))
+    reg.BuildDT(); o.build_dt(); reg.set_nd(3000); o.set_nd(3000); reg.Initialize(); o.initialize()
+    for k in range(2):
+        R0 = np.eye(3) if k == 0 else rand_rot(rng).astype(np.float64)
+        t0 = np.zeros(3) if k == 0 else rng.uniform(-0.1, 0.1, 3)
+        e, R, t, corr = reg.ICP(R0, t0)
+        eo, Ro, to, co = o.icp(R0, t0)
+        assert np.abs(R - Ro).max() < 1e-12 and np.abs(t - to).max() < 1e-12 and np.array_equal(corr, co)
+        assert abs(e - eo) <= REL * eo   # the trimmed DT re-score is a tree sum over the selected residuals (north_star tolerance)
+
+
 @pytest.mark.parametrize("name,fp,golden_err,compat", [("pair1", False, 8.45388, 133), ("pair1", True, 9.37283, 133), ("pair2", False, 16.1742, 118)])
 def test_register_cavity_golden(g, name, fp, golden_err, compat):
     """full Register against the reference's shipped outputs: Error / Compatibilities / R / t (output/similar1.txt,
