@@ -149,6 +149,30 @@ def test_icp(g, po):
         assert e == eo and np.abs(R - Ro).max() < 1e-12 and np.abs(t - to).max() < 1e-12 and np.array_equal(corr, co)
 
 
+def test_icp_duplicated_model_points(g, po):
+    """NN tie rule: with exactly duplicated model points several indices share the smallest distance.  The exhaustive kernel returns
+    the lowest index, the reference's kd-tree (nanoflann) whichever leaf it reaches first; the matched COORDINATES, and with them
+    err, R and t, are the same (checked against the reference compiled from its sources when present, else the restatement)."""
+    rng = np.random.default_rng(33)
+    base = rng.normal(size=(150, 3)); base = (0.7 * base / np.abs(base).max()).astype(np.float32)
+    model = np.concatenate([base, base[::-1], base[:50]]).astype(np.float32)   # every point 2 or 3 times, in different orders
+    data = (base[:120] + rng.normal(scale=0.02, size=(120, 3))).astype(np.float32)
+    kw = dict(distTransSize=32)
+    kind = "ref" if po.available("ref") else "port"
+    reg = g.GoICP(model, data, g.upstream_config(**kw))
+    o = po.Oracle(kind, model, data, po.upstream_config(**kw))
+    reg.BuildDT(); o.build_dt(); reg.set_nd(120); o.set_nd(120); reg.Initialize(); o.initialize()
+    R0 = rand_rot(rng).astype(np.float64) @ np.eye(3); t0 = rng.uniform(-0.05, 0.05, 3)
+    for Rs, ts in ((np.eye(3), np.zeros(3)), (R0, t0)):
+        e, R, t, corr = reg.ICP(Rs, ts)
+        eo, Ro, to, co = o.icp(Rs, ts)
+        assert e == eo and np.abs(R - Ro).max() < 1e-12 and np.abs(t - to).max() < 1e-12
+        corr, co = np.asarray(corr), np.asarray(co)
+        assert np.array_equal(model[corr], model[co])                 # same matched coordinates ...
+        first = {tuple(pt): i for i, pt in reversed(list(enumerate(map(tuple, model))))}
+        assert all(first[tuple(model[c])] == c for c in corr)          # ... and this library always names the lowest index
+
+
 def test_icp_trimmed_large_source(g, po):
     """trimmed ICP (jly_icp3d.hpp:252-255: qsort of the point references by distance, the closest 80 % enter the update) with more
     source points than one 2048-key sort block: Nd = 3000.  Pose and correspondences equal the CPU restatement's."""
