@@ -385,15 +385,15 @@ def main():
             "note": "algorithmic bytes per eval per SURVEY 8(d): 4 B DT voxel + 20.25 B corner-term gathers when regularization>0. `achieved` = evals x bytes / CUDA-event time of search_kernel (ONE launch per step: the rotation BnB, "
                     "every InnerBnB call and every ICP of the batch run inside it), `achieved_aggregate` = evals x bytes / step time per GPU, `achieved_dt_gather_only` counts the 4 B DT voxel alone. Only evals of calls the reference order "
                     "consumes are counted (look-ahead calls that are abandoned and corner evals are not). The 20^3 volumes are staged into shared memory by TMA (cp.async.bulk) once per pair and CTA, so the gathers are LDS and DRAM sees "
-                    "staging, queue and memo traffic only: the binding limit is SM issue + the serial phases of each queue pop, not HBM (ncu at this occupancy: issue-active 46 %, 36 % of warp samples at a CTA barrier) -- see DESIGN.md "
-                    "section 4 and profiles/. `traffic` = dram__bytes_read + dram__bytes_write of one ncu-profiled launch of the same kernel at 592 CTAs (profiles/*_search_traffic.json)"}
-    import glob
-    profs = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_search_traffic.json")))
-    if profs:
-        try:
-            roof["traffic"] = json.load(open(profs[-1])).get("dram_bytes_per_launch")
-        except Exception:
-            pass
+                    "staging, queue and memo traffic only: the binding limit is SM issue + the serial phases of each queue pop, not HBM (ncu on this launch: issue-active 56 %, 34 % of warp samples at a CTA barrier) -- see DESIGN.md "
+                    "section 4 and profiles/. `traffic` = dram__bytes_read + dram__bytes_write of one ncu-profiled launch of the same kernel on the same 4096-pair workload at 592 CTAs (profiles/search_traffic.json; null for other workloads): queue slabs, corner memo and slot records, ~0.5 % of the algorithmic bytes"}
+    # DRAM bytes of one ncu-profiled launch of the same kernel on the same workload (4096 pairs, 592 CTAs): profiles/search_traffic.json
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "search_traffic.json")))
+        if int(tj.get("pairs_per_launch", 0)) == args.pairs and not args.fpfh:
+            roof["traffic"] = tj.get("dram_bytes_per_launch")
+    except Exception:
+        pass
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
             "config": config_dict(args), "pairs_per_s": args.pairs * world * args.steps / (dev_ms * 1e-3), "ms_per_pair": dev_ms / args.steps / args.pairs,
