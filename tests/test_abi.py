@@ -58,3 +58,24 @@ def test_cpp_dropin_builds(g):
     """the header-only C++ mirror of the reference classes compiles and links against the C-ABI library"""
     subprocess.check_call(["make", "-s", "-B", "-C", os.path.join(ROOT, "examples")])
     assert os.path.exists(os.path.join(ROOT, "examples", "goicp_demo")) and os.path.exists(os.path.join(ROOT, "examples", "GoICP_b200"))
+
+
+def test_bench_reference_arm_contract(po):
+    """`bench.py --impl reference` (the reference's own CPU implementation on the host cores: no GPU involved, so it runs here):
+    one JSON line with the keys of the bench contract, the same metric / unit / config as the GPU arm, `impl: reference`, a
+    `cpu_baseline` describing the run and an `e2e` block repeating the line's value with zero copy bytes."""
+    import json, sys
+    if not (po.available("ref") or po.available("port")):
+        pytest.skip("no oracle library built")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-pairs", "4"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "cube_point_bound_evals_per_sec" and d["unit"] == "evals/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 1 and d["n_gpus"] == 1 and d["vs_baseline"] is None
+    assert d["config"]["workload"].startswith("BO1-shaped") and d["config"]["pairs_per_gpu"] == 4096
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "pairs" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
