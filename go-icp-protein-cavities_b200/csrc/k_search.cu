@@ -46,11 +46,14 @@ struct OwnerSh {
     int action, actOwner, actSlot, actCancel;
     int noMorePairs, lastSpawnJ, manager;
     int waited;
+    // incremental look-ahead: a full walk of the queue's front is made every WALK_EVERY pops; in between only the nodes pushed since
+    // the last call are attached, if their lower bound lies inside the window the last walk covered
+    int walkLeft, lastTarget, nNew; float winLb; float newLb[8]; alignas(16) unsigned newKey[8][4]; float newW[8];
     int waitPolls;               // manager mode: polls spent waiting for a helper to take the call the search needs next
     int quiet;                   // rotation nodes popped since the incumbent last improved: look-ahead grows 1, 3, 7, ... with it (calls made under an incumbent that is about to improve are wasted)
     // results of the current node's children as last fetched by the warp (a slot that was done then stays done until the owner frees it)
     unsigned pfState[8]; float pfOpt[8]; alignas(64) unsigned pfOut[8][16];   // (rows are read as InnerOut records)
-    int cand[64]; unsigned long long candKey[64]; int ncand;
+    unsigned short cand[64]; unsigned candKey[64]; int ncand;   // frontier of the look-ahead walk: heap positions and their 32-bit keys (lb bits, low 6 bits clear)
 };
 
 __device__ __forceinline__ unsigned ld_vol(const unsigned* p) { return *reinterpret_cast<const volatile unsigned*>(p); }
@@ -130,6 +133,7 @@ struct Cta {   // what every routine of this file needs about the CTA's place in
     RNodeD* rq;              // this CTA's rotation queue
     IcpState* icp;           // this CTA's two ICP states
     int me, lane;
+    float* scr;              // >= 4 KB of shared memory that is idle while the scheduler runs (the staging region of the calls)
 };
 __device__ __forceinline__ unsigned st_of(unsigned w) { return w & 0xFFu; }
 __device__ __forceinline__ unsigned queued_word(unsigned prio) { return SL_QUEUED | (prio & 0xFFFFFF00u); }   // prio: float bits of the node's lb (>= 0: bit order = value order)
@@ -260,6 +264,10 @@ __device__ __forceinline__ void prefetch_group(Cta& c) {
     __syncwarp();
 }
 
+__device__ __forceinline__ void note_pushed(OwnerSh& os, const RNodeD& n) {   // lane 0
+    if (os.nNew < 8) { const int q = os.nNew++; os.newLb[q] = n.lb; os.newW[q] = n.w; os.newKey[q][0] = (unsigned)n.l; os.newKey[q][1] = __float_as_uint(n.a); os.newKey[q][2] = __float_as_uint(n.b); os.newKey[q][3] = __float_as_uint(n.c); }
+    else os.walkLeft = 0;
+}
 // ---- the OuterBnB state machine, lane 0 of the owner's warp 0.  Returns what it needs next. --------------------------------------
 __device__ __forceinline__ int owner_serial(Cta& c) {
     OwnerSh& os = c.os;
@@ -269,7 +277,7 @@ __device__ __forceinline__ int owner_serial(Cta& c) {
         case OW_START: {   // initial error (:601-627) and ICP from the identity (:634)
             const PairDev& P = A.pairs[os.pair];
             { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); A.outs[os.pair].tStartMs = (float)((now - A.ctl->t0ns) * 1e-6); }
-            os.quiet = 0;
+            os.quiet = 0; os.walkLeft = 0; os.lastTarget = -1; os.nNew = 0; os.winLb = 0.f;
             os.SSE = P.SSEThresh; os.optComp = 0; os.status = 0; os.nEvents = 0; os.heapN = 0; os.lastLb = 0.f; os.needLbOnly = 0;
             for (int k = 0; k < 6; k++) os.cnt[k] = 0;
             for (int k = 0; k < 9; k++) os.optR[k] = (k % 4 == 0) ? 1.0 : 0.0;
@@ -320,7 +328,9 @@ __device__ __forceinline__ int owner_serial(Cta& c) {
                 int g = lookup_group(c, key);   // calls made ahead of time for this node?
                 atomicAdd(&A.ctl->dbg[g >= 0 ? 12 : 13], 1ull);
                 if (g < 0) {
-                    while ((g = alloc_group(c, -1)) < 0) __nanosleep(200);   // every group has calls running (they stop at their next pop if abandoned)
+                    // (no victim: every group has calls running -- they stop at their next pop if abandoned -- or carries the current
+                    //  walk stamp, which the pops between two full walks do not advance: age them; the next look-ahead is a full walk)
+                    while ((g = alloc_group(c, -1)) < 0) { os.walkStamp++; os.walkLeft = 0; __nanosleep(200); }
                     *reinterpret_cast<uint4*>(os.grpKey[g]) = key;
                 }
                 os.grpStamp[g] = os.walkStamp + 1u;   // the walk that follows must not take it away
@@ -345,7 +355,7 @@ __device__ __forceinline__ int owner_serial(Cta& c) {
                 if (st == SL_DONE) return RQ_AGAIN;   // finished meanwhile: fetch its record
                 if (st == SL_SKIP) { os.j++; break; }
                 if (st == SL_FREE) {
-                    if (A.specMax > 0 && os.lastSpawnJ != os.j && os.cnt[0] >= 16) { os.lastSpawnJ = os.j; return RQ_SPAWN; }   // helpers may have appeared since the last pop
+                    if (A.specMax > 0 && os.lastSpawnJ != os.j && os.cnt[0] >= 16) { os.lastSpawnJ = os.j; os.walkLeft = 0; return RQ_SPAWN; }   // helpers may have appeared since the last pop
                     const RNodeD ch = child_of(os.par, os.j);
                     float R[9];
                     if (!child_rotation(A.fma != 0, ch, R)) { os.j++; break; }
@@ -403,7 +413,7 @@ __device__ __forceinline__ int owner_serial(Cta& c) {
                 if (!(o.err2 >= os.optError)) {                                             // :863-871
                     RNodeD nr = child_of(os.par, os.j); nr.ub = os.ubChild; nr.lb = o.err2;
                     if (os.heapN >= A.rqCap) { os.status = GOICP_SR_OVERFLOW; finish_pair(c, 0); os.phase = OW_NONE; break; }
-                    rq_push(c.rq, os.heapN, nr);
+                    rq_push(c.rq, os.heapN, nr); note_pushed(os, nr);
                 }
             } else {
                 os.cnt[0]++; os.cnt[1] += o.pops; os.cnt[2] += o.subcubes;
@@ -411,7 +421,7 @@ __device__ __forceinline__ int owner_serial(Cta& c) {
                 if (!(o.err >= os.optError)) {
                     RNodeD nr = child_of(os.par, os.j); nr.ub = os.ubChild; nr.lb = o.err;
                     if (os.heapN >= A.rqCap) { os.status = GOICP_SR_OVERFLOW; finish_pair(c, 0); os.phase = OW_NONE; break; }
-                    rq_push(c.rq, os.heapN, nr);
+                    rq_push(c.rq, os.heapN, nr); note_pushed(os, nr);
                 }
                 os.needLbOnly = 0;
             }
@@ -444,9 +454,9 @@ __device__ __forceinline__ int owner_serial(Cta& c) {
                 os.heapN = m;
                 atomicAdd(&A.ctl->dbg[10], (unsigned long long)(clock64() - tp0));
             }
-            { int g; while ((g = alloc_group(c, -1)) < 0) __nanosleep(200); os.par.group = g; *reinterpret_cast<uint4*>(os.grpKey[g]) = node_key(os.par); os.grpStamp[g] = os.walkStamp + 1u; }   // the old group drains (calls of the previous incumbent)
+            { int g; while ((g = alloc_group(c, -1)) < 0) { os.walkStamp++; __nanosleep(200); } os.par.group = g; *reinterpret_cast<uint4*>(os.grpKey[g]) = node_key(os.par); os.grpStamp[g] = os.walkStamp + 1u; }   // the old group drains (calls of the previous incumbent)
             for (int k = 0; k < 8; k++) os.pfState[k] = SL_FREE;
-            os.lastSpawnJ = os.j;
+            os.lastSpawnJ = os.j; os.walkLeft = 0;
             os.phase = OW_CHILD;
             return RQ_SPAWN;
         }
@@ -506,22 +516,74 @@ __device__ __forceinline__ void spawn_spec(Cta& c) {
     // The next nodes in pop order: the queue is a binary heap, so they are reached from the root through a frontier of candidate
     // positions whose keys sit in shared memory and are compared by all lanes at once.  The walk is only made when several groups
     // are missing (one walk then attaches them all).
-    if (lane == 0) { os.walkStamp++; os.grpStamp[os.par.group] = os.walkStamp; os.specGroups = 0; os.ncand = 0; if (os.heapN > 0) { os.cand[0] = 0; const RNodeD nd = ld_node(c.rq); os.candKey[0] = ((unsigned long long)__float_as_uint(nd.lb) << 32) | ((unsigned long long)(unsigned)nd.l << 8); os.ncand = 1; } }
+    constexpr int WALK_EVERY = 4;
+    // (the decision and the count come from lane 0 through shuffles: lane 0 rewrites both words below, and lanes of a warp do not
+    //  run in lock-step -- a lane that read them late would take the other branch and the warp-wide operations would never meet)
+    int fast = 0, nNewL = 0;
+    if (lane == 0) { fast = (os.walkLeft > 0 && target == os.lastTarget) ? 1 : 0; nNewL = os.nNew; }
+    fast = __shfl_sync(GOICP_FULL, fast, 0);
+    if (fast) {
+        // fast path: the window of the last full walk still stands; only the nodes pushed since then can have entered it
+        const int nNew = __shfl_sync(GOICP_FULL, nNewL, 0);
+        const float winLb = os.winLb, optE = os.optError, sse = os.SSE;
+        __syncwarp();
+        bool ok = true;
+        for (int q = 0; q < nNew && ok; q++) {
+            const float lb = os.newLb[q];
+            if (lb > winLb || (optE - lb) <= sse) continue;
+            const uint4 key = *reinterpret_cast<const uint4*>(os.newKey[q]);
+            int g = lookup_group_w(c, key);
+            if (g >= 0) continue;
+            if (lane == 0) g = alloc_group(c, os.par.group);
+            g = __shfl_sync(GOICP_FULL, g, 0);
+            if (g < 0) { ok = false; break; }   // the groups of nodes that fell out of the window are only recognised by a full walk
+            if (lane == 0) { *reinterpret_cast<uint4*>(os.grpKey[g]) = key; os.grpStamp[g] = os.walkStamp; os.specGroups++; }
+            if (lane < 8) {
+                RNodeD nd; nd.l = (int)key.x; nd.a = __uint_as_float(key.y); nd.b = __uint_as_float(key.z); nd.c = __uint_as_float(key.w); nd.w = os.newW[q]; nd.lb = lb; nd.ub = 0.f; nd.group = -1;
+                const int sidx = 8 * g + lane;
+                const RNodeD ch = child_of(nd, lane);
+                float R[9];
+                if (!child_rotation(A.fma != 0, ch, R)) st_vol(c.st + sidx, SL_SKIP);
+                else { fill_request(c, c.slots + sidx, ch, R, false); __threadfence(); st_vol(c.st + sidx, queued_word(__float_as_uint(lb) | 0x100u)); published++; }
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+        if (ok) {
+            if (lane == 0) { os.nNew = 0; os.walkLeft--; }
+            published = __reduce_add_sync(GOICP_FULL, published);
+            if (lane == 0 && published) { atomicAdd(&c.hdr->nQueued, (unsigned)published); atomicOr(&A.ctl->wantHelp[c.me >> 5], 1u << (c.me & 31)); }
+            __syncwarp();
+            return;
+        }
+    }
+    if (lane == 0) { os.nNew = 0; os.walkLeft = WALK_EVERY - 1; os.lastTarget = target; os.winLb = 0.f; }
+    __syncwarp();
+    // The top of the heap (first TOPN positions: where nearly every node of the walk and its children sit) is copied to shared memory
+    // with all lanes' loads in flight at once; the walk then pays one global round trip instead of two per node.
+    constexpr int TOPN = 127;
+    RNodeD* top = reinterpret_cast<RNodeD*>(c.scr);
+    const int topN = target > 0 ? min(os.heapN, TOPN) : 0;
+    for (int k = lane; k < topN; k += 32) top[k] = ld_node(c.rq + k);
+    __syncwarp();
+    auto node_at = [&](int pos) -> RNodeD { return pos < topN ? top[pos] : ld_node(c.rq + pos); };
+    if (lane == 0) { os.walkStamp++; os.grpStamp[os.par.group] = os.walkStamp; os.specGroups = 0; os.ncand = 0; if (os.heapN > 0) { os.cand[0] = 0; os.candKey[0] = __float_as_uint(node_at(0).lb) & ~63u; os.ncand = 1; } }
     __syncwarp();
     for (int it = 0; it < target; it++) {
         const int nc = os.ncand;
-        if (nc == 0) break;
-        unsigned long long best = ~0ull;
-        for (int k = lane; k < nc; k += 32) { const unsigned long long key = os.candKey[k] | (unsigned)k; best = key < best ? key : best; }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(GOICP_FULL, best, o); best = v < best ? v : best; }
-        const int k = (int)(best & 0xFFu);
+        if (nc == 0) { if (lane == 0) os.winLb = 3.0e38f; break; }   // the whole queue is inside the window
+        // (the order of the walk only decides which calls are made ahead of time, never a result: lb truncated to 26 bits, ties in
+        //  frontier order, so that the minimum is one warp reduction)
+        unsigned best = ~0u;
+        for (int k = lane; k < nc; k += 32) { const unsigned key = os.candKey[k] | (unsigned)k; best = key < best ? key : best; }
+        best = __reduce_min_sync(GOICP_FULL, best);
+        const int k = (int)(best & 63u);
         const int pos = os.cand[k];
         __syncwarp();
         if (lane < 2) {   // the node leaves the frontier, its two heap children enter
             const int cp = 2 * pos + 1 + lane;
-            unsigned long long key = 0; const bool have = cp < os.heapN;
-            if (have) { const RNodeD nd = ld_node(c.rq + cp); key = ((unsigned long long)__float_as_uint(nd.lb) << 32) | ((unsigned long long)(unsigned)nd.l << 8); }
+            unsigned key = 0; const bool have = cp < os.heapN;
+            if (have) key = __float_as_uint(node_at(cp).lb) & ~63u;
             const unsigned hm = __ballot_sync(0x3u, have);
             int n2 = nc - 1;
             if (lane == 0) { os.cand[k] = os.cand[n2]; os.candKey[k] = os.candKey[n2]; }
@@ -531,15 +593,15 @@ __device__ __forceinline__ void spawn_spec(Cta& c) {
             if (lane == 0) os.ncand = min(62, n2 + __popc(hm));
         }
         __syncwarp();
-        const RNodeD nd = ld_node(c.rq + pos);
+        const RNodeD nd = node_at(pos);
         if ((os.optError - nd.lb) <= os.SSE) break;   // the search ends when this node is popped (:685)
         const uint4 key = node_key(nd);
         int g = lookup_group_w(c, key);
-        if (g >= 0) { if (lane == 0) os.grpStamp[g] = os.walkStamp; __syncwarp(); continue; }   // its calls are already out
+        if (g >= 0) { if (lane == 0) { os.grpStamp[g] = os.walkStamp; os.winLb = nd.lb; } __syncwarp(); continue; }   // its calls are already out
         if (lane == 0) g = alloc_group(c, os.par.group);
         g = __shfl_sync(GOICP_FULL, g, 0);
         if (g < 0) break;
-        if (lane == 0) { *reinterpret_cast<uint4*>(os.grpKey[g]) = key; os.grpStamp[g] = os.walkStamp; os.specGroups++; }
+        if (lane == 0) { *reinterpret_cast<uint4*>(os.grpKey[g]) = key; os.grpStamp[g] = os.walkStamp; os.specGroups++; os.winLb = nd.lb; }   // (winLb: the window reaches this far)
         if (lane < 8) {
             const int sidx = 8 * g + lane;
             const RNodeD ch = child_of(nd, lane);
@@ -726,7 +788,7 @@ search_kernel(const SearchArgs A) {
     for (;;) {
         __syncthreads();
         if (warp == 0) {
-            Cta c{A, os, A.slots + (size_t)blockIdx.x * SR_NSLOT, A.states + (size_t)blockIdx.x * SR_NSLOT, A.hdrs + blockIdx.x, reinterpret_cast<RNodeD*>(A.rq) + (size_t)blockIdx.x * 2 * A.rqCap, A.icp + 2 * (size_t)blockIdx.x, (int)blockIdx.x, lane};
+            Cta c{A, os, A.slots + (size_t)blockIdx.x * SR_NSLOT, A.states + (size_t)blockIdx.x * SR_NSLOT, A.hdrs + blockIdx.x, reinterpret_cast<RNodeD*>(A.rq) + (size_t)blockIdx.x * 2 * A.rqCap, A.icp + 2 * (size_t)blockIdx.x, (int)blockIdx.x, lane, icpTile};
             const long long t0 = clock64(); schedule(c); if (lane == 0) s_tIdle += clock64() - t0;
         }
         __syncthreads();
