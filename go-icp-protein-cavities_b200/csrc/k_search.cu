@@ -46,7 +46,7 @@ struct OwnerSh {
     int action, actOwner, actSlot, actCancel;
     int noMorePairs, lastSpawnJ, manager;
     int waited;
-    // incremental look-ahead: a full walk of the queue's front is made every WALK_EVERY pops; in between only the nodes pushed since
+    // incremental look-ahead: a full walk of the queue's front is made every SearchArgs.walkEvery pops; in between only the nodes pushed since
     // the last call are attached, if their lower bound lies inside the window the last walk covered
     int walkLeft, lastTarget, nNew; float winLb; float newLb[8]; alignas(16) unsigned newKey[8][4]; float newW[8];
     int waitPolls;               // manager mode: polls spent waiting for a helper to take the call the search needs next
@@ -516,7 +516,6 @@ __device__ __forceinline__ void spawn_spec(Cta& c) {
     // The next nodes in pop order: the queue is a binary heap, so they are reached from the root through a frontier of candidate
     // positions whose keys sit in shared memory and are compared by all lanes at once.  The walk is only made when several groups
     // are missing (one walk then attaches them all).
-    constexpr int WALK_EVERY = 4;
     // (the decision and the count come from lane 0 through shuffles: lane 0 rewrites both words below, and lanes of a warp do not
     //  run in lock-step -- a lane that read them late would take the other branch and the warp-wide operations would never meet)
     int fast = 0, nNewL = 0;
@@ -557,7 +556,7 @@ __device__ __forceinline__ void spawn_spec(Cta& c) {
             return;
         }
     }
-    if (lane == 0) { os.nNew = 0; os.walkLeft = WALK_EVERY - 1; os.lastTarget = target; os.winLb = 0.f; }
+    if (lane == 0) { os.nNew = 0; os.walkLeft = A.walkEvery - 1; os.lastTarget = target; os.winLb = 0.f; }
     __syncwarp();
     // The top of the heap (first TOPN positions: where nearly every node of the walk and its children sit) is copied to shared memory
     // with all lanes' loads in flight at once; the walk then pays one global round trip instead of two per node.

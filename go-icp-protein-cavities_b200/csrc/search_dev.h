@@ -54,6 +54,7 @@ struct SearchArgs {
     int fma;             // which build of sinf / cosf the host libm runs (libm_exact.h)
     int specMax;         // most slot groups attached to rotation-queue nodes (0: never speculate)
     int quietRamp;       // 1: after an improvement the look-ahead restarts at 1 node and doubles per rotation pop
+    int walkEvery;       // a full look-ahead walk of the queue front every walkEvery-th rotation pop (in between: incremental)
     int managerRatio;    // an owner stops running calls itself (and only manages) once helpers >= managerRatio x owners (0: never)
     int deepCalls;       // a pair asks for help while unclaimed pairs remain once it has consumed this many InnerBnB calls (one more group per multiple)
     SearchCtl* ctl; OwnerHdr* hdrs; SearchSlot* slots; unsigned* states; void* rq; int rqCap; IcpState* icp; PairOut* outs;
