@@ -708,7 +708,9 @@ __device__ __forceinline__ void schedule(Cta& c) {
         if (os.pair >= 0) {
             int rq = 0;
             const long long tq0 = clock64();
-            if (os.phase == OW_CHILD && os.j < 8) prefetch_group(c);
+            // (decided by lane 0 and broadcast: lane 0 rewrites phase and j in owner_serial below, and a lane that evaluated the condition
+            //  late would walk into prefetch_group's warp-wide operations alone)
+            { int pf = (os.phase == OW_CHILD && os.j < 8) ? 1 : 0; pf = __shfl_sync(GOICP_FULL, pf, 0); if (pf) prefetch_group(c); }
             if (lane == 0) { rq = owner_serial(c); atomicAdd(&A.ctl->dbg[0], (unsigned long long)(clock64() - tq0)); }
             rq = __shfl_sync(GOICP_FULL, rq, 0);
             __syncwarp();
